@@ -460,7 +460,7 @@ static void update_osp(orc_world* w) {
 static void physics_process_reference(orc_world* w) {
     update_osp(w);
     int n = w->n_ent;
-    char* prev = (char*)malloc(n); char* newc = (char*)calloc(n, 1);
+    char* prev = (char*)malloc((size_t)n + 1); char* newc = (char*)calloc((size_t)n + 1, 1);
     for (int e = 0; e < n; e++) prev[e] = (w->ent[e].st.flags & F_CONTACT) ? 1 : 0;
     for (int li = 0; li < w->n_leaves; li++) {
         node_t* leaf = w->leaves[li];
