@@ -1,0 +1,204 @@
+/* reboot_physics.h -- C ABI of the B200-native ReBoot physics step (libreboot_b200.so).
+ *
+ * Drop-in boundary for the reference's physics path. Every entry point names the reference
+ * interface it replaces (paths relative to the reference root). Plain C: opaque handle, plain
+ * pointers and sizes, int status codes; nothing throws across this boundary. The library is
+ * CUDA-only (sm_100a): there is no CPU fallback and rb_world_create fails loudly without a device.
+ *
+ * Reference surface being replaced
+ *   class Physics            physics/include/Physics.h:29-52   (addEntities / addEntity / run / visualize)
+ *   Physics::_physicsProcess physics/src/Physics.cpp:81-208    (the step)
+ *   Entity::_updateKinematics, setPosition, setVelocity        model/src/Entity.cpp:131-142, 373-395
+ *   class StateVector        math/include/StateVector.h:32-73  (state setters / getters, update)
+ *   Geometry::addSphere / addTriangle                           physics/include/Geometry.h:42-46
+ *
+ * Ids are dense uint32 in insertion order: geom ids for static triangle geometry (Triangle-type
+ * entities), body ids for sphere models (Sphere-type entities). Threading follows the reference:
+ * one caller thread per world; rb_step only enqueues work on the world's CUDA stream, the
+ * query/get calls synchronise (the reference's physics thread produces, its render thread reads
+ * under Physics::_lock, Physics.h:44).
+ */
+#ifndef REBOOT_PHYSICS_H
+#define REBOOT_PHYSICS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rb_world rb_world;
+
+/* status codes (the reference returns void everywhere and fails by UB; SURVEY.md §8b "Errors") */
+enum {
+    RB_OK = 0,
+    RB_ERR_INVALID = 1,      /* bad argument / NaN input / call in the wrong phase */
+    RB_ERR_OOM = 2,          /* host or device allocation failed */
+    RB_ERR_CAPACITY = 3,     /* output buffer too small; required size reported */
+    RB_ERR_CUDA = 4,         /* CUDA runtime error, see rb_last_error */
+    RB_ERR_NCCL = 5,         /* NCCL error, see rb_last_error */
+    RB_ERR_NO_DEVICE = 6     /* no CUDA device: the product has no CPU path */
+};
+
+/* body flag bits (StateVector::_active/_gravity/_contact, math/include/StateVector.h:39-43) */
+enum { RB_ACTIVE = 1u, RB_GRAVITY = 2u, RB_CONTACT = 4u };
+
+/* Compile-time constants of the reference exposed as configuration; rb_config_default() fills the
+ * reference's values. */
+typedef struct rb_config {
+    float    world_half;     /* 1000  : OSP root cube is 2000^3 at the origin, physics/src/Physics.cpp:7-9 */
+    float    gravity;        /* -9.8  : math/include/StateVector.h:28 */
+    float    friction;       /* 0.95  : math/include/StateVector.h:30 */
+    float    pushout;        /* 1.0001: math/src/GeometryMath.cpp:509 */
+    float    ss_damp;        /* 0.1   : math/src/GeometryMath.cpp:537,549 */
+    float    margin_cap;     /* broadphase candidate margin cap in world units (ours; 0.25) */
+    int32_t  device;         /* CUDA device ordinal */
+    void*    stream;         /* cudaStream_t to enqueue on; NULL = the world creates its own */
+    uint64_t max_contacts;   /* device contact-buffer capacity; 0 = 4 per sphere + 1024 */
+    /* spatial slab owned by this world along x (multi-GPU); defaults cover the whole world */
+    float    slab_lo, slab_hi;
+    int32_t  rank, nranks;
+} rb_config;
+
+/* initial state of a body: StateVector setters, math/include/StateVector.h:48-60 */
+typedef struct rb_body_init {
+    float    pos[3];
+    float    vel[3];
+    uint32_t flags;          /* RB_ACTIVE | RB_GRAVITY (RB_CONTACT starts clear) */
+} rb_body_init;
+
+/* one contact of the last step / detect call.  Reference payload: Physics::_triangleIntersectionList
+ * (map<Entity*, set<Triangle*>>, physics/include/Physics.h:28,36) plus the sphere-sphere hits that
+ * the reference resolves but never reports; depth / normal as SURVEY.md §8(a) a15-a16 derives them. */
+typedef struct rb_contact {
+    uint32_t kind;           /* 0 = sphere-sphere, 1 = sphere-triangle */
+    uint32_t body;           /* body id of the sphere (lower body id for sphere-sphere) */
+    uint32_t sphere;         /* sphere index inside that body */
+    uint32_t other;          /* kind 0: other body id; kind 1: geom id */
+    uint32_t other_prim;     /* kind 0: sphere index inside the other body; kind 1: triangle index inside the geom */
+    float    depth;          /* kind 0: rA+rB-|cA-cB| ; kind 1: r-|P-q| */
+    float    normal[3];      /* kind 0: normalize(cA-cB) ; kind 1: normalize(P-q) */
+} rb_contact;
+
+typedef struct rb_stats_t {
+    uint64_t steps;               /* rb_step calls so far */
+    uint64_t tests_ss, tests_st;  /* exact narrowphase predicate evaluations (cumulative) */
+    uint64_t cand_ss, cand_st;    /* broadphase candidates visited (cumulative) */
+    uint64_t hits_ss, hits_st;    /* contacts recorded (cumulative) */
+    uint64_t contacts_last;       /* contacts produced by the last step / detect (may exceed capacity) */
+    uint64_t contacts_dropped;    /* contacts that did not fit the device buffer (cumulative) */
+    uint64_t margin_overflow;     /* bodies displaced further than their candidate margin (cumulative) */
+    uint32_t n_bodies, n_spheres, n_geoms, n_tris;
+    uint32_t sphere_cols_x, sphere_cols_z, tri_cols_x, tri_cols_z;
+    uint64_t device_bytes;        /* HBM held by this world */
+    uint32_t halo_sent_last, halo_recv_last; /* multi-GPU: boundary spheres exchanged in the last step */
+    uint32_t migrated_out_last, migrated_in_last;
+} rb_stats_t;
+
+void        rb_config_default(rb_config* cfg);
+
+/* Physics::Physics() -- physics/src/Physics.cpp:7-12 */
+int         rb_world_create(const rb_config* cfg, rb_world** out);
+/* Physics::~Physics() -- physics/src/Physics.cpp:14-16 (the reference frees nothing; we do) */
+void        rb_world_destroy(rb_world* w);
+/* last error text of this world (or of the failed create when w == NULL) */
+const char* rb_last_error(const rb_world* w);
+
+/* add-static-geometry: a Triangle-type entity. Geometry::addTriangle (physics/src/Geometry.cpp:11-13)
+ * for ntri triangles; xyz9 = ntri * (A.xyz, B.xyz, C.xyz) in WORLD coordinates (the reference never
+ * transforms triangles, physics/src/Geometry.cpp:33-37). Static geometry is inactive. */
+int         rb_add_static_geometry(rb_world* w, uint32_t ntri, const float* xyz9, uint32_t* geom_id);
+
+/* add-model: a Sphere-type entity. Geometry::addSphere (physics/src/Geometry.cpp:15-17) for each
+ * object-space sphere (x,y,z,r) + Entity ctor (model/src/Entity.cpp:24,45): world_xform16 is the
+ * row-major _worldSpaceTransform (NULL = identity; last row must be 0 0 0 1). */
+int         rb_add_model(rb_world* w, uint32_t nspheres, const float* obj_center_radius4,
+                         const float* world_xform16, const rb_body_init* init, uint32_t* body_id);
+
+/* bulk add-model: n bodies sharing nothing. sphere_start has n+1 CSR offsets into
+ * obj_center_radius4; world_scale (nullable) is a per-body uniform scale of W; pos3/vel3 are n*3;
+ * flags n. Returns the first body id. */
+int         rb_add_models(rb_world* w, uint32_t n, const uint32_t* sphere_start,
+                          const float* obj_center_radius4, const float* world_scale,
+                          const float* pos3, const float* vel3, const uint32_t* flags,
+                          uint32_t* first_body_id);
+
+/* Physics::addEntities -- physics/src/Physics.cpp:26-45 (builds the broadphase; call once, Q9).
+ * Uploads the SoA state, builds the static triangle grid, primes the model transforms like
+ * Entity::_updateKinematics(0). */
+int         rb_build(rb_world* w);
+
+/* One reference tick (engine/src/MasterClock.cpp:36-45): every Entity::_updateKinematics(ms)
+ * (model/src/Entity.cpp:131-142) followed by Physics::_physicsProcess(ms)
+ * (physics/src/Physics.cpp:81-208). Asynchronous on the world's stream. */
+int         rb_step(rb_world* w, int ms);
+/* Only the Entity::_updateKinematics half of the tick (integration + sphere world transform). */
+int         rb_integrate(rb_world* w, int ms);
+/* Only the Physics::_physicsProcess half (broadphase + narrowphase + resolution + contact flags). */
+int         rb_collide(rb_world* w);
+/* Frozen-state detection: the collision half with both resolutions turned into no-ops; state and
+ * contact flags untouched. Fills the contact buffer (SURVEY.md §8c level L1). */
+int         rb_detect(rb_world* w);
+/* block until everything enqueued so far has finished */
+int         rb_sync(rb_world* w);
+
+/* query-contacts: Physics::visualize -- physics/src/Physics.cpp:51-79. Contacts of the last
+ * step/detect, de-duplicated, sorted by (kind, body, sphere, other, other_prim) when sorted != 0.
+ * *n receives the number available; RB_ERR_CAPACITY if cap is too small (nothing is written). */
+int         rb_query_contacts(rb_world* w, rb_contact* out, uint64_t cap, uint64_t* n, int sorted);
+/* number of contacts of the last step without copying them (synchronises) */
+int         rb_contact_count(rb_world* w, uint64_t* n);
+
+/* StateVector getters, math/include/StateVector.h:62-72; any pointer may be NULL.
+ * pos4/vel4: n_bodies * 4 floats (x,y,z,pad), flags: n_bodies. Synchronises. */
+int         rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags);
+/* Entity::getMVP / getPrevMVP model-matrix translations ([3],[7],[11]) as n_bodies * 4 floats */
+int         rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4);
+/* angular state, n_bodies * 4 floats each */
+int         rb_get_angular(rb_world* w, float* ang_pos4, float* ang_vel4);
+/* world-space spheres as Sphere::getPosition/getRadius see them: n_spheres * 4 floats */
+int         rb_get_world_spheres(rb_world* w, float* xyzr4);
+
+/* StateVector::setLinearPosition / setLinearVelocity (StateVector.cpp:122-135) for `count` bodies
+ * starting at `first`; pos4/vel4 are count*4 floats, either may be NULL. Like the reference these
+ * do not touch the model matrices until the next step. */
+int         rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4);
+/* StateVector::setActive / setGravity / setContact (StateVector.cpp:117-120, 169-177): for each of
+ * `count` bodies starting at `first`, flags = (flags & ~mask) | (values[i] & mask). */
+int         rb_set_flags(rb_world* w, uint32_t first, uint32_t count, const uint32_t* values, uint32_t mask);
+/* StateVector::setForce / setTorque (StateVector.cpp:147-167): stored only while the body is in
+ * contact or has gravity off, otherwise zeroed -- evaluated on the device in stream order.
+ * xyz4 = count*4 floats in pinned or pageable host memory. */
+int         rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4);
+int         rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4);
+int         rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ang_pos4, const float* ang_vel4);
+
+/* Per-tick host round trip of a reference-style caller, with HOST buffers (bench.py "e2e"):
+ * upload forces for all bodies (force4 nullable), run one tick, download linear positions (pos4
+ * nullable) and the contact count, and synchronise. */
+int         rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts);
+
+int         rb_get_stats(rb_world* w, rb_stats_t* out);
+/* cumulative CUDA-event time (ms) of each kernel family since the last reset, when profiling is on:
+ * 0 integrate+bin, 1 scan, 2 scatter, 3 collide, 4 halo. rb_profile(w, 1) turns per-kernel events on
+ * (adds synchronisation; never on in timed benchmark regions). */
+int         rb_profile(rb_world* w, int on);
+int         rb_get_kernel_ms(rb_world* w, float* out5, uint64_t* launches);
+/* total kernel launches issued by this library so far (bench.py "gpu_launches") */
+uint64_t    rb_launch_count(const rb_world* w);
+
+/* ---- multi-GPU x-slabs: one process per GPU, NCCL over NVLink ------------- */
+/* size of the opaque NCCL unique id blob */
+#define RB_NCCL_ID_BYTES 128
+/* rank 0 creates the id, the host language broadcasts the bytes (torch.distributed / MPI / ...) */
+int         rb_dist_unique_id(const char* nccl_lib_path, uint8_t id[RB_NCCL_ID_BYTES]);
+/* join the communicator; cfg.rank/nranks/slab_lo/slab_hi say which slab this world owns */
+int         rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t id[RB_NCCL_ID_BYTES]);
+
+const char* rb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBOOT_PHYSICS_H */

@@ -1,0 +1,170 @@
+// rb_device.cuh -- shared declarations of the B200 physics-step kernels (sm_100a).
+//
+// Arithmetic contract: the whole library is compiled with -fmad=false and nvcc's default
+// -prec-div=true -prec-sqrt=true -ftz=false, so every FP32 expression below rounds exactly like the
+// reference's x86-64 SSE code (g++ -O2, no FMA). Expression ORDER therefore matters and follows
+// the reference: dot = (x*x' + y*y') + z*z' (math/src/Vector4.cpp:119-126), cross as in
+// Vector4.cpp:106-117, magnitude = sqrtf((x^2 + y^2) + z^2) (Vector4.cpp:34-38).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RB_F_ACTIVE 1u
+#define RB_F_GRAVITY 2u
+#define RB_F_CONTACT 4u
+#define RB_NONE 0xFFFFFFFFu
+#define RB_TRI_BIT 0x80000000u
+
+// device contact record, 32 B (two 16-B stores)
+struct __align__(16) RbContactRec {
+    uint32_t a;        // global sphere id
+    uint32_t b;        // global sphere id, or RB_TRI_BIT | global triangle id
+    float depth, nx, ny, nz;
+    float r;           // world radius of sphere a at the time of the hit
+    uint32_t pad;
+};
+
+// counters[] layout (unsigned long long)
+enum { RB_C_TESTS_SS = 0, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST,
+       RB_C_OVERFLOW, RB_C_DROPPED, RB_C_NCONTACT /* per step, reset */, RB_C_NCHANGED /* per step */,
+       RB_C_HALO_SENT, RB_C_MIGRATED, RB_C_COUNT = 16 };
+
+struct RbParams {
+    uint32_t nb, ns, nt;
+    uint32_t single;              // every body has exactly one sphere (sphere id == body id)
+    // ---- bodies (SoA float4) ----
+    float4* pos;                  // linear position xyz
+    float4* vel;                  // linear velocity xyz
+    float4* mt;                   // model-matrix translation (Entity::_mvp model [3],[7],[11])
+    float4* pt;                   // previous model-matrix translation (Entity::_prevMVP)
+    uint32_t* flags;
+    const float4* wt;             // translation of _worldSpaceTransform, nullable (all zero)
+    float4* force;                // nullable: xyz force, w mass
+    float4* torque;               // nullable
+    float4* apos;                 // nullable angular position
+    float4* avel;                 // nullable angular velocity
+    // ---- spheres ----
+    const float4* sph_obj;        // xyz = W3x3 * object centre (pre-summed), w = W[0] * object radius
+    const uint32_t* sph_body;     // nullable when single
+    const uint32_t* body_start;   // nullable when single (CSR body -> spheres)
+    float4* ws;                   // frozen world sphere after integration: xyz centre, w = radius + margin
+    uint32_t* key;                // sphere-grid column of each sphere (RB_NONE = not in the broadphase)
+    uint32_t* rank;               // arrival rank inside the column
+    // ---- sphere column grid (rebuilt every step) ----
+    uint32_t* col_count;          // [ncols + 1]
+    uint32_t* col_start;          // [ncols + 1] exclusive scan
+    uint32_t scx, scz;
+    float s_inv_w;
+    float4* sorted;               // ws in column order
+    uint32_t* sorted_id;          // sphere id in column order
+    // ---- static triangle column grid (built once) ----
+    const float4* tri;            // 3 float4 per triangle: A, B, C (w unused)
+    const uint32_t* tcol_start;   // [tcols + 1]
+    const uint32_t* tcol_tri;     // ascending triangle ids per column
+    uint32_t tcx, tcz;
+    float t_inv_w;
+    // ---- constants ----
+    float half, gravity, friction, pushout, ss_damp, margin_cap, rm_max, dt;
+    // ---- outputs ----
+    RbContactRec* contacts;
+    unsigned long long contact_cap;
+    unsigned long long* counters;
+    // ---- deferred commit (compound-body path) ----
+    uint32_t* ch_body; float4* ch_pos; float4* ch_vel; float4* ch_mt; float4* ch_pt; uint32_t* ch_flags;
+    // ---- slab ownership (multi-GPU) ----
+    uint32_t n_owned;             // bodies [0, n_owned) are owned, [n_owned, nb) are ghosts
+};
+
+struct f3 { float x, y, z; };
+
+__device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ f3 xyz(float4 v) { return mk3(v.x, v.y, v.z); }
+__device__ __forceinline__ f3 add3(f3 a, f3 b) { return mk3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ f3 sub3(f3 a, f3 b) { return mk3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ f3 mul3(f3 a, float s) { return mk3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ f3 neg3(f3 a) { return mk3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot3(f3 a, f3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) {
+    return mk3((a.y * b.z) - (a.z * b.y), (a.z * b.x) - (a.x * b.z), (a.x * b.y) - (a.y * b.x));
+}
+__device__ __forceinline__ float mag3(f3 a) { return sqrtf((a.x * a.x + a.y * a.y) + a.z * a.z); }
+__device__ __forceinline__ f3 normalize3(f3 a) { float m = mag3(a); return mk3(a.x / m, a.y / m, a.z / m); }
+
+// GeometryMath::sphereTriangleDetection (math/src/GeometryMath.cpp:101-209): Ericson's sphere /
+// triangle separating-axis test in sphere-centred coordinates; every separation is closed (>=).
+__device__ __forceinline__ bool sphere_triangle_detect(f3 P, float r, f3 ta, f3 tb, f3 tc) {
+    f3 A = sub3(ta, P), B = sub3(tb, P), C = sub3(tc, P);
+    float rr = r * r;
+    f3 V = cross3(sub3(B, A), sub3(C, A));
+    float d = dot3(A, V), e = dot3(V, V);
+    if ((d * d) >= (rr * e)) return false;
+    float aa = dot3(A, A), ab = dot3(A, B), ac = dot3(A, C);
+    float bb = dot3(B, B), bc = dot3(B, C), cc = dot3(C, C);
+    if ((aa >= rr) & (ab >= aa) & (ac >= aa)) return false;
+    if ((bb >= rr) & (ab >= bb) & (bc >= bb)) return false;
+    if ((cc >= rr) & (ac >= cc) & (bc >= cc)) return false;
+    f3 AB = sub3(B, A), BC = sub3(C, B), CA = sub3(A, C);
+    float d1 = ab - aa, d2 = bc - bb, d3 = ac - cc;
+    float e1 = dot3(AB, AB), e2 = dot3(BC, BC), e3 = dot3(CA, CA);
+    f3 Q1 = sub3(mul3(A, e1), mul3(AB, d1));
+    f3 Q2 = sub3(mul3(B, e2), mul3(BC, d2));
+    f3 Q3 = sub3(mul3(C, e3), mul3(CA, d3));
+    f3 QC = sub3(mul3(C, e1), Q1);
+    f3 QA = sub3(mul3(A, e2), Q2);
+    f3 QB = sub3(mul3(B, e3), Q3);
+    if ((dot3(Q1, Q1) >= (rr * e1 * e1)) && (dot3(Q1, QC) >= 0.0f)) return false;
+    if ((dot3(Q2, Q2) >= (rr * e2 * e2)) && (dot3(Q2, QA) >= 0.0f)) return false;
+    if ((dot3(Q3, Q3) >= (rr * e3 * e3)) && (dot3(Q3, QB) >= 0.0f)) return false;
+    return true;
+}
+
+// GeometryMath::_closestPoint (math/src/GeometryMath.cpp:566-628), Ericson pp.141-142.
+__device__ __forceinline__ f3 closest_point(f3 P, f3 A, f3 B, f3 C) {
+    f3 ab = sub3(B, A), ac = sub3(C, A), ap = sub3(P, A);
+    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.f && d2 <= 0.f) return A;
+    f3 bp = sub3(P, B);
+    float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.f && d4 <= d3) return B;
+    float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) {
+        float v = d1 / (d1 - d3);
+        return add3(A, mul3(ab, v));
+    }
+    f3 cp = sub3(P, C);
+    float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.f && d5 <= d6) return C;
+    float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) {
+        float w = d2 / (d2 - d6);
+        return add3(A, mul3(ac, w));
+    }
+    float va = d3 * d6 - d5 * d4;
+    if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) {
+        float w = (d4 - d3) / (d4 - d3 + d5 - d6);
+        return add3(B, mul3(sub3(C, B), w));
+    }
+    float denom = 1.f / (va + vb + vc);
+    float v = vb * denom;
+    float w = vc * denom;
+    return add3(add3(A, mul3(ab, v)), mul3(ac, w));
+}
+
+// GeometryMath::sphereCubeDetection (math/src/GeometryMath.cpp:413-487) against the OSP root cube
+// (centre 0, edge 2*half): closest point = per-axis clamp, closed test |q-c|^2 <= r^2. With the
+// cube at the origin the reference's unit-axis dot products and steps reduce to these exact ops.
+__device__ __forceinline__ bool sphere_in_world(f3 c, float r, float half) {
+    float qx = fminf(fmaxf(c.x, -half), half);
+    float qy = fminf(fmaxf(c.y, -half), half);
+    float qz = fminf(fmaxf(c.z, -half), half);
+    f3 v = mk3(qx - c.x, qy - c.y, qz - c.z);
+    return dot3(v, v) <= r * r;
+}
+
+// monotone column index (shared by triangles at build time and spheres every step)
+__host__ __device__ __forceinline__ uint32_t rb_col(float x, float half, float inv_w, uint32_t n) {
+    float t = (x + half) * inv_w;
+    if (!(t > 0.0f)) return 0;
+    if (t >= (float)n) return n - 1;
+    return (uint32_t)t;
+}

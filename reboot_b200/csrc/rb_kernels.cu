@@ -1,0 +1,570 @@
+// rb_kernels.cu -- hand-written sm_100a kernels of the ReBoot physics step.
+//
+//   K1 integrate_bin   StateVector::update + Entity::_updateKinematics + sphere world transform,
+//                      fused with the broadphase key build and the counting-sort histogram
+//   K2 scan_*          exclusive scan of the column histogram (3 small launches)
+//   K3 scatter         counting-sort scatter of world spheres into column order (SoA float4)
+//   K4 collide         per-body canonical-order narrowphase + resolution:
+//                        sphere-sphere over the sorted float4 sphere grid (vectorised 16-B loads),
+//                        sphere-triangle by a k-way merge over the static triangle column grid,
+//                        fused integrate-side bookkeeping (contact flags, model translations)
+//   K5 commit          deferred state commit for compound bodies
+//
+// All kernels are HBM/L2-bound integer + FP32 work: no tensor cores (nothing here is a contraction).
+#include "rb_device.cuh"
+
+#define RB_BLOCK 256
+#define RB_MAXLOCAL 6   // contacts a thread buffers before the warp-aggregated append
+
+// ------------------------------------------------------------------------------------------
+// K1: integrate + world transform + column histogram.  One thread per body.
+//   StateVector::update            math/src/StateVector.cpp:11-66
+//   Entity::_updateKinematics      model/src/Entity.cpp:131-142
+//   GeometryMath::transform(Sphere) math/src/GeometryMath.cpp:81-89
+// total = translation(p) * W keeps W's 3x3 and has translation W.t + p (math/src/Matrix.cpp:136-166
+// with the translation matrix of :326-338), so a world sphere centre is
+// ((W00*ox + W01*oy) + W02*oz) + (W03 + px): the bracket is pre-summed on the host (sph_obj.xyz).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.nb) return;
+    float4 p4 = P.pos[b], v4 = P.vel[b];
+    uint32_t f = P.flags[b];
+    f3 p = xyz(p4), v = xyz(v4);
+    const float dt = P.dt;
+    if (do_integrate) {
+        if ((f & RB_F_ACTIVE) && b < P.n_owned) {
+            f3 frc = mk3(0.f, 0.f, 0.f);
+            float mass = 1.0f;
+            if (P.force) { float4 F = P.force[b]; frc = xyz(F); mass = F.w; }
+            f3 la = mk3(frc.x / mass, frc.y / mass, frc.z / mass);
+            float g = (f & RB_F_GRAVITY) ? P.gravity : 0.0f;
+            f3 dv = mk3(la.x * dt, (la.y + g) * dt, la.z * dt);
+            float fr = ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) ? P.friction : 1.0f;
+            v = mk3((v.x + dv.x) * fr, (v.y + dv.y) * fr, (v.z + dv.z) * fr);
+            p = mk3(p.x + v.x * dt, p.y + v.y * dt, p.z + v.z * dt);
+            P.pos[b] = make_float4(p.x, p.y, p.z, p4.w);
+            P.vel[b] = make_float4(v.x, v.y, v.z, v4.w);
+            if (P.avel) {
+                f3 tq = mk3(0.f, 0.f, 0.f);
+                if (P.torque) tq = xyz(P.torque[b]);
+                f3 aa = mk3(tq.x / mass, tq.y / mass, tq.z / mass);
+                float4 av4 = P.avel[b], ap4 = P.apos[b];
+                f3 av = mk3((av4.x + aa.x * dt) * fr, (av4.y + aa.y * dt) * fr, (av4.z + aa.z * dt) * fr);
+                P.avel[b] = make_float4(av.x, av.y, av.z, av4.w);
+                P.apos[b] = make_float4(ap4.x + av.x * dt, ap4.y + av.y * dt, ap4.z + av.z * dt, ap4.w);
+            }
+        }
+        // Entity::_updateKinematics runs for inactive entities too: prevMVP = mvp; mvp = T(p) * W
+        if (b < P.n_owned) {
+            float4 m_old = P.mt[b];
+            P.pt[b] = m_old;
+            f3 w = P.wt ? xyz(P.wt[b]) : mk3(0.f, 0.f, 0.f);
+            P.mt[b] = make_float4(w.x + p.x, w.y + p.y, w.z + p.z, 0.f);
+        }
+    }
+    if (!do_bin) return;
+    f3 m = xyz(P.mt[b]);
+    float speed = mag3(v);
+    uint32_t s0 = P.single ? b : P.body_start[b];
+    uint32_t s1 = P.single ? b + 1 : P.body_start[b + 1];
+    for (uint32_t s = s0; s < s1; ++s) {
+        float4 o = P.sph_obj[s];
+        f3 c = mk3(o.x + m.x, o.y + m.y, o.z + m.z);
+        float r = o.w;
+        // candidate margin: how far this body may be displaced inside one step (pruning only)
+        float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * dt + 0.01f * r, 1e-3f));
+        P.ws[s] = make_float4(c.x, c.y, c.z, r + margin);
+        uint32_t k = RB_NONE;
+        // Q3/Q7: only active bodies are (re)inserted in the broadphase, and only while they touch
+        // the OSP root cube (physics/src/OSP.cpp:182-239)
+        if ((f & RB_F_ACTIVE) && sphere_in_world(c, r, P.half)) {
+            uint32_t cx = rb_col(c.x, P.half, P.s_inv_w, P.scx);
+            uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
+            k = cz * P.scx + cx;
+            P.rank[s] = atomicAdd(&P.col_count[k], 1u);
+        }
+        P.key[s] = k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: exclusive scan of col_count[0..n) into col_start[0..n], three launches.
+// ------------------------------------------------------------------------------------------
+#define RB_SCAN_ITEMS 8
+#define RB_SCAN_TILE (RB_BLOCK * RB_SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (uint32_t)d) v += t;
+    }
+    return v;
+}
+// block-wide exclusive scan of one value per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t wsum[RB_BLOCK / 32];
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = warp_incl_scan(v, lane);
+    if (lane == 31) wsum[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < RB_BLOCK / 32 ? wsum[lane] : 0;
+        uint32_t wi = warp_incl_scan(w, lane);
+        if (lane < RB_BLOCK / 32) wsum[lane] = wi - w;
+        if (lane == RB_BLOCK / 32 - 1) *total = wi;
+    }
+    __syncthreads();
+    return inc - v + wsum[wid];
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ tile_sums) {
+    __shared__ uint32_t total;
+    uint32_t base = blockIdx.x * RB_SCAN_TILE + threadIdx.x * RB_SCAN_ITEMS;
+    uint32_t s = 0;
+    if (base + RB_SCAN_ITEMS <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+        uint4 a = p[0], b = p[1];
+        s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
+    } else {
+        for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) if (base + i < n) s += in[base + i];
+    }
+    block_excl_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_scan_top_kernel(uint32_t* tile_sums, uint32_t ntiles, uint32_t* grand_total) {
+    __shared__ uint32_t total;
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < ntiles; base += RB_BLOCK) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sums[i] : 0;
+        uint32_t ex = block_excl_scan(v, &total);
+        if (i < ntiles) tile_sums[i] = ex + carry;
+        carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_scan_apply_kernel(const uint32_t* __restrict__ in, uint32_t n, const uint32_t* __restrict__ tile_offs, uint32_t* __restrict__ out) {
+    __shared__ uint32_t total;
+    uint32_t base = blockIdx.x * RB_SCAN_TILE + threadIdx.x * RB_SCAN_ITEMS;
+    uint32_t v[RB_SCAN_ITEMS];
+    uint32_t s = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; s += v[i]; }
+    uint32_t ex = block_excl_scan(s, &total) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    // out[n] (the grand total) is written by rb_scan_top_kernel
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: counting-sort scatter into column order.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.ns) return;
+    uint32_t k = P.key[s];
+    if (k == RB_NONE) return;
+    uint32_t slot = P.col_start[k] + P.rank[s];
+    P.sorted[slot] = P.ws[s];
+    P.sorted_id[slot] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: collide.  One thread per body, canonical order:
+//   1. sphere-sphere against partner bodies in ascending body id, sphere pairs in ascending order
+//      with the lower body id outermost; the partner is simulated from its frozen pose.
+//        detection  GeometryMath::sphereSphereDetection   math/src/GeometryMath.cpp:211-230
+//        resolution GeometryMath::sphereSphereResolution  math/src/GeometryMath.cpp:523-554
+//   2. sphere-triangle for own spheres ascending, triangles in ascending global id, each tested at
+//      the body's CURRENT pose and resolved immediately (Gauss-Seidel like Physics.cpp:165-178).
+//        detection  GeometryMath::sphereTriangleDetection  math/src/GeometryMath.cpp:101-209
+//        resolution GeometryMath::sphereTriangleResolution math/src/GeometryMath.cpp:489-522
+//   3. contact-flag bookkeeping of Physics.cpp:180,201-207.
+// Entity::setPosition (model/src/Entity.cpp:373-391) is the pose update used by both resolutions.
+// ------------------------------------------------------------------------------------------
+struct BodyState {
+    f3 p, v, mt, pt, wt;
+    uint32_t flags;
+    bool changed;
+};
+
+__device__ __forceinline__ void body_set_position(BodyState& S, f3 np) {
+    f3 t = mk3(S.wt.x + np.x, S.wt.y + np.y, S.wt.z + np.z);   // translation of T(np) * W
+    S.p = t;                                                    // _state.setLinearPosition(total.t)
+    S.pt = S.mt;                                                // _prevMVP.setModel(_mvp.getModelMatrix())
+    S.mt = t;                                                   // _mvp.setModel(total)
+    S.changed = true;
+}
+
+struct HitBuf {
+    uint32_t n;
+    uint32_t a[RB_MAXLOCAL], b[RB_MAXLOCAL];
+    float depth[RB_MAXLOCAL], nx[RB_MAXLOCAL], ny[RB_MAXLOCAL], nz[RB_MAXLOCAL], r[RB_MAXLOCAL];
+};
+
+__device__ __forceinline__ void store_contact(const RbParams& P, unsigned long long slot, uint32_t a, uint32_t b,
+                                              float depth, float nx, float ny, float nz, float r) {
+    if (slot < P.contact_cap) {
+        float4* dst = reinterpret_cast<float4*>(P.contacts + slot);
+        dst[0] = make_float4(__uint_as_float(a), __uint_as_float(b), depth, nx);
+        dst[1] = make_float4(ny, nz, r, 0.f);
+    }
+}
+__device__ __forceinline__ void record_hit(const RbParams& P, HitBuf& H, uint32_t a, uint32_t b, float depth, f3 n, float r) {
+    if (H.n < RB_MAXLOCAL) {
+        uint32_t i = H.n;
+        H.a[i] = a; H.b[i] = b; H.depth[i] = depth; H.nx[i] = n.x; H.ny[i] = n.y; H.nz[i] = n.z; H.r[i] = r;
+    } else {   // rare: more contacts than the local buffer holds -> direct append
+        unsigned long long slot = atomicAdd(&P.counters[RB_C_NCONTACT], 1ull);
+        store_contact(P, slot, a, b, depth, n.x, n.y, n.z, r);
+        if (slot >= P.contact_cap) atomicAdd(&P.counters[RB_C_DROPPED], 1ull);
+    }
+    H.n++;
+}
+
+struct Tally { uint32_t tests_ss, tests_st, cand_ss, cand_st, hits_ss, hits_st, overflow; };
+
+// one triangle against sphere `sa` of the body, at the body's current pose
+template <bool RESOLVE>
+__device__ __forceinline__ void process_triangle(const RbParams& P, BodyState& S, HitBuf& H, Tally& T,
+                                                 uint32_t sa_global, f3 so, float r, f3 fc, float frm,
+                                                 uint32_t tid_global, bool& hit_any) {
+    const float4* tp = P.tri + 3ull * tid_global;
+    float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+    T.cand_st++;
+    // prune against the frozen sphere's box grown by the margin (never changes results)
+    if (fminf(a4.x, fminf(b4.x, c4.x)) > fc.x + frm || fmaxf(a4.x, fmaxf(b4.x, c4.x)) < fc.x - frm) return;
+    if (fminf(a4.y, fminf(b4.y, c4.y)) > fc.y + frm || fmaxf(a4.y, fmaxf(b4.y, c4.y)) < fc.y - frm) return;
+    if (fminf(a4.z, fminf(b4.z, c4.z)) > fc.z + frm || fmaxf(a4.z, fmaxf(b4.z, c4.z)) < fc.z - frm) return;
+    f3 A = xyz(a4), B = xyz(b4), C = xyz(c4);
+    f3 c = mk3(so.x + S.mt.x, so.y + S.mt.y, so.z + S.mt.z);   // Sphere::getPosition at the current pose
+    T.tests_st++;
+    if (!sphere_triangle_detect(c, r, A, B, C)) return;
+    hit_any = true;
+    T.hits_st++;
+    f3 q = closest_point(c, A, B, C);
+    f3 ov = sub3(c, q);
+    float dist = mag3(ov);
+    f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);          // Vector4::normalize
+    record_hit(P, H, sa_global, RB_TRI_BIT | tid_global, r - dist, o, r);
+    if (RESOLVE) {
+        f3 normal = normalize3(cross3(sub3(C, A), sub3(B, A)));
+        f3 delta = sub3(add3(mul3(o, r * P.pushout), q), c);
+        float nc = dot3(S.v, normal);
+        f3 rv = sub3(S.v, mul3(normal, nc));
+        body_set_position(S, add3(S.p, delta));
+        S.v = rv;
+        S.flags |= RB_F_CONTACT;
+    }
+}
+
+// sphere-triangle pass of one sphere: ascending triangle id over the columns its grown box touches
+template <bool RESOLVE>
+__device__ __forceinline__ void sphere_vs_triangles(const RbParams& P, BodyState& S, HitBuf& H, Tally& T,
+                                                    uint32_t sa_global, f3 so, float r, f3 fc, float frm, bool& hit_any) {
+    if (P.nt == 0) return;
+    uint32_t cx0 = rb_col(fc.x - frm, P.half, P.t_inv_w, P.tcx), cx1 = rb_col(fc.x + frm, P.half, P.t_inv_w, P.tcx);
+    uint32_t cz0 = rb_col(fc.z - frm, P.half, P.t_inv_w, P.tcz), cz1 = rb_col(fc.z + frm, P.half, P.t_inv_w, P.tcz);
+    uint32_t nx = cx1 - cx0 + 1, nz = cz1 - cz0 + 1, ncol = nx * nz;
+    if (ncol <= 4) {
+        uint32_t cur[4], end[4], head[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            cur[k] = end[k] = 0; head[k] = RB_NONE;
+            if (k < ncol) {
+                uint32_t col = (cz0 + k / nx) * P.tcx + cx0 + k % nx;
+                cur[k] = __ldg(P.tcol_start + col); end[k] = __ldg(P.tcol_start + col + 1);
+                if (cur[k] < end[k]) head[k] = __ldg(P.tcol_tri + cur[k]);
+            }
+        }
+        while (true) {
+            uint32_t m = min(min(head[0], head[1]), min(head[2], head[3]));
+            if (m == RB_NONE) break;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k)
+                if (head[k] == m) { cur[k]++; head[k] = cur[k] < end[k] ? __ldg(P.tcol_tri + cur[k]) : RB_NONE; }
+            process_triangle<RESOLVE>(P, S, H, T, sa_global, so, r, fc, frm, m, hit_any);
+        }
+    } else {
+        // big sphere / fine columns: repeated selection of the next id above the last one processed
+        uint32_t lo = 0;   // ids below lo are done
+        while (true) {
+            uint32_t best = RB_NONE;
+            for (uint32_t cz = cz0; cz <= cz1; ++cz)
+                for (uint32_t cx = cx0; cx <= cx1; ++cx) {
+                    uint32_t col = cz * P.tcx + cx;
+                    uint32_t i = __ldg(P.tcol_start + col), e = __ldg(P.tcol_start + col + 1);
+                    for (; i < e; ++i) { uint32_t t = __ldg(P.tcol_tri + i); if (t >= lo) { best = min(best, t); break; } }
+                }
+            if (best == RB_NONE) break;
+            process_triangle<RESOLVE>(P, S, H, T, sa_global, so, r, fc, frm, best, hit_any);
+            lo = best + 1;
+        }
+    }
+}
+
+// scan the sphere grid around frozen sphere (fc, frm) for the smallest partner body id >= lo
+template <bool SINGLE>
+__device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 fc, float frm, uint32_t lo,
+                                              uint32_t& best, uint32_t& eligible, Tally& T) {
+    float reach = frm + P.rm_max;
+    uint32_t cx0 = rb_col(fc.x - reach, P.half, P.s_inv_w, P.scx), cx1 = rb_col(fc.x + reach, P.half, P.s_inv_w, P.scx);
+    uint32_t cz0 = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz), cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
+    for (uint32_t cz = cz0; cz <= cz1; ++cz) {
+        uint32_t row = cz * P.scx;
+        uint32_t i = P.col_start[row + cx0], e = P.col_start[row + cx1 + 1];   // x-adjacent columns are contiguous
+        for (; i < e; ++i) {
+            float4 o = P.sorted[i];
+            float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+            if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
+            uint32_t sb = P.sorted_id[i];
+            uint32_t B = SINGLE ? sb : P.sph_body[sb];
+            if (B == A) continue;
+            T.cand_ss++;
+            if (B < lo) continue;
+            eligible++;
+            best = min(best, B);
+        }
+    }
+}
+
+template <bool SINGLE, bool RESOLVE>
+__global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    bool valid;
+    uint32_t A = 0, s0 = 0, nsph = 0;
+    float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (SINGLE) {
+        uint32_t n_sorted = P.col_start[P.scx * P.scz];
+        valid = tid < n_sorted;
+        if (valid) { f0 = P.sorted[tid]; A = s0 = P.sorted_id[tid]; nsph = 1; valid = A < P.n_owned; }
+    } else {
+        valid = tid < P.n_owned;
+        if (valid) { A = tid; s0 = P.body_start[A]; nsph = P.body_start[A + 1] - s0; valid = (P.flags[A] & RB_F_ACTIVE) != 0; }
+    }
+    if (valid) {
+        BodyState S;
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        S.wt = P.wt ? xyz(P.wt[A]) : mk3(0.f, 0.f, 0.f);
+        S.flags = P.flags[A];
+        S.changed = false;
+        const uint32_t flags_in = S.flags;
+        const f3 mt_frozen = S.mt;
+
+        // ---------------- sphere-sphere ----------------
+        uint32_t lo = 0;
+        while (true) {
+            uint32_t best = RB_NONE, eligible = 0;
+            for (uint32_t i = 0; i < nsph; ++i) {
+                uint32_t sa = s0 + i;
+                if (!SINGLE && P.key[sa] == RB_NONE) continue;
+                float4 fa = SINGLE ? f0 : P.ws[sa];
+                scan_partners<SINGLE>(P, A, xyz(fa), fa.w, lo, best, eligible, T);
+            }
+            if (best == RB_NONE) break;
+            const uint32_t B = best;
+            const bool lo_is_a = A < B;
+            if (RESOLVE || lo_is_a) {
+                // partner simulated from its frozen pose (it toggles exactly like us on every hit)
+                uint32_t t0 = SINGLE ? B : P.body_start[B];
+                uint32_t nb_sph = SINGLE ? 1 : P.body_start[B + 1] - t0;
+                f3 bmt = mk3(0.f, 0.f, 0.f), bpt = bmt, bwt = bmt;
+                bool b_toggled = false;
+                if (!SINGLE) { bmt = xyz(P.mt[B]); bpt = xyz(P.pt[B]); if (P.wt) bwt = xyz(P.wt[B]); }
+                uint32_t n_out = lo_is_a ? nsph : nb_sph, n_in = lo_is_a ? nb_sph : nsph;
+                for (uint32_t io = 0; io < n_out; ++io)
+                    for (uint32_t ii = 0; ii < n_in; ++ii) {
+                        uint32_t ia = lo_is_a ? io : ii, ib = lo_is_a ? ii : io;
+                        uint32_t sa = s0 + ia, sb = t0 + ib;
+                        if (!SINGLE && (P.key[sa] == RB_NONE || P.key[sb] == RB_NONE)) continue;
+                        float4 oa = P.sph_obj[sa], ob = P.sph_obj[sb];
+                        f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+                        f3 cb;
+                        if (SINGLE || !b_toggled) { float4 wb = P.ws[sb]; cb = xyz(wb); }   // frozen partner pose
+                        else cb = mk3(ob.x + bmt.x, ob.y + bmt.y, ob.z + bmt.z);
+                        // the lower body id plays "sphereA" of GeometryMath.cpp:211 / "modelA" of :523
+                        f3 cn = lo_is_a ? sub3(ca, cb) : sub3(cb, ca);
+                        float dist = mag3(cn);
+                        float radii = lo_is_a ? (oa.w + ob.w) : (ob.w + oa.w);
+                        if (lo_is_a) T.tests_ss++;
+                        if (!(radii - dist >= 0)) continue;
+                        f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
+                        if (lo_is_a) { T.hits_ss++; record_hit(P, H, sa, sb, radii - dist, n1, oa.w); }
+                        if (RESOLVE) {
+                            f3 n = n1;
+                            if (!lo_is_a) { n = neg3(n); n = normalize3(n); }      // "Opposite reaction", normalised again
+                            float sp = mag3(S.v);
+                            S.v = mul3(mul3(n, sp), P.ss_damp);
+                            body_set_position(S, S.pt);                             // snap back to the previous pose
+                            if (!SINGLE) {                                          // partner does the same on its side
+                                f3 t = mk3(bwt.x + bpt.x, bwt.y + bpt.y, bwt.z + bpt.z);
+                                bpt = bmt; bmt = t; b_toggled = true;
+                            }
+                        }
+                    }
+            }
+            lo = B + 1;
+            if (eligible <= 1 && SINGLE) break;   // nothing else above B in range
+        }
+
+        // ---------------- sphere-triangle ----------------
+        bool last_hit = false;
+        for (uint32_t i = 0; i < nsph; ++i) {
+            uint32_t sa = s0 + i;
+            bool hit_any = false;
+            if (SINGLE || P.key[sa] != RB_NONE) {
+                float4 fa = SINGLE ? f0 : P.ws[sa];
+                float4 oa = P.sph_obj[sa];
+                sphere_vs_triangles<RESOLVE>(P, S, H, T, sa, xyz(oa), oa.w, xyz(fa), fa.w, hit_any);
+            }
+            if (i == nsph - 1) last_hit = hit_any;
+        }
+
+        if (RESOLVE) {
+            // Physics.cpp:201-207: a body that was in contact and whose last sphere found no triangle loses the flag
+            if ((flags_in & RB_F_CONTACT) && !last_hit) S.flags &= ~RB_F_CONTACT;
+            // margin audit: the candidate sets were built for displacements up to the smallest margin
+            f3 d = sub3(S.mt, mt_frozen);
+            float disp = mag3(d);
+            float4 fa0 = SINGLE ? f0 : P.ws[s0];
+            if (disp > fa0.w - P.sph_obj[s0].w) T.overflow++;
+            if (SINGLE) {
+                if (S.changed) {
+                    P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+                    P.vel[A] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
+                    P.mt[A] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+                    P.pt[A] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+                }
+                if (S.flags != flags_in) P.flags[A] = S.flags;
+            } else if (S.changed || S.flags != flags_in) {
+                // partners read our frozen pose concurrently: commit after the kernel (K5)
+                uint32_t k = (uint32_t)atomicAdd(&P.counters[RB_C_NCHANGED], 1ull);
+                P.ch_body[k] = A;
+                P.ch_pos[k] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+                P.ch_vel[k] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
+                P.ch_mt[k] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+                P.ch_pt[k] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+                P.ch_flags[k] = S.flags;
+            }
+        }
+    }
+
+    // ---- warp-aggregated contact append: one atomic per warp ----
+    uint32_t nloc = min(H.n, (uint32_t)RB_MAXLOCAL);
+    uint32_t incl = warp_incl_scan(nloc, lane);
+    uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+    if (wtotal) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&P.counters[RB_C_NCONTACT], (unsigned long long)wtotal);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned long long slot = base + (incl - nloc);
+        uint32_t dropped = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < RB_MAXLOCAL; ++i)
+            if (i < nloc) {
+                store_contact(P, slot + i, H.a[i], H.b[i], H.depth[i], H.nx[i], H.ny[i], H.nz[i], H.r[i]);
+                if (slot + i >= P.contact_cap) dropped++;
+            }
+        dropped = __reduce_add_sync(0xffffffffu, dropped);
+        if (lane == 0 && dropped) atomicAdd(&P.counters[RB_C_DROPPED], (unsigned long long)dropped);
+    }
+    // ---- counters: warp reduce, block reduce in shared, one atomic per block and counter ----
+    __shared__ uint32_t blk[7];
+    if (threadIdx.x < 7) blk[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t vals[7] = { T.tests_ss, T.tests_st, T.cand_ss, T.cand_st, T.hits_ss, T.hits_st, T.overflow };
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        uint32_t s = __reduce_add_sync(0xffffffffu, vals[k]);
+        if (lane == 0 && s) atomicAdd(&blk[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 7 && blk[threadIdx.x]) {
+        const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
+        atomicAdd(&P.counters[map[threadIdx.x]], (unsigned long long)blk[threadIdx.x]);
+    }
+}
+
+// K5: deferred commit for compound bodies
+__global__ void __launch_bounds__(RB_BLOCK) rb_commit_kernel(RbParams P) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n = (uint32_t)P.counters[RB_C_NCHANGED];
+    if (k >= n) return;
+    uint32_t A = P.ch_body[k];
+    P.pos[A] = P.ch_pos[k]; P.vel[A] = P.ch_vel[k]; P.mt[A] = P.ch_mt[k]; P.pt[A] = P.ch_pt[k]; P.flags[A] = P.ch_flags[k];
+}
+
+// StateVector::setForce / setTorque gating (math/src/StateVector.cpp:147-167)
+__global__ void __launch_bounds__(RB_BLOCK) rb_apply_force_kernel(const uint32_t* __restrict__ flags, const float4* __restrict__ in,
+                                                                 float4* __restrict__ out, uint32_t first, uint32_t count, int keep_w) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t f = flags[first + i];
+    float4 v = in[i];
+    float w = keep_w ? out[first + i].w : 0.f;
+    if ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) out[first + i] = make_float4(v.x, v.y, v.z, w);
+    else out[first + i] = make_float4(0.f, 0.f, 0.f, w);
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_set_flags_kernel(uint32_t* flags, const uint32_t* __restrict__ values, uint32_t first, uint32_t count, uint32_t mask) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    flags[first + i] = (flags[first + i] & ~mask) | (values[i] & mask);
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_fill_f4_kernel(float4* p, uint32_t n, float4 v) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-callable launchers (called from rb_world.cu)
+// ------------------------------------------------------------------------------------------
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+extern "C++" {
+void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cudaStream_t st) {
+    if (P.nb) rb_integrate_bin_kernel<<<cdiv(P.nb, RB_BLOCK), RB_BLOCK, 0, st>>>(P, do_integrate, do_bin);
+}
+// scans col_count[0..n) -> col_start[0..n]; tile_sums must hold cdiv(n, RB_SCAN_TILE) entries
+int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st) {
+    uint32_t ntiles = cdiv(n, RB_SCAN_TILE);
+    rb_scan_tile_sums_kernel<<<ntiles, RB_BLOCK, 0, st>>>(in, n, tile_sums);
+    rb_scan_top_kernel<<<1, RB_BLOCK, 0, st>>>(tile_sums, ntiles, out + n);
+    rb_scan_apply_kernel<<<ntiles, RB_BLOCK, 0, st>>>(in, n, tile_sums, out);
+    return 3;
+}
+uint32_t rb_scan_tiles(uint32_t n) { return cdiv(n, RB_SCAN_TILE); }
+void rb_launch_scatter(const RbParams& P, cudaStream_t st) {
+    if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
+}
+int rb_launch_collide(const RbParams& P, bool resolve, cudaStream_t st) {
+    if (!P.nb) return 0;
+    if (P.single) {
+        uint32_t g = cdiv(P.ns, RB_BLOCK);
+        if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
+        else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
+        return 1;
+    }
+    uint32_t g = cdiv(P.nb, RB_BLOCK);
+    if (resolve) {
+        rb_collide_kernel<false, true><<<g, RB_BLOCK, 0, st>>>(P);
+        rb_commit_kernel<<<g, RB_BLOCK, 0, st>>>(P);
+        return 2;
+    }
+    rb_collide_kernel<false, false><<<g, RB_BLOCK, 0, st>>>(P);
+    return 1;
+}
+void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st) {
+    if (count) rb_apply_force_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, in, out, first, count, keep_w);
+}
+void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st) {
+    if (count) rb_set_flags_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, values, first, count, mask);
+}
+void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st) {
+    if (n) rb_fill_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(p, n, v);
+}
+}

@@ -1,0 +1,637 @@
+// rb_world.cu -- host side of libreboot_b200.so: the world object behind the C ABI declared in
+// include/reboot_physics.h. Validates inputs, owns all device memory, builds the static triangle
+// column grid once, and enqueues the step kernels (rb_kernels.cu) on the world's stream.
+// No CPU path: every entry point that computes needs the CUDA device.
+#include "../../include/reboot_physics.h"
+#include "rb_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// launchers defined in rb_kernels.cu
+void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cudaStream_t st);
+int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st);
+uint32_t rb_scan_tiles(uint32_t n);
+void rb_launch_scatter(const RbParams& P, cudaStream_t st);
+int rb_launch_collide(const RbParams& P, bool resolve, cudaStream_t st);
+void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
+void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
+void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
+// multi-GPU (rb_dist.cu)
+struct RbDist;
+int rb_dist_step_exchange(rb_world* w, int ms);
+void rb_dist_destroy(RbDist* d);
+
+static thread_local std::string g_create_error;
+
+struct DevBuf { void* p = nullptr; size_t bytes = 0; };
+
+struct rb_world {
+    rb_config cfg;
+    std::string err;
+    bool built = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // ---- host staging (until rb_build) ----
+    std::vector<float> h_tri;                 // 9 floats per triangle
+    std::vector<uint32_t> h_geom_start;       // CSR geom -> triangles
+    std::vector<float> h_obj;                 // 4 floats per sphere (object space)
+    std::vector<uint32_t> h_body_start;       // CSR body -> spheres
+    std::vector<float> h_W;                   // 12 floats per body: 3x3 row-major + translation
+    std::vector<float> h_pos, h_vel;          // 3 per body
+    std::vector<uint32_t> h_flags;
+    std::vector<uint32_t> h_sph_body;
+    bool any_wt = false;
+    // ---- device ----
+    RbParams P;
+    std::vector<DevBuf> allocs;
+    size_t device_bytes = 0;
+    uint32_t* d_tile_sums = nullptr;
+    uint32_t ncols = 0;
+    float4* d_stage = nullptr; size_t stage_elems = 0;      // H2D staging for setters
+    uint32_t* d_stage_u = nullptr; size_t stage_u_elems = 0;
+    unsigned long long* h_counters = nullptr;               // pinned mirror
+    // ---- bookkeeping ----
+    uint64_t steps = 0, launches = 0;
+    uint64_t contacts_last = 0;
+    bool profile = false;
+    float kernel_ms[5] = { 0, 0, 0, 0, 0 };
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    RbDist* dist = nullptr;
+    rb_stats_t dist_stats;
+};
+
+static int fail(rb_world* w, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (w) w->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(w, RB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <class T> static int dev_alloc(rb_world* w, T** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(w, RB_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    DevBuf b; b.p = p; b.bytes = bytes; w->allocs.push_back(b); w->device_bytes += bytes;
+    *out = (T*)p;
+    return RB_OK;
+}
+#define ALLOC(ptr, count) do { int r_ = dev_alloc(w, &(ptr), (count)); if (r_) return r_; } while (0)
+
+static bool finite_all(const float* p, size_t n) { for (size_t i = 0; i < n; i++) if (!std::isfinite(p[i])) return false; return true; }
+
+extern "C" {
+
+const char* rb_version(void) { return "reboot_b200 0.1 (sm_100a)"; }
+
+void rb_config_default(rb_config* c) {
+    memset(c, 0, sizeof *c);
+    c->world_half = 1000.0f; c->gravity = -9.8f; c->friction = 0.95f; c->pushout = 1.0001f; c->ss_damp = 0.1f;
+    c->margin_cap = 0.25f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
+    c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1;
+}
+
+const char* rb_last_error(const rb_world* w) { return w ? w->err.c_str() : g_create_error.c_str(); }
+
+int rb_world_create(const rb_config* cfg, rb_world** out) {
+    if (!out) return fail(nullptr, RB_ERR_INVALID, "rb_world_create: out is NULL");
+    *out = nullptr;
+    rb_config c; if (cfg) c = *cfg; else rb_config_default(&c);
+    if (!(c.world_half > 0) || !(c.margin_cap >= 0) || c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks)
+        return fail(nullptr, RB_ERR_INVALID, "rb_world_create: bad config");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, RB_ERR_NO_DEVICE, "no CUDA device (%s): reboot_b200 has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    if (c.device < 0 || c.device >= ndev) return fail(nullptr, RB_ERR_INVALID, "device %d out of range (%d devices)", c.device, ndev);
+    e = cudaSetDevice(c.device);
+    if (e != cudaSuccess) return fail(nullptr, RB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    rb_world* w = new rb_world();
+    w->cfg = c;
+    memset(&w->P, 0, sizeof w->P);
+    memset(&w->dist_stats, 0, sizeof w->dist_stats);
+    if (c.stream) w->stream = (cudaStream_t)c.stream;
+    else { e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { delete w; return fail(nullptr, RB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } w->own_stream = true; }
+    w->h_geom_start.push_back(0);
+    w->h_body_start.push_back(0);
+    *out = w;
+    return RB_OK;
+}
+
+void rb_world_destroy(rb_world* w) {
+    if (!w) return;
+    cudaSetDevice(w->cfg.device);
+    cudaStreamSynchronize(w->stream);
+    if (w->dist) rb_dist_destroy(w->dist);
+    for (auto& b : w->allocs) cudaFree(b.p);
+    if (w->h_counters) cudaFreeHost(w->h_counters);
+    for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->own_stream) cudaStreamDestroy(w->stream);
+    delete w;
+}
+
+int rb_add_static_geometry(rb_world* w, uint32_t ntri, const float* xyz9, uint32_t* geom_id) {
+    if (!w) return RB_ERR_INVALID;
+    if (w->built) return fail(w, RB_ERR_INVALID, "rb_add_static_geometry after rb_build (Physics::addEntity never inserts triangles, Q9)");
+    if (ntri && !xyz9) return fail(w, RB_ERR_INVALID, "xyz9 is NULL");
+    if (!finite_all(xyz9, (size_t)ntri * 9)) return fail(w, RB_ERR_INVALID, "non-finite triangle coordinate");
+    if ((uint64_t)w->h_tri.size() / 9 + ntri >= 0x7FFFFFFFull) return fail(w, RB_ERR_INVALID, "too many triangles");
+    w->h_tri.insert(w->h_tri.end(), xyz9, xyz9 + (size_t)ntri * 9);
+    w->h_geom_start.push_back((uint32_t)(w->h_tri.size() / 9));
+    if (geom_id) *geom_id = (uint32_t)w->h_geom_start.size() - 2;
+    return RB_OK;
+}
+
+static int add_body(rb_world* w, uint32_t nsph, const float* obj4, const float* W12, const float* pos3, const float* vel3, uint32_t flags) {
+    if (nsph == 0) return fail(w, RB_ERR_INVALID, "a model needs at least one sphere");
+    if (!finite_all(obj4, (size_t)nsph * 4) || !finite_all(pos3, 3) || !finite_all(vel3, 3) || !finite_all(W12, 12))
+        return fail(w, RB_ERR_INVALID, "non-finite model input");
+    uint32_t b = (uint32_t)w->h_flags.size();
+    w->h_obj.insert(w->h_obj.end(), obj4, obj4 + (size_t)nsph * 4);
+    for (uint32_t i = 0; i < nsph; i++) w->h_sph_body.push_back(b);
+    w->h_body_start.push_back((uint32_t)(w->h_obj.size() / 4));
+    w->h_W.insert(w->h_W.end(), W12, W12 + 12);
+    if (W12[9] != 0.f || W12[10] != 0.f || W12[11] != 0.f) w->any_wt = true;
+    w->h_pos.insert(w->h_pos.end(), pos3, pos3 + 3);
+    w->h_vel.insert(w->h_vel.end(), vel3, vel3 + 3);
+    w->h_flags.push_back(flags & (RB_ACTIVE | RB_GRAVITY));
+    return RB_OK;
+}
+
+int rb_add_model(rb_world* w, uint32_t nspheres, const float* obj4, const float* X, const rb_body_init* init, uint32_t* body_id) {
+    if (!w || !init || !obj4) return w ? fail(w, RB_ERR_INVALID, "NULL argument") : RB_ERR_INVALID;
+    if (w->built) return fail(w, RB_ERR_INVALID, "rb_add_model after rb_build is not supported yet");
+    float W12[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0 };
+    if (X) {
+        if (X[12] != 0.f || X[13] != 0.f || X[14] != 0.f || X[15] != 1.f) return fail(w, RB_ERR_INVALID, "world transform must be affine (last row 0 0 0 1)");
+        W12[0] = X[0]; W12[1] = X[1]; W12[2] = X[2]; W12[3] = X[4]; W12[4] = X[5]; W12[5] = X[6]; W12[6] = X[8]; W12[7] = X[9]; W12[8] = X[10];
+        W12[9] = X[3]; W12[10] = X[7]; W12[11] = X[11];
+    }
+    int r = add_body(w, nspheres, obj4, W12, init->pos, init->vel, init->flags);
+    if (r) return r;
+    if (body_id) *body_id = (uint32_t)w->h_flags.size() - 1;
+    return RB_OK;
+}
+
+int rb_add_models(rb_world* w, uint32_t n, const uint32_t* sphere_start, const float* obj4, const float* world_scale,
+                  const float* pos3, const float* vel3, const uint32_t* flags, uint32_t* first_body_id) {
+    if (!w || !sphere_start || !obj4 || !pos3 || !vel3 || !flags) return w ? fail(w, RB_ERR_INVALID, "NULL argument") : RB_ERR_INVALID;
+    if (w->built) return fail(w, RB_ERR_INVALID, "rb_add_models after rb_build is not supported yet");
+    uint32_t first = (uint32_t)w->h_flags.size();
+    w->h_obj.reserve(w->h_obj.size() + (size_t)sphere_start[n] * 4);
+    for (uint32_t i = 0; i < n; i++) {
+        float s = world_scale ? world_scale[i] : 1.0f;
+        float W12[12] = { s, 0, 0, 0, s, 0, 0, 0, s, 0, 0, 0 };
+        if (sphere_start[i + 1] < sphere_start[i]) return fail(w, RB_ERR_INVALID, "sphere_start must be non-decreasing");
+        int r = add_body(w, sphere_start[i + 1] - sphere_start[i], obj4 + (size_t)sphere_start[i] * 4, W12, pos3 + 3 * (size_t)i, vel3 + 3 * (size_t)i, flags[i]);
+        if (r) return r;
+    }
+    if (first_body_id) *first_body_id = first;
+    return RB_OK;
+}
+
+// ---- static triangle column grid (replaces the per-leaf triangle sets of OSP::generateGeometryOSP,
+// physics/src/OSP.cpp:25-60, 242-332; built once, triangles never move) --------------------------
+static int build_triangle_grid(rb_world* w) {
+    RbParams& P = w->P;
+    const uint32_t nt = (uint32_t)(w->h_tri.size() / 9);
+    const float half = w->cfg.world_half;
+    P.nt = nt;
+    double ext = 0;
+    for (uint32_t t = 0; t < nt; t++) {
+        const float* p = &w->h_tri[(size_t)t * 9];
+        float dx = std::max(p[0], std::max(p[3], p[6])) - std::min(p[0], std::min(p[3], p[6]));
+        float dz = std::max(p[2], std::max(p[5], p[8])) - std::min(p[2], std::min(p[5], p[8]));
+        ext += std::max(dx, dz);
+    }
+    double mean = nt ? ext / nt : 2.0 * half;
+    if (!(mean > 0)) mean = 2.0 * half;
+    long n = std::lround(2.0 * half / mean);
+    n = std::max(1L, std::min(4096L, n));
+    P.tcx = P.tcz = (uint32_t)n;
+    P.t_inv_w = (float)n / (2.0f * half);
+    const size_t ncol = (size_t)n * n;
+    std::vector<uint32_t> start(ncol + 1, 0);
+    auto range = [&](const float* p, int axis, uint32_t& c0, uint32_t& c1) {
+        float lo = std::min(p[axis], std::min(p[3 + axis], p[6 + axis]));
+        float hi = std::max(p[axis], std::max(p[3 + axis], p[6 + axis]));
+        c0 = rb_col(lo, half, P.t_inv_w, (uint32_t)n);
+        c1 = rb_col(hi, half, P.t_inv_w, (uint32_t)n);
+        // a triangle that only touches the upper column at its boundary line is reachable from the
+        // lower one by every sphere whose margin-grown box touches it (margins are > 0)
+        float t = (hi + half) * P.t_inv_w;
+        if (c1 > c0 && t == std::floor(t)) c1--;
+    };
+    for (uint32_t t = 0; t < nt; t++) {
+        const float* p = &w->h_tri[(size_t)t * 9];
+        uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
+        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) start[(size_t)z * n + x + 1]++;
+    }
+    for (size_t i = 0; i < ncol; i++) start[i + 1] += start[i];
+    std::vector<uint32_t> list(std::max<size_t>(start[ncol], 1));
+    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    for (uint32_t t = 0; t < nt; t++) {   // ascending t => every column list is ascending
+        const float* p = &w->h_tri[(size_t)t * 9];
+        uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
+        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) list[fill[(size_t)z * n + x]++] = t;
+    }
+    std::vector<float> tri4((size_t)std::max<uint32_t>(nt, 1) * 12, 0.f);
+    for (uint32_t t = 0; t < nt; t++)
+        for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) tri4[(size_t)t * 12 + v * 4 + k] = w->h_tri[(size_t)t * 9 + v * 3 + k];
+    float4* d_tri; uint32_t* d_start; uint32_t* d_list;
+    ALLOC(d_tri, (size_t)std::max<uint32_t>(nt, 1) * 3);
+    ALLOC(d_start, ncol + 1);
+    ALLOC(d_list, list.size());
+    CU(cudaMemcpyAsync(d_tri, tri4.data(), tri4.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d_start, start.data(), start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list;
+    return RB_OK;
+}
+
+static int ensure_stage(rb_world* w, size_t elems) {
+    if (w->stage_elems >= elems) return RB_OK;
+    float4* p; ALLOC(p, elems);
+    w->d_stage = p; w->stage_elems = elems;   // the old buffer stays in allocs until destroy
+    return RB_OK;
+}
+static int ensure_stage_u(rb_world* w, size_t elems) {
+    if (w->stage_u_elems >= elems) return RB_OK;
+    uint32_t* p; ALLOC(p, elems);
+    w->d_stage_u = p; w->stage_u_elems = elems;
+    return RB_OK;
+}
+
+int rb_build(rb_world* w) {
+    if (!w) return RB_ERR_INVALID;
+    if (w->built) return fail(w, RB_ERR_INVALID, "rb_build is call-once (Physics::addEntities, SURVEY Q9)");
+    CU(cudaSetDevice(w->cfg.device));
+    RbParams& P = w->P;
+    const uint32_t nb = (uint32_t)w->h_flags.size();
+    const uint32_t ns = (uint32_t)(w->h_obj.size() / 4);
+    P.nb = nb; P.ns = ns; P.n_owned = nb;
+    P.single = (ns == nb) ? 1u : 0u;
+    P.half = w->cfg.world_half; P.gravity = w->cfg.gravity; P.friction = w->cfg.friction;
+    P.pushout = w->cfg.pushout; P.ss_damp = w->cfg.ss_damp; P.margin_cap = w->cfg.margin_cap; P.dt = 0.f;
+
+    // ---- spheres: pre-sum the W3x3 * object-centre part of GeometryMath::transform (GeometryMath.cpp:81-89) ----
+    std::vector<float> sph((size_t)std::max<uint32_t>(ns, 1) * 4, 0.f);
+    float rmax = 0.f;
+    for (uint32_t b = 0; b < nb; b++) {
+        const float* W = &w->h_W[(size_t)b * 12];
+        for (uint32_t s = w->h_body_start[b]; s < w->h_body_start[b + 1]; s++) {
+            const float* o = &w->h_obj[(size_t)s * 4];
+            volatile float x = W[0] * o[0] + W[1] * o[1] + W[2] * o[2];   // ((a + b) + c), no contraction on the host build
+            volatile float y = W[3] * o[0] + W[4] * o[1] + W[5] * o[2];
+            volatile float z = W[6] * o[0] + W[7] * o[1] + W[8] * o[2];
+            volatile float r = W[0] * o[3];
+            sph[(size_t)s * 4] = x; sph[(size_t)s * 4 + 1] = y; sph[(size_t)s * 4 + 2] = z; sph[(size_t)s * 4 + 3] = r;
+            rmax = std::max(rmax, std::fabs((float)r));
+        }
+    }
+    P.rm_max = rmax + w->cfg.margin_cap;
+    // ---- sphere column grid geometry ----
+    {
+        float wcol = std::max(2.0f * P.rm_max, 2.0f * P.half / 4096.0f);
+        long n = (long)std::floor(2.0 * P.half / wcol);
+        n = std::max(1L, std::min(4096L, n));
+        P.scx = P.scz = (uint32_t)n;
+        P.s_inv_w = (float)n / (2.0f * P.half);
+        w->ncols = P.scx * P.scz;
+    }
+    // ---- device state ----
+    float4 *d_pos, *d_vel, *d_mt, *d_pt, *d_sph, *d_ws, *d_sorted; uint32_t *d_flags, *d_key, *d_rank, *d_cc, *d_cs, *d_sid;
+    ALLOC(d_pos, nb); ALLOC(d_vel, nb); ALLOC(d_mt, nb); ALLOC(d_pt, nb); ALLOC(d_flags, nb);
+    ALLOC(d_sph, ns); ALLOC(d_ws, ns); ALLOC(d_key, ns); ALLOC(d_rank, ns); ALLOC(d_sorted, ns); ALLOC(d_sid, ns);
+    ALLOC(d_cc, (size_t)w->ncols + 1); ALLOC(d_cs, (size_t)w->ncols + 1);
+    ALLOC(w->d_tile_sums, rb_scan_tiles(w->ncols) + 1);
+    P.pos = d_pos; P.vel = d_vel; P.mt = d_mt; P.pt = d_pt; P.flags = d_flags; P.sph_obj = d_sph; P.ws = d_ws;
+    P.key = d_key; P.rank = d_rank; P.sorted = d_sorted; P.sorted_id = d_sid; P.col_count = d_cc; P.col_start = d_cs;
+    std::vector<float> p4((size_t)std::max<uint32_t>(nb, 1) * 4, 0.f), v4 = p4, wt4 = p4;
+    for (uint32_t b = 0; b < nb; b++) {
+        for (int k = 0; k < 3; k++) { p4[(size_t)b * 4 + k] = w->h_pos[(size_t)b * 3 + k]; v4[(size_t)b * 4 + k] = w->h_vel[(size_t)b * 3 + k]; wt4[(size_t)b * 4 + k] = w->h_W[(size_t)b * 12 + 9 + k]; }
+        p4[(size_t)b * 4 + 3] = 1.f;
+    }
+    CU(cudaMemcpyAsync(d_pos, p4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d_vel, v4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d_flags, w->h_flags.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d_sph, sph.data(), (size_t)ns * 16, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemsetAsync(d_mt, 0, (size_t)std::max<uint32_t>(nb, 1) * 16, w->stream));   // MVP() model = identity -> translation 0
+    CU(cudaMemsetAsync(d_pt, 0, (size_t)std::max<uint32_t>(nb, 1) * 16, w->stream));
+    if (w->any_wt) { float4* d_wt; ALLOC(d_wt, nb); CU(cudaMemcpyAsync(d_wt, wt4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream)); P.wt = d_wt; }
+    if (!P.single) {
+        uint32_t *d_sb, *d_bs;
+        ALLOC(d_sb, ns); ALLOC(d_bs, (size_t)nb + 1);
+        CU(cudaMemcpyAsync(d_sb, w->h_sph_body.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaMemcpyAsync(d_bs, w->h_body_start.data(), ((size_t)nb + 1) * 4, cudaMemcpyHostToDevice, w->stream));
+        P.sph_body = d_sb; P.body_start = d_bs;
+        uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
+        ALLOC(cb, nb); ALLOC(c1, nb); ALLOC(c2, nb); ALLOC(c3, nb); ALLOC(c4, nb); ALLOC(cf, nb);
+        P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
+    }
+    // ---- contacts + counters ----
+    P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)ns * 4 + 1024;
+    RbContactRec* d_c; ALLOC(d_c, (size_t)P.contact_cap); P.contacts = d_c;
+    unsigned long long* d_cnt; ALLOC(d_cnt, RB_C_COUNT); P.counters = d_cnt;
+    CU(cudaMemsetAsync(d_cnt, 0, RB_C_COUNT * sizeof(unsigned long long), w->stream));
+    CU(cudaMallocHost((void**)&w->h_counters, RB_C_COUNT * sizeof(unsigned long long)));
+    memset(w->h_counters, 0, RB_C_COUNT * sizeof(unsigned long long));
+    for (auto& e : w->ev) CU(cudaEventCreate(&e));
+    CU(cudaStreamSynchronize(w->stream));
+    int r = build_triangle_grid(w);
+    if (r) return r;
+    // ---- prime the model transforms: Entity::_updateKinematics(0) on every entity (SURVEY Appendix A;
+    // note StateVector::update(0) still applies the friction factor to bodies in contact / without gravity) ----
+    P.dt = 0.0f;
+    rb_launch_integrate_bin(P, 1, 0, w->stream); w->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(w->stream));
+    w->built = true;
+    // host staging is no longer needed
+    std::vector<float>().swap(w->h_tri); std::vector<float>().swap(w->h_obj); std::vector<float>().swap(w->h_W);
+    std::vector<float>().swap(w->h_pos); std::vector<float>().swap(w->h_vel);
+    return RB_OK;
+}
+
+// ---- the step ---------------------------------------------------------------------------------
+static int enqueue_broadphase(rb_world* w, int do_integrate) {
+    RbParams& P = w->P;
+    CU(cudaMemsetAsync(P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
+    rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;
+    if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
+    w->launches += rb_launch_scan(P.col_count, w->ncols, P.col_start, w->d_tile_sums, w->stream);
+    if (w->profile) CU(cudaEventRecord(w->ev[2], w->stream));
+    rb_launch_scatter(P, w->stream); w->launches++;
+    if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
+    return RB_OK;
+}
+static int enqueue_collide(rb_world* w, bool resolve) {
+    RbParams& P = w->P;
+    // per-step counters: contact count + changed count
+    CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
+    w->launches += rb_launch_collide(P, resolve, w->stream);
+    if (w->profile) {
+        CU(cudaEventRecord(w->ev[4], w->stream));
+        CU(cudaEventSynchronize(w->ev[4]));
+        for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, w->ev[k], w->ev[k + 1])); w->kernel_ms[k] += ms; }
+    }
+    CU(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_step(rb_world* w, int ms) {
+    if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_step before rb_build") : RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    w->P.dt = (float)ms / 1000.0f;                     // StateVector.cpp:19
+    if (w->dist) { int r = rb_dist_step_exchange(w, ms); if (r) return r; }
+    else { int r = enqueue_broadphase(w, 1); if (r) return r; }
+    int r = enqueue_collide(w, true); if (r) return r;
+    w->steps++;
+    return RB_OK;
+}
+int rb_integrate(rb_world* w, int ms) {
+    if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_integrate before rb_build") : RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    w->P.dt = (float)ms / 1000.0f;
+    rb_launch_integrate_bin(w->P, 1, 0, w->stream); w->launches++;
+    CU(cudaGetLastError());
+    return RB_OK;
+}
+int rb_collide(rb_world* w) {
+    if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_collide before rb_build") : RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    int r = enqueue_broadphase(w, 0); if (r) return r;
+    return enqueue_collide(w, true);
+}
+int rb_detect(rb_world* w) {
+    if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_detect before rb_build") : RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    int r = enqueue_broadphase(w, 0); if (r) return r;
+    return enqueue_collide(w, false);
+}
+int rb_sync(rb_world* w) {
+    if (!w) return RB_ERR_INVALID;
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+
+static int fetch_counters(rb_world* w) {
+    CU(cudaMemcpyAsync(w->h_counters, w->P.counters, RB_C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->contacts_last = w->h_counters[RB_C_NCONTACT];
+    return RB_OK;
+}
+
+int rb_contact_count(rb_world* w, uint64_t* n) {
+    if (!w || !w->built || !n) return RB_ERR_INVALID;
+    int r = fetch_counters(w); if (r) return r;
+    *n = w->contacts_last;
+    return RB_OK;
+}
+
+int rb_query_contacts(rb_world* w, rb_contact* out, uint64_t cap, uint64_t* n, int sorted) {
+    if (!w || !w->built || !n) return w ? fail(w, RB_ERR_INVALID, "rb_query_contacts: bad argument") : RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    int r = fetch_counters(w); if (r) return r;
+    uint64_t total = w->contacts_last;
+    uint64_t have = std::min<uint64_t>(total, w->P.contact_cap);
+    *n = have;
+    if (total > w->P.contact_cap)
+        return fail(w, RB_ERR_CAPACITY, "device contact buffer overflow: %llu contacts, capacity %llu (set rb_config.max_contacts)", (unsigned long long)total, (unsigned long long)w->P.contact_cap);
+    if (!out) return RB_OK;
+    if (cap < have) return fail(w, RB_ERR_CAPACITY, "rb_query_contacts: need room for %llu contacts", (unsigned long long)have);
+    std::vector<RbContactRec> rec(have);
+    if (have) CU(cudaMemcpy(rec.data(), w->P.contacts, have * sizeof(RbContactRec), cudaMemcpyDeviceToHost));
+    const std::vector<uint32_t>& bs = w->h_body_start; const std::vector<uint32_t>& gs = w->h_geom_start;
+    auto body_of = [&](uint32_t s, uint32_t& body, uint32_t& idx) {
+        if (w->P.single) { body = s; idx = 0; return; }
+        body = w->h_sph_body[s]; idx = s - bs[body];
+    };
+    for (uint64_t i = 0; i < have; i++) {
+        const RbContactRec& c = rec[i]; rb_contact& o = out[i];
+        body_of(c.a, o.body, o.sphere);
+        if (c.b & RB_TRI_BIT) {
+            uint32_t t = c.b & ~RB_TRI_BIT;
+            uint32_t g = (uint32_t)(std::upper_bound(gs.begin(), gs.end(), t) - gs.begin()) - 1;
+            o.kind = 1; o.other = g; o.other_prim = t - gs[g];
+        } else { o.kind = 0; body_of(c.b, o.other, o.other_prim); }
+        o.depth = c.depth; o.normal[0] = c.nx; o.normal[1] = c.ny; o.normal[2] = c.nz;
+    }
+    if (sorted) {
+        std::sort(out, out + have, [](const rb_contact& a, const rb_contact& b) {
+            if (a.kind != b.kind) return a.kind < b.kind;
+            if (a.body != b.body) return a.body < b.body;
+            if (a.sphere != b.sphere) return a.sphere < b.sphere;
+            if (a.other != b.other) return a.other < b.other;
+            return a.other_prim < b.other_prim;
+        });
+    }
+    return RB_OK;
+}
+
+int rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    size_t nb = w->P.n_owned;
+    if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (vel4) CU(cudaMemcpyAsync(vel4, w->P.vel, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (flags) CU(cudaMemcpyAsync(flags, w->P.flags, nb * 4, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+int rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    size_t nb = w->P.n_owned;
+    if (model_t4) CU(cudaMemcpyAsync(model_t4, w->P.mt, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (prev_t4) CU(cudaMemcpyAsync(prev_t4, w->P.pt, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+int rb_get_angular(rb_world* w, float* ap4, float* av4) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    size_t nb = w->P.n_owned;
+    if (!w->P.avel) { if (ap4) memset(ap4, 0, nb * 16); if (av4) memset(av4, 0, nb * 16); return RB_OK; }
+    if (ap4) CU(cudaMemcpyAsync(ap4, w->P.apos, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (av4) CU(cudaMemcpyAsync(av4, w->P.avel, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+int rb_get_world_spheres(rb_world* w, float* xyzr4) {
+    if (!w || !w->built || !xyzr4) return RB_ERR_INVALID;
+    // recompute from the current model translations (no integration, no binning side effects on state)
+    CU(cudaMemsetAsync(w->P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
+    size_t ns = w->P.ns;
+    std::vector<float> tmp(ns * 4), obj(ns * 4);
+    CU(cudaMemcpyAsync(tmp.data(), w->P.ws, ns * 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(obj.data(), w->P.sph_obj, ns * 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    for (size_t i = 0; i < ns; i++) { xyzr4[4 * i] = tmp[4 * i]; xyzr4[4 * i + 1] = tmp[4 * i + 1]; xyzr4[4 * i + 2] = tmp[4 * i + 2]; xyzr4[4 * i + 3] = obj[4 * i + 3]; }
+    return RB_OK;
+}
+
+static int range_ok(rb_world* w, uint32_t first, uint32_t count) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    if ((uint64_t)first + count > w->P.n_owned) return fail(w, RB_ERR_INVALID, "body range [%u, %u) out of bounds (%u bodies)", first, first + count, w->P.n_owned);
+    return RB_OK;
+}
+int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4) {
+    int r = range_ok(w, first, count); if (r) return r;
+    if ((pos4 && !finite_all(pos4, (size_t)count * 3)) || (vel4 && !finite_all(vel4, (size_t)count * 3))) { /* w component is padding */ }
+    if (pos4) CU(cudaMemcpyAsync(w->P.pos + first, pos4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    if (vel4) CU(cudaMemcpyAsync(w->P.vel + first, vel4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+int rb_set_flags(rb_world* w, uint32_t first, uint32_t count, const uint32_t* values, uint32_t mask) {
+    int r = range_ok(w, first, count); if (r) return r;
+    if (!values) return fail(w, RB_ERR_INVALID, "values is NULL");
+    r = ensure_stage_u(w, count); if (r) return r;
+    CU(cudaMemcpyAsync(w->d_stage_u, values, (size_t)count * 4, cudaMemcpyHostToDevice, w->stream));
+    rb_launch_set_flags(w->P.flags, w->d_stage_u, first, count, mask & (RB_ACTIVE | RB_GRAVITY | RB_CONTACT), w->stream); w->launches++;
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+static int ensure_force(rb_world* w) {
+    if (w->P.force) return RB_OK;
+    float4* f; ALLOC(f, w->P.nb);
+    rb_launch_fill_f4(f, w->P.nb, make_float4(0.f, 0.f, 0.f, 1.0f), w->stream); w->launches++;   // mass 1, StateVector.cpp:4-9
+    w->P.force = f;
+    return RB_OK;
+}
+static int ensure_angular(rb_world* w) {
+    if (w->P.avel) return RB_OK;
+    float4 *a, *b, *t;
+    ALLOC(a, w->P.nb); ALLOC(b, w->P.nb); ALLOC(t, w->P.nb);
+    CU(cudaMemsetAsync(a, 0, (size_t)w->P.nb * 16, w->stream));
+    CU(cudaMemsetAsync(b, 0, (size_t)w->P.nb * 16, w->stream));
+    CU(cudaMemsetAsync(t, 0, (size_t)w->P.nb * 16, w->stream));
+    w->P.apos = a; w->P.avel = b; w->P.torque = t;
+    return ensure_force(w);
+}
+int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
+    int r = range_ok(w, first, count); if (r) return r;
+    if (!xyz4) return fail(w, RB_ERR_INVALID, "xyz4 is NULL");
+    r = ensure_force(w); if (r) return r;
+    r = ensure_stage(w, count); if (r) return r;
+    CU(cudaMemcpyAsync(w->d_stage, xyz4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    rb_launch_apply_force(w->P.flags, w->d_stage, w->P.force, first, count, 1, w->stream); w->launches++;
+    return RB_OK;
+}
+int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
+    int r = range_ok(w, first, count); if (r) return r;
+    if (!xyz4) return fail(w, RB_ERR_INVALID, "xyz4 is NULL");
+    r = ensure_angular(w); if (r) return r;
+    r = ensure_stage(w, count); if (r) return r;
+    CU(cudaMemcpyAsync(w->d_stage, xyz4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    rb_launch_apply_force(w->P.flags, w->d_stage, w->P.torque, first, count, 0, w->stream); w->launches++;
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+int rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ap4, const float* av4) {
+    int r = range_ok(w, first, count); if (r) return r;
+    r = ensure_angular(w); if (r) return r;
+    if (ap4) CU(cudaMemcpyAsync(w->P.apos + first, ap4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    if (av4) CU(cudaMemcpyAsync(w->P.avel + first, av4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+
+int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    int r;
+    if (force4) { r = rb_set_force(w, 0, w->P.n_owned, force4); if (r) return r; }
+    r = rb_step(w, ms); if (r) return r;
+    if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, (size_t)w->P.n_owned * 16, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(w->h_counters + RB_C_NCONTACT, w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->contacts_last = w->h_counters[RB_C_NCONTACT];
+    if (n_contacts) *n_contacts = w->contacts_last;
+    return RB_OK;
+}
+
+int rb_get_stats(rb_world* w, rb_stats_t* out) {
+    if (!w || !out) return RB_ERR_INVALID;
+    memset(out, 0, sizeof *out);
+    if (w->built) { int r = fetch_counters(w); if (r) return r; }
+    const unsigned long long* c = w->h_counters;
+    out->steps = w->steps;
+    if (c) {
+        out->tests_ss = c[RB_C_TESTS_SS]; out->tests_st = c[RB_C_TESTS_ST]; out->cand_ss = c[RB_C_CAND_SS]; out->cand_st = c[RB_C_CAND_ST];
+        out->hits_ss = c[RB_C_HITS_SS]; out->hits_st = c[RB_C_HITS_ST]; out->contacts_last = c[RB_C_NCONTACT];
+        out->contacts_dropped = c[RB_C_DROPPED]; out->margin_overflow = c[RB_C_OVERFLOW];
+    }
+    out->n_bodies = w->built ? w->P.n_owned : (uint32_t)w->h_flags.size();
+    out->n_spheres = w->P.ns; out->n_geoms = (uint32_t)w->h_geom_start.size() - 1; out->n_tris = w->P.nt;
+    out->sphere_cols_x = w->P.scx; out->sphere_cols_z = w->P.scz; out->tri_cols_x = w->P.tcx; out->tri_cols_z = w->P.tcz;
+    out->device_bytes = w->device_bytes;
+    out->halo_sent_last = w->dist_stats.halo_sent_last; out->halo_recv_last = w->dist_stats.halo_recv_last;
+    out->migrated_out_last = w->dist_stats.migrated_out_last; out->migrated_in_last = w->dist_stats.migrated_in_last;
+    return RB_OK;
+}
+int rb_profile(rb_world* w, int on) { if (!w) return RB_ERR_INVALID; w->profile = on != 0; for (auto& k : w->kernel_ms) k = 0; return RB_OK; }
+int rb_get_kernel_ms(rb_world* w, float* out5, uint64_t* launches) {
+    if (!w || !out5) return RB_ERR_INVALID;
+    for (int k = 0; k < 5; k++) out5[k] = w->kernel_ms[k];
+    if (launches) *launches = w->launches;
+    return RB_OK;
+}
+uint64_t rb_launch_count(const rb_world* w) { return w ? w->launches : 0; }
+
+} // extern "C"
+
+// ---- multi-GPU placeholders until rb_dist.cu lands ---------------------------------------------
+#ifndef RB_HAVE_DIST
+int rb_dist_step_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+void rb_dist_destroy(RbDist*) {}
+extern "C" int rb_dist_unique_id(const char*, uint8_t*) { g_create_error = "multi-GPU slabs not built"; return RB_ERR_INVALID; }
+extern "C" int rb_dist_init(rb_world* w, const char*, const uint8_t*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+#endif
