@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 physics step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--settle S] [--impl reference]
+
+A "step" is one physics tick (engine/src/MasterClock.cpp:36-45: every Entity::_updateKinematics,
+then Physics::_physicsProcess) of config C3: 1,000,000 spheres (r=0.5) vs a 2,000,000-triangle
+procedural heightfield, measured in the SETTLED regime (S untimed ticks first) -- the steady state
+and the heavier of the two regimes; the free-fall figure is reported beside it.
+
+N > 1 (one process per GPU under torchrun) is the weak-scaled C3: N x 1M spheres of radius 0.5/sqrt(N)
+on a (1000*sqrt(N))^2-cell terrain inside the same 2000^3 world, x-slab partitioned, static geometry
+replicated, boundary spheres exchanged every tick with NCCL. value = N * ticks/s (each tick processes
+N C3-sized units), so weak-scaling efficiency is value_N / (N * value_1).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref = its unmodified
+physics/ + math/ sources; falls back to the C port) on a bounded spatial sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DT_MS = 5
+C3_SPHERES = 1_000_000
+C3_G = 1000
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------
+def c3_weak_scene(nranks: int, rank: int, seed: int = 1234):
+    """C3 weak-scaled to `nranks` slabs (nranks == 1 is exactly C3). Returns (scene of this rank, slab)."""
+    from reboot_b200 import scenes
+    s = math.sqrt(nranks)
+    G = int(round(C3_G * s))
+    c = 2000.0 / G
+    r = 0.5 / s
+    lo = -1000.0 + 2000.0 * rank / nranks
+    hi = -1000.0 + 2000.0 * (rank + 1) / nranks
+    tris, h = scenes.terrain_triangles(G, c, seed)
+    rng = np.random.Generator(np.random.PCG64(seed + 1 + 1000 * rank * (nranks > 1)))
+    half = G * c / 2.0 - 2.0
+    n = C3_SPHERES
+    x = rng.uniform(max(lo, -half), min(hi, half), n)
+    z = rng.uniform(-half, half, n)
+    y = rng.uniform(2.0 / s, 12.0 / s, n) + scenes._height_upper(h, G, c, x, z)
+    pos = np.stack([x, y, z], axis=1).astype(np.float32)
+    sc = scenes.Scene(name=f"C3x{nranks}", tris=[tris], meta=dict(G=G, c=c, r=r, seed=seed),
+                      **scenes._single_sphere_bodies(pos, np.zeros_like(pos), r))
+    return sc, (lo, hi)
+
+
+def cpu_sample_scene(frac: int, seed: int = 1234):
+    """A spatial 1/frac tile of C3 at the same sphere and triangle density."""
+    from reboot_b200 import scenes
+    G = max(8, int(round(C3_G / math.sqrt(frac))))
+    n = int(round(C3_SPHERES * (G * G) / (C3_G * C3_G)))
+    return scenes.falling_spheres(n, G, 2.0, 0.5, (2.0, 12.0), True, seed, f"C3/{frac}"), (G * G) / (C3_G * C3_G)
+
+
+def time_cpu_reference(frac: int, settle: int, steps: int):
+    """Times the reference CPU path on a bounded sample. Returns dict for cpu_baseline / --impl reference."""
+    from oracle import ref_binding as rb
+    sc, fraction = cpu_sample_scene(frac)
+    if rb.available():
+        kind = "reference"
+        w = rb.RefWorld(sc)
+        build_s = w.build_seconds
+        t0 = time.perf_counter(); w.bench(DT_MS, settle); t_settle = time.perf_counter() - t0
+        w.reset_counters()
+        secs = w.bench(DT_MS, steps)
+        c = w.counters()
+        tests = c["tests_ss"] + c["tests_st"]
+    else:
+        from oracle import port_binding as pb
+        kind = "port"
+        t0 = time.perf_counter(); w = pb.OrcWorld(sc); build_s = time.perf_counter() - t0
+        w.set_record(False)
+        t0 = time.perf_counter()
+        for _ in range(settle):
+            w.step(DT_MS, pb.ORDER_REFERENCE)
+        t_settle = time.perf_counter() - t0
+        w.L.orc_reset_counters(w.h)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            w.step(DT_MS, pb.ORDER_REFERENCE)
+        secs = time.perf_counter() - t0
+        c = w.counters()
+        tests = c["tests_ss"] + c["tests_st"]
+    sample_steps_s = steps / secs
+    return dict(value=sample_steps_s * fraction, unit="steps/s", cores=1, kind=kind,
+                sample=(f"{sc.n_bodies} spheres on a {sc.meta['G']}x{sc.meta['G']}-cell terrain ({sc.n_tris} tris) = 1/{1/fraction:.0f} spatial tile of C3 "
+                        f"at the same density; {settle} settle ticks then {steps} timed ticks at {sample_steps_s:.2f} sample-steps/s, scaled by the tile fraction; "
+                        f"octree build {build_s:.2f}s and settle {t_settle:.1f}s not timed; single-threaded like the reference's physics thread"),
+                sample_steps_per_s=sample_steps_s, sample_tests_per_s=tests / secs, fraction=fraction)
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    t0 = time.time()
+    cb = time_cpu_reference(args.ref_frac, args.ref_settle, max(3, min(args.steps, 20)))
+    line = {
+        "impl": "reference", "metric": "physics steps/s @1M spheres vs 2M-tri terrain (C3, settled)", "value": cb["value"], "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: 1M spheres r=0.5 vs 2M-triangle heightfield, settled regime (bounded CPU sample, scaled)"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "contact_tests_per_s": cb["sample_tests_per_s"], "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from reboot_b200 import World
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    N = args.gpus
+    if world_size != N:
+        if world_size == 1 and N > 1:
+            raise SystemExit(f"--gpus {N} needs torchrun --nproc-per-node {N}")
+        N = world_size
+    torch.cuda.set_device(local_rank)
+    if N > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if N > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream()
+    sc, slab = c3_weak_scene(N, rank)
+    w = World(sc, device=local_rank, stream=stream.cuda_stream, slab=slab, rank=rank, nranks=N,
+              max_contacts=8 * sc.n_spheres, build=False)
+    w.build()
+    if N > 1:
+        from reboot_b200 import dist as rbdist
+        rbdist.init_world(w, rank, N)
+
+    def timed(nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(nsteps):
+                w.step(DT_MS)
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if N > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms / nsteps
+
+    # ---- free-fall regime (reported beside the headline) ----
+    for _ in range(max(3, args.warmup)):
+        w.step(DT_MS)
+    st_a = w.stats()
+    ff_ms = timed(min(args.steps, 100))
+    st_b = w.stats()
+    ff_tests = (st_b["tests_ss"] + st_b["tests_st"] - st_a["tests_ss"] - st_a["tests_st"]) / min(args.steps, 100)
+    # ---- settle, warm up, timed region ----
+    for _ in range(args.settle):
+        w.step(DT_MS)
+    for _ in range(max(3, args.warmup)):
+        w.step(DT_MS)
+    w.sync()
+    st0 = w.stats(); l0 = w.launch_count()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_step = timed(args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    st1 = w.stats(); l1 = w.launch_count()
+    tests_step = (st1["tests_ss"] + st1["tests_st"] - st0["tests_ss"] - st0["tests_st"]) / args.steps
+    contacts = st1["contacts_last"]
+    # ---- per-kernel durations (CUDA events on the same stream), same number of ticks, right after ----
+    w.profile(True)
+    for _ in range(args.steps):
+        w.step(DT_MS)
+    w.sync()
+    kms, _ = w.kernel_ms()
+    w.profile(False)
+    collide_ms = kms["collide"] / args.steps
+    # algorithmic bytes of one collide launch (DESIGN.md "roofline"): every in-grid sphere once (16 B),
+    # every triangle once (36 B), every contact record (24 B), every resolved body's state read+write (64 B)
+    resolved = min(contacts, st1["n_bodies"])
+    alg_bytes = st1["n_spheres"] * 16 + st1["n_tris"] * 36 + contacts * 24 + resolved * 64
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (collide_ms * 1e-3) / 1e9
+    # whole-step algorithmic bytes: N_body*64 + N_tri*36 + N_contact*24
+    step_bytes = st1["n_bodies"] * 64 + st1["n_tris"] * 36 + contacts * 24
+    # ---- e2e: the per-tick host round trip through the C ABI with pinned HOST buffers ----
+    nb = st1["n_bodies"]
+    force = torch.zeros((nb, 4), dtype=torch.float32).pin_memory()
+    pos = torch.zeros((nb, 4), dtype=torch.float32).pin_memory()
+    e2e_steps = max(10, min(args.steps, 50))
+    for _ in range(3):
+        w.L.rb_step_host(w.h, DT_MS, force.data_ptr(), pos.data_ptr(), None)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        rc = w.L.rb_step_host(w.h, DT_MS, force.data_ptr(), pos.data_ptr(), None)
+        assert rc == 0
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000 / e2e_steps
+    if N > 1:
+        t = torch.tensor([e2e_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
+    final = w.stats()
+    if rank == 0:
+        cpu = None
+        if N == 1 and not args.no_cpu:
+            cpu = time_cpu_reference(args.cpu_frac, args.cpu_settle, args.cpu_steps)
+        line = {
+            "metric": "physics steps/s @1M spheres vs 2M-tri terrain (C3, settled)", "value": N * 1000.0 / ms_step, "unit": "steps/s",
+            "n_gpus": N, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": ("C3: 1,000,000 spheres r=0.5 vs 2,000,000-triangle procedural heightfield (sphere-triangle + sphere-sphere + integration)"
+                                    if N == 1 else f"C3 weak-scaled x{N}: {N}x1M spheres r={sc.meta['r']:.4f} on a {sc.meta['G']}^2-cell terrain ({sc.n_tris} tris replicated), x-slabs + NCCL halo"),
+                       "regime": f"settled ({args.settle} untimed ticks first)", "dt_ms": DT_MS,
+                       "l2": "working set > L2: state + sorted spheres + grids + triangles ~ 0.3 GB per GPU, no flush needed",
+                       "unit_note": "value = n_gpus x ticks/s (each tick advances n_gpus C3-sized units)"},
+            "e2e": {"value": N * 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": nb * 16, "d2h_bytes_per_step": nb * 16 + 8, "ms_per_step": e2e_ms,
+                    "note": "rb_step_host: forces H2D from pinned host memory, tick, positions + contact count D2H, sync"},
+            "gpu_launches": int(l1 - l0),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "rb_collide_kernel<single,resolve>", "kernel_ms": collide_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                         "kernel_ms_all": {k: v / args.steps for k, v in kms.items()}},
+            "contact_tests_per_s": N * tests_step * 1000.0 / ms_step, "contact_tests_per_step": tests_step, "contacts_per_step": contacts,
+            "free_fall": {"ms_per_step": ff_ms, "steps_per_s": N * 1000.0 / ff_ms, "contact_tests_per_step": ff_tests},
+            "audit": {"contacts_dropped": final["contacts_dropped"], "margin_overflow": final["margin_overflow"],
+                      "halo_sent_last": final["halo_sent_last"], "halo_recv_last": final["halo_recv_last"], "device_bytes": final["device_bytes"]},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    w.close()
+    if N > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--settle", type=int, default=600)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-frac", type=int, default=1024)
+    ap.add_argument("--cpu-settle", type=int, default=400)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--ref-frac", type=int, default=512)
+    ap.add_argument("--ref-settle", type=int, default=400)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -146,7 +146,7 @@ class World:
 
     def contact_sets(self, contacts=None):
         """(ss[n,4] = bodyA,sphereA,bodyB,sphereB ; st[n,4] = body,sphere,geom,tri), sorted unique --
-        same convention as oracle.*_binding.contact_sets."""
+        body / geom ids as the C ABI reports them."""
         c = self.contacts() if contacts is None else contacts
         a = np.stack([c["body"], c["sphere"], c["other"], c["other_prim"]], axis=1).astype(np.int32)
         ss = a[c["kind"] == 0]

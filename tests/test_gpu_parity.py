@@ -1,0 +1,307 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against
+  * the committed golden fixtures generated from the reference's own compiled sources,
+  * the CPU oracle (oracle/reboot_oracle.c) on the same seeded inputs,
+  * size-independent properties at BASELINE.json's full C3 size.
+Bar: bit-exact contact sets and integration; resolved state bit-exact vs the canonical-order oracle
+and vs the reference wherever the reference's result cannot depend on its hash/leaf order."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from util import bits, golden_scenes, order_independent_mask, restart, tri_bases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def World():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from reboot_b200 import World as W
+    return W
+
+
+@pytest.mark.parametrize("name", ["c1", "compound", "pile", "c2"])
+def test_L1_frozen_contact_sets_match_reference(World, golden, name):
+    """Integration bit-exact, then frozen-state detection gives exactly the reference's contact sets."""
+    sc, cps = golden_scenes()[name]
+    g = golden[name]
+    for cp in cps:
+        w = restart(World, sc, g, name, cp)
+        w.integrate(sc.dt_ms)
+        s = w.state()
+        assert np.array_equal(bits(s["pos"]), bits(g[f"{name}_k{cp}_sint_pos"]))
+        assert np.array_equal(bits(s["vel"]), bits(g[f"{name}_k{cp}_sint_vel"]))
+        w.detect()
+        ss, st = w.contact_sets()
+        assert np.array_equal(ss, g[f"{name}_k{cp}_frozen_ss"]), (name, cp)
+        assert np.array_equal(st, g[f"{name}_k{cp}_frozen_st"]), (name, cp)
+        s2 = w.state()   # detection must not touch state
+        assert np.array_equal(bits(s2["pos"]), bits(s["pos"])) and np.array_equal(s2["flags"], s["flags"])
+        w.close()
+
+
+@pytest.mark.parametrize("name", ["c1", "compound", "pile", "c2"])
+def test_L2_one_tick_matches_reference_where_order_free(World, golden, name):
+    """One tick from the reference's state: positions, velocities and flags equal the reference's next
+    state bit-for-bit on bodies whose result is order-free; sphere-sphere resolved bodies within 1e-5
+    relative (the "modelA"/"modelB" role follows pointer-hash order in the reference). Depths and
+    normals of the reported contacts match the reference's hit log within 1e-5 relative."""
+    sc, cps = golden_scenes()[name]
+    g = golden[name]
+    nb, ng = sc.n_bodies, len(sc.tris)
+    tb = tri_bases(sc)
+    for cp in cps:
+        w = restart(World, sc, g, name, cp)
+        w.step(sc.dt_ms)
+        s = w.state()
+        hi, hf = g[f"{name}_k{cp}_hits_i"], g[f"{name}_k{cp}_hits_f"]
+        exact, ssok = order_independent_mask(hi, ng, nb, tb)
+        rp, rv, rf = g[f"{name}_k{cp}_s1_pos"], g[f"{name}_k{cp}_s1_vel"], g[f"{name}_k{cp}_s1_flags"]
+        bad = (bits(s["pos"]) != bits(rp)).any(1) | (bits(s["vel"]) != bits(rv)).any(1)
+        assert int((bad & exact).sum()) <= max(1, int(0.002 * nb)), (name, cp)
+        assert np.allclose(s["pos"][ssok], rp[ssok], rtol=1e-5, atol=1e-6)
+        assert np.allclose(s["vel"][ssok], rv[ssok], rtol=1e-5, atol=1e-6)
+        if name in ("c1", "c2"):
+            assert np.array_equal(s["flags"][exact & ~bad], rf[exact & ~bad])
+        # contact payload: depth / normal of every reference sphere-triangle hit of an order-free body
+        c = w.contacts()
+        mine = {(int(r["body"]), int(r["sphere"]), int(r["other"]), int(r["other_prim"])): r for r in c[c["kind"] == 1]}
+        n_cmp = 0
+        for (kind, ea, sa, eb, pb), f in zip(hi, hf):
+            if kind != 1 or not exact[ea - ng] or bad[ea - ng]:
+                continue
+            r = mine[(ea - ng, sa, eb, pb)]
+            assert np.allclose(r["depth"], f[0], rtol=1e-5, atol=1e-6)
+            assert np.allclose(r["normal"], f[1:4], rtol=1e-5, atol=1e-6, equal_nan=True)
+            n_cmp += 1
+        if name in ("c1", "compound") and cp > 0:
+            assert n_cmp > 0
+        w.close()
+
+
+@pytest.mark.parametrize("name,nsteps", [("c1", 250), ("compound", 60), ("pile", 12), ("c2", 6)])
+def test_trajectory_bit_exact_vs_canonical_oracle(World, port, name, nsteps):
+    """Same seeded scene stepped on the GPU and by the CPU oracle in canonical order: positions,
+    velocities, flags, model / previous-model translations and contact sets identical every tick."""
+    sc, _ = golden_scenes()[name]
+    w = World(sc)
+    o = port.OrcWorld(sc, octree=False)
+    for k in range(nsteps):
+        w.step(sc.dt_ms)
+        o.step(sc.dt_ms, port.ORDER_CANONICAL)
+        if k % 10 == 9 or k == nsteps - 1 or k < 2:
+            a, b = w.state(), o.state()
+            for key in ("pos", "vel", "model_t", "prev_t"):
+                assert np.array_equal(bits(a[key]), bits(b[key])), (name, k, key)
+            assert np.array_equal(a["flags"], b["flags"]), (name, k)
+            ga, gb = w.contact_sets(), o.contact_sets()
+            assert np.array_equal(ga[0], gb[0]) and np.array_equal(ga[1], gb[1]), (name, k)
+    st = w.stats()
+    oc = o.counters()
+    assert st["contacts_dropped"] == 0
+    assert st["hits_st"] > 0 or name in ("pile", "c2")
+    assert oc["tests_ss"] >= 0
+    w.close()
+
+
+def test_voronoi_micro_vectors_through_the_kernels(World, golden):
+    """Every hand-built sphere/triangle micro vector (face, edge and vertex regions; penetrating,
+    exactly touching = miss (Q5), separated; degenerate triangles) as one world: pair (i, i) is
+    reported iff the reference predicate says hit."""
+    m = golden["micro"]
+    n = 2253   # the structured cases; the random bulk is covered by the scene tests
+    w = World()
+    w.add_static_geometry(m["st_tri"][:n])
+    obj = np.zeros((n, 4), np.float32); obj[:, 3] = m["st_r"][:n]
+    w.add_models(np.arange(n + 1), obj, m["st_c"][:n], np.zeros((n, 3), np.float32), np.full(n, 3, np.uint32))
+    w.build()
+    w.detect()
+    _, st = w.contact_sets()
+    got = np.zeros(n, np.int32)
+    diag = st[st[:, 0] == st[:, 3]]
+    got[diag[:, 0]] = 1
+    assert np.array_equal(got, m["st_hit"][:n])
+    w.close()
+
+
+def test_sphere_sphere_micro_vectors(World, golden):
+    """Touching spheres are a HIT (Q5). Pairs are placed as two-body worlds sharing one big world."""
+    m = golden["micro"]
+    n = 300
+    a, b = m["ss_a"][:n].copy(), m["ss_b"][:n].copy()
+    w = World(max_contacts=600 * 600)   # the pairs overlap each other too; only pair (2k, 2k+1) is checked
+    pos = np.zeros((2 * n, 3), np.float32); obj = np.zeros((2 * n, 4), np.float32)
+    pos[0::2], pos[1::2] = a[:, :3], b[:, :3]
+    obj[0::2, 3], obj[1::2, 3] = a[:, 3], b[:, 3]
+    w.add_models(np.arange(2 * n + 1), obj, pos, np.zeros_like(pos), np.full(2 * n, 1, np.uint32))
+    w.build()
+    w.detect()
+    ss, _ = w.contact_sets()
+    got = np.zeros(n, np.int32)
+    for r in ss:
+        if r[0] % 2 == 0 and r[2] == r[0] + 1:
+            got[r[0] // 2] = 1
+    assert np.array_equal(got, m["ss_hit"][:n])
+    w.close()
+
+
+def test_integration_bit_exact_with_forces_and_angular(World, golden, port):
+    """StateVector::update incl. force, torque, angular state, gravity / contact friction, inactive
+    bodies; setForce / setTorque gating (StateVector.cpp:147-167)."""
+    m = golden["micro"]
+    io, flags = m["sv_in"], m["sv_flags"]
+    n = io.shape[0]
+    w = World()
+    obj = np.zeros((n, 4), np.float32); obj[:, 3] = 1e-3
+    w.add_models(np.arange(n + 1), obj, io[:, 0:3], io[:, 3:6], (flags & 3).astype(np.uint32))
+    w.build()
+    # build primes with _updateKinematics(0): friction applies to gravity-off bodies -> restore velocity
+    w.set_state(0, vel=io[:, 3:6])
+    w.set_flags(0, flags.astype(np.uint32), 4)
+    w.set_angular(0, io[:, 6:9], io[:, 9:12])
+    w.set_force(0, io[:, 12:15])
+    w.set_torque(0, io[:, 15:18])
+    gate = ((flags & 4) != 0) | ((flags & 2) == 0)
+    exp_in = io.copy()
+    exp_in[~gate, 12:] = 0
+    for k in range(7):
+        w.integrate(5)
+    s = w.state(); ap, av = w.angular()
+    exp = port.state_update(exp_in, flags, 5, 7)
+    assert np.array_equal(bits(s["pos"]), bits(exp[:, 0:3])) and np.array_equal(bits(s["vel"]), bits(exp[:, 3:6]))
+    assert np.array_equal(bits(ap), bits(exp[:, 6:9])) and np.array_equal(bits(av), bits(exp[:, 9:12]))
+    # rows whose force passes the gate also match the reference-generated fixture directly
+    ref7 = m["sv_out_5ms_7"]
+    assert np.array_equal(bits(s["pos"][gate]), bits(ref7[gate, 0:3]))
+    w.close()
+
+
+def test_edge_cases(World, port):
+    from reboot_b200 import RebootError, scenes
+    # empty world
+    w = World(); w.build(); w.step(5); w.detect(); assert w.contact_count() == 0 and len(w.contacts()) == 0; w.close()
+    # static geometry only
+    tris, _ = scenes.terrain_triangles(8, 2.0, 1)
+    w = World(); w.add_static_geometry(tris); w.build(); w.step(5); assert w.contact_count() == 0; w.close()
+    # ragged compound bodies (1, 3 and 5 spheres), one inactive body, one sphere outside the world cube (Q7)
+    w = World(); o = port.OrcWorld()
+    w.add_static_geometry(tris); o.L.orc_add_geom(o.h, tris.shape[0], tris); o.n_geoms = 1
+    rng = np.random.default_rng(4)
+    specs = [(1, (0.0, 1.2, 0.0), 3), (3, (2.0, 1.3, 1.0), 3), (5, (-3.0, 1.4, 2.0), 3), (1, (1.0, 1.1, -3.0), 2), (1, (1000.6, 0.0, 0.0), 3), (1, (1000.4, 0.0, 0.0), 3)]
+    for ns, p, fl in specs:
+        obj = np.zeros((ns, 4), np.float32); obj[:, :3] = rng.uniform(-0.3, 0.3, (ns, 3)); obj[:, 3] = 0.5
+        w.add_model(obj, p, (0, -1, 0), fl)
+        o.L.orc_add_body(o.h, ns, obj, None, np.array(p, np.float32), np.array([0, -1, 0], np.float32), fl & 1, (fl >> 1) & 1); o.n_bodies += 1
+    w.build(); o.build(False)
+    for k in range(40):
+        w.step(5); o.step(5, port.ORDER_CANONICAL)
+    a, b = w.state(), o.state()
+    assert np.array_equal(bits(a["pos"]), bits(b["pos"])) and np.array_equal(a["flags"], b["flags"])
+    assert np.array_equal(bits(a["pos"][3]), bits(np.array(specs[3][1], np.float32)))   # inactive body never moves
+    assert a["flags"][0] & 4 and a["flags"][2] & 4                                       # resting bodies are in contact
+    # error paths: add after build, NaN input, capacity
+    with pytest.raises(RebootError):
+        w.add_static_geometry(tris)
+    w.close()
+    w = World()
+    with pytest.raises(RebootError):
+        w.add_model([[0, 0, 0, 0.5]], (float("nan"), 0, 0))
+    with pytest.raises(RebootError):
+        w.add_model(np.zeros((0, 4), np.float32), (0, 0, 0))
+    w.close()
+    sc = scenes.pile(64, 5, 0.5, 0)
+    w = World(sc, max_contacts=4)
+    w.detect()
+    with pytest.raises(RebootError) as e:
+        w.contacts()
+    assert e.value.code == 3 and w.stats()["contacts_dropped"] > 0
+    w.close()
+
+
+def test_world_transform_scale_translation_and_big_sphere(World, port):
+    """W = scale (Q2: radius = W[0]*r), W with a translation (Q1: setPosition accumulates W.t), and a
+    sphere much larger than the triangle columns (selection walk instead of the 4-way merge)."""
+    from reboot_b200 import scenes
+    tris, _ = scenes.terrain_triangles(24, 2.0, 2)
+    w = World(); o = port.OrcWorld()
+    w.add_static_geometry(tris); o.L.orc_add_geom(o.h, tris.shape[0], tris); o.n_geoms = 1
+    bodies = [([[0, 0, 0, 0.25]], (3.0, 1.5, 3.0), np.diag([2, 2, 2, 1]).astype(np.float32)),
+              ([[0, 0, 0, 0.5], [0.4, 0, 0, 0.3]], (-6.0, 1.8, 2.0), np.array([[1, 0, 0, 0.5], [0, 1, 0, 0.25], [0, 0, 1, -0.5], [0, 0, 0, 1]], np.float32)),
+              ([[0, 0, 0, 3.5]], (10.0, 4.6, -8.0), None),
+              ([[0, 0, 0, 0.5]], (-12.0, 1.9, -12.0), None)]
+    for obj, p, X in bodies:
+        obj = np.array(obj, np.float32)
+        w.add_model(obj, p, (0.5, -2, 0.25), 3, X)
+        o.L.orc_add_body(o.h, obj.shape[0], obj, None if X is None else np.ascontiguousarray(X).ctypes.data_as(C.c_void_p),
+                         np.array(p, np.float32), np.array([0.5, -2, 0.25], np.float32), 1, 1); o.n_bodies += 1
+    w.build(); o.build(False)
+    o.L.orc_set_prune_slack(o.h, 8.0)
+    assert np.array_equal(bits(w.world_spheres()[:, :3][0]), bits(o.world_spheres(0, 1)[0, :3]))
+    assert w.world_spheres()[0, 3] == 0.5
+    for k in range(80):
+        w.step(5); o.step(5, port.ORDER_CANONICAL)
+    a, b = w.state(), o.state()
+    for key in ("pos", "vel", "model_t", "prev_t"):
+        assert np.array_equal(bits(a[key]), bits(b[key])), key
+    assert np.array_equal(a["flags"], b["flags"]) and (a["flags"] & 4).any()
+    w.close()
+
+
+def test_full_size_c3_properties(World, port):
+    """BASELINE.json config 3 at full size (1M spheres vs 2M-triangle terrain): size-independent
+    properties -- nothing dropped, margin never exceeded, detection idempotent and state-neutral,
+    sampled contacts re-verified with the oracle predicate, sampled spheres re-checked for completeness
+    against every nearby terrain triangle, step_host round trip consistent."""
+    from reboot_b200 import scenes
+    sc = scenes.config3()
+    assert sc.n_bodies == 1_000_000 and sc.n_tris == 2_000_000
+    w = World(sc)
+    for k in range(260):    # long enough for the lowest spheres to land
+        w.step(5)
+    st = w.stats()
+    assert st["contacts_dropped"] == 0 and st["margin_overflow"] == 0 and st["hits_st"] > 1000
+    w.integrate(5)
+    s0 = w.state()
+    w.detect(); c1 = w.contacts()
+    w.detect(); c2 = w.contacts()
+    assert len(c1) > 1000 and np.array_equal(c1, c2)
+    s1 = w.state()
+    assert np.array_equal(bits(s0["pos"]), bits(s1["pos"])) and np.array_equal(s0["flags"], s1["flags"])
+    tris = sc.tris[0]
+    rng = np.random.default_rng(0)
+    stc = c1[c1["kind"] == 1]
+    pick = stc[rng.choice(len(stc), 3000, replace=False)]
+    centers = s0["pos"][pick["body"]]
+    assert port.pred_sphere_triangle(centers, 0.5, tris[pick["other_prim"]]).all()
+    ssc = c1[c1["kind"] == 0]
+    if len(ssc):
+        d = np.linalg.norm(s0["pos"][ssc["body"]].astype(np.float64) - s0["pos"][ssc["other"]], axis=1)
+        assert (d <= 1.0 + 1e-5).all() and (ssc["body"] < ssc["other"]).all()
+    # completeness on a sample: every terrain triangle within 2 cells of the sphere, tested on the CPU
+    G, c = 1000, 2.0
+    have = set(zip(stc["body"].tolist(), stc["other_prim"].tolist()))
+    sample = rng.choice(sc.n_bodies, 1500, replace=False)
+    cells_x = np.clip(np.floor((s0["pos"][sample, 0] + G * c / 2) / c).astype(int), 0, G - 1)
+    cells_z = np.clip(np.floor((s0["pos"][sample, 2] + G * c / 2) / c).astype(int), 0, G - 1)
+    cs, ts, owner = [], [], []
+    for b, cx, cz in zip(sample, cells_x, cells_z):
+        for dz in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                x, z = cx + dx, cz + dz
+                if 0 <= x < G and 0 <= z < G:
+                    for t in (2 * (z * G + x), 2 * (z * G + x) + 1):
+                        cs.append(s0["pos"][b]); ts.append(t); owner.append(b)
+    hit = port.pred_sphere_triangle(np.array(cs), 0.5, tris[np.array(ts)])
+    expect = set((int(o), int(t)) for o, t, h in zip(owner, ts, hit) if h)
+    sample_set = set(sample.tolist())
+    got = set((b, t) for (b, t) in have if b in sample_set)
+    assert expect == got
+    # host round trip: positions returned by the per-tick host call equal the device state
+    pos4 = np.zeros((sc.n_bodies, 4), np.float32)
+    n = w.step_host(5, None, pos4)
+    s2 = w.state()
+    assert np.array_equal(bits(pos4[:, :3]), bits(s2["pos"])) and n == w.contact_count()
+    w.close()

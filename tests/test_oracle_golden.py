@@ -1,0 +1,124 @@
+"""CPU suite: the plain-C oracle (oracle/reboot_oracle.c) against the committed golden fixtures that
+tests/golden/make_golden.py generated from the reference's own compiled sources (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from util import bits, golden_scenes, order_independent_mask, restart, tri_bases
+
+
+def test_sphere_triangle_predicate_and_closest_point(golden, port):
+    m = golden["micro"]
+    assert np.array_equal(port.pred_sphere_triangle(m["st_c"], m["st_r"], m["st_tri"]), m["st_hit"])
+    q = port.closest_point(m["st_c"], m["st_tri"])
+    same = (bits(q) == bits(m["st_closest"])) | (np.isnan(q) & np.isnan(m["st_closest"]))
+    assert same.all()
+    assert 0.05 < m["st_hit"].mean() < 0.95  # fixture exercises both outcomes
+
+
+def test_sphere_sphere_predicate(golden, port):
+    m = golden["micro"]
+    assert np.array_equal(port.pred_sphere_sphere(m["ss_a"], m["ss_b"]), m["ss_hit"])
+    # Q5: exact touching is a HIT for sphere-sphere (first fixture row: centres 1 apart, radii 0.5+0.5)
+    assert m["ss_hit"][0] == 1 and m["ss_hit"][1] == 0
+
+
+def test_sphere_cube_and_triangle_cube_predicates(golden, port):
+    m = golden["micro"]
+    assert np.array_equal(port.pred_sphere_cube(m["sc_s"], m["sc_cube"]), m["sc_hit"])
+    assert np.array_equal(port.pred_triangle_cube(m["tc_tri"], m["tc_cube"]), m["tc_hit"])
+    assert m["sc_hit"][0] == 1 and m["sc_hit"][1] == 0  # closed boundary
+
+
+def test_state_vector_update_bit_exact(golden, port):
+    m = golden["micro"]
+    for key, ms, n in (("sv_out_5ms_1", 5, 1), ("sv_out_5ms_7", 5, 7), ("sv_out_16ms_3", 16, 3)):
+        out = port.state_update(m["sv_in"], m["sv_flags"], ms, n)
+        assert np.array_equal(bits(out), bits(m[key])), key
+
+
+# (pile / c2 are multi-partner sphere-sphere scenes: their trajectories depend on the reference's
+# pointer-hash entity order from the first tick on, so they are gated by L1 and masked L2 below)
+@pytest.mark.parametrize("name,upto", [("c1", 99), ("compound", 19)])
+def test_reference_order_trajectory_matches_reference(golden, port, name, upto):
+    """The restated octree + leaf loops reproduce the reference run from tick 0: state bit-exact at
+    every checkpoint, same hit multiset, same narrowphase test counts."""
+    sc, cps = golden_scenes()[name]
+    g = golden[name]
+    o = port.OrcWorld(sc)
+    assert o.leaf_count() == int(g[f"{name}_leaves"][0])
+
+    def same_state(s, tag, cp):
+        # bit-exact except for bodies a sphere-sphere resolution touched: which of the two plays
+        # "modelA" (GeometryMath.cpp:523) follows libstdc++'s pointer-hash order in the reference and
+        # ascending index here, and "modelB" normalises its normal twice -> last-ulp differences
+        rp, rv, rf = g[f"{name}_k{cp}_{tag}_pos"], g[f"{name}_k{cp}_{tag}_vel"], g[f"{name}_k{cp}_{tag}_flags"]
+        assert np.array_equal(s["flags"], rf)
+        assert np.allclose(s["pos"], rp, rtol=1e-5, atol=1e-5) and np.allclose(s["vel"], rv, rtol=1e-4, atol=1e-5)
+        bad = (bits(s["pos"]) != bits(rp)).any(1) | (bits(s["vel"]) != bits(rv)).any(1)
+        if name in ("c1", "compound"):
+            assert bad.mean() < 0.05, (tag, cp, bad.mean())
+    k = 0
+    for cp in [c for c in cps if c <= upto]:
+        while k < cp:
+            o.step(sc.dt_ms, port.ORDER_REFERENCE); k += 1
+        same_state(o.state(), "s0", cp)
+        o.step(sc.dt_ms, port.ORDER_REFERENCE); k += 1
+        same_state(o.state(), "s1", cp)
+        a, f = o.hits()
+        ga = g[f"{name}_k{cp}_hits_i"].copy()
+        ga[:, 1] -= len(sc.tris)                      # fixture stores entity ids; the port reports body ids
+        ga[ga[:, 0] == 0, 3] -= len(sc.tris)
+        # which body the reference's unordered_map visits first is libstdc++ pointer-hash order: compare
+        # sphere-sphere hits as unordered pairs
+        def canon(h):
+            h = h.copy()
+            sw = (h[:, 0] == 0) & ((h[:, 1] > h[:, 3]) | ((h[:, 1] == h[:, 3]) & (h[:, 2] > h[:, 4])))
+            h[sw] = h[sw][:, [0, 3, 4, 1, 2]]
+            return np.unique(h, axis=0)
+        assert np.array_equal(canon(a), canon(ga))
+
+
+@pytest.mark.parametrize("name", ["c1", "compound", "pile", "c2"])
+def test_integration_and_frozen_contact_sets_match_reference(golden, port, name):
+    """L1: restart from the reference's state, integrate (bit-exact), then frozen-state detection in
+    canonical order gives exactly the reference's de-duplicated contact sets."""
+    sc, cps = golden_scenes()[name]
+    g = golden[name]
+    for cp in cps:
+        o = restart(port.OrcWorld, sc, g, name, cp, octree=False)
+        o.integrate(sc.dt_ms)
+        s = o.state()
+        assert np.array_equal(bits(s["pos"]), bits(g[f"{name}_k{cp}_sint_pos"]))
+        assert np.array_equal(bits(s["vel"]), bits(g[f"{name}_k{cp}_sint_vel"]))
+        ss, st = o.contact_sets(o.detect(port.ORDER_CANONICAL))
+        assert np.array_equal(ss, g[f"{name}_k{cp}_frozen_ss"]), (name, cp)
+        assert np.array_equal(st, g[f"{name}_k{cp}_frozen_st"]), (name, cp)
+
+
+@pytest.mark.parametrize("name", ["c1", "compound", "pile", "c2"])
+def test_canonical_order_one_tick_matches_reference_where_order_free(golden, port, name):
+    """L2: one canonical-order tick from the reference's state equals the reference's next state on
+    every body whose result cannot depend on leaf / hash order (bit-exact; SS-resolved bodies within
+    1e-5 relative because which body plays "modelA" differs)."""
+    sc, cps = golden_scenes()[name]
+    g = golden[name]
+    nb, ng = sc.n_bodies, len(sc.tris)
+    tb = tri_bases(sc)
+    checked = 0
+    for cp in cps:
+        o = restart(port.OrcWorld, sc, g, name, cp, octree=False)
+        o.step(sc.dt_ms, port.ORDER_CANONICAL)
+        s = o.state()
+        exact, ssok = order_independent_mask(g[f"{name}_k{cp}_hits_i"], ng, nb, tb)
+        rp, rv, rf = g[f"{name}_k{cp}_s1_pos"], g[f"{name}_k{cp}_s1_vel"], g[f"{name}_k{cp}_s1_flags"]
+        bad = (bits(s["pos"]) != bits(rp)).any(1) | (bits(s["vel"]) != bits(rv)).any(1)
+        n_bad = int((bad & exact).sum())
+        # the only admissible source of a difference inside `exact` is a sphere that a resolution pushed
+        # into a triangle of a leaf it was not registered in (never re-tested by the reference this tick)
+        assert n_bad <= max(1, int(0.002 * nb)), (name, cp, n_bad)
+        assert np.allclose(s["pos"][ssok], rp[ssok], rtol=1e-5, atol=1e-6)
+        assert np.allclose(s["vel"][ssok], rv[ssok], rtol=1e-5, atol=1e-6)
+        checked += int(exact.sum() + ssok.sum())
+        if name == "c1":
+            assert (exact | ssok).mean() > 0.9
+    assert checked > 0
