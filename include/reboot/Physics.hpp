@@ -1,0 +1,233 @@
+// reboot/Physics.hpp -- header-only C++ facade over the C ABI (include/reboot_physics.h) that keeps
+// the reference's physics-side class and method names so reference-style host code compiles against
+// the B200 path unchanged:
+//
+//     Physics* physics = new Physics();          // physics/include/Physics.h:46
+//     physics->addEntities(entityList);          // Physics.h:48 (engine/src/EngineManager.cpp:223)
+//     physics->run();                            // Physics.h:51 (EngineManager.cpp:224)
+//     ...
+//     physics->visualize();                      // Physics.h:50 (EngineManager.cpp:470)
+//
+// Types mirrored (value types, no GL/FBX baggage): Vector4 (math/include/Vector4.h:25-58), Matrix
+// (math/include/Matrix.h:82-117, row-major 4x4), Sphere / Triangle / Geometry / GeometryType
+// (physics/include/{Sphere,Triangle,Geometry}.h), StateVector (math/include/StateVector.h:32-73),
+// Model and Entity (only the members the physics path touches: model/include/Entity.h:50-68).
+// The tick itself runs on the GPU; this file only marshals.
+#pragma once
+#include "../reboot_physics.h"
+
+#include <functional>
+#include <map>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace reboot {
+
+class Vector4 {
+    float _vec[4];
+public:
+    Vector4() : _vec{0.f, 0.f, 0.f, 1.f} {}
+    Vector4(float x, float y, float z, float w = 1.0f) : _vec{x, y, z, w} {}
+    float getx() const { return _vec[0]; }
+    float gety() const { return _vec[1]; }
+    float getz() const { return _vec[2]; }
+    float getw() const { return _vec[3]; }
+    float* getFlatBuffer() { return _vec; }
+};
+
+class Matrix {
+    float _matrix[16];
+public:
+    Matrix() : _matrix{1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1} {}
+    float* getFlatBuffer() { return _matrix; }
+    const float* data() const { return _matrix; }
+    static Matrix translation(float x, float y, float z) { Matrix m; m._matrix[3] = x; m._matrix[7] = y; m._matrix[11] = z; return m; }
+    static Matrix scale(float s) { Matrix m; m._matrix[0] = m._matrix[5] = m._matrix[10] = s; return m; }
+};
+
+class Sphere {
+    float _radius; Vector4 _position;
+public:
+    Sphere(float radius, Vector4 position) : _radius(radius), _position(position) {}
+    Vector4 getObjectPosition() const { return _position; }
+    float getObjectRadius() const { return _radius; }
+};
+
+class Triangle {
+    Vector4 _points[3];
+public:
+    Triangle(Vector4 A, Vector4 B, Vector4 C) : _points{A, B, C} {}
+    const Vector4* getTrianglePoints() const { return _points; }
+};
+
+enum class GeometryType { Triangle = 0, Sphere = 1 };
+
+class Geometry {
+    std::vector<Sphere> _spheres; std::vector<Triangle> _triangles;
+public:
+    void addTriangle(Triangle t) { _triangles.push_back(t); }
+    void addSphere(Sphere s) { _spheres.push_back(s); }
+    std::vector<Triangle>* getTriangles() { return &_triangles; }
+    std::vector<Sphere>* getSpheres() { return &_spheres; }
+};
+
+class Model {
+    GeometryType _type; Geometry _geometry;
+public:
+    explicit Model(GeometryType t) : _type(t) {}
+    GeometryType getGeometryType() const { return _type; }
+    Geometry* getGeometry() { return &_geometry; }
+};
+
+class Physics;
+
+// Host-side mirror of one body's StateVector. Setters before Physics::addEntities define the initial
+// state; afterwards they are forwarded to the device (same gating as StateVector.cpp:147-167 for
+// setForce/setTorque, applied on the device). Getters return the last Physics::syncState() snapshot.
+class StateVector {
+    friend class Physics; friend class Entity;
+    Vector4 _linearPosition, _linearVelocity, _force, _torque;
+    bool _active = false, _gravity = true, _contact = false;
+    Physics* _owner = nullptr; uint32_t _body = 0;
+    inline void push_pos(); inline void push_vel(); inline void push_flags(uint32_t mask); inline void push_force(); inline void push_torque();
+public:
+    void setLinearPosition(Vector4 p) { _linearPosition = p; push_pos(); }
+    void setLinearVelocity(Vector4 v) { _linearVelocity = v; push_vel(); }
+    void setActive(bool a) { _active = a; push_flags(RB_ACTIVE); }
+    void setGravity(bool g) { _gravity = g; push_flags(RB_GRAVITY); }
+    void setContact(bool c) { _contact = c; push_flags(RB_CONTACT); }
+    void setForce(Vector4 f) { _force = f; push_force(); }
+    void setTorque(Vector4 t) { _torque = t; push_torque(); }
+    Vector4 getLinearPosition() const { return _linearPosition; }
+    Vector4 getLinearVelocity() const { return _linearVelocity; }
+    bool getActive() const { return _active; }
+    bool getContact() const { return _contact; }
+    float getMass() const { return 1.0f; }
+};
+
+class Entity {
+    friend class Physics;
+    Model* _model; Matrix _worldSpaceTransform; StateVector _state;
+    Vector4 _modelTranslation, _prevModelTranslation;
+    uint32_t _id = 0;       // geom id (Triangle type) or body id (Sphere type) once added
+public:
+    explicit Entity(Model* model, Matrix worldSpaceTransform = Matrix()) : _model(model), _worldSpaceTransform(worldSpaceTransform) {}
+    StateVector* getStateVector() { return &_state; }
+    Model* getModel() { return _model; }
+    Geometry* getGeometry() { return _model->getGeometry(); }
+    Matrix getWorldSpaceTransform() const { return _worldSpaceTransform; }
+    // translations of Entity::getMVP()/getPrevMVP() model matrices ([3],[7],[11]) at the last syncState()
+    Vector4 getModelTranslation() const { return _modelTranslation; }
+    Vector4 getPrevModelTranslation() const { return _prevModelTranslation; }
+    void setVelocity(Vector4 v) { _state.setLinearVelocity(v); }
+};
+
+// (geometry entity, triangle index) pairs per sphere entity: the reference's
+// ModelIntersections = std::map<Entity*, std::set<Triangle*>> (Physics.h:28) with indices for pointers
+using ModelIntersections = std::map<Entity*, std::set<std::pair<Entity*, uint32_t>>>;
+
+class Physics {
+    friend class StateVector;
+    rb_world* _w = nullptr;
+    std::vector<Entity*> _entities, _bodies, _geoms;
+    ModelIntersections _triangleIntersectionList;
+    bool _built = false;
+    static void ck(rb_world* w, int rc) { if (rc) throw std::runtime_error(std::string("reboot_b200: ") + rb_last_error(w)); }
+public:
+    // Physics::Physics -- physics/src/Physics.cpp:7-12 (OSP 2000^3, leaf cap 500 -> config defaults)
+    explicit Physics(const rb_config* cfg = nullptr) { int rc = rb_world_create(cfg, &_w); if (rc) throw std::runtime_error(std::string("reboot_b200: ") + rb_last_error(nullptr)); }
+    ~Physics() { rb_world_destroy(_w); }
+    Physics(const Physics&) = delete; Physics& operator=(const Physics&) = delete;
+
+    // Physics::addEntities -- physics/src/Physics.cpp:26-45 (call once; builds the broadphase)
+    void addEntities(std::vector<Entity*> entities) {
+        for (Entity* e : entities) {
+            _entities.push_back(e);
+            if (e->getModel()->getGeometryType() == GeometryType::Triangle) {
+                std::vector<float> xyz; xyz.reserve(e->getGeometry()->getTriangles()->size() * 9);
+                for (const Triangle& t : *e->getGeometry()->getTriangles())
+                    for (int k = 0; k < 3; k++) { const Vector4& p = t.getTrianglePoints()[k]; xyz.push_back(p.getx()); xyz.push_back(p.gety()); xyz.push_back(p.getz()); }
+                ck(_w, rb_add_static_geometry(_w, (uint32_t)(xyz.size() / 9), xyz.data(), &e->_id));
+                _geoms.push_back(e);
+            } else {
+                std::vector<float> obj;
+                for (const Sphere& s : *e->getGeometry()->getSpheres()) { Vector4 p = s.getObjectPosition(); obj.push_back(p.getx()); obj.push_back(p.gety()); obj.push_back(p.getz()); obj.push_back(s.getObjectRadius()); }
+                rb_body_init init; StateVector& st = e->_state;
+                init.pos[0] = st._linearPosition.getx(); init.pos[1] = st._linearPosition.gety(); init.pos[2] = st._linearPosition.getz();
+                init.vel[0] = st._linearVelocity.getx(); init.vel[1] = st._linearVelocity.gety(); init.vel[2] = st._linearVelocity.getz();
+                init.flags = (st._active ? RB_ACTIVE : 0u) | (st._gravity ? RB_GRAVITY : 0u);
+                ck(_w, rb_add_model(_w, (uint32_t)(obj.size() / 4), obj.data(), e->_worldSpaceTransform.data(), &init, &e->_id));
+                st._owner = this; st._body = e->_id;
+                _bodies.push_back(e);
+            }
+        }
+        ck(_w, rb_build(_w));
+        _built = true;
+    }
+    // Physics::run -- physics/src/Physics.cpp:18-24 subscribes _physicsProcess to the 5 ms kinematics
+    // tick; here the caller (or a MasterClock-style thread) drives tick() itself.
+    void run() {}
+    // one kinematics tick: every Entity::_updateKinematics(ms) then Physics::_physicsProcess(ms)
+    void tick(int milliseconds = 5) { ck(_w, rb_step(_w, milliseconds)); }
+    // refresh every Entity's StateVector / model translations from the device
+    void syncState() {
+        size_t n = _bodies.size(); if (!n) return;
+        std::vector<float> p(n * 4), v(n * 4), m(n * 4), pm(n * 4); std::vector<uint32_t> f(n);
+        ck(_w, rb_get_state(_w, p.data(), v.data(), f.data()));
+        ck(_w, rb_get_model_translations(_w, m.data(), pm.data()));
+        for (size_t i = 0; i < n; i++) {
+            Entity* e = _bodies[i]; StateVector& s = e->_state;
+            s._linearPosition = Vector4(p[4 * i], p[4 * i + 1], p[4 * i + 2]); s._linearVelocity = Vector4(v[4 * i], v[4 * i + 1], v[4 * i + 2]);
+            s._active = f[i] & RB_ACTIVE; s._gravity = f[i] & RB_GRAVITY; s._contact = f[i] & RB_CONTACT;
+            e->_modelTranslation = Vector4(m[4 * i], m[4 * i + 1], m[4 * i + 2]); e->_prevModelTranslation = Vector4(pm[4 * i], pm[4 * i + 1], pm[4 * i + 2]);
+        }
+    }
+    // Physics::visualize -- physics/src/Physics.cpp:51-79: hands the triangles in contact per entity to a
+    // consumer (the reference's DebugShader) and clears the list.
+    void visualize(const std::function<void(Entity*, const std::set<std::pair<Entity*, uint32_t>>&)>& consumer = nullptr) {
+        uint64_t n = 0; ck(_w, rb_contact_count(_w, &n));
+        std::vector<rb_contact> c(n ? n : 1);
+        ck(_w, rb_query_contacts(_w, c.data(), c.size(), &n, 1));
+        for (uint64_t i = 0; i < n; i++) if (c[i].kind == 1) _triangleIntersectionList[_bodies[c[i].body]].insert({_geoms[c[i].other], c[i].other_prim});
+        if (consumer) for (auto& kv : _triangleIntersectionList) consumer(kv.first, kv.second);
+        _triangleIntersectionList.clear();
+    }
+    const ModelIntersections& intersections() {   // contacts of the last tick without clearing
+        _triangleIntersectionList.clear(); uint64_t n = 0; ck(_w, rb_contact_count(_w, &n));
+        std::vector<rb_contact> c(n ? n : 1); ck(_w, rb_query_contacts(_w, c.data(), c.size(), &n, 1));
+        for (uint64_t i = 0; i < n; i++) if (c[i].kind == 1) _triangleIntersectionList[_bodies[c[i].body]].insert({_geoms[c[i].other], c[i].other_prim});
+        return _triangleIntersectionList;
+    }
+    rb_world* handle() { return _w; }
+};
+
+inline void StateVector::push_pos() {
+    if (!_owner || !_owner->_built) return;
+    float p[4] = {_linearPosition.getx(), _linearPosition.gety(), _linearPosition.getz(), 1.f};
+    Physics::ck(_owner->_w, rb_set_state(_owner->_w, _body, 1, p, nullptr));
+}
+inline void StateVector::push_vel() {
+    if (!_owner || !_owner->_built) return;
+    float v[4] = {_linearVelocity.getx(), _linearVelocity.gety(), _linearVelocity.getz(), 0.f};
+    Physics::ck(_owner->_w, rb_set_state(_owner->_w, _body, 1, nullptr, v));
+}
+inline void StateVector::push_flags(uint32_t mask) {
+    if (!_owner || !_owner->_built) return;
+    uint32_t f = (_active ? RB_ACTIVE : 0u) | (_gravity ? RB_GRAVITY : 0u) | (_contact ? RB_CONTACT : 0u);
+    Physics::ck(_owner->_w, rb_set_flags(_owner->_w, _body, 1, &f, mask));
+}
+inline void StateVector::push_force() {
+    if (!_owner || !_owner->_built) return;
+    float f[4] = {_force.getx(), _force.gety(), _force.getz(), 0.f};
+    Physics::ck(_owner->_w, rb_set_force(_owner->_w, _body, 1, f)); Physics::ck(_owner->_w, rb_sync(_owner->_w));
+}
+inline void StateVector::push_torque() {
+    if (!_owner || !_owner->_built) return;
+    float t[4] = {_torque.getx(), _torque.gety(), _torque.getz(), 0.f};
+    Physics::ck(_owner->_w, rb_set_torque(_owner->_w, _body, 1, t));
+}
+
+} // namespace reboot
