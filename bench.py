@@ -205,8 +205,9 @@ def run_ours(args):
 
     stream = torch.cuda.Stream()
     sc, slab = c3_weak_scene(N, rank)
+    ids = (np.arange(sc.n_bodies, dtype=np.uint32) + np.uint32(rank * C3_SPHERES)) if N > 1 else None
     w = World(sc, device=local_rank, stream=stream.cuda_stream, slab=slab, rank=rank, nranks=N,
-              max_contacts=8 * sc.n_spheres, build=False)
+              max_contacts=8 * sc.n_spheres, build=False, ids=ids, rm_max_hint=float(sc.meta["r"]))
     w.build()
     if N > 1:
         from reboot_b200 import dist as rbdist

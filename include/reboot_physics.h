@@ -59,6 +59,7 @@ typedef struct rb_config {
     /* spatial slab owned by this world along x (multi-GPU); defaults cover the whole world */
     float    slab_lo, slab_hi;
     int32_t  rank, nranks;
+    float    rm_max_hint;    /* multi-GPU: largest world-space sphere radius over ALL ranks (0 = this rank's own) */
 } rb_config;
 
 /* initial state of a body: StateVector setters, math/include/StateVector.h:48-60 */
@@ -195,6 +196,17 @@ uint64_t    rb_launch_count(const rb_world* w);
 int         rb_dist_unique_id(const char* nccl_lib_path, uint8_t id[RB_NCCL_ID_BYTES]);
 /* join the communicator; cfg.rank/nranks/slab_lo/slab_hi say which slab this world owns */
 int         rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t id[RB_NCCL_ID_BYTES]);
+
+/* global body ids of a slab world: set before rb_build (default: local insertion index), read back for
+ * the bodies currently owned, in the same order as rb_get_state's rows (ownership migrates) */
+int         rb_set_body_ids(rb_world* w, const uint32_t* ids, uint32_t n);
+int         rb_get_body_ids(rb_world* w, uint32_t* ids_out);
+
+/* Slab worlds of ONE process (any mix of devices; also several slabs on one device for testing):
+ * attach the in-process neighbours instead of rb_dist_init, then advance all slabs in lockstep. */
+int         rb_dist_attach_peers(rb_world* w, rb_world* left, rb_world* right);
+int         rb_step_group(rb_world** worlds, int n, int ms);
+int         rb_detect_group(rb_world** worlds, int n);
 
 const char* rb_version(void);
 

@@ -20,7 +20,7 @@ class RbConfig(C.Structure):
     _fields_ = [("world_half", C.c_float), ("gravity", C.c_float), ("friction", C.c_float), ("pushout", C.c_float),
                 ("ss_damp", C.c_float), ("margin_cap", C.c_float), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("max_contacts", C.c_uint64), ("slab_lo", C.c_float), ("slab_hi", C.c_float),
-                ("rank", C.c_int32), ("nranks", C.c_int32)]
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("rm_max_hint", C.c_float)]
 
 
 class RbBodyInit(C.Structure):
@@ -80,6 +80,11 @@ SIGNATURES = {
     "rb_launch_count": (C.c_uint64, [_P]),
     "rb_dist_unique_id": (C.c_int, [C.c_char_p, _P]),
     "rb_dist_init": (C.c_int, [_P, C.c_char_p, _P]),
+    "rb_set_body_ids": (C.c_int, [_P, _P, C.c_uint32]),
+    "rb_get_body_ids": (C.c_int, [_P, _P]),
+    "rb_dist_attach_peers": (C.c_int, [_P, _P, _P]),
+    "rb_step_group": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    "rb_detect_group": (C.c_int, [C.POINTER(_P), C.c_int]),
     "rb_version": (C.c_char_p, []),
 }
 

@@ -72,8 +72,16 @@ struct RbParams {
     // ---- deferred commit (compound-body path) ----
     uint32_t* ch_body; float4* ch_pos; float4* ch_vel; float4* ch_mt; float4* ch_pt; uint32_t* ch_flags;
     // ---- slab ownership (multi-GPU) ----
-    uint32_t n_owned;             // bodies [0, n_owned) are owned, [n_owned, nb) are ghosts
+    uint32_t n_owned;             // bodies [0, n_owned) are owned (host value; single-GPU worlds)
+    const uint32_t* dn;           // device counts {n_owned, n_ghost} of slab worlds (NULL otherwise):
+                                  // local bodies [0, dn[0]) are owned, [dn[0], dn[0]+dn[1]) are ghosts
+    const uint32_t* gid;          // global body id per local body (NULL: id == local index)
+    float s_x0;                   // x origin of the sphere column grid (-half for whole-world grids)
 };
+
+__device__ __forceinline__ uint32_t rb_n_owned(const RbParams& P) { return P.dn ? P.dn[0] : P.n_owned; }
+__device__ __forceinline__ uint32_t rb_n_local(const RbParams& P) { return P.dn ? P.dn[0] + P.dn[1] : P.ns; }
+__device__ __forceinline__ uint32_t rb_gid(const RbParams& P, uint32_t local) { return P.gid ? P.gid[local] : local; }
 
 struct f3 { float x, y, z; };
 
@@ -162,6 +170,7 @@ __device__ __forceinline__ bool sphere_in_world(f3 c, float r, float half) {
 }
 
 // monotone column index (shared by triangles at build time and spheres every step)
+// (x + half) with half = -origin: whole-world grids start at -half, slab grids at s_x0
 __host__ __device__ __forceinline__ uint32_t rb_col(float x, float half, float inv_w, uint32_t n) {
     float t = (x + half) * inv_w;
     if (!(t > 0.0f)) return 0;

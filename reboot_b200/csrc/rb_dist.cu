@@ -1,0 +1,371 @@
+// rb_dist.cu -- multi-GPU x-slabs: one world per GPU owns the bodies whose centre
+// lies in its x-slab; static geometry is replicated. Every tick, between integration and the
+// broadphase, each world
+//   1. packs (K6a) the owned spheres that can reach a neighbour's slab ("ghosts", 32 B each) and the
+//      bodies that crossed a face ("migrants", full state, 96 B each) into two fixed-capacity buffers,
+//   2. exchanges them with the left/right neighbour -- NCCL send/recv over NVLink on the world's own
+//      stream (one group call, no host sync, no count round trip: the counts ride in the buffer), or a
+//      device-to-device copy when the neighbour world lives in the same process (tests, single GPU),
+//   3. removes its emigrants (swap-remove), appends immigrants as owned bodies and ghosts behind them
+//      (K6b-d), and bins everything into the slab-local sphere grid (K6e).
+// Bodies carry a global id; the canonical order of the narrowphase is defined on global ids, so the
+// result is bit-identical to a single world holding all bodies (tests/test_dist_*).
+// Resolution only writes the sphere's own body (GeometryMath.cpp:489-554), so ghosts are read-only.
+#include "rb_internal.h"
+
+#include <dlfcn.h>
+
+#define RB_BLOCK 256
+
+// ---- exchange buffer layout -------------------------------------------------------------------
+struct __align__(16) RbHaloHeader { uint32_t n_ghost, n_migr, ghost_overflow, migr_overflow; };
+struct __align__(16) RbGhostRec { float4 ws; float r; uint32_t gid; uint32_t pad0, pad1; };                 // 32 B
+struct __align__(16) RbMigrRec { float4 pos, vel, mt, pt, obj; uint32_t flags, gid, pad0, pad1; };          // 96 B
+
+struct RbHaloBuf {
+    uint8_t* base = nullptr; size_t bytes = 0;
+    RbHaloHeader* hdr() const { return (RbHaloHeader*)base; }
+    RbGhostRec* ghosts() const { return (RbGhostRec*)(base + sizeof(RbHaloHeader)); }
+    RbMigrRec* migr(uint32_t ghost_cap) const { return (RbMigrRec*)(base + sizeof(RbHaloHeader) + (size_t)ghost_cap * sizeof(RbGhostRec)); }
+};
+
+struct RbDistParams {
+    RbHaloHeader* out_hdr[2]; RbGhostRec* out_ghost[2]; RbMigrRec* out_migr[2];      // 0 = left, 1 = right
+    const RbHaloHeader* in_hdr[2]; const RbGhostRec* in_ghost[2]; const RbMigrRec* in_migr[2];
+    RbGhostRec* self_ghost; uint32_t* self_cnt;     // emigrants stay visible to their old owner for this tick
+    uint32_t* emig; uint32_t* emig_cnt;             // local indices of emigrants
+    uint32_t ghost_cap, migr_cap, cap_local;
+    float slab_lo, slab_hi; int has_left, has_right;
+    uint32_t* dn;                                   // {n_owned, n_ghost}
+    uint32_t* gid; float4* sph_obj_w; unsigned long long* counters;
+};
+
+// ---- NCCL through dlopen (no link-time dependency; the host says which libnccl to use) -----------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+struct NcclApi {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId_t*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId_t, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int NCCL_UINT8 = 1;   // ncclUint8 in nccl.h's ncclDataType_t
+
+static int load_nccl(rb_world* w, const char* path) {
+    if (g_nccl.h) return RB_OK;
+    const char* cands[] = { path, "libnccl.so.2", "libnccl.so" };
+    void* h = nullptr;
+    for (const char* c : cands) { if (c && *c) { h = dlopen(c, RTLD_NOW | RTLD_GLOBAL); if (h) break; } }
+    if (!h) return fail(w, RB_ERR_NCCL, "cannot dlopen NCCL (%s): %s", path ? path : "libnccl.so.2", dlerror());
+#define SYM(field, name) do { *(void**)(&g_nccl.field) = dlsym(h, name); if (!g_nccl.field) return fail(w, RB_ERR_NCCL, "NCCL symbol %s missing", name); } while (0)
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.h = h;
+    return RB_OK;
+}
+#define NC(call) do { int r_ = (call); if (r_ != 0) return fail(w, RB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+
+struct RbDist {
+    ncclComm_t comm = nullptr;
+    rb_world* peer[2] = { nullptr, nullptr };       // in-process neighbours (left, right)
+    RbHaloBuf out[2], in[2];
+    RbDistParams D;
+    uint32_t ghost_cap = 0, migr_cap = 0;
+    uint32_t* h_dn = nullptr;                        // pinned
+    RbHaloHeader* h_hdr = nullptr;                   // pinned, 4 headers (out L/R, in L/R)
+};
+
+// ---- K6a: pack ghosts and migrants ----------------------------------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_halo_pack_kernel(RbParams P, RbDistParams D) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= D.dn[0]) return;
+    float4 s = P.ws[b];
+    uint32_t f = P.flags[b];
+    bool in_grid = P.key[b] != RB_NONE;            // active and touching the root cube (K1)
+    float r = D.sph_obj_w[b].w;
+    int dir = -1;
+    if (s.x < D.slab_lo && D.has_left) dir = 0; else if (s.x >= D.slab_hi && D.has_right) dir = 1;
+    if (dir >= 0 && (f & RB_F_ACTIVE)) {
+        uint32_t k = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
+        if (k < D.migr_cap) {
+            RbMigrRec m; m.pos = P.pos[b]; m.vel = P.vel[b]; m.mt = P.mt[b]; m.pt = P.pt[b]; m.obj = D.sph_obj_w[b];
+            m.flags = f; m.gid = D.gid[b]; m.pad0 = m.pad1 = 0;
+            D.out_migr[dir][k] = m;
+            D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
+            if (in_grid) { uint32_t g = atomicAdd(D.self_cnt, 1u); if (g < D.ghost_cap) { RbGhostRec q; q.ws = s; q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0; D.self_ghost[g] = q; } }
+        } else atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u);   // stays owned here one more tick
+        return;
+    }
+    if (!in_grid) return;
+    float reach = s.w + P.rm_max;                   // own grown radius + the largest grown radius anywhere
+    RbGhostRec q; q.ws = s; q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0;
+    if (D.has_left && s.x - reach < D.slab_lo) {
+        uint32_t k = atomicAdd(&D.out_hdr[0]->n_ghost, 1u);
+        if (k < D.ghost_cap) D.out_ghost[0][k] = q; else atomicAdd(&D.out_hdr[0]->ghost_overflow, 1u);
+    }
+    if (D.has_right && s.x + reach >= D.slab_hi) {
+        uint32_t k = atomicAdd(&D.out_hdr[1]->n_ghost, 1u);
+        if (k < D.ghost_cap) D.out_ghost[1][k] = q; else atomicAdd(&D.out_hdr[1]->ghost_overflow, 1u);
+    }
+}
+
+// ---- K6b: swap-remove the emigrants (few per tick; one thread keeps it simple and ordered) --------
+__global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t m = *D.emig_cnt;
+    uint32_t n = D.dn[0];
+    // descending order so that the element moved into a hole is never itself a pending hole
+    for (uint32_t i = 1; i < m; ++i) { uint32_t v = D.emig[i]; int j = (int)i - 1; while (j >= 0 && D.emig[j] < v) { D.emig[j + 1] = D.emig[j]; --j; } D.emig[j + 1] = v; }
+    float4* sph = D.sph_obj_w;
+    for (uint32_t i = 0; i < m; ++i) {
+        uint32_t h = D.emig[i], last = n - 1;
+        if (h != last) {
+            P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
+            sph[h] = sph[last]; D.gid[h] = D.gid[last]; P.ws[h] = P.ws[last]; P.key[h] = P.key[last];
+        }
+        n = last;
+    }
+    D.dn[0] = n;
+    D.counters[RB_C_MIGRATED] = m;
+}
+
+// ---- K6c: immigrants become owned bodies -----------------------------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_halo_immigrate_kernel(RbParams P, RbDistParams D) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n0 = min(D.in_hdr[0] ? D.in_hdr[0]->n_migr : 0u, D.migr_cap);
+    uint32_t n1 = min(D.in_hdr[1] ? D.in_hdr[1]->n_migr : 0u, D.migr_cap);
+    if (t >= n0 + n1) return;
+    const RbMigrRec m = t < n0 ? D.in_migr[0][t] : D.in_migr[1][t - n0];
+    uint32_t i = atomicAdd(&D.dn[0], 1u);
+    if (i >= D.cap_local) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_OVERFLOW], 1ull); return; }
+    P.pos[i] = m.pos; P.vel[i] = m.vel; P.mt[i] = m.mt; P.pt[i] = m.pt; P.flags[i] = m.flags;
+    D.sph_obj_w[i] = m.obj; D.gid[i] = m.gid;
+    // same world sphere K1 computed on the old owner (same state, same formula)
+    f3 c = mk3(m.obj.x + m.mt.x, m.obj.y + m.mt.y, m.obj.z + m.mt.z);
+    float speed = mag3(xyz(m.vel));
+    float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * P.dt + 0.01f * m.obj.w, 1e-3f));
+    P.ws[i] = make_float4(c.x, c.y, c.z, m.obj.w + margin);
+    P.key[i] = ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) ? 0u : RB_NONE;
+}
+
+// ---- K6d: ghosts go behind the owned bodies ---------------------------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_halo_ghost_kernel(RbParams P, RbDistParams D) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n0 = min(D.in_hdr[0] ? D.in_hdr[0]->n_ghost : 0u, D.ghost_cap);
+    uint32_t n1 = min(D.in_hdr[1] ? D.in_hdr[1]->n_ghost : 0u, D.ghost_cap);
+    uint32_t n2 = min(*D.self_cnt, D.ghost_cap);
+    if (t >= n0 + n1 + n2) return;
+    const RbGhostRec q = t < n0 ? D.in_ghost[0][t] : (t < n0 + n1 ? D.in_ghost[1][t - n0] : D.self_ghost[t - n0 - n1]);
+    uint32_t i = D.dn[0] + atomicAdd(&D.dn[1], 1u);
+    if (i >= D.cap_local) { atomicSub(&D.dn[1], 1u); atomicAdd(&D.counters[RB_C_OVERFLOW], 1ull); return; }
+    P.ws[i] = q.ws;
+    D.sph_obj_w[i] = make_float4(0.f, 0.f, 0.f, q.r);
+    D.gid[i] = q.gid;
+    P.flags[i] = RB_F_ACTIVE;
+    P.key[i] = 0u;
+}
+
+// ---- K6e: bin owned + ghosts into the slab-local sphere grid -----------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_halo_bin_kernel(RbParams P) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.dn[0] + P.dn[1]) return;
+    if (P.key[s] == RB_NONE) return;
+    float4 c = P.ws[s];
+    uint32_t cx = rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
+    uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
+    uint32_t k = cz * P.scx + cx;
+    P.key[s] = k;
+    P.rank[s] = atomicAdd(&P.col_count[k], 1u);
+}
+
+static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// ---- host ---------------------------------------------------------------------------------------
+static int dist_alloc(rb_world* w) {
+    if (w->dist) return RB_OK;
+    if (!w->built || !w->d_dn) return fail(w, RB_ERR_INVALID, "distributed init needs a built world created with rb_config.nranks > 1");
+    RbDist* d = new RbDist();
+    d->ghost_cap = std::max<uint32_t>(65536u, w->n_owned_host / 8);
+    d->migr_cap = std::max<uint32_t>(4096u, w->n_owned_host / 64);
+    size_t bytes = sizeof(RbHaloHeader) + (size_t)d->ghost_cap * sizeof(RbGhostRec) + (size_t)d->migr_cap * sizeof(RbMigrRec);
+    for (int k = 0; k < 2; k++) {
+        uint8_t *o, *i; ALLOC(o, bytes); ALLOC(i, bytes);
+        CU(cudaMemsetAsync(o, 0, bytes, w->stream)); CU(cudaMemsetAsync(i, 0, bytes, w->stream));
+        d->out[k].base = o; d->out[k].bytes = bytes; d->in[k].base = i; d->in[k].bytes = bytes;
+    }
+    RbGhostRec* sg; uint32_t *em, *cnts; ALLOC(sg, d->ghost_cap); ALLOC(em, d->migr_cap * 2 + 16); ALLOC(cnts, 4);
+    CU(cudaMemsetAsync(cnts, 0, 16, w->stream));
+    CU(cudaMallocHost((void**)&d->h_dn, 4 * sizeof(uint32_t)));
+    CU(cudaMallocHost((void**)&d->h_hdr, 4 * sizeof(RbHaloHeader)));
+    RbDistParams& D = d->D;
+    memset(&D, 0, sizeof D);
+    for (int k = 0; k < 2; k++) {
+        D.out_hdr[k] = d->out[k].hdr(); D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap);
+        D.in_hdr[k] = d->in[k].hdr(); D.in_ghost[k] = d->in[k].ghosts(); D.in_migr[k] = d->in[k].migr(d->ghost_cap);
+    }
+    D.self_ghost = sg; D.self_cnt = cnts; D.emig = em; D.emig_cnt = cnts + 1;
+    D.ghost_cap = d->ghost_cap; D.migr_cap = d->migr_cap; D.cap_local = w->cap_local;
+    D.slab_lo = w->cfg.slab_lo; D.slab_hi = w->cfg.slab_hi;
+    D.has_left = w->cfg.rank > 0; D.has_right = w->cfg.rank < w->cfg.nranks - 1;
+    D.dn = w->d_dn; D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj); D.counters = w->P.counters;
+    CU(cudaStreamSynchronize(w->stream));
+    w->dist = d;
+    return RB_OK;
+}
+
+void rb_dist_destroy(RbDist* d) {
+    if (!d) return;
+    if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    if (d->h_dn) cudaFreeHost(d->h_dn);
+    if (d->h_hdr) cudaFreeHost(d->h_hdr);
+    delete d;
+}
+
+int rb_dist_refresh_counts(rb_world* w) {
+    if (!w->d_dn) return RB_OK;
+    uint32_t tmp[4];
+    CU(cudaMemcpyAsync(tmp, w->d_dn, sizeof tmp, cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaStreamSynchronize(w->stream));
+    w->n_owned_host = tmp[0];
+    if (w->dist) {
+        RbDist* d = w->dist;
+        CU(cudaMemcpy(&d->h_hdr[0], d->out[0].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&d->h_hdr[1], d->out[1].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&d->h_hdr[2], d->in[0].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&d->h_hdr[3], d->in[1].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        w->dist_stats.halo_sent_last = d->h_hdr[0].n_ghost + d->h_hdr[1].n_ghost;
+        w->dist_stats.halo_recv_last = (w->dist->D.has_left ? d->h_hdr[2].n_ghost : 0) + (w->dist->D.has_right ? d->h_hdr[3].n_ghost : 0);
+        w->dist_stats.migrated_out_last = d->h_hdr[0].n_migr + d->h_hdr[1].n_migr;
+        w->dist_stats.migrated_in_last = (w->dist->D.has_left ? d->h_hdr[2].n_migr : 0) + (w->dist->D.has_right ? d->h_hdr[3].n_migr : 0);
+        if (d->h_hdr[0].ghost_overflow || d->h_hdr[1].ghost_overflow || d->h_hdr[0].migr_overflow || d->h_hdr[1].migr_overflow)
+            return fail(w, RB_ERR_CAPACITY, "halo buffer overflow (ghost cap %u, migrant cap %u)", d->ghost_cap, d->migr_cap);
+    }
+    return RB_OK;
+}
+
+// phase A: integrate + pack (everything before the exchange)
+static int dist_phase_a(rb_world* w, int do_integrate) {
+    RbDist* d = w->dist; RbParams& P = w->P;
+    CU(cudaMemsetAsync(P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->d_dn + 1, 0, sizeof(uint32_t), w->stream));                       // n_ghost
+    CU(cudaMemsetAsync(d->D.self_cnt, 0, 2 * sizeof(uint32_t), w->stream));                 // self ghosts + emigrants
+    CU(cudaMemsetAsync(d->out[0].base, 0, sizeof(RbHaloHeader), w->stream));
+    CU(cudaMemsetAsync(d->out[1].base, 0, sizeof(RbHaloHeader), w->stream));
+    if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
+    rb_launch_integrate_bin(P, do_integrate, 0, w->stream); w->launches++;
+    if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));
+    rb_halo_pack_kernel<<<cdiv(w->cap_local, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D); w->launches++;
+    return RB_OK;
+}
+// phase B: unpack + bin + scan + scatter (everything after the exchange)
+static int dist_phase_b(rb_world* w) {
+    RbDist* d = w->dist; RbParams& P = w->P;
+    rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->D);
+    rb_halo_immigrate_kernel<<<cdiv(2 * d->migr_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
+    rb_halo_ghost_kernel<<<cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
+    rb_halo_bin_kernel<<<cdiv(w->cap_local, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P);
+    w->launches += 4;
+    CU(cudaGetLastError());
+    int r = enqueue_broadphase_tail(w);
+    if (w->profile) {   // halo time = pack .. bin, reported as family 4
+        // ev[5] = before pack, ev[1] = before scan (recorded by the tail)
+    }
+    return r;
+}
+
+static int dist_exchange_nccl(rb_world* w) {
+    RbDist* d = w->dist;
+    int rank = w->cfg.rank, n = w->cfg.nranks;
+    NC(g_nccl.GroupStart());
+    if (rank > 0) { NC(g_nccl.Send(d->out[0].base, d->out[0].bytes, NCCL_UINT8, rank - 1, d->comm, w->stream)); NC(g_nccl.Recv(d->in[0].base, d->in[0].bytes, NCCL_UINT8, rank - 1, d->comm, w->stream)); }
+    if (rank < n - 1) { NC(g_nccl.Send(d->out[1].base, d->out[1].bytes, NCCL_UINT8, rank + 1, d->comm, w->stream)); NC(g_nccl.Recv(d->in[1].base, d->in[1].bytes, NCCL_UINT8, rank + 1, d->comm, w->stream)); }
+    NC(g_nccl.GroupEnd());
+    return RB_OK;
+}
+
+int rb_dist_step_exchange(rb_world* w, int do_integrate) {
+    RbDist* d = w->dist;
+    if (!d->comm) return fail(w, RB_ERR_INVALID, "this slab world has in-process neighbours: step it with rb_step_group");
+    int r = dist_phase_a(w, do_integrate); if (r) return r;
+    r = dist_exchange_nccl(w); if (r) return r;
+    return dist_phase_b(w);
+}
+
+extern "C" {
+
+int rb_dist_unique_id(const char* nccl_lib_path, uint8_t id[RB_NCCL_ID_BYTES]) {
+    int r = load_nccl(nullptr, nccl_lib_path); if (r) return r;
+    ncclUniqueId_t u; memset(&u, 0, sizeof u);
+    int e = g_nccl.GetUniqueId(&u);
+    if (e) { g_create_error = std::string("ncclGetUniqueId failed: ") + g_nccl.GetErrorString(e); return RB_ERR_NCCL; }
+    memcpy(id, &u, RB_NCCL_ID_BYTES);
+    return RB_OK;
+}
+
+int rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t id[RB_NCCL_ID_BYTES]) {
+    if (!w) return RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    int r = load_nccl(w, nccl_lib_path); if (r) return r;
+    r = dist_alloc(w); if (r) return r;
+    ncclUniqueId_t u; memcpy(&u, id, RB_NCCL_ID_BYTES);
+    NC(g_nccl.CommInitRank(&w->dist->comm, w->cfg.nranks, u, w->cfg.rank));
+    return RB_OK;
+}
+
+// In-process neighbours (left / right may be NULL at the world edge): the slab worlds of one process,
+// on one or several devices, stepped in lockstep by rb_step_group. Used by the single-GPU tests of the
+// multi-rank path and by single-process multi-GPU hosts.
+int rb_dist_attach_peers(rb_world* w, rb_world* left, rb_world* right) {
+    if (!w) return RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    int r = dist_alloc(w); if (r) return r;
+    w->dist->peer[0] = left; w->dist->peer[1] = right;
+    return RB_OK;
+}
+
+static int group_collide(rb_world** ws, int n, int ms, int do_integrate, int resolve);
+
+int rb_step_group(rb_world** ws, int n, int ms) { return group_collide(ws, n, ms, 1, 1); }
+int rb_detect_group(rb_world** ws, int n) { return group_collide(ws, n, 0, 0, 0); }
+
+} // extern "C"
+
+int rb_collide_only(rb_world* w, bool resolve);   // rb_world.cu
+
+static int group_collide(rb_world** ws, int n, int ms, int do_integrate, int resolve) {
+    for (int i = 0; i < n; i++) {
+        rb_world* w = ws[i];
+        if (!w || !w->dist) return w ? fail(w, RB_ERR_INVALID, "rb_step_group: world %d has no peers attached", i) : RB_ERR_INVALID;
+        CU(cudaSetDevice(w->cfg.device));
+        if (do_integrate) w->P.dt = (float)ms / 1000.0f;
+        int r = dist_phase_a(w, do_integrate); if (r) return r;
+    }
+    for (int i = 0; i < n; i++) { rb_world* w = ws[i]; CU(cudaSetDevice(w->cfg.device)); CU(cudaStreamSynchronize(w->stream)); }
+    for (int i = 0; i < n; i++) {          // exchange: my out[right] -> right's in[left], my out[left] -> left's in[right]
+        rb_world* w = ws[i]; RbDist* d = w->dist;
+        CU(cudaSetDevice(w->cfg.device));
+        for (int k = 0; k < 2; k++) {
+            rb_world* p = d->peer[k];
+            if (!p) continue;
+            RbHaloBuf& dst = p->dist->in[1 - k];
+            CU(cudaMemcpyAsync(dst.base, d->out[k].base, d->out[k].bytes, cudaMemcpyDefault, w->stream));
+        }
+    }
+    for (int i = 0; i < n; i++) { rb_world* w = ws[i]; CU(cudaSetDevice(w->cfg.device)); CU(cudaStreamSynchronize(w->stream)); }
+    for (int i = 0; i < n; i++) {
+        rb_world* w = ws[i];
+        CU(cudaSetDevice(w->cfg.device));
+        int r = dist_phase_b(w); if (r) return r;
+        r = rb_collide_only(w, resolve != 0); if (r) return r;
+        if (do_integrate) w->steps++;
+    }
+    return RB_OK;
+}

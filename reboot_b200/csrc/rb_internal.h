@@ -1,0 +1,93 @@
+// rb_internal.h -- host-side internals shared by rb_world.cu and rb_dist.cu (not part of the ABI).
+#pragma once
+#include "../../include/reboot_physics.h"
+#include "rb_device.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+// launchers defined in rb_kernels.cu
+void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cudaStream_t st);
+int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st);
+uint32_t rb_scan_tiles(uint32_t n);
+void rb_launch_scatter(const RbParams& P, cudaStream_t st);
+int rb_launch_collide(const RbParams& P, bool resolve, cudaStream_t st);
+void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
+void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
+void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
+// multi-GPU (rb_dist.cu)
+struct RbDist;
+int rb_dist_step_exchange(rb_world* w, int ms);
+void rb_dist_destroy(RbDist* d);
+int rb_dist_refresh_counts(rb_world* w);
+extern "C" int enqueue_broadphase_tail(rb_world* w);
+
+extern thread_local std::string g_create_error;
+
+struct DevBuf { void* p = nullptr; size_t bytes = 0; };
+
+struct rb_world {
+    rb_config cfg;
+    std::string err;
+    bool built = false;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // ---- host staging (until rb_build) ----
+    std::vector<float> h_tri;                 // 9 floats per triangle
+    std::vector<uint32_t> h_geom_start;       // CSR geom -> triangles
+    std::vector<float> h_obj;                 // 4 floats per sphere (object space)
+    std::vector<uint32_t> h_body_start;       // CSR body -> spheres
+    std::vector<float> h_W;                   // 12 floats per body: 3x3 row-major + translation
+    std::vector<float> h_pos, h_vel;          // 3 per body
+    std::vector<uint32_t> h_flags;
+    std::vector<uint32_t> h_sph_body;
+    bool any_wt = false;
+    // ---- device ----
+    RbParams P;
+    std::vector<DevBuf> allocs;
+    size_t device_bytes = 0;
+    uint32_t* d_tile_sums = nullptr;
+    uint32_t ncols = 0;
+    float4* d_stage = nullptr; size_t stage_elems = 0;      // H2D staging for setters
+    uint32_t* d_stage_u = nullptr; size_t stage_u_elems = 0;
+    unsigned long long* h_counters = nullptr;               // pinned mirror
+    // ---- bookkeeping ----
+    uint64_t steps = 0, launches = 0;
+    uint64_t contacts_last = 0;
+    bool profile = false;
+    float kernel_ms[5] = { 0, 0, 0, 0, 0 };
+    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    RbDist* dist = nullptr;
+    rb_stats_t dist_stats;
+    // ---- slab worlds (rb_dist.cu) ----
+    uint32_t cap_local = 0;                  // capacity of the per-body / per-sphere arrays
+    uint32_t* d_dn = nullptr;                // device {n_owned, n_ghost}
+    uint32_t* d_gid = nullptr;
+    std::vector<uint32_t> h_gid;             // ids given before rb_build
+    uint32_t n_owned_host = 0;               // last value read back
+};
+
+static inline int fail(rb_world* w, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (w) w->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(w, RB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+template <class T> static inline int dev_alloc(rb_world* w, T** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(w, RB_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    DevBuf b; b.p = p; b.bytes = bytes; w->allocs.push_back(b); w->device_bytes += bytes;
+    *out = (T*)p;
+    return RB_OK;
+}
+#define ALLOC(ptr, count) do { int r_ = dev_alloc(w, &(ptr), (count)); if (r_) return r_; } while (0)
+

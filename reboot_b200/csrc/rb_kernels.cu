@@ -27,13 +27,14 @@
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= P.nb) return;
+    const uint32_t n_owned = rb_n_owned(P);
+    if (b >= (P.dn ? n_owned : P.nb)) return;
     float4 p4 = P.pos[b], v4 = P.vel[b];
     uint32_t f = P.flags[b];
     f3 p = xyz(p4), v = xyz(v4);
     const float dt = P.dt;
     if (do_integrate) {
-        if ((f & RB_F_ACTIVE) && b < P.n_owned) {
+        if ((f & RB_F_ACTIVE) && b < n_owned) {
             f3 frc = mk3(0.f, 0.f, 0.f);
             float mass = 1.0f;
             if (P.force) { float4 F = P.force[b]; frc = xyz(F); mass = F.w; }
@@ -56,14 +57,14 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
             }
         }
         // Entity::_updateKinematics runs for inactive entities too: prevMVP = mvp; mvp = T(p) * W
-        if (b < P.n_owned) {
+        if (b < n_owned) {
             float4 m_old = P.mt[b];
             P.pt[b] = m_old;
             f3 w = P.wt ? xyz(P.wt[b]) : mk3(0.f, 0.f, 0.f);
             P.mt[b] = make_float4(w.x + p.x, w.y + p.y, w.z + p.z, 0.f);
         }
     }
-    if (!do_bin) return;
+    if (!do_bin && !P.dn) return;
     f3 m = xyz(P.mt[b]);
     float speed = mag3(v);
     uint32_t s0 = P.single ? b : P.body_start[b];
@@ -79,10 +80,12 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
         // Q3/Q7: only active bodies are (re)inserted in the broadphase, and only while they touch
         // the OSP root cube (physics/src/OSP.cpp:182-239)
         if ((f & RB_F_ACTIVE) && sphere_in_world(c, r, P.half)) {
-            uint32_t cx = rb_col(c.x, P.half, P.s_inv_w, P.scx);
-            uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
-            k = cz * P.scx + cx;
-            P.rank[s] = atomicAdd(&P.col_count[k], 1u);
+            if (do_bin) {
+                uint32_t cx = rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
+                uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
+                k = cz * P.scx + cx;
+                P.rank[s] = atomicAdd(&P.col_count[k], 1u);
+            } else k = 0;   // slab worlds bin after the halo exchange (rb_bin_kernel)
         }
         P.key[s] = k;
     }
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scan_apply_kernel(const uint32_t*
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.ns) return;
+    if (s >= rb_n_local(P)) return;
     uint32_t k = P.key[s];
     if (k == RB_NONE) return;
     uint32_t slot = P.col_start[k] + P.rank[s];
@@ -306,11 +309,12 @@ __device__ __forceinline__ void sphere_vs_triangles(const RbParams& P, BodyState
 }
 
 // scan the sphere grid around frozen sphere (fc, frm) for the smallest partner body id >= lo
+// (ids are global body ids; best_local is the partner's local body index)
 template <bool SINGLE>
 __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 fc, float frm, uint32_t lo,
-                                              uint32_t& best, uint32_t& eligible, Tally& T) {
+                                              uint32_t& best, uint32_t& best_local, uint32_t& eligible, Tally& T) {
     float reach = frm + P.rm_max;
-    uint32_t cx0 = rb_col(fc.x - reach, P.half, P.s_inv_w, P.scx), cx1 = rb_col(fc.x + reach, P.half, P.s_inv_w, P.scx);
+    uint32_t cx0 = rb_col(fc.x - reach, -P.s_x0, P.s_inv_w, P.scx), cx1 = rb_col(fc.x + reach, -P.s_x0, P.s_inv_w, P.scx);
     uint32_t cz0 = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz), cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
     for (uint32_t cz = cz0; cz <= cz1; ++cz) {
         uint32_t row = cz * P.scx;
@@ -320,12 +324,13 @@ __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 
             float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
             if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
             uint32_t sb = P.sorted_id[i];
-            uint32_t B = SINGLE ? sb : P.sph_body[sb];
-            if (B == A) continue;
+            uint32_t Bl = SINGLE ? sb : P.sph_body[sb];
+            if (Bl == A) continue;
             T.cand_ss++;
+            uint32_t B = rb_gid(P, Bl);
             if (B < lo) continue;
             eligible++;
-            best = min(best, B);
+            if (B < best) { best = B; best_local = Bl; }
         }
     }
 }
@@ -342,7 +347,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
     if (SINGLE) {
         uint32_t n_sorted = P.col_start[P.scx * P.scz];
         valid = tid < n_sorted;
-        if (valid) { f0 = P.sorted[tid]; A = s0 = P.sorted_id[tid]; nsph = 1; valid = A < P.n_owned; }
+        if (valid) { f0 = P.sorted[tid]; A = s0 = P.sorted_id[tid]; nsph = 1; valid = A < rb_n_owned(P); }
     } else {
         valid = tid < P.n_owned;
         if (valid) { A = tid; s0 = P.body_start[A]; nsph = P.body_start[A + 1] - s0; valid = (P.flags[A] & RB_F_ACTIVE) != 0; }
@@ -357,18 +362,19 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
         const f3 mt_frozen = S.mt;
 
         // ---------------- sphere-sphere ----------------
+        const uint32_t gA = rb_gid(P, A);
         uint32_t lo = 0;
         while (true) {
-            uint32_t best = RB_NONE, eligible = 0;
+            uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
             for (uint32_t i = 0; i < nsph; ++i) {
                 uint32_t sa = s0 + i;
                 if (!SINGLE && P.key[sa] == RB_NONE) continue;
                 float4 fa = SINGLE ? f0 : P.ws[sa];
-                scan_partners<SINGLE>(P, A, xyz(fa), fa.w, lo, best, eligible, T);
+                scan_partners<SINGLE>(P, A, xyz(fa), fa.w, lo, best, best_local, eligible, T);
             }
             if (best == RB_NONE) break;
-            const uint32_t B = best;
-            const bool lo_is_a = A < B;
+            const uint32_t B = best_local;
+            const bool lo_is_a = gA < best;
             if (RESOLVE || lo_is_a) {
                 // partner simulated from its frozen pose (it toggles exactly like us on every hit)
                 uint32_t t0 = SINGLE ? B : P.body_start[B];
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
                         if (lo_is_a) T.tests_ss++;
                         if (!(radii - dist >= 0)) continue;
                         f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
-                        if (lo_is_a) { T.hits_ss++; record_hit(P, H, sa, sb, radii - dist, n1, oa.w); }
+                        if (lo_is_a) { T.hits_ss++; record_hit(P, H, SINGLE ? gA : sa, SINGLE ? best : sb, radii - dist, n1, oa.w); }
                         if (RESOLVE) {
                             f3 n = n1;
                             if (!lo_is_a) { n = neg3(n); n = normalize3(n); }      // "Opposite reaction", normalised again
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
                         }
                     }
             }
-            lo = B + 1;
+            lo = best + 1;
             if (eligible <= 1 && SINGLE) break;   // nothing else above B in range
         }
 
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
             if (SINGLE || P.key[sa] != RB_NONE) {
                 float4 fa = SINGLE ? f0 : P.ws[sa];
                 float4 oa = P.sph_obj[sa];
-                sphere_vs_triangles<RESOLVE>(P, S, H, T, sa, xyz(oa), oa.w, xyz(fa), fa.w, hit_any);
+                sphere_vs_triangles<RESOLVE>(P, S, H, T, SINGLE ? gA : sa, xyz(oa), oa.w, xyz(fa), fa.w, hit_any);
             }
             if (i == nsph - 1) last_hit = hit_any;
         }

@@ -2,88 +2,9 @@
 // include/reboot_physics.h. Validates inputs, owns all device memory, builds the static triangle
 // column grid once, and enqueues the step kernels (rb_kernels.cu) on the world's stream.
 // No CPU path: every entry point that computes needs the CUDA device.
-#include "../../include/reboot_physics.h"
-#include "rb_device.cuh"
+#include "rb_internal.h"
 
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstring>
-#include <string>
-#include <vector>
-
-// launchers defined in rb_kernels.cu
-void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cudaStream_t st);
-int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st);
-uint32_t rb_scan_tiles(uint32_t n);
-void rb_launch_scatter(const RbParams& P, cudaStream_t st);
-int rb_launch_collide(const RbParams& P, bool resolve, cudaStream_t st);
-void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
-void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
-void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
-// multi-GPU (rb_dist.cu)
-struct RbDist;
-int rb_dist_step_exchange(rb_world* w, int ms);
-void rb_dist_destroy(RbDist* d);
-
-static thread_local std::string g_create_error;
-
-struct DevBuf { void* p = nullptr; size_t bytes = 0; };
-
-struct rb_world {
-    rb_config cfg;
-    std::string err;
-    bool built = false;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    // ---- host staging (until rb_build) ----
-    std::vector<float> h_tri;                 // 9 floats per triangle
-    std::vector<uint32_t> h_geom_start;       // CSR geom -> triangles
-    std::vector<float> h_obj;                 // 4 floats per sphere (object space)
-    std::vector<uint32_t> h_body_start;       // CSR body -> spheres
-    std::vector<float> h_W;                   // 12 floats per body: 3x3 row-major + translation
-    std::vector<float> h_pos, h_vel;          // 3 per body
-    std::vector<uint32_t> h_flags;
-    std::vector<uint32_t> h_sph_body;
-    bool any_wt = false;
-    // ---- device ----
-    RbParams P;
-    std::vector<DevBuf> allocs;
-    size_t device_bytes = 0;
-    uint32_t* d_tile_sums = nullptr;
-    uint32_t ncols = 0;
-    float4* d_stage = nullptr; size_t stage_elems = 0;      // H2D staging for setters
-    uint32_t* d_stage_u = nullptr; size_t stage_u_elems = 0;
-    unsigned long long* h_counters = nullptr;               // pinned mirror
-    // ---- bookkeeping ----
-    uint64_t steps = 0, launches = 0;
-    uint64_t contacts_last = 0;
-    bool profile = false;
-    float kernel_ms[5] = { 0, 0, 0, 0, 0 };
-    cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
-    RbDist* dist = nullptr;
-    rb_stats_t dist_stats;
-};
-
-static int fail(rb_world* w, int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-    if (w) w->err = buf; else g_create_error = buf;
-    return code;
-}
-#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(w, RB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
-
-template <class T> static int dev_alloc(rb_world* w, T** out, size_t count) {
-    void* p = nullptr;
-    size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) return fail(w, RB_ERR_OOM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
-    DevBuf b; b.p = p; b.bytes = bytes; w->allocs.push_back(b); w->device_bytes += bytes;
-    *out = (T*)p;
-    return RB_OK;
-}
-#define ALLOC(ptr, count) do { int r_ = dev_alloc(w, &(ptr), (count)); if (r_) return r_; } while (0)
+thread_local std::string g_create_error;
 
 static bool finite_all(const float* p, size_t n) { for (size_t i = 0; i < n; i++) if (!std::isfinite(p[i])) return false; return true; }
 
@@ -95,7 +16,7 @@ void rb_config_default(rb_config* c) {
     memset(c, 0, sizeof *c);
     c->world_half = 1000.0f; c->gravity = -9.8f; c->friction = 0.95f; c->pushout = 1.0001f; c->ss_damp = 0.1f;
     c->margin_cap = 0.25f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
-    c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1;
+    c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1; c->rm_max_hint = 0.0f;
 }
 
 const char* rb_last_error(const rb_world* w) { return w ? w->err.c_str() : g_create_error.c_str(); }
@@ -277,13 +198,21 @@ int rb_build(rb_world* w) {
     RbParams& P = w->P;
     const uint32_t nb = (uint32_t)w->h_flags.size();
     const uint32_t ns = (uint32_t)(w->h_obj.size() / 4);
-    P.nb = nb; P.ns = ns; P.n_owned = nb;
+    const bool slab = w->cfg.nranks > 1;
     P.single = (ns == nb) ? 1u : 0u;
+    if (slab && !P.single) return fail(w, RB_ERR_INVALID, "slab (multi-GPU) worlds support single-sphere bodies only in this version");
+    if (slab && w->any_wt) return fail(w, RB_ERR_INVALID, "slab (multi-GPU) worlds need W.t = 0");
+    // slab worlds keep room for immigrants and ghosts; counts live on the device (P.dn)
+    const uint32_t ghost_cap = slab ? std::max<uint32_t>(65536u, nb / 8) : 0;
+    const uint32_t cap = slab ? nb + std::max<uint32_t>(nb / 4, 4096u) + 3 * ghost_cap : nb;
+    w->cap_local = cap;
+    P.nb = cap; P.ns = slab ? cap : ns; P.n_owned = nb;
+    w->n_owned_host = nb;
     P.half = w->cfg.world_half; P.gravity = w->cfg.gravity; P.friction = w->cfg.friction;
     P.pushout = w->cfg.pushout; P.ss_damp = w->cfg.ss_damp; P.margin_cap = w->cfg.margin_cap; P.dt = 0.f;
 
     // ---- spheres: pre-sum the W3x3 * object-centre part of GeometryMath::transform (GeometryMath.cpp:81-89) ----
-    std::vector<float> sph((size_t)std::max<uint32_t>(ns, 1) * 4, 0.f);
+    std::vector<float> sph((size_t)std::max<uint32_t>(slab ? cap : ns, 1) * 4, 0.f);
     float rmax = 0.f;
     for (uint32_t b = 0; b < nb; b++) {
         const float* W = &w->h_W[(size_t)b * 12];
@@ -297,20 +226,44 @@ int rb_build(rb_world* w) {
             rmax = std::max(rmax, std::fabs((float)r));
         }
     }
+    if (slab && w->cfg.rm_max_hint > rmax) rmax = w->cfg.rm_max_hint;   // every rank must use the same reach
     P.rm_max = rmax + w->cfg.margin_cap;
     // ---- sphere column grid geometry ----
     {
         float wcol = std::max(2.0f * P.rm_max, 2.0f * P.half / 4096.0f);
         long n = (long)std::floor(2.0 * P.half / wcol);
         n = std::max(1L, std::min(4096L, n));
-        P.scx = P.scz = (uint32_t)n;
+        P.scz = (uint32_t)n;
         P.s_inv_w = (float)n / (2.0f * P.half);
+        P.s_x0 = -P.half;
+        P.scx = (uint32_t)n;
+        if (slab) {
+            // the grid only spans this slab plus a pad for ghosts and drift; spheres beyond clamp into the
+            // edge columns (the column function is monotone, so this only costs speed, never correctness)
+            float cw = 2.0f * P.half / (float)n;
+            float pad = 8.0f * cw;
+            float lo = std::max(-P.half, w->cfg.slab_lo - pad), hi = std::min(P.half, w->cfg.slab_hi + pad);
+            long c0 = (long)std::floor((lo + P.half) / cw);
+            P.s_x0 = -P.half + (float)c0 * cw;
+            P.scx = (uint32_t)std::max(1L, std::min((long)n, (long)std::ceil((hi - P.s_x0) / cw)));
+        }
         w->ncols = P.scx * P.scz;
     }
     // ---- device state ----
     float4 *d_pos, *d_vel, *d_mt, *d_pt, *d_sph, *d_ws, *d_sorted; uint32_t *d_flags, *d_key, *d_rank, *d_cc, *d_cs, *d_sid;
-    ALLOC(d_pos, nb); ALLOC(d_vel, nb); ALLOC(d_mt, nb); ALLOC(d_pt, nb); ALLOC(d_flags, nb);
-    ALLOC(d_sph, ns); ALLOC(d_ws, ns); ALLOC(d_key, ns); ALLOC(d_rank, ns); ALLOC(d_sorted, ns); ALLOC(d_sid, ns);
+    const size_t nba = slab ? cap : nb, nsa = slab ? cap : ns;
+    ALLOC(d_pos, nba); ALLOC(d_vel, nba); ALLOC(d_mt, nba); ALLOC(d_pt, nba); ALLOC(d_flags, nba);
+    ALLOC(d_sph, nsa); ALLOC(d_ws, nsa); ALLOC(d_key, nsa); ALLOC(d_rank, nsa); ALLOC(d_sorted, nsa); ALLOC(d_sid, nsa);
+    if (slab) {
+        ALLOC(w->d_dn, 4); ALLOC(w->d_gid, nba);
+        uint32_t dn0[4] = { nb, 0, 0, 0 };
+        CU(cudaMemcpyAsync(w->d_dn, dn0, sizeof dn0, cudaMemcpyHostToDevice, w->stream));
+        std::vector<uint32_t> ids(nb);
+        for (uint32_t i = 0; i < nb; i++) ids[i] = i < w->h_gid.size() ? w->h_gid[i] : i;
+        CU(cudaMemcpyAsync(w->d_gid, ids.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        P.dn = w->d_dn; P.gid = w->d_gid;
+    }
     ALLOC(d_cc, (size_t)w->ncols + 1); ALLOC(d_cs, (size_t)w->ncols + 1);
     ALLOC(w->d_tile_sums, rb_scan_tiles(w->ncols) + 1);
     P.pos = d_pos; P.vel = d_vel; P.mt = d_mt; P.pt = d_pt; P.flags = d_flags; P.sph_obj = d_sph; P.ws = d_ws;
@@ -324,8 +277,8 @@ int rb_build(rb_world* w) {
     CU(cudaMemcpyAsync(d_vel, v4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_flags, w->h_flags.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_sph, sph.data(), (size_t)ns * 16, cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemsetAsync(d_mt, 0, (size_t)std::max<uint32_t>(nb, 1) * 16, w->stream));   // MVP() model = identity -> translation 0
-    CU(cudaMemsetAsync(d_pt, 0, (size_t)std::max<uint32_t>(nb, 1) * 16, w->stream));
+    CU(cudaMemsetAsync(d_mt, 0, std::max<size_t>(nba, 1) * 16, w->stream));   // MVP() model = identity -> translation 0
+    CU(cudaMemsetAsync(d_pt, 0, std::max<size_t>(nba, 1) * 16, w->stream));
     if (w->any_wt) { float4* d_wt; ALLOC(d_wt, nb); CU(cudaMemcpyAsync(d_wt, wt4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream)); P.wt = d_wt; }
     if (!P.single) {
         uint32_t *d_sb, *d_bs;
@@ -338,7 +291,7 @@ int rb_build(rb_world* w) {
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
     }
     // ---- contacts + counters ----
-    P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)ns * 4 + 1024;
+    P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(slab ? cap : ns) * 4 + 1024;
     RbContactRec* d_c; ALLOC(d_c, (size_t)P.contact_cap); P.contacts = d_c;
     unsigned long long* d_cnt; ALLOC(d_cnt, RB_C_COUNT); P.counters = d_cnt;
     CU(cudaMemsetAsync(d_cnt, 0, RB_C_COUNT * sizeof(unsigned long long), w->stream));
@@ -362,17 +315,22 @@ int rb_build(rb_world* w) {
 }
 
 // ---- the step ---------------------------------------------------------------------------------
-static int enqueue_broadphase(rb_world* w, int do_integrate) {
+int enqueue_broadphase_tail(rb_world* w) {
     RbParams& P = w->P;
-    CU(cudaMemsetAsync(P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
-    if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
-    rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;
     if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
     w->launches += rb_launch_scan(P.col_count, w->ncols, P.col_start, w->d_tile_sums, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[2], w->stream));
     rb_launch_scatter(P, w->stream); w->launches++;
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
     return RB_OK;
+}
+static int enqueue_broadphase(rb_world* w, int do_integrate) {
+    RbParams& P = w->P;
+    if (w->dist) return rb_dist_step_exchange(w, do_integrate);
+    CU(cudaMemsetAsync(P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
+    rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;
+    return enqueue_broadphase_tail(w);
 }
 static int enqueue_collide(rb_world* w, bool resolve) {
     RbParams& P = w->P;
@@ -392,9 +350,8 @@ int rb_step(rb_world* w, int ms) {
     if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_step before rb_build") : RB_ERR_INVALID;
     CU(cudaSetDevice(w->cfg.device));
     w->P.dt = (float)ms / 1000.0f;                     // StateVector.cpp:19
-    if (w->dist) { int r = rb_dist_step_exchange(w, ms); if (r) return r; }
-    else { int r = enqueue_broadphase(w, 1); if (r) return r; }
-    int r = enqueue_collide(w, true); if (r) return r;
+    int r = enqueue_broadphase(w, 1); if (r) return r;
+    r = enqueue_collide(w, true); if (r) return r;
     w->steps++;
     return RB_OK;
 }
@@ -480,7 +437,8 @@ int rb_query_contacts(rb_world* w, rb_contact* out, uint64_t cap, uint64_t* n, i
 
 int rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags) {
     if (!w || !w->built) return RB_ERR_INVALID;
-    size_t nb = w->P.n_owned;
+    if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
+    size_t nb = w->n_owned_host;
     if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, nb * 16, cudaMemcpyDeviceToHost, w->stream));
     if (vel4) CU(cudaMemcpyAsync(vel4, w->P.vel, nb * 16, cudaMemcpyDeviceToHost, w->stream));
     if (flags) CU(cudaMemcpyAsync(flags, w->P.flags, nb * 4, cudaMemcpyDeviceToHost, w->stream));
@@ -489,7 +447,8 @@ int rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags) {
 }
 int rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4) {
     if (!w || !w->built) return RB_ERR_INVALID;
-    size_t nb = w->P.n_owned;
+    if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
+    size_t nb = w->n_owned_host;
     if (model_t4) CU(cudaMemcpyAsync(model_t4, w->P.mt, nb * 16, cudaMemcpyDeviceToHost, w->stream));
     if (prev_t4) CU(cudaMemcpyAsync(prev_t4, w->P.pt, nb * 16, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
@@ -509,7 +468,7 @@ int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     // recompute from the current model translations (no integration, no binning side effects on state)
     CU(cudaMemsetAsync(w->P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
     rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
-    size_t ns = w->P.ns;
+    size_t ns = w->d_dn ? w->n_owned_host : w->P.ns;
     std::vector<float> tmp(ns * 4), obj(ns * 4);
     CU(cudaMemcpyAsync(tmp.data(), w->P.ws, ns * 16, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaMemcpyAsync(obj.data(), w->P.sph_obj, ns * 16, cudaMemcpyDeviceToHost, w->stream));
@@ -520,7 +479,7 @@ int rb_get_world_spheres(rb_world* w, float* xyzr4) {
 
 static int range_ok(rb_world* w, uint32_t first, uint32_t count) {
     if (!w || !w->built) return RB_ERR_INVALID;
-    if ((uint64_t)first + count > w->P.n_owned) return fail(w, RB_ERR_INVALID, "body range [%u, %u) out of bounds (%u bodies)", first, first + count, w->P.n_owned);
+    if ((uint64_t)first + count > w->n_owned_host) return fail(w, RB_ERR_INVALID, "body range [%u, %u) out of bounds (%u bodies)", first, first + count, w->n_owned_host);
     return RB_OK;
 }
 int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4) {
@@ -588,13 +547,27 @@ int rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ap4
 int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts) {
     if (!w || !w->built) return RB_ERR_INVALID;
     int r;
-    if (force4) { r = rb_set_force(w, 0, w->P.n_owned, force4); if (r) return r; }
+    if (force4) { r = rb_set_force(w, 0, w->n_owned_host, force4); if (r) return r; }
     r = rb_step(w, ms); if (r) return r;
-    if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, (size_t)w->P.n_owned * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, (size_t)w->n_owned_host * 16, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaMemcpyAsync(w->h_counters + RB_C_NCONTACT, w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     w->contacts_last = w->h_counters[RB_C_NCONTACT];
     if (n_contacts) *n_contacts = w->contacts_last;
+    return RB_OK;
+}
+
+int rb_set_body_ids(rb_world* w, const uint32_t* ids, uint32_t n) {
+    if (!w || !ids) return RB_ERR_INVALID;
+    if (w->built) return fail(w, RB_ERR_INVALID, "rb_set_body_ids after rb_build");
+    w->h_gid.assign(ids, ids + n);
+    return RB_OK;
+}
+int rb_get_body_ids(rb_world* w, uint32_t* out) {
+    if (!w || !w->built || !out) return RB_ERR_INVALID;
+    if (!w->d_gid) { for (uint32_t i = 0; i < w->n_owned_host; i++) out[i] = i; return RB_OK; }
+    int r = rb_dist_refresh_counts(w); if (r) return r;
+    CU(cudaMemcpy(out, w->d_gid, (size_t)w->n_owned_host * 4, cudaMemcpyDeviceToHost));
     return RB_OK;
 }
 
@@ -609,8 +582,9 @@ int rb_get_stats(rb_world* w, rb_stats_t* out) {
         out->hits_ss = c[RB_C_HITS_SS]; out->hits_st = c[RB_C_HITS_ST]; out->contacts_last = c[RB_C_NCONTACT];
         out->contacts_dropped = c[RB_C_DROPPED]; out->margin_overflow = c[RB_C_OVERFLOW];
     }
-    out->n_bodies = w->built ? w->P.n_owned : (uint32_t)w->h_flags.size();
-    out->n_spheres = w->P.ns; out->n_geoms = (uint32_t)w->h_geom_start.size() - 1; out->n_tris = w->P.nt;
+    if (w->built && w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
+    out->n_bodies = w->built ? w->n_owned_host : (uint32_t)w->h_flags.size();
+    out->n_spheres = w->d_dn ? w->n_owned_host : w->P.ns; out->n_geoms = (uint32_t)w->h_geom_start.size() - 1; out->n_tris = w->P.nt;
     out->sphere_cols_x = w->P.scx; out->sphere_cols_z = w->P.scz; out->tri_cols_x = w->P.tcx; out->tri_cols_z = w->P.tcz;
     out->device_bytes = w->device_bytes;
     out->halo_sent_last = w->dist_stats.halo_sent_last; out->halo_recv_last = w->dist_stats.halo_recv_last;
@@ -628,10 +602,16 @@ uint64_t rb_launch_count(const rb_world* w) { return w ? w->launches : 0; }
 
 } // extern "C"
 
+int rb_collide_only(rb_world* w, bool resolve) { return enqueue_collide(w, resolve); }
+
 // ---- multi-GPU placeholders until rb_dist.cu lands ---------------------------------------------
 #ifndef RB_HAVE_DIST
 int rb_dist_step_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+int rb_dist_refresh_counts(rb_world*) { return RB_OK; }
 void rb_dist_destroy(RbDist*) {}
 extern "C" int rb_dist_unique_id(const char*, uint8_t*) { g_create_error = "multi-GPU slabs not built"; return RB_ERR_INVALID; }
 extern "C" int rb_dist_init(rb_world* w, const char*, const uint8_t*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+extern "C" int rb_dist_attach_peers(rb_world* w, rb_world*, rb_world*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+extern "C" int rb_step_group(rb_world**, int, int) { return RB_ERR_INVALID; }
+extern "C" int rb_detect_group(rb_world**, int) { return RB_ERR_INVALID; }
 #endif

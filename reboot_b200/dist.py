@@ -1,0 +1,147 @@
+"""Multi-GPU x-slabs: host-side partitioning and rendezvous.
+
+One process per GPU: every rank owns the bodies whose centre starts in its slab of the x axis, static
+geometry is replicated, and `rb_step` exchanges boundary spheres and migrants with the two neighbours
+through NCCL on the world's own stream. The NCCL unique id is created by rank 0 and broadcast with
+whatever the host already has -- here `torch.distributed`.
+
+`SlabGroup` runs the same slab worlds inside ONE process in lockstep (`rb_step_group`, device-to-device
+copies instead of NCCL): used to test the whole multi-rank path on a single GPU and usable by
+single-process multi-GPU hosts.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+from . import _lib
+from .world import World
+
+
+def slab_bounds(rank: int, nranks: int, half: float = 1000.0):
+    return (-half + 2.0 * half * rank / nranks, -half + 2.0 * half * (rank + 1) / nranks)
+
+
+def owner_of(x: np.ndarray, nranks: int, half: float = 1000.0) -> np.ndarray:
+    """Rank owning a body whose centre has this x (slab r covers [lo_r, hi_r); the outer slabs are open-ended)."""
+    r = np.floor((np.asarray(x, np.float64) + half) * nranks / (2.0 * half)).astype(np.int64)
+    return np.clip(r, 0, nranks - 1)
+
+
+def partition_scene(scene, nranks: int, rank: int, half: float = 1000.0):
+    """(sub-scene with the bodies this rank owns at t=0, global body ids, slab, r_max over all ranks)."""
+    if scene.n_spheres != scene.n_bodies:
+        raise ValueError("slab worlds support single-sphere bodies only in this version")
+    own = owner_of(scene.body_pos[:, 0] + scene.obj_spheres[:, 0], nranks, half) == rank
+    ids = np.nonzero(own)[0].astype(np.uint32)
+    s = copy.copy(scene)
+    s.body_pos = np.ascontiguousarray(scene.body_pos[own]); s.body_vel = np.ascontiguousarray(scene.body_vel[own])
+    s.body_active = scene.body_active[own]; s.body_gravity = scene.body_gravity[own]; s.body_scale = scene.body_scale[own]
+    s.obj_spheres = np.ascontiguousarray(scene.obj_spheres[own]); s.sphere_start = np.arange(len(ids) + 1, dtype=np.int32)
+    rmax = float((scene.obj_spheres[:, 3] * scene.body_scale).max()) if scene.n_bodies else 0.0
+    return s, ids, slab_bounds(rank, nranks, half), rmax
+
+
+def find_nccl() -> str:
+    """The libnccl torch itself loaded (so the process holds ONE NCCL), else whatever the loader finds."""
+    try:
+        import nvidia.nccl  # noqa: F401
+        for d in nvidia.nccl.__path__:
+            hits = sorted(glob.glob(os.path.join(d, "lib", "libnccl.so*")))
+            if hits:
+                return hits[0]
+    except Exception:
+        pass
+    for pat in ("/usr/lib/x86_64-linux-gnu/libnccl.so.2", "/usr/local/graft/bin/libnccl.so.2*"):
+        hits = sorted(glob.glob(pat))
+        if hits:
+            return hits[0]
+    return "libnccl.so.2"
+
+
+def broadcast_unique_id(make_id, rank: int, device=None) -> np.ndarray:
+    """Rank 0 calls make_id() -> 128 bytes; everybody gets them via torch.distributed."""
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(_lib.RB_NCCL_ID_BYTES, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.from_numpy(np.frombuffer(bytes(make_id()), dtype=np.uint8).copy())
+    if device is not None:
+        t = t.to(device)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
+def init_world(w: World, rank: int, nranks: int):
+    """Join the slab communicator (call after w.build())."""
+    import torch
+    L = w.L
+    path = find_nccl().encode()
+
+    def make_id():
+        buf = (C.c_uint8 * _lib.RB_NCCL_ID_BYTES)()
+        rc = L.rb_dist_unique_id(path, buf)
+        if rc:
+            raise RuntimeError((L.rb_last_error(None) or b"").decode())
+        return bytes(buf)
+
+    uid = broadcast_unique_id(make_id, rank, torch.device("cuda", torch.cuda.current_device()))
+    buf = (C.c_uint8 * _lib.RB_NCCL_ID_BYTES).from_buffer_copy(uid.tobytes())
+    w._ck(L.rb_dist_init(w.h, path, buf))
+
+
+class SlabGroup:
+    """N slab worlds of one scene in one process, stepped in lockstep."""
+
+    def __init__(self, scene, nslabs: int, device: int = 0, **kw):
+        self.L = _lib.load()
+        self.worlds = []
+        for r in range(nslabs):
+            sub, ids, slab, rmax = partition_scene(scene, nslabs, r)
+            w = World(sub, device=device, slab=slab, rank=r, nranks=nslabs, ids=ids, rm_max_hint=rmax, **kw)
+            self.worlds.append(w)
+        for r, w in enumerate(self.worlds):
+            left = self.worlds[r - 1].h if r > 0 else None
+            right = self.worlds[r + 1].h if r < nslabs - 1 else None
+            w._ck(self.L.rb_dist_attach_peers(w.h, left, right))
+        self._arr = (C.c_void_p * nslabs)(*[w.h for w in self.worlds])
+
+    def step(self, ms: int = 5):
+        rc = self.L.rb_step_group(self._arr, len(self.worlds), ms)
+        if rc:
+            raise RuntimeError("rb_step_group failed: " + "; ".join((self.L.rb_last_error(w.h) or b"").decode() for w in self.worlds))
+
+    def detect(self):
+        rc = self.L.rb_detect_group(self._arr, len(self.worlds))
+        if rc:
+            raise RuntimeError("rb_detect_group failed: " + "; ".join((self.L.rb_last_error(w.h) or b"").decode() for w in self.worlds))
+
+    def state(self, n_total: int):
+        """Global state arrays indexed by global body id."""
+        out = dict(pos=np.zeros((n_total, 3), np.float32), vel=np.zeros((n_total, 3), np.float32), flags=np.zeros(n_total, np.int32),
+                   model_t=np.zeros((n_total, 3), np.float32), prev_t=np.zeros((n_total, 3), np.float32), owner=np.full(n_total, -1, np.int32))
+        for r, w in enumerate(self.worlds):
+            s = w.state()
+            ids = w.body_ids()
+            assert (out["owner"][ids] == -1).all(), "a body is owned twice"
+            for k in ("pos", "vel", "flags", "model_t", "prev_t"):
+                out[k][ids] = s[k]
+            out["owner"][ids] = r
+        return out
+
+    def contact_sets(self):
+        ss, st = [], []
+        for w in self.worlds:
+            a, b = w.contact_sets()
+            ss.append(a); st.append(b)
+        ss = np.unique(np.concatenate(ss), axis=0) if any(len(a) for a in ss) else np.zeros((0, 4), np.int32)
+        st = np.unique(np.concatenate(st), axis=0) if any(len(a) for a in st) else np.zeros((0, 4), np.int32)
+        return ss, st
+
+    def close(self):
+        for w in self.worlds:
+            w.close()

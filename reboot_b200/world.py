@@ -23,7 +23,7 @@ class RebootError(RuntimeError):
 
 class World:
     def __init__(self, scene=None, device: int = 0, stream=None, max_contacts: int = 0, margin_cap: float | None = None,
-                 slab=None, rank: int = 0, nranks: int = 1, build: bool = True):
+                 slab=None, rank: int = 0, nranks: int = 1, build: bool = True, ids=None, rm_max_hint: float = 0.0):
         self.L = _lib.load()
         cfg = RbConfig()
         self.L.rb_config_default(C.byref(cfg))
@@ -35,7 +35,9 @@ class World:
         if slab is not None:
             cfg.slab_lo, cfg.slab_hi = slab
         cfg.rank, cfg.nranks = rank, nranks
+        cfg.rm_max_hint = rm_max_hint
         self.cfg = cfg
+        self._ids = ids
         h = C.c_void_p()
         rc = self.L.rb_world_create(C.byref(cfg), C.byref(h))
         if rc:
@@ -106,7 +108,17 @@ class World:
         self.add_models(scene.sphere_start, scene.obj_spheres, scene.body_pos, scene.body_vel, flags, scale)
 
     def build(self):
+        if self._ids is not None:
+            ids = np.ascontiguousarray(self._ids, dtype=np.uint32)
+            self._ck(self.L.rb_set_body_ids(self.h, ptr(ids), ids.shape[0]))
         self._ck(self.L.rb_build(self.h))
+
+    def body_ids(self) -> np.ndarray:
+        """Global ids of the bodies this world currently owns, row-aligned with state()."""
+        n = self.stats()["n_bodies"]
+        out = np.zeros(max(n, 1), np.uint32)
+        self._ck(self.L.rb_get_body_ids(self.h, ptr(out)))
+        return out[:n]
 
     # -- the tick --
     def step(self, ms: int = 5):
