@@ -103,7 +103,21 @@ def scene_golden(sc, checkpoints, prefix):
     log of tick k+1, and the frozen-state contact sets right after the integration half of tick k+1."""
     out = {}
     w = rb.RefWorld(sc)
-    out[f"{prefix}_leaves"] = np.array([len(w.leaves()[0])], dtype=np.int32)
+    cube, ntri, _ = w.leaves()
+    out[f"{prefix}_leaves"] = np.array([len(cube)], dtype=np.int32)
+    tl = cube[ntri > 0].astype(np.float64)          # leaves that hold triangles: (cx, cy, cz, edge)
+    radii = (sc.obj_spheres[:, 3] * np.repeat(sc.body_scale, np.diff(sc.sphere_start))).astype(np.float64)
+    rmax_body = np.maximum.reduceat(radii + np.linalg.norm(sc.obj_spheres[:, :3], axis=1), sc.sphere_start[:-1])
+
+    def leaves_touched(pos):
+        """per body: how many triangle-bearing octree leaves its (slightly grown) bounding sphere touches --
+        bodies touching >= 2 are where the reference's per-leaf order / last-leaf-wins contact flag (Q6) applies"""
+        cnt = np.zeros(pos.shape[0], np.int32)
+        for c in tl:
+            q = np.clip(pos.astype(np.float64), c[:3] - c[3] / 2, c[:3] + c[3] / 2)
+            d2 = ((q - pos) ** 2).sum(1)
+            cnt += d2 <= (rmax_body + 1e-3) ** 2
+        return cnt
     k = 0
     for cp in checkpoints:
         while k < cp:
@@ -116,6 +130,7 @@ def scene_golden(sc, checkpoints, prefix):
         out[f"{prefix}_k{cp}_frozen_ss"] = ss.astype(np.int32)
         out[f"{prefix}_k{cp}_frozen_st"] = st.astype(np.int32)
         s_int = w.state()
+        out[f"{prefix}_k{cp}_leaves_touched"] = leaves_touched(s_int["pos"])
         w.collide(sc.dt_ms); k += 1
         a, f = w.hits()
         s1 = w.state()

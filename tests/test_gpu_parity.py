@@ -58,19 +58,22 @@ def test_L2_one_tick_matches_reference_where_order_free(World, golden, name):
         w.step(sc.dt_ms)
         s = w.state()
         hi, hf = g[f"{name}_k{cp}_hits_i"], g[f"{name}_k{cp}_hits_f"]
-        exact, ssok = order_independent_mask(hi, ng, nb, tb)
+        exact, ssok = order_independent_mask(hi, ng, nb, tb, g[f"{name}_k{cp}_frozen_ss"], g[f"{name}_k{cp}_frozen_st"])
         rp, rv, rf = g[f"{name}_k{cp}_s1_pos"], g[f"{name}_k{cp}_s1_vel"], g[f"{name}_k{cp}_s1_flags"]
         bad = (bits(s["pos"]) != bits(rp)).any(1) | (bits(s["vel"]) != bits(rv)).any(1)
         assert int((bad & exact).sum()) <= max(1, int(0.002 * nb)), (name, cp)
         assert np.allclose(s["pos"][ssok], rp[ssok], rtol=1e-5, atol=1e-6)
         assert np.allclose(s["vel"][ssok], rv[ssok], rtol=1e-5, atol=1e-6)
         if name in ("c1", "c2"):
-            # contact flag: the reference keeps the result of the LAST leaf that holds the sphere
-            # (Physics.cpp:180); without leaves the canonical rule is "any hit of the last
-            # sphere", so a body straddling two leaves may differ in the flag only
+            # contact flag: the reference keeps the result of the LAST octree leaf that holds the sphere
+            # (Physics.cpp:180). Without leaves the canonical rule is "any hit of the last
+            # sphere": identical for every body that touches at most one triangle-bearing leaf; only
+            # bodies straddling leaves may differ, and only in the contact bit.
             ok = exact & ~bad
-            assert (s["flags"][ok] != rf[ok]).mean() < 0.01
+            one_leaf = g[f"{name}_k{cp}_leaves_touched"] <= 1
+            assert np.array_equal(s["flags"][ok & one_leaf], rf[ok & one_leaf])
             assert np.array_equal(s["flags"][ok] & 3, rf[ok] & 3)
+            assert (s["flags"][ok] != rf[ok]).mean() < 0.10
         # contact payload: depth / normal of every reference sphere-triangle hit of an order-free body
         c = w.contacts()
         mine = {(int(r["body"]), int(r["sphere"]), int(r["other"]), int(r["other_prim"])): r for r in c[c["kind"] == 1]}

@@ -47,14 +47,17 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def order_independent_mask(hits_i, n_geoms, n_bodies, tri_base):
+def order_independent_mask(hits_i, n_geoms, n_bodies, tri_base, frozen_ss=None, frozen_st=None):
     """Bodies whose reference result in this tick cannot depend on the reference's leaf / hash
     iteration order (SURVEY.md §8c level L2):
-      * no hits at all, or
-      * only sphere-triangle hits whose global triangle ids are strictly ascending in the
-        reference's own hit order (== the canonical order), or
-      * exactly one sphere-sphere hit, no sphere-triangle hit, and the partner likewise.
-    Returns (mask_exact, mask_ss): bodies to compare bit-exactly / with the SS tolerance."""
+      * no sphere-sphere contact at the frozen state and no sphere-sphere hit in the log, and the
+        sphere-triangle hits (if any) have strictly ascending global triangle ids in the reference's own
+        hit order (== the canonical order)                                        -> compare bit-exactly
+      * an ISOLATED sphere-sphere pair: each of the two bodies overlaps exactly one other body at the
+        frozen state (each other), touches no triangle at the frozen state, and the log holds exactly
+        one hit for the pair                                                       -> compare with the
+        sphere-sphere tolerance (which body plays "modelA" follows pointer-hash order in the reference)
+    Returns (mask_exact, mask_ss)."""
     ss_cnt = np.zeros(n_bodies, np.int32)
     st_cnt = np.zeros(n_bodies, np.int32)
     st_bad = np.zeros(n_bodies, bool)
@@ -72,8 +75,14 @@ def order_independent_mask(hits_i, n_geoms, n_bodies, tri_base):
             if t <= last_tri[a]:
                 st_bad[a] = True
             last_tri[a] = t
-    exact = (ss_cnt == 0) & ~st_bad
-    ss_ok = (ss_cnt == 1) & (st_cnt == 0)
+    deg = np.zeros(n_bodies, np.int32)
+    touches_tri = np.zeros(n_bodies, bool)
+    if frozen_ss is not None and len(frozen_ss):
+        np.add.at(deg, frozen_ss[:, 0], 1); np.add.at(deg, frozen_ss[:, 2], 1)
+    if frozen_st is not None and len(frozen_st):
+        touches_tri[frozen_st[:, 0]] = True
+    exact = (ss_cnt == 0) & (deg == 0) & ~st_bad
+    ss_ok = (ss_cnt == 1) & (st_cnt == 0) & (deg == 1) & ~touches_tri
     ss_ok &= np.where(partner >= 0, ss_ok[np.clip(partner, 0, n_bodies - 1)], False)
     return exact, ss_ok
 
