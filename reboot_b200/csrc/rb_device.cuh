@@ -61,6 +61,7 @@ struct RbParams {
     const float4* tri;            // 3 float4 per triangle: A, B, C (w unused)
     const uint32_t* tcol_start;   // [tcols + 1]
     const uint32_t* tcol_tri;     // ascending triangle ids per column
+    const float2* tcol_yr;        // per column: (min y, max y) over its triangles (empty: +inf, -inf)
     uint32_t tcx, tcz;
     float t_inv_w;
     // ---- constants ----

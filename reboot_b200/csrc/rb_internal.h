@@ -16,7 +16,7 @@ void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cu
 int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st);
 uint32_t rb_scan_tiles(uint32_t n);
 void rb_launch_scatter(const RbParams& P, cudaStream_t st);
-int rb_launch_collide(const RbParams& P, bool resolve, cudaStream_t st);
+int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st);
 void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
 void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
 void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
@@ -59,6 +59,7 @@ struct rb_world {
     // ---- bookkeeping ----
     uint64_t steps = 0, launches = 0;
     uint64_t contacts_last = 0;
+    int collide_variant = 2;
     bool profile = false;
     float kernel_ms[5] = { 0, 0, 0, 0, 0 };
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };

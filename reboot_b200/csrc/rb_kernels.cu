@@ -171,7 +171,10 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P) {
     if (k == RB_NONE) return;
     uint32_t slot = P.col_start[k] + P.rank[s];
     P.sorted[slot] = P.ws[s];
-    P.sorted_id[slot] = s;
+    // bit 31: the body's contact flag, so that the collide kernel needs no per-body gather for bodies
+    // that touch nothing this tick (Physics.cpp:201-207 only needs "was in contact")
+    uint32_t body = P.single ? s : P.sph_body[s];
+    P.sorted_id[slot] = s | ((P.flags[body] & RB_F_CONTACT) ? RB_TRI_BIT : 0u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -253,7 +256,7 @@ __device__ __forceinline__ void process_triangle(const RbParams& P, BodyState& S
     f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);          // Vector4::normalize
     record_hit(P, H, sa_global, RB_TRI_BIT | tid_global, r - dist, o, r);
     if (RESOLVE) {
-        f3 normal = normalize3(cross3(sub3(C, A), sub3(B, A)));
+        f3 normal = mk3(a4.w, b4.w, c4.w);          // normalize((C-A)x(B-A)), pre-computed at build
         f3 delta = sub3(add3(mul3(o, r * P.pushout), q), c);
         float nc = dot3(S.v, normal);
         f3 rv = sub3(S.v, mul3(normal, nc));
@@ -308,6 +311,45 @@ __device__ __forceinline__ void sphere_vs_triangles(const RbParams& P, BodyState
     }
 }
 
+// contact append (one atomic per warp) + counters (one atomic per block and counter); every thread of
+// the block must call this
+__device__ __forceinline__ void collide_epilogue(const RbParams& P, HitBuf& H, Tally& T, const uint32_t lane) {
+    // ---- warp-aggregated contact append: one atomic per warp ----
+    uint32_t nloc = min(H.n, (uint32_t)RB_MAXLOCAL);
+    uint32_t incl = warp_incl_scan(nloc, lane);
+    uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
+    if (wtotal) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&P.counters[RB_C_NCONTACT], (unsigned long long)wtotal);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        unsigned long long slot = base + (incl - nloc);
+        uint32_t dropped = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < RB_MAXLOCAL; ++i)
+            if (i < nloc) {
+                store_contact(P, slot + i, H.a[i], H.b[i], H.depth[i], H.nx[i], H.ny[i], H.nz[i], H.r[i]);
+                if (slot + i >= P.contact_cap) dropped++;
+            }
+        dropped = __reduce_add_sync(0xffffffffu, dropped);
+        if (lane == 0 && dropped) atomicAdd(&P.counters[RB_C_DROPPED], (unsigned long long)dropped);
+    }
+    // ---- counters: warp reduce, block reduce in shared, one atomic per block and counter ----
+    __shared__ uint32_t blk[7];
+    if (threadIdx.x < 7) blk[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t vals[7] = { T.tests_ss, T.tests_st, T.cand_ss, T.cand_st, T.hits_ss, T.hits_st, T.overflow };
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        uint32_t s = __reduce_add_sync(0xffffffffu, vals[k]);
+        if (lane == 0 && s) atomicAdd(&blk[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 7 && blk[threadIdx.x]) {
+        const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
+        atomicAdd(&P.counters[map[threadIdx.x]], (unsigned long long)blk[threadIdx.x]);
+    }
+}
+
 // scan the sphere grid around frozen sphere (fc, frm) for the smallest partner body id >= lo
 // (ids are global body ids; best_local is the partner's local body index)
 template <bool SINGLE>
@@ -323,7 +365,7 @@ __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 
             float4 o = P.sorted[i];
             float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
             if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
-            uint32_t sb = P.sorted_id[i];
+            uint32_t sb = P.sorted_id[i] & ~RB_TRI_BIT;
             uint32_t Bl = SINGLE ? sb : P.sph_body[sb];
             if (Bl == A) continue;
             T.cand_ss++;
@@ -347,7 +389,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
     if (SINGLE) {
         uint32_t n_sorted = P.col_start[P.scx * P.scz];
         valid = tid < n_sorted;
-        if (valid) { f0 = P.sorted[tid]; A = s0 = P.sorted_id[tid]; nsph = 1; valid = A < rb_n_owned(P); }
+        if (valid) { f0 = P.sorted[tid]; A = s0 = P.sorted_id[tid] & ~RB_TRI_BIT; nsph = 1; valid = A < rb_n_owned(P); }
     } else {
         valid = tid < P.n_owned;
         if (valid) { A = tid; s0 = P.body_start[A]; nsph = P.body_start[A + 1] - s0; valid = (P.flags[A] & RB_F_ACTIVE) != 0; }
@@ -460,40 +502,252 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
         }
     }
 
-    // ---- warp-aggregated contact append: one atomic per warp ----
-    uint32_t nloc = min(H.n, (uint32_t)RB_MAXLOCAL);
-    uint32_t incl = warp_incl_scan(nloc, lane);
-    uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
-    if (wtotal) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&P.counters[RB_C_NCONTACT], (unsigned long long)wtotal);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        unsigned long long slot = base + (incl - nloc);
-        uint32_t dropped = 0;
+    collide_epilogue(P, H, T, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 (single-sphere bodies), phased so that the lanes of a warp do the same kind of work at the same
+// time (the v1 kernel above ran ~9 of 32 lanes on average):
+//   P1  one scan of the sphere grid: partners passing the cheap reject, kept sorted by global id
+//   P2  sphere-sphere tests / resolutions in ascending partner id
+//   P3  merge walk over the triangle columns (skipping columns whose y range the grown sphere misses),
+//       AABB prune against the frozen box, surviving triangle ids staged in shared memory
+//   P4  lock-step exact tests of the staged triangles at the body's current pose, resolving inline
+//   P5  flags, state write-back, contact append
+// Same canonical order and arithmetic as the v1 kernel (bit-identical results).
+// ------------------------------------------------------------------------------------------
+#define RB_CAND_MAX 12
+#define RB_SSCAND_MAX 4
+
+template <bool RESOLVE>
+__device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, HitBuf& H, Tally& T,
+                                               uint32_t A, uint32_t gA, float4 oa, uint32_t Bl, uint32_t gB) {
+    const bool lo_is_a = gA < gB;
+    if (!RESOLVE && !lo_is_a) return;
+    float4 wb = P.ws[Bl];                       // partner at its frozen pose
+    float rb = P.sph_obj[Bl].w;
+    f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+    f3 cb = xyz(wb);
+    f3 cn = lo_is_a ? sub3(ca, cb) : sub3(cb, ca);          // lower id plays sphereA / modelA
+    float dist = mag3(cn);
+    float radii = lo_is_a ? (oa.w + rb) : (rb + oa.w);
+    if (lo_is_a) T.tests_ss++;
+    if (!(radii - dist >= 0)) return;
+    f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
+    if (lo_is_a) { T.hits_ss++; record_hit(P, H, gA, gB, radii - dist, n1, oa.w); }
+    if (RESOLVE) {
+        f3 n = n1;
+        if (!lo_is_a) { n = neg3(n); n = normalize3(n); }
+        float sp = mag3(S.v);
+        S.v = mul3(mul3(n, sp), P.ss_damp);
+        body_set_position(S, S.pt);
+    }
+}
+
+template <bool RESOLVE>
+__global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_single_kernel(RbParams P) {
+    __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    const uint32_t n_sorted = P.col_start[P.scx * P.scz];
+    bool valid = tid < n_sorted;
+    uint32_t A = 0;
+    float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool had_contact = false;
+    if (valid) {
+        f0 = P.sorted[tid];
+        uint32_t sid = P.sorted_id[tid];
+        A = sid & ~RB_TRI_BIT; had_contact = (sid & RB_TRI_BIT) != 0;
+        valid = A < rb_n_owned(P);
+    }
+    // body state is loaded lazily: a body with no partner and no staged triangle needs none of it
+    BodyState S; S.changed = false; S.flags = 0;
+    S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t gA = valid ? rb_gid(P, A) : 0u;
+    const f3 fc = xyz(f0);
+    const float frm = f0.w;
+
+    // ---------------- P1: partner scan ----------------
+    uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
 #pragma unroll
-        for (uint32_t i = 0; i < RB_MAXLOCAL; ++i)
-            if (i < nloc) {
-                store_contact(P, slot + i, H.a[i], H.b[i], H.depth[i], H.nx[i], H.ny[i], H.nz[i], H.r[i]);
-                if (slot + i >= P.contact_cap) dropped++;
+    for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+    uint32_t npart = 0;
+    {
+        // every lane walks its (up to 3) z-rows entry by entry; the loop is warp-uniform so the lanes
+        // stay in lock step (independent thread scheduling would otherwise let sub-groups run ahead)
+        uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0, ni = 0, ne = 0;
+        if (valid) {
+            float reach = frm + P.rm_max;
+            cx0 = rb_col(fc.x - reach, -P.s_x0, P.s_inv_w, P.scx); cx1 = rb_col(fc.x + reach, -P.s_x0, P.s_inv_w, P.scx);
+            cz = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz); cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
+            i = P.col_start[cz * P.scx + cx0]; e = P.col_start[cz * P.scx + cx1 + 1];
+            if (cz < cz1) { ni = P.col_start[(cz + 1) * P.scx + cx0]; ne = P.col_start[(cz + 1) * P.scx + cx1 + 1]; }   // next row, in flight early
+        }
+        while (true) {
+            while (i >= e && cz < cz1) {
+                ++cz; i = ni; e = ne;
+                if (cz < cz1) { ni = P.col_start[(cz + 1) * P.scx + cx0]; ne = P.col_start[(cz + 1) * P.scx + cx1 + 1]; }
             }
-        dropped = __reduce_add_sync(0xffffffffu, dropped);
-        if (lane == 0 && dropped) atomicAdd(&P.counters[RB_C_DROPPED], (unsigned long long)dropped);
-    }
-    // ---- counters: warp reduce, block reduce in shared, one atomic per block and counter ----
-    __shared__ uint32_t blk[7];
-    if (threadIdx.x < 7) blk[threadIdx.x] = 0;
-    __syncthreads();
-    uint32_t vals[7] = { T.tests_ss, T.tests_st, T.cand_ss, T.cand_st, T.hits_ss, T.hits_st, T.overflow };
+            const bool work = i < e;
+            if (!__any_sync(0xffffffffu, work)) break;
+            if (work) {
+                float4 o = P.sorted[i];
+                float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+                if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
+                    uint32_t Bl = P.sorted_id[i] & ~RB_TRI_BIT;
+                    if (Bl != A) {
+                        T.cand_ss++;
+                        uint32_t g = rb_gid(P, Bl);
+                        if (RESOLVE || g > gA) {           // detection: the lower id reports the pair
+                            npart++;
+                            // keep the RB_SSCAND_MAX smallest ids, ascending
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        uint32_t s = __reduce_add_sync(0xffffffffu, vals[k]);
-        if (lane == 0 && s) atomicAdd(&blk[k], s);
+                            for (int k = 0; k < RB_SSCAND_MAX; ++k)
+                                if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = Bl; g = tg; Bl = tl; }
+                        }
+                    }
+                }
+                ++i;
+            }
+            __syncwarp();
+        }
     }
-    __syncthreads();
-    if (threadIdx.x < 7 && blk[threadIdx.x]) {
-        const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
-        atomicAdd(&P.counters[map[threadIdx.x]], (unsigned long long)blk[threadIdx.x]);
+    // ---------------- P3: stage sphere-triangle candidates ----------------
+    uint32_t nc = 0;
+    bool st_slow = false;
+    {
+        uint32_t cur[4], end[4], head[4];
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) { cur[k] = end[k] = 0; head[k] = RB_NONE; }
+        if (valid && P.nt) {
+            uint32_t cx0 = rb_col(fc.x - frm, P.half, P.t_inv_w, P.tcx), cx1 = rb_col(fc.x + frm, P.half, P.t_inv_w, P.tcx);
+            uint32_t cz0 = rb_col(fc.z - frm, P.half, P.t_inv_w, P.tcz), cz1 = rb_col(fc.z + frm, P.half, P.t_inv_w, P.tcz);
+            uint32_t nx = cx1 - cx0 + 1, ncol = nx * (cz1 - cz0 + 1);
+            if (ncol > 4) st_slow = true;
+            else {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    if (k < ncol) {
+                        uint32_t col = (cz0 + k / nx) * P.tcx + cx0 + k % nx;
+                        float2 yr = __ldg(P.tcol_yr + col);
+                        if (!(yr.x > fc.y + frm || yr.y < fc.y - frm)) {      // column holds something at this height
+                            cur[k] = __ldg(P.tcol_start + col); end[k] = __ldg(P.tcol_start + col + 1);
+                            if (cur[k] < end[k]) head[k] = __ldg(P.tcol_tri + cur[k]);
+                        }
+                    }
+                }
+            }
+        }
+        while (true) {      // warp-uniform: one merged triangle id per lane and iteration
+            uint32_t m = st_slow ? RB_NONE : min(min(head[0], head[1]), min(head[2], head[3]));
+            if (!__any_sync(0xffffffffu, m != RB_NONE)) break;
+            if (m != RB_NONE) {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (head[k] == m) { cur[k]++; head[k] = cur[k] < end[k] ? __ldg(P.tcol_tri + cur[k]) : RB_NONE; }
+                const float4* tp = P.tri + 3ull * m;
+                float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                T.cand_st++;
+                bool keep = !(fminf(a4.x, fminf(b4.x, c4.x)) > fc.x + frm || fmaxf(a4.x, fmaxf(b4.x, c4.x)) < fc.x - frm);
+                keep = keep && !(fminf(a4.y, fminf(b4.y, c4.y)) > fc.y + frm || fmaxf(a4.y, fmaxf(b4.y, c4.y)) < fc.y - frm);
+                keep = keep && !(fminf(a4.z, fminf(b4.z, c4.z)) > fc.z + frm || fmaxf(a4.z, fmaxf(b4.z, c4.z)) < fc.z - frm);
+                if (keep) {
+                    if (nc == RB_CAND_MAX) st_slow = true;        // too many: the generic walk takes over
+                    else s_cand[nc++][threadIdx.x] = m;
+                }
+            }
+            __syncwarp();
+        }
     }
+    // ---------------- lazy state load ----------------
+    const bool need = valid && (npart || nc || st_slow);
+    if (need) {
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        if (P.wt) S.wt = xyz(P.wt[A]);
+        S.flags = P.flags[A];
+        oa = P.sph_obj[A];
+    }
+    const uint32_t flags_in = S.flags;
+    const f3 mt_frozen = S.mt;
+
+    // ---------------- P2: sphere-sphere in ascending partner id ----------------
+#pragma unroll
+    for (int k = 0; k < RB_SSCAND_MAX; ++k) {
+        if (!__any_sync(0xffffffffu, pg[k] != RB_NONE)) break;
+        if (pg[k] != RB_NONE) ss_pair_single<RESOLVE>(P, S, H, T, A, gA, oa, pl[k], pg[k]);
+        __syncwarp();
+    }
+    if (npart > RB_SSCAND_MAX) {            // crowded: continue above the last staged id by rescanning
+        uint32_t lo = pg[RB_SSCAND_MAX - 1] + 1;
+        while (true) {
+            uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
+            scan_partners<true>(P, A, fc, frm, lo, best, best_local, eligible, T);
+            if (best == RB_NONE) break;
+            ss_pair_single<RESOLVE>(P, S, H, T, A, gA, oa, best_local, best);
+            lo = best + 1;
+            if (eligible <= 1) break;
+        }
+    }
+
+    // ---------------- P4: lock-step exact tests at the current pose ----------------
+    bool hit_any = false;
+    if (st_slow) {
+        T.cand_st = 0;      // the generic walk recounts
+        sphere_vs_triangles<RESOLVE>(P, S, H, T, gA, xyz(oa), oa.w, fc, frm, hit_any);
+    }
+    if (st_slow) nc = 0;
+    const uint32_t nmax = __reduce_max_sync(0xffffffffu, nc);
+    for (uint32_t j = 0; j < nmax; ++j) {       // warp-uniform trip count, explicit reconvergence
+        if (j < nc) {
+            const uint32_t t = s_cand[j][threadIdx.x];
+            const float4* tp = P.tri + 3ull * t;
+            float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+            f3 TA = xyz(a4), TB = xyz(b4), TC = xyz(c4);
+            f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+            T.tests_st++;
+            if (sphere_triangle_detect(c, oa.w, TA, TB, TC)) {
+                hit_any = true;
+                T.hits_st++;
+                f3 q = closest_point(c, TA, TB, TC);
+                f3 ov = sub3(c, q);
+                float dist = mag3(ov);
+                f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
+                record_hit(P, H, gA, RB_TRI_BIT | t, oa.w - dist, o, oa.w);
+                if (RESOLVE) {
+                    // triangle normal normalize((C-A)x(B-A)) is static: pre-computed at build (w lanes)
+                    f3 normal = mk3(a4.w, b4.w, c4.w);
+                    f3 delta = sub3(add3(mul3(o, oa.w * P.pushout), q), c);
+                    float ncomp = dot3(S.v, normal);
+                    f3 rv = sub3(S.v, mul3(normal, ncomp));
+                    body_set_position(S, add3(S.p, delta));
+                    S.v = rv;
+                    S.flags |= RB_F_CONTACT;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // ---------------- P5: flags, write-back ----------------
+    if (RESOLVE && valid) {
+        if (need) {
+            if ((flags_in & RB_F_CONTACT) && !hit_any) S.flags &= ~RB_F_CONTACT;     // Physics.cpp:201-207
+            float disp = mag3(sub3(S.mt, mt_frozen));
+            if (disp > frm - oa.w) T.overflow++;
+            if (S.changed) {
+                P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+                P.vel[A] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
+                P.mt[A] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+                P.pt[A] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+            }
+            if (S.flags != flags_in) P.flags[A] = S.flags;
+        } else if (had_contact) {
+            atomicAnd(&P.flags[A], ~RB_F_CONTACT);       // touched nothing: lose the contact flag, no state gather
+        }
+    }
+    collide_epilogue(P, H, T, lane);
 }
 
 // K5: deferred commit for compound bodies
@@ -547,12 +801,17 @@ uint32_t rb_scan_tiles(uint32_t n) { return cdiv(n, RB_SCAN_TILE); }
 void rb_launch_scatter(const RbParams& P, cudaStream_t st) {
     if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
 }
-int rb_launch_collide(const RbParams& P, bool resolve, cudaStream_t st) {
+int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st) {
     if (!P.nb) return 0;
     if (P.single) {
         uint32_t g = cdiv(P.ns, RB_BLOCK);
-        if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
-        else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
+        if (variant == 1) {     // first-generation kernel, kept for A/B checks (RB_COLLIDE_V1=1)
+            if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
+            else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
+        } else {
+            if (resolve) rb_collide_single_kernel<true><<<g, RB_BLOCK, 0, st>>>(P);
+            else rb_collide_single_kernel<false><<<g, RB_BLOCK, 0, st>>>(P);
+        }
         return 1;
     }
     uint32_t g = cdiv(P.nb, RB_BLOCK);

@@ -42,6 +42,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     else { e = cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking); if (e != cudaSuccess) { delete w; return fail(nullptr, RB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); } w->own_stream = true; }
     w->h_geom_start.push_back(0);
     w->h_body_start.push_back(0);
+    { const char* v = getenv("RB_COLLIDE_V1"); if (v && *v == '1') w->collide_variant = 1; }
     *out = w;
     return RB_OK;
 }
@@ -163,10 +164,32 @@ static int build_triangle_grid(rb_world* w) {
         uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
         for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) list[fill[(size_t)z * n + x]++] = t;
     }
+    std::vector<float> yr(ncol * 2);
+    for (size_t i = 0; i < ncol; i++) { yr[2 * i] = INFINITY; yr[2 * i + 1] = -INFINITY; }
+    for (uint32_t t = 0; t < nt; t++) {
+        const float* p = &w->h_tri[(size_t)t * 9];
+        float lo = std::min(p[1], std::min(p[4], p[7])), hi = std::max(p[1], std::max(p[4], p[7]));
+        uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
+        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) { size_t c = (size_t)z * n + x; yr[2 * c] = std::min(yr[2 * c], lo); yr[2 * c + 1] = std::max(yr[2 * c + 1], hi); }
+    }
     std::vector<float> tri4((size_t)std::max<uint32_t>(nt, 1) * 12, 0.f);
-    for (uint32_t t = 0; t < nt; t++)
+    for (uint32_t t = 0; t < nt; t++) {
         for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) tri4[(size_t)t * 12 + v * 4 + k] = w->h_tri[(size_t)t * 9 + v * 3 + k];
-    float4* d_tri; uint32_t* d_start; uint32_t* d_list;
+        // static triangle normal of GeometryMath::sphereTriangleResolution (GeometryMath.cpp:499-503):
+        // normalize((C - A) x (B - A)) in the reference's FP32 rounding order, stored in the w lanes
+        const float* p = &w->h_tri[(size_t)t * 9];
+        volatile float ux = p[6] - p[0], uy = p[7] - p[1], uz = p[8] - p[2];     // C - A
+        volatile float vx = p[3] - p[0], vy = p[4] - p[1], vz = p[5] - p[2];     // B - A
+        volatile float m1 = uy * vz, m2 = uz * vy, m3 = uz * vx, m4 = ux * vz, m5 = ux * vy, m6 = uy * vx;
+        volatile float nx = m1 - m2, ny = m3 - m4, nz = m5 - m6;
+        volatile float s1 = nx * nx, s2 = ny * ny, s3 = nz * nz;
+        volatile float s12 = s1 + s2; volatile float ss = s12 + s3;
+        volatile float mag = sqrtf(ss);
+        tri4[(size_t)t * 12 + 3] = nx / mag; tri4[(size_t)t * 12 + 7] = ny / mag; tri4[(size_t)t * 12 + 11] = nz / mag;
+    }
+    float4* d_tri; uint32_t* d_start; uint32_t* d_list; float2* d_yr;
+    ALLOC(d_yr, ncol);
+    CU(cudaMemcpyAsync(d_yr, yr.data(), yr.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
     ALLOC(d_tri, (size_t)std::max<uint32_t>(nt, 1) * 3);
     ALLOC(d_start, ncol + 1);
     ALLOC(d_list, list.size());
@@ -174,7 +197,7 @@ static int build_triangle_grid(rb_world* w) {
     CU(cudaMemcpyAsync(d_start, start.data(), start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list;
+    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list; P.tcol_yr = d_yr;
     return RB_OK;
 }
 
@@ -336,7 +359,7 @@ static int enqueue_collide(rb_world* w, bool resolve) {
     RbParams& P = w->P;
     // per-step counters: contact count + changed count
     CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
-    w->launches += rb_launch_collide(P, resolve, w->stream);
+    w->launches += rb_launch_collide(P, resolve, w->collide_variant, w->stream);
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));

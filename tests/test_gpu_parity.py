@@ -313,3 +313,25 @@ def test_full_size_c3_properties(World, port):
     s2 = w.state()
     assert np.array_equal(bits(pos4[:, :3]), bits(s2["pos"])) and n == w.contact_count()
     w.close()
+
+
+def test_phased_kernel_bit_identical_to_first_generation_kernel(World, monkeypatch):
+    """The phased single-sphere collide kernel (default) and the first-generation kernel
+    (RB_COLLIDE_V1=1) implement the same canonical order: identical state and contacts on a dense scene."""
+    from reboot_b200 import scenes
+    sc = scenes.falling_spheres(60000, 200, 2.0, 0.5, (0.3, 4.0), True, 21, "ab")
+    monkeypatch.setenv("RB_COLLIDE_V1", "1")
+    w1 = World(sc)
+    monkeypatch.delenv("RB_COLLIDE_V1")
+    w2 = World(sc)
+    for k in range(200):
+        w1.step(5); w2.step(5)
+    a, b = w1.state(), w2.state()
+    for key in ("pos", "vel", "model_t", "prev_t"):
+        assert np.array_equal(bits(a[key]), bits(b[key])), key
+    assert np.array_equal(a["flags"], b["flags"])
+    assert np.array_equal(w1.contacts(), w2.contacts())
+    s1, s2 = w1.stats(), w2.stats()
+    assert s1["tests_st"] == s2["tests_st"] and s1["hits_st"] == s2["hits_st"] and s1["hits_ss"] == s2["hits_ss"] and s1["tests_ss"] == s2["tests_ss"]
+    assert s2["hits_ss"] > 1000 and s2["hits_st"] > 100000
+    w1.close(); w2.close()
