@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libreboot_b200.so")
+LIB_PATH = os.environ.get("REBOOT_B200_LIB", os.path.join(_HERE, "csrc", "libreboot_b200.so"))   # env override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "reboot_physics.h")
 
 RB_OK, RB_ERR_INVALID, RB_ERR_OOM, RB_ERR_CAPACITY, RB_ERR_CUDA, RB_ERR_NCCL, RB_ERR_NO_DEVICE = range(7)

@@ -254,7 +254,7 @@ int rb_dist_refresh_counts(rb_world* w) {
 // phase A: integrate + pack (everything before the exchange)
 static int dist_phase_a(rb_world* w, int do_integrate) {
     RbDist* d = w->dist; RbParams& P = w->P;
-    CU(cudaMemsetAsync(P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));
     CU(cudaMemsetAsync(w->d_dn + 1, 0, sizeof(uint32_t), w->stream));                       // n_ghost
     CU(cudaMemsetAsync(d->D.self_cnt, 0, 2 * sizeof(uint32_t), w->stream));                 // self ghosts + emigrants
     CU(cudaMemsetAsync(d->out[0].base, 0, sizeof(RbHaloHeader), w->stream));

@@ -15,6 +15,7 @@
 void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cudaStream_t st);
 int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile_sums, cudaStream_t st);
 uint32_t rb_scan_tiles(uint32_t n);
+int rb_launch_scan_lookback(const uint32_t* in, uint32_t n, uint32_t* out, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_scatter(const RbParams& P, cudaStream_t st);
 int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st);
 void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
@@ -52,6 +53,8 @@ struct rb_world {
     std::vector<DevBuf> allocs;
     size_t device_bytes = 0;
     uint32_t* d_tile_sums = nullptr;
+    unsigned long long* d_scan_status = nullptr; uint32_t* d_scan_ticket = nullptr; size_t hist_clear_bytes = 0;
+    int scan_variant = 2;
     uint32_t ncols = 0;
     float4* d_stage = nullptr; size_t stage_elems = 0;      // H2D staging for setters
     uint32_t* d_stage_u = nullptr; size_t stage_u_elems = 0;

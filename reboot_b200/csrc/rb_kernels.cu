@@ -161,6 +161,73 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scan_apply_kernel(const uint32_t*
     // out[n] (the grand total) is written by rb_scan_top_kernel
 }
 
+// K2 (default): single-pass exclusive scan with decoupled look-back (Merrill & Garland): one launch, each
+// tile of 2048 counts is read once and written once. `status[t]` packs (flag << 32 | value): flag 1 =
+// tile aggregate available, 2 = inclusive prefix available. Tile ids are handed out by an atomic ticket
+// so that a tile only ever waits on tiles that are already running. ticket + status are zeroed by the
+// same memset that clears the histogram (they sit right behind it).
+__global__ void __launch_bounds__(RB_BLOCK) rb_scan_lookback_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                                                                    unsigned long long* status, uint32_t* ticket) {
+    __shared__ uint32_t s_tile, s_total, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * RB_SCAN_TILE + threadIdx.x * RB_SCAN_ITEMS;
+    uint32_t v[RB_SCAN_ITEMS];
+    uint32_t sum = 0;
+    if (base + RB_SCAN_ITEMS <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+        uint4 a = p[0], b = p[1];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0;
+    }
+#pragma unroll
+    for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) sum += v[i];
+    uint32_t ex = block_excl_scan(sum, &s_total);
+    if (threadIdx.x < 32) {          // warp 0 publishes the tile aggregate and looks back 32 tiles at a time
+        const uint32_t lane = threadIdx.x;
+        const uint32_t total = s_total;
+        uint32_t prefix = 0;
+        if (tile == 0) {
+            if (lane == 0) atomicExch(&status[0], (2ull << 32) | total);
+        } else {
+            if (lane == 0) atomicExch(&status[tile], (1ull << 32) | total);
+            int idx = (int)tile - 1 - (int)lane;          // lane 0 looks at the nearest predecessor
+            while (true) {
+                unsigned long long st = (2ull << 32);     // virtual inclusive 0 in front of tile 0
+                if (idx >= 0) { do { st = atomicAdd(&status[idx], 0ull); } while ((st >> 32) == 0); }
+                const uint32_t incl = __ballot_sync(0xffffffffu, (st >> 32) == 2);
+                if (incl) {
+                    const uint32_t first = __ffs(incl) - 1;       // nearest tile that already holds its inclusive prefix
+                    prefix += __reduce_add_sync(0xffffffffu, lane <= first ? (uint32_t)st : 0u);
+                    break;
+                }
+                prefix += __reduce_add_sync(0xffffffffu, (uint32_t)st);
+                idx -= 32;
+            }
+            if (lane == 0) atomicExch(&status[tile], (2ull << 32) | (unsigned long long)(prefix + total));
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if ((tile + 1) * RB_SCAN_TILE >= n) out[n] = prefix + total;      // grand total behind the last element
+        }
+    }
+    __syncthreads();
+    ex += s_prefix;
+    if (base + RB_SCAN_ITEMS <= n) {
+        uint4 a, b;
+        a.x = ex; ex += v[0]; a.y = ex; ex += v[1]; a.z = ex; ex += v[2]; a.w = ex; ex += v[3];
+        b.x = ex; ex += v[4]; b.y = ex; ex += v[5]; b.z = ex; ex += v[6]; b.w = ex;
+        uint4* q = reinterpret_cast<uint4*>(out + base);
+        q[0] = a; q[1] = b;
+    } else {
+#pragma unroll
+        for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) { if (base + i < n) out[base + i] = ex; ex += v[i]; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // K3: counting-sort scatter into column order.
 // ------------------------------------------------------------------------------------------
@@ -518,6 +585,9 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
 // ------------------------------------------------------------------------------------------
 #define RB_CAND_MAX 12
 #define RB_SSCAND_MAX 4
+#ifndef RB_COLLIDE_MINBLOCKS
+#define RB_COLLIDE_MINBLOCKS 3
+#endif
 
 template <bool RESOLVE>
 __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, HitBuf& H, Tally& T,
@@ -545,7 +615,7 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
 }
 
 template <bool RESOLVE>
-__global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_single_kernel(RbParams P) {
+__global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -798,6 +868,11 @@ int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile
     return 3;
 }
 uint32_t rb_scan_tiles(uint32_t n) { return cdiv(n, RB_SCAN_TILE); }
+// single launch; status/ticket must have been zeroed (they live behind the histogram, see rb_build)
+int rb_launch_scan_lookback(const uint32_t* in, uint32_t n, uint32_t* out, unsigned long long* status, uint32_t* ticket, cudaStream_t st) {
+    rb_scan_lookback_kernel<<<cdiv(n, RB_SCAN_TILE), RB_BLOCK, 0, st>>>(in, n, out, status, ticket);
+    return 1;
+}
 void rb_launch_scatter(const RbParams& P, cudaStream_t st) {
     if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
 }

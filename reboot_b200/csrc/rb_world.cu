@@ -43,6 +43,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     w->h_geom_start.push_back(0);
     w->h_body_start.push_back(0);
     { const char* v = getenv("RB_COLLIDE_V1"); if (v && *v == '1') w->collide_variant = 1; }
+    { const char* v = getenv("RB_SCAN_V1"); if (v && *v == '1') w->scan_variant = 1; }
     *out = w;
     return RB_OK;
 }
@@ -287,7 +288,14 @@ int rb_build(rb_world* w) {
         CU(cudaStreamSynchronize(w->stream));
         P.dn = w->d_dn; P.gid = w->d_gid;
     }
-    ALLOC(d_cc, (size_t)w->ncols + 1); ALLOC(d_cs, (size_t)w->ncols + 1);
+    {   // histogram | pad | ticket | status  -- one allocation so that one memset clears all of it every tick
+        size_t hist = (((size_t)w->ncols + 1) * 4 + 15) / 16 * 16;
+        size_t tiles = rb_scan_tiles(w->ncols) + 1;
+        uint8_t* blob; ALLOC(blob, hist + 16 + tiles * 8);
+        d_cc = (uint32_t*)blob; w->d_scan_ticket = (uint32_t*)(blob + hist); w->d_scan_status = (unsigned long long*)(blob + hist + 16);
+        w->hist_clear_bytes = hist + 16 + tiles * 8;
+    }
+    ALLOC(d_cs, (size_t)w->ncols + 1);
     ALLOC(w->d_tile_sums, rb_scan_tiles(w->ncols) + 1);
     P.pos = d_pos; P.vel = d_vel; P.mt = d_mt; P.pt = d_pt; P.flags = d_flags; P.sph_obj = d_sph; P.ws = d_ws;
     P.key = d_key; P.rank = d_rank; P.sorted = d_sorted; P.sorted_id = d_sid; P.col_count = d_cc; P.col_start = d_cs;
@@ -341,7 +349,8 @@ int rb_build(rb_world* w) {
 int enqueue_broadphase_tail(rb_world* w) {
     RbParams& P = w->P;
     if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
-    w->launches += rb_launch_scan(P.col_count, w->ncols, P.col_start, w->d_tile_sums, w->stream);
+    if (w->scan_variant == 1) w->launches += rb_launch_scan(P.col_count, w->ncols, P.col_start, w->d_tile_sums, w->stream);
+    else w->launches += rb_launch_scan_lookback(P.col_count, w->ncols, P.col_start, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[2], w->stream));
     rb_launch_scatter(P, w->stream); w->launches++;
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
@@ -350,7 +359,7 @@ int enqueue_broadphase_tail(rb_world* w) {
 static int enqueue_broadphase(rb_world* w, int do_integrate) {
     RbParams& P = w->P;
     if (w->dist) return rb_dist_step_exchange(w, do_integrate);
-    CU(cudaMemsetAsync(P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;
     return enqueue_broadphase_tail(w);
@@ -489,7 +498,7 @@ int rb_get_angular(rb_world* w, float* ap4, float* av4) {
 int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     if (!w || !w->built || !xyzr4) return RB_ERR_INVALID;
     // recompute from the current model translations (no integration, no binning side effects on state)
-    CU(cudaMemsetAsync(w->P.col_count, 0, ((size_t)w->ncols + 1) * sizeof(uint32_t), w->stream));
+    CU(cudaMemsetAsync(w->P.col_count, 0, w->hist_clear_bytes, w->stream));
     rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
     size_t ns = w->d_dn ? w->n_owned_host : w->P.ns;
     std::vector<float> tmp(ns * 4), obj(ns * 4);
