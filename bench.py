@@ -178,7 +178,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "contact_tests_per_s": cb["sample_tests_per_s"], "wall_s": time.time() - t0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -310,14 +310,28 @@ def run_ours(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     w.close()
     if N > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner, torchrun notices) has been routed to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

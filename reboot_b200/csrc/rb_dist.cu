@@ -193,8 +193,8 @@ static int dist_alloc(rb_world* w) {
     if (w->dist) return RB_OK;
     if (!w->built || !w->d_dn) return fail(w, RB_ERR_INVALID, "distributed init needs a built world created with rb_config.nranks > 1");
     RbDist* d = new RbDist();
-    d->ghost_cap = std::max<uint32_t>(65536u, w->n_owned_host / 8);
-    d->migr_cap = std::max<uint32_t>(4096u, w->n_owned_host / 64);
+    d->ghost_cap = w->ghost_cap;
+    d->migr_cap = std::max<uint32_t>(1024u, w->ghost_cap / 8);
     size_t bytes = sizeof(RbHaloHeader) + (size_t)d->ghost_cap * sizeof(RbGhostRec) + (size_t)d->migr_cap * sizeof(RbMigrRec);
     for (int k = 0; k < 2; k++) {
         uint8_t *o, *i; ALLOC(o, bytes); ALLOC(i, bytes);

@@ -149,8 +149,12 @@ static int build_triangle_grid(rb_world* w) {
         c1 = rb_col(hi, half, P.t_inv_w, (uint32_t)n);
         // a triangle that only touches the upper column at its boundary line is reachable from the
         // lower one by every sphere whose margin-grown box touches it (margins are > 0)
-        float t = (hi + half) * P.t_inv_w;
-        if (c1 > c0 && t == std::floor(t)) c1--;
+        // (tolerance 2.5e-4 world units < the smallest candidate margin of 1e-3, so lattices whose cell
+        // size is not exactly representable still register one column per cell)
+        float t = (hi - 2.5e-4f + half) * P.t_inv_w;
+        uint32_t c1t = rb_col(hi - 2.5e-4f, half, P.t_inv_w, (uint32_t)n);
+        if (c1 > c0 && c1t < c1) c1 = c1t;
+        (void)t;
     };
     for (uint32_t t = 0; t < nt; t++) {
         const float* p = &w->h_tri[(size_t)t * 9];
@@ -227,7 +231,15 @@ int rb_build(rb_world* w) {
     if (slab && !P.single) return fail(w, RB_ERR_INVALID, "slab (multi-GPU) worlds support single-sphere bodies only in this version");
     if (slab && w->any_wt) return fail(w, RB_ERR_INVALID, "slab (multi-GPU) worlds need W.t = 0");
     // slab worlds keep room for immigrants and ghosts; counts live on the device (P.dn)
-    const uint32_t ghost_cap = slab ? std::max<uint32_t>(65536u, nb / 8) : 0;
+    // ghosts per face ~ n * reach / slab width; keep 16x headroom (overflow is detected and reported)
+    uint32_t ghost_cap = 0;
+    if (slab) {
+        float rr = 0.f; for (size_t i = 3; i < w->h_obj.size(); i += 4) rr = std::max(rr, std::fabs(w->h_obj[i]));
+        rr = std::max(rr, w->cfg.rm_max_hint);
+        double frac = 2.0 * (rr + w->cfg.margin_cap) / std::max(1e-3, (double)(w->cfg.slab_hi - w->cfg.slab_lo));
+        ghost_cap = (uint32_t)std::min<double>(nb / 2 + 8192.0, std::max(8192.0, 16.0 * nb * frac));
+    }
+    w->ghost_cap = ghost_cap;
     const uint32_t cap = slab ? nb + std::max<uint32_t>(nb / 4, 4096u) + 3 * ghost_cap : nb;
     w->cap_local = cap;
     P.nb = cap; P.ns = slab ? cap : ns; P.n_owned = nb;
