@@ -29,6 +29,23 @@ enum { RB_C_TESTS_SS = 0, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_S
        RB_C_OVERFLOW, RB_C_DROPPED, RB_C_NCONTACT /* per step, reset */, RB_C_NCHANGED /* per step */,
        RB_C_HALO_SENT, RB_C_MIGRATED, RB_C_COUNT = 16 };
 
+// ---- multi-GPU halo exchange records (rb_dist.cu) ------------------------------------------------
+struct __align__(16) RbHaloHeader { uint32_t n_ghost, n_migr, ghost_overflow, migr_overflow; };
+struct __align__(16) RbGhostRec { float4 ws; float r; uint32_t gid; uint32_t pad0, pad1; };                 // 32 B
+struct __align__(16) RbMigrRec { float4 pos, vel, mt, pt, obj; uint32_t flags, gid, pad0, pad1; };          // 96 B
+
+struct RbDistParams {
+    RbHaloHeader* out_hdr[2]; RbGhostRec* out_ghost[2]; RbMigrRec* out_migr[2];      // 0 = left, 1 = right
+    const RbHaloHeader* in_hdr[2]; const RbGhostRec* in_ghost[2]; const RbMigrRec* in_migr[2];
+    RbGhostRec* self_ghost; uint32_t* self_cnt;     // emigrants stay visible to their old owner for this tick
+    uint32_t* emig; uint32_t* emig_cnt;             // local indices of emigrants
+    uint32_t ghost_cap, migr_cap, cap_local;
+    float slab_lo, slab_hi; int has_left, has_right;
+    uint32_t* dn;                                   // {n_owned, n_ghost}
+    uint32_t* gid; float4* sph_obj_w; unsigned long long* counters;
+};
+
+
 struct RbParams {
     uint32_t nb, ns, nt;
     uint32_t single;              // every body has exactly one sphere (sphere id == body id)
@@ -78,6 +95,7 @@ struct RbParams {
                                   // local bodies [0, dn[0]) are owned, [dn[0], dn[0]+dn[1]) are ghosts
     const uint32_t* gid;          // global body id per local body (NULL: id == local index)
     float s_x0;                   // x origin of the sphere column grid (-half for whole-world grids)
+    const RbDistParams* dp;       // device copy of the halo parameters (slab worlds with neighbours), else NULL
 };
 
 __device__ __forceinline__ uint32_t rb_n_owned(const RbParams& P) { return P.dn ? P.dn[0] : P.n_owned; }

@@ -17,27 +17,11 @@
 
 #define RB_BLOCK 256
 
-// ---- exchange buffer layout -------------------------------------------------------------------
-struct __align__(16) RbHaloHeader { uint32_t n_ghost, n_migr, ghost_overflow, migr_overflow; };
-struct __align__(16) RbGhostRec { float4 ws; float r; uint32_t gid; uint32_t pad0, pad1; };                 // 32 B
-struct __align__(16) RbMigrRec { float4 pos, vel, mt, pt, obj; uint32_t flags, gid, pad0, pad1; };          // 96 B
-
 struct RbHaloBuf {
     uint8_t* base = nullptr; size_t bytes = 0;
     RbHaloHeader* hdr() const { return (RbHaloHeader*)base; }
     RbGhostRec* ghosts() const { return (RbGhostRec*)(base + sizeof(RbHaloHeader)); }
     RbMigrRec* migr(uint32_t ghost_cap) const { return (RbMigrRec*)(base + sizeof(RbHaloHeader) + (size_t)ghost_cap * sizeof(RbGhostRec)); }
-};
-
-struct RbDistParams {
-    RbHaloHeader* out_hdr[2]; RbGhostRec* out_ghost[2]; RbMigrRec* out_migr[2];      // 0 = left, 1 = right
-    const RbHaloHeader* in_hdr[2]; const RbGhostRec* in_ghost[2]; const RbMigrRec* in_migr[2];
-    RbGhostRec* self_ghost; uint32_t* self_cnt;     // emigrants stay visible to their old owner for this tick
-    uint32_t* emig; uint32_t* emig_cnt;             // local indices of emigrants
-    uint32_t ghost_cap, migr_cap, cap_local;
-    float slab_lo, slab_hi; int has_left, has_right;
-    uint32_t* dn;                                   // {n_owned, n_ghost}
-    uint32_t* gid; float4* sph_obj_w; unsigned long long* counters;
 };
 
 // ---- NCCL through dlopen (no link-time dependency; the host says which libnccl to use) -----------
@@ -83,39 +67,7 @@ struct RbDist {
     RbHaloHeader* h_hdr = nullptr;                   // pinned, 4 headers (out L/R, in L/R)
 };
 
-// ---- K6a: pack ghosts and migrants ----------------------------------------------------------------
-__global__ void __launch_bounds__(RB_BLOCK) rb_halo_pack_kernel(RbParams P, RbDistParams D) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= D.dn[0]) return;
-    float4 s = P.ws[b];
-    uint32_t f = P.flags[b];
-    bool in_grid = P.key[b] != RB_NONE;            // active and touching the root cube (K1)
-    float r = D.sph_obj_w[b].w;
-    int dir = -1;
-    if (s.x < D.slab_lo && D.has_left) dir = 0; else if (s.x >= D.slab_hi && D.has_right) dir = 1;
-    if (dir >= 0 && (f & RB_F_ACTIVE)) {
-        uint32_t k = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
-        if (k < D.migr_cap) {
-            RbMigrRec m; m.pos = P.pos[b]; m.vel = P.vel[b]; m.mt = P.mt[b]; m.pt = P.pt[b]; m.obj = D.sph_obj_w[b];
-            m.flags = f; m.gid = D.gid[b]; m.pad0 = m.pad1 = 0;
-            D.out_migr[dir][k] = m;
-            D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
-            if (in_grid) { uint32_t g = atomicAdd(D.self_cnt, 1u); if (g < D.ghost_cap) { RbGhostRec q; q.ws = s; q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0; D.self_ghost[g] = q; } }
-        } else atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u);   // stays owned here one more tick
-        return;
-    }
-    if (!in_grid) return;
-    float reach = s.w + P.rm_max;                   // own grown radius + the largest grown radius anywhere
-    RbGhostRec q; q.ws = s; q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0;
-    if (D.has_left && s.x - reach < D.slab_lo) {
-        uint32_t k = atomicAdd(&D.out_hdr[0]->n_ghost, 1u);
-        if (k < D.ghost_cap) D.out_ghost[0][k] = q; else atomicAdd(&D.out_hdr[0]->ghost_overflow, 1u);
-    }
-    if (D.has_right && s.x + reach >= D.slab_hi) {
-        uint32_t k = atomicAdd(&D.out_hdr[1]->n_ghost, 1u);
-        if (k < D.ghost_cap) D.out_ghost[1][k] = q; else atomicAdd(&D.out_hdr[1]->ghost_overflow, 1u);
-    }
-}
+// K6a (pack ghosts and migrants) is fused into rb_integrate_bin_kernel (rb_kernels.cu).
 
 // ---- K6b: swap-remove the emigrants (few per tick; one thread keeps it simple and ordered) --------
 __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D) {
@@ -129,7 +81,7 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D) {
         uint32_t h = D.emig[i], last = n - 1;
         if (h != last) {
             P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
-            sph[h] = sph[last]; D.gid[h] = D.gid[last]; P.ws[h] = P.ws[last]; P.key[h] = P.key[last];
+            sph[h] = sph[last]; D.gid[h] = D.gid[last]; P.ws[h] = P.ws[last]; P.key[h] = P.key[last]; P.rank[h] = P.rank[last];
         }
         n = last;
     }
@@ -153,7 +105,12 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_immigrate_kernel(RbParams P,
     float speed = mag3(xyz(m.vel));
     float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * P.dt + 0.01f * m.obj.w, 1e-3f));
     P.ws[i] = make_float4(c.x, c.y, c.z, m.obj.w + margin);
-    P.key[i] = ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) ? 0u : RB_NONE;
+    uint32_t k = RB_NONE;
+    if ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) {
+        k = rb_col(c.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
+        P.rank[i] = atomicAdd(&P.col_count[k], 1u);
+    }
+    P.key[i] = k;
 }
 
 // ---- K6d: ghosts go behind the owned bodies ---------------------------------------------------------
@@ -170,20 +127,9 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_ghost_kernel(RbParams P, RbD
     D.sph_obj_w[i] = make_float4(0.f, 0.f, 0.f, q.r);
     D.gid[i] = q.gid;
     P.flags[i] = RB_F_ACTIVE;
-    P.key[i] = 0u;
-}
-
-// ---- K6e: bin owned + ghosts into the slab-local sphere grid -----------------------------------------
-__global__ void __launch_bounds__(RB_BLOCK) rb_halo_bin_kernel(RbParams P) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.dn[0] + P.dn[1]) return;
-    if (P.key[s] == RB_NONE) return;
-    float4 c = P.ws[s];
-    uint32_t cx = rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
-    uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
-    uint32_t k = cz * P.scx + cx;
-    P.key[s] = k;
-    P.rank[s] = atomicAdd(&P.col_count[k], 1u);
+    uint32_t k = rb_col(q.ws.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(q.ws.x, -P.s_x0, P.s_inv_w, P.scx);
+    P.key[i] = k;
+    P.rank[i] = atomicAdd(&P.col_count[k], 1u);
 }
 
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -216,7 +162,10 @@ static int dist_alloc(rb_world* w) {
     D.slab_lo = w->cfg.slab_lo; D.slab_hi = w->cfg.slab_hi;
     D.has_left = w->cfg.rank > 0; D.has_right = w->cfg.rank < w->cfg.nranks - 1;
     D.dn = w->d_dn; D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj); D.counters = w->P.counters;
+    RbDistParams* d_dp; ALLOC(d_dp, 1);
+    CU(cudaMemcpyAsync(d_dp, &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    w->P.dp = d_dp;
     w->dist = d;
     return RB_OK;
 }
@@ -260,9 +209,8 @@ static int dist_phase_a(rb_world* w, int do_integrate) {
     CU(cudaMemsetAsync(d->out[0].base, 0, sizeof(RbHaloHeader), w->stream));
     CU(cudaMemsetAsync(d->out[1].base, 0, sizeof(RbHaloHeader), w->stream));
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
-    rb_launch_integrate_bin(P, do_integrate, 0, w->stream); w->launches++;
+    rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;     // integrate + bin + halo pack
     if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));
-    rb_halo_pack_kernel<<<cdiv(w->cap_local, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D); w->launches++;
     return RB_OK;
 }
 // phase B: unpack + bin + scan + scatter (everything after the exchange)
@@ -271,8 +219,7 @@ static int dist_phase_b(rb_world* w) {
     rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->D);
     rb_halo_immigrate_kernel<<<cdiv(2 * d->migr_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
     rb_halo_ghost_kernel<<<cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
-    rb_halo_bin_kernel<<<cdiv(w->cap_local, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P);
-    w->launches += 4;
+    w->launches += 3;
     CU(cudaGetLastError());
     int r = enqueue_broadphase_tail(w);
     if (w->profile) {   // halo time = pack .. bin, reported as family 4

@@ -79,13 +79,43 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
         uint32_t k = RB_NONE;
         // Q3/Q7: only active bodies are (re)inserted in the broadphase, and only while they touch
         // the OSP root cube (physics/src/OSP.cpp:182-239)
-        if ((f & RB_F_ACTIVE) && sphere_in_world(c, r, P.half)) {
+        bool in_grid = (f & RB_F_ACTIVE) && sphere_in_world(c, r, P.half);
+        if (P.dp && do_bin && (f & RB_F_ACTIVE)) {
+            // K6a fused here: slab worlds hand migrants and ghosts to the halo buffers while the sphere is
+            // still in registers (single-sphere bodies: s == b)
+            const RbDistParams& D = *P.dp;
+            int dir = -1;
+            if (c.x < D.slab_lo && D.has_left) dir = 0; else if (c.x >= D.slab_hi && D.has_right) dir = 1;
+            if (dir >= 0) {
+                uint32_t kk = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
+                if (kk < D.migr_cap) {
+                    RbMigrRec mr; mr.pos = make_float4(p.x, p.y, p.z, p4.w); mr.vel = make_float4(v.x, v.y, v.z, v4.w);
+                    mr.mt = P.mt[b]; mr.pt = P.pt[b]; mr.obj = o; mr.flags = f; mr.gid = D.gid[b]; mr.pad0 = mr.pad1 = 0;
+                    D.out_migr[dir][kk] = mr;
+                    D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
+                    if (in_grid) { uint32_t g = atomicAdd(D.self_cnt, 1u); if (g < D.ghost_cap) { RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0; D.self_ghost[g] = q; } }
+                    in_grid = false;        // leaves this slab: not binned here
+                } else atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u);   // stays owned here one more tick
+            } else if (in_grid) {
+                float reach = r + margin + P.rm_max;   // own grown radius + the largest grown radius anywhere
+                RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0;
+                if (D.has_left && c.x - reach < D.slab_lo) {
+                    uint32_t kk = atomicAdd(&D.out_hdr[0]->n_ghost, 1u);
+                    if (kk < D.ghost_cap) D.out_ghost[0][kk] = q; else atomicAdd(&D.out_hdr[0]->ghost_overflow, 1u);
+                }
+                if (D.has_right && c.x + reach >= D.slab_hi) {
+                    uint32_t kk = atomicAdd(&D.out_hdr[1]->n_ghost, 1u);
+                    if (kk < D.ghost_cap) D.out_ghost[1][kk] = q; else atomicAdd(&D.out_hdr[1]->ghost_overflow, 1u);
+                }
+            }
+        }
+        if (in_grid) {
             if (do_bin) {
                 uint32_t cx = rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
                 uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
                 k = cz * P.scx + cx;
                 P.rank[s] = atomicAdd(&P.col_count[k], 1u);
-            } else k = 0;   // slab worlds bin after the halo exchange (rb_bin_kernel)
+            } else k = 0;
         }
         P.key[s] = k;
     }
