@@ -46,6 +46,8 @@ struct RbDistParams {
 };
 
 
+#define RB_STRIPES 64
+
 struct RbParams {
     uint32_t nb, ns, nt;
     uint32_t single;              // every body has exactly one sphere (sphere id == body id)
@@ -79,6 +81,7 @@ struct RbParams {
     const uint32_t* tcol_start;   // [tcols + 1]
     const uint32_t* tcol_tri;     // ascending triangle ids per column
     const float2* tcol_yr;        // per column: (min y, max y) over its triangles (empty: +inf, -inf)
+    const float4* tcol_ent;       // 2 float4 per column entry: (minx,maxx,minz,maxz) (miny,maxy,id bits,0)
     uint32_t tcx, tcz;
     float t_inv_w;
     // ---- constants ----
@@ -87,6 +90,7 @@ struct RbParams {
     RbContactRec* contacts;
     unsigned long long contact_cap;
     unsigned long long* counters;
+    unsigned long long* stripes;  // RB_STRIPES x RB_C_COUNT striped copies of the cumulative test / hit counters
     // ---- deferred commit (compound-body path) ----
     uint32_t* ch_body; float4* ch_pos; float4* ch_vel; float4* ch_mt; float4* ch_pt; uint32_t* ch_flags;
     // ---- slab ownership (multi-GPU) ----

@@ -430,20 +430,15 @@ __device__ __forceinline__ void collide_epilogue(const RbParams& P, HitBuf& H, T
         dropped = __reduce_add_sync(0xffffffffu, dropped);
         if (lane == 0 && dropped) atomicAdd(&P.counters[RB_C_DROPPED], (unsigned long long)dropped);
     }
-    // ---- counters: warp reduce, block reduce in shared, one atomic per block and counter ----
-    __shared__ uint32_t blk[7];
-    if (threadIdx.x < 7) blk[threadIdx.x] = 0;
-    __syncthreads();
+    // ---- counters: warp reduce, then one atomic per warp and counter on a striped copy (no block barrier,
+    // little contention); the host sums the RB_STRIPES stripes when it reads the statistics ----
     uint32_t vals[7] = { T.tests_ss, T.tests_st, T.cand_ss, T.cand_st, T.hits_ss, T.hits_st, T.overflow };
+    const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
+    const uint32_t stripe = ((blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5)) & (RB_STRIPES - 1);
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
-        uint32_t s = __reduce_add_sync(0xffffffffu, vals[k]);
-        if (lane == 0 && s) atomicAdd(&blk[k], s);
-    }
-    __syncthreads();
-    if (threadIdx.x < 7 && blk[threadIdx.x]) {
-        const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
-        atomicAdd(&P.counters[map[threadIdx.x]], (unsigned long long)blk[threadIdx.x]);
+        uint32_t sum = __reduce_add_sync(0xffffffffu, vals[k]);
+        if (lane == 0 && sum) atomicAdd(&P.stripes[stripe * RB_C_COUNT + map[k]], (unsigned long long)sum);
     }
 }
 
@@ -716,12 +711,15 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
         }
     }
     // ---------------- P3: stage sphere-triangle candidates ----------------
+    // Column entries carry the triangle's box (32 B, contiguous per column), so the prune needs no
+    // vertex gather: survivors are staged, then sorted + de-duplicated (ascending global id = the
+    // canonical order; a triangle registered in two columns shows up twice).
     uint32_t nc = 0;
     bool st_slow = false;
     {
-        uint32_t cur[4], end[4], head[4];
+        uint32_t cur[4], end[4];
 #pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) { cur[k] = end[k] = 0; head[k] = RB_NONE; }
+        for (uint32_t k = 0; k < 4; ++k) cur[k] = end[k] = 0;
         if (valid && P.nt) {
             uint32_t cx0 = rb_col(fc.x - frm, P.half, P.t_inv_w, P.tcx), cx1 = rb_col(fc.x + frm, P.half, P.t_inv_w, P.tcx);
             uint32_t cz0 = rb_col(fc.z - frm, P.half, P.t_inv_w, P.tcz), cz1 = rb_col(fc.z + frm, P.half, P.t_inv_w, P.tcz);
@@ -735,32 +733,46 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
                         float2 yr = __ldg(P.tcol_yr + col);
                         if (!(yr.x > fc.y + frm || yr.y < fc.y - frm)) {      // column holds something at this height
                             cur[k] = __ldg(P.tcol_start + col); end[k] = __ldg(P.tcol_start + col + 1);
-                            if (cur[k] < end[k]) head[k] = __ldg(P.tcol_tri + cur[k]);
                         }
                     }
                 }
             }
         }
-        while (true) {      // warp-uniform: one merged triangle id per lane and iteration
-            uint32_t m = st_slow ? RB_NONE : min(min(head[0], head[1]), min(head[2], head[3]));
-            if (!__any_sync(0xffffffffu, m != RB_NONE)) break;
-            if (m != RB_NONE) {
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k)
-                    if (head[k] == m) { cur[k]++; head[k] = cur[k] < end[k] ? __ldg(P.tcol_tri + cur[k]) : RB_NONE; }
-                const float4* tp = P.tri + 3ull * m;
-                float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
-                T.cand_st++;
-                bool keep = !(fminf(a4.x, fminf(b4.x, c4.x)) > fc.x + frm || fmaxf(a4.x, fmaxf(b4.x, c4.x)) < fc.x - frm);
-                keep = keep && !(fminf(a4.y, fminf(b4.y, c4.y)) > fc.y + frm || fmaxf(a4.y, fmaxf(b4.y, c4.y)) < fc.y - frm);
-                keep = keep && !(fminf(a4.z, fminf(b4.z, c4.z)) > fc.z + frm || fmaxf(a4.z, fmaxf(b4.z, c4.z)) < fc.z - frm);
-                if (keep) {
-                    if (nc == RB_CAND_MAX) st_slow = true;        // too many: the generic walk takes over
-                    else s_cand[nc++][threadIdx.x] = m;
+        for (uint32_t k = 0; k < 4; ++k) {
+            while (true) {      // warp-uniform walk of column k, one entry per lane and iteration
+                const bool work = cur[k] < end[k];
+                if (!__any_sync(0xffffffffu, work)) break;
+                if (work) {
+                    const float4* ep = P.tcol_ent + 2ull * cur[k];
+                    float4 e0 = __ldg(ep), e1 = __ldg(ep + 1);          // (minx,maxx,minz,maxz) (miny,maxy,id,-)
+                    cur[k]++;
+                    T.cand_st++;
+                    bool keep = !(e0.x > fc.x + frm || e0.y < fc.x - frm) && !(e0.z > fc.z + frm || e0.w < fc.z - frm) &&
+                                !(e1.x > fc.y + frm || e1.y < fc.y - frm);
+                    if (keep) {
+                        if (nc == RB_CAND_MAX) { st_slow = true; cur[k] = end[k]; }    // too many: the generic walk takes over
+                        else s_cand[nc++][threadIdx.x] = __float_as_uint(e1.z);
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
+        if (st_slow) nc = 0;
+        // insertion sort + de-duplication of the (few) staged ids, in this thread's shared-memory column
+        for (uint32_t i = 1; i < nc; ++i) {
+            uint32_t v = s_cand[i][threadIdx.x];
+            int j = (int)i - 1;
+            while (j >= 0 && s_cand[j][threadIdx.x] > v) { s_cand[j + 1][threadIdx.x] = s_cand[j][threadIdx.x]; --j; }
+            s_cand[j + 1][threadIdx.x] = v;
+        }
+        uint32_t nu = 0;
+        for (uint32_t i = 0; i < nc; ++i) {
+            uint32_t v = s_cand[i][threadIdx.x];
+            if (nu == 0 || s_cand[nu - 1][threadIdx.x] != v) s_cand[nu++][threadIdx.x] = v;
+        }
+        nc = nu;
+        __syncwarp();
     }
     // ---------------- lazy state load ----------------
     const bool need = valid && (npart || nc || st_slow);
@@ -798,13 +810,15 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
         T.cand_st = 0;      // the generic walk recounts
         sphere_vs_triangles<RESOLVE>(P, S, H, T, gA, xyz(oa), oa.w, fc, frm, hit_any);
     }
-    if (st_slow) nc = 0;
     const uint32_t nmax = __reduce_max_sync(0xffffffffu, nc);
+    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4;
+    uint32_t t = 0;
+    if (nc) { t = s_cand[0][threadIdx.x]; const float4* tp = P.tri + 3ull * t; a4 = __ldg(tp); b4 = __ldg(tp + 1); c4 = __ldg(tp + 2); }
     for (uint32_t j = 0; j < nmax; ++j) {       // warp-uniform trip count, explicit reconvergence
+        // the next triangle's vertices are requested before this one is tested
+        float4 na4 = a4, nb4 = b4, nc4 = c4; uint32_t nt_ = t;
+        if (j + 1 < nc) { nt_ = s_cand[j + 1][threadIdx.x]; const float4* tp = P.tri + 3ull * nt_; na4 = __ldg(tp); nb4 = __ldg(tp + 1); nc4 = __ldg(tp + 2); }
         if (j < nc) {
-            const uint32_t t = s_cand[j][threadIdx.x];
-            const float4* tp = P.tri + 3ull * t;
-            float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
             f3 TA = xyz(a4), TB = xyz(b4), TC = xyz(c4);
             f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
             T.tests_st++;
@@ -828,6 +842,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
                 }
             }
         }
+        a4 = na4; b4 = nb4; c4 = nc4; t = nt_;
         __syncwarp();
     }
     // ---------------- P5: flags, write-back ----------------

@@ -164,10 +164,19 @@ static int build_triangle_grid(rb_world* w) {
     for (size_t i = 0; i < ncol; i++) start[i + 1] += start[i];
     std::vector<uint32_t> list(std::max<size_t>(start[ncol], 1));
     std::vector<uint32_t> fill(start.begin(), start.end() - 1);
+    std::vector<float> ent(list.size() * 8, 0.f);
     for (uint32_t t = 0; t < nt; t++) {   // ascending t => every column list is ascending
         const float* p = &w->h_tri[(size_t)t * 9];
         uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
-        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) list[fill[(size_t)z * n + x]++] = t;
+        float bx0 = std::min(p[0], std::min(p[3], p[6])), bx1 = std::max(p[0], std::max(p[3], p[6]));
+        float by0 = std::min(p[1], std::min(p[4], p[7])), by1 = std::max(p[1], std::max(p[4], p[7]));
+        float bz0 = std::min(p[2], std::min(p[5], p[8])), bz1 = std::max(p[2], std::max(p[5], p[8]));
+        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) {
+            uint32_t k = fill[(size_t)z * n + x]++;
+            list[k] = t;
+            float* e = &ent[(size_t)k * 8];
+            e[0] = bx0; e[1] = bx1; e[2] = bz0; e[3] = bz1; e[4] = by0; e[5] = by1; memcpy(&e[6], &t, 4); e[7] = 0.f;
+        }
     }
     std::vector<float> yr(ncol * 2);
     for (size_t i = 0; i < ncol; i++) { yr[2 * i] = INFINITY; yr[2 * i + 1] = -INFINITY; }
@@ -192,7 +201,9 @@ static int build_triangle_grid(rb_world* w) {
         volatile float mag = sqrtf(ss);
         tri4[(size_t)t * 12 + 3] = nx / mag; tri4[(size_t)t * 12 + 7] = ny / mag; tri4[(size_t)t * 12 + 11] = nz / mag;
     }
-    float4* d_tri; uint32_t* d_start; uint32_t* d_list; float2* d_yr;
+    float4* d_tri; uint32_t* d_start; uint32_t* d_list; float2* d_yr; float4* d_ent;
+    ALLOC(d_ent, std::max<size_t>(list.size(), 1) * 2);
+    CU(cudaMemcpyAsync(d_ent, ent.data(), ent.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
     ALLOC(d_yr, ncol);
     CU(cudaMemcpyAsync(d_yr, yr.data(), yr.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
     ALLOC(d_tri, (size_t)std::max<uint32_t>(nt, 1) * 3);
@@ -202,7 +213,7 @@ static int build_triangle_grid(rb_world* w) {
     CU(cudaMemcpyAsync(d_start, start.data(), start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list; P.tcol_yr = d_yr;
+    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list; P.tcol_yr = d_yr; P.tcol_ent = d_ent;
     return RB_OK;
 }
 
@@ -336,10 +347,10 @@ int rb_build(rb_world* w) {
     // ---- contacts + counters ----
     P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(slab ? cap : ns) * 4 + 1024;
     RbContactRec* d_c; ALLOC(d_c, (size_t)P.contact_cap); P.contacts = d_c;
-    unsigned long long* d_cnt; ALLOC(d_cnt, RB_C_COUNT); P.counters = d_cnt;
-    CU(cudaMemsetAsync(d_cnt, 0, RB_C_COUNT * sizeof(unsigned long long), w->stream));
-    CU(cudaMallocHost((void**)&w->h_counters, RB_C_COUNT * sizeof(unsigned long long)));
-    memset(w->h_counters, 0, RB_C_COUNT * sizeof(unsigned long long));
+    unsigned long long* d_cnt; ALLOC(d_cnt, RB_C_COUNT * (RB_STRIPES + 1)); P.counters = d_cnt; P.stripes = d_cnt + RB_C_COUNT;
+    CU(cudaMemsetAsync(d_cnt, 0, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long), w->stream));
+    CU(cudaMallocHost((void**)&w->h_counters, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long)));
+    memset(w->h_counters, 0, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long));
     for (auto& e : w->ev) CU(cudaEventCreate(&e));
     CU(cudaStreamSynchronize(w->stream));
     int r = build_triangle_grid(w);
@@ -426,8 +437,13 @@ int rb_sync(rb_world* w) {
 }
 
 static int fetch_counters(rb_world* w) {
-    CU(cudaMemcpyAsync(w->h_counters, w->P.counters, RB_C_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaMemcpyAsync(w->h_counters, w->P.counters, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    for (int k = 0; k <= RB_C_OVERFLOW; k++) {          // cumulative test / hit counters live in the stripes
+        unsigned long long sum = w->h_counters[k];      // base copy (halo capacity overflow is counted there)
+        for (int st = 0; st < RB_STRIPES; st++) sum += w->h_counters[(size_t)(st + 1) * RB_C_COUNT + k];
+        w->h_counters[k] = sum;
+    }
     w->contacts_last = w->h_counters[RB_C_NCONTACT];
     return RB_OK;
 }
