@@ -106,6 +106,15 @@ __device__ __forceinline__ uint32_t rb_n_owned(const RbParams& P) { return P.dn 
 __device__ __forceinline__ uint32_t rb_n_local(const RbParams& P) { return P.dn ? P.dn[0] + P.dn[1] : P.ns; }
 __device__ __forceinline__ uint32_t rb_gid(const RbParams& P, uint32_t local) { return P.gid ? P.gid[local] : local; }
 
+// K7 arguments: every per-body array pair (current rows -> re-ordered rows)
+#define RB_REORDER_MAX 10
+struct RbReorder {
+    const float4* src4[RB_REORDER_MAX]; float4* dst4[RB_REORDER_MAX]; int n4;
+    const uint32_t* src_flags; uint32_t* dst_flags;
+    const uint32_t* src_gid; uint32_t* dst_gid; uint32_t* inv;
+    uint32_t* rest_counter;
+};
+
 struct f3 { float x, y, z; };
 
 __device__ __forceinline__ f3 mk3(float x, float y, float z) { f3 r; r.x = x; r.y = y; r.z = z; return r; }

@@ -18,8 +18,12 @@ uint32_t rb_scan_tiles(uint32_t n);
 int rb_launch_scan_lookback(const uint32_t* in, uint32_t n, uint32_t* out, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_scatter(const RbParams& P, cudaStream_t st);
 int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st);
-void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
-void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
+void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, const uint32_t* inv, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
+void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t* inv, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
+void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st);
+void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st);
+void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st);
+void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st);
 void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
 // multi-GPU (rb_dist.cu)
 struct RbDist;
@@ -63,6 +67,12 @@ struct rb_world {
     uint64_t steps = 0, launches = 0;
     uint64_t contacts_last = 0;
     int collide_variant = 2;
+    // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----
+    int reorder_every = 32;                  // ticks between re-orderings (0 = never)
+    uint32_t* d_inv = nullptr;               // body id -> row
+    uint32_t* d_gid_alt = nullptr; uint32_t* d_flags_alt = nullptr; uint32_t* d_rest = nullptr;
+    float4* alt4[RB_REORDER_MAX] = {};
+    float4* d_io4 = nullptr; uint32_t* d_io_u = nullptr;   // id-ordered staging for host IO
     bool profile = false;
     float kernel_ms[5] = { 0, 0, 0, 0, 0 };
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };

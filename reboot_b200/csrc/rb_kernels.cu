@@ -874,25 +874,63 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_commit_kernel(RbParams P) {
     P.pos[A] = P.ch_pos[k]; P.vel[A] = P.ch_vel[k]; P.mt[A] = P.ch_mt[k]; P.pt[A] = P.ch_pt[k]; P.flags[A] = P.ch_flags[k];
 }
 
-// StateVector::setForce / setTorque gating (math/src/StateVector.cpp:147-167)
+// StateVector::setForce / setTorque gating (math/src/StateVector.cpp:147-167). `inv` maps a body id to its
+// current row (NULL = identity): worlds re-order their rows spatially from time to time.
 __global__ void __launch_bounds__(RB_BLOCK) rb_apply_force_kernel(const uint32_t* __restrict__ flags, const float4* __restrict__ in,
-                                                                 float4* __restrict__ out, uint32_t first, uint32_t count, int keep_w) {
+                                                                 float4* __restrict__ out, const uint32_t* __restrict__ inv,
+                                                                 uint32_t first, uint32_t count, int keep_w) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    uint32_t f = flags[first + i];
+    uint32_t row = inv ? inv[first + i] : first + i;
+    uint32_t f = flags[row];
     float4 v = in[i];
-    float w = keep_w ? out[first + i].w : 0.f;
-    if ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) out[first + i] = make_float4(v.x, v.y, v.z, w);
-    else out[first + i] = make_float4(0.f, 0.f, 0.f, w);
+    float w = keep_w ? out[row].w : 0.f;
+    if ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) out[row] = make_float4(v.x, v.y, v.z, w);
+    else out[row] = make_float4(0.f, 0.f, 0.f, w);
 }
-__global__ void __launch_bounds__(RB_BLOCK) rb_set_flags_kernel(uint32_t* flags, const uint32_t* __restrict__ values, uint32_t first, uint32_t count, uint32_t mask) {
+__global__ void __launch_bounds__(RB_BLOCK) rb_set_flags_kernel(uint32_t* flags, const uint32_t* __restrict__ values, const uint32_t* __restrict__ inv,
+                                                               uint32_t first, uint32_t count, uint32_t mask) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    flags[first + i] = (flags[first + i] & ~mask) | (values[i] & mask);
+    uint32_t row = inv ? inv[first + i] : first + i;
+    flags[row] = (flags[row] & ~mask) | (values[i] & mask);
 }
 __global__ void __launch_bounds__(RB_BLOCK) rb_fill_f4_kernel(float4* p, uint32_t n, float4 v) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+// rows -> id order (readback) and id order -> rows (setters)
+__global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_f4_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ gid, float4* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[gid[i]] = rows[i];
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_u32_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ gid, uint32_t* __restrict__ out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[gid[i]] = rows[i];
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_ids_to_rows_f4_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ inv, float4* __restrict__ rows, uint32_t first, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) rows[inv[first + i]] = in[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: spatial re-ordering of the body rows (single-sphere worlds). Bodies are gathered and scattered by
+// body row all over the step; keeping the rows in the order of the last counting sort turns those random
+// 32-B sector accesses into streams. Row order is invisible outside: ids travel with the rows (gid / inv).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_reorder_kernel(RbParams P, RbReorder R) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nb) return;
+    uint32_t k = P.key[i];
+    uint32_t j;
+    if (k != RB_NONE) j = P.col_start[k] + P.rank[i];                                    // its slot in the last sort
+    else j = P.col_start[P.scx * P.scz] + atomicAdd(R.rest_counter, 1u);                 // not in the grid: behind
+#pragma unroll 1
+    for (int a = 0; a < R.n4; ++a) R.dst4[a][j] = R.src4[a][i];
+    R.dst_flags[j] = R.src_flags[i];
+    uint32_t g = R.src_gid ? R.src_gid[i] : i;
+    R.dst_gid[j] = g;
+    R.inv[g] = j;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -943,13 +981,25 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
     rb_collide_kernel<false, false><<<g, RB_BLOCK, 0, st>>>(P);
     return 1;
 }
-void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, uint32_t first, uint32_t count, int keep_w, cudaStream_t st) {
-    if (count) rb_apply_force_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, in, out, first, count, keep_w);
+void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, const uint32_t* inv, uint32_t first, uint32_t count, int keep_w, cudaStream_t st) {
+    if (count) rb_apply_force_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, in, out, inv, first, count, keep_w);
 }
-void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st) {
-    if (count) rb_set_flags_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, values, first, count, mask);
+void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t* inv, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st) {
+    if (count) rb_set_flags_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, values, inv, first, count, mask);
 }
 void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st) {
     if (n) rb_fill_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(p, n, v);
+}
+void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st) {
+    if (n) rb_rows_to_ids_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n);
+}
+void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st) {
+    if (n) rb_rows_to_ids_u32_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n);
+}
+void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st) {
+    if (count) rb_ids_to_rows_f4_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(in, inv, rows, first, count);
+}
+void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st) {
+    if (P.nb) rb_reorder_kernel<<<cdiv(P.nb, RB_BLOCK), RB_BLOCK, 0, st>>>(P, *(const RbReorder*)R);
 }
 }

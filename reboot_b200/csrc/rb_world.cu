@@ -8,6 +8,7 @@ thread_local std::string g_create_error;
 
 static bool finite_all(const float* p, size_t n) { for (size_t i = 0; i < n; i++) if (!std::isfinite(p[i])) return false; return true; }
 
+
 extern "C" {
 
 const char* rb_version(void) { return "reboot_b200 0.1 (sm_100a)"; }
@@ -44,6 +45,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     w->h_body_start.push_back(0);
     { const char* v = getenv("RB_COLLIDE_V1"); if (v && *v == '1') w->collide_variant = 1; }
     { const char* v = getenv("RB_SCAN_V1"); if (v && *v == '1') w->scan_variant = 1; }
+    { const char* v = getenv("RB_REORDER_EVERY"); if (v && *v) w->reorder_every = atoi(v); }
     *out = w;
     return RB_OK;
 }
@@ -230,6 +232,64 @@ static int ensure_stage_u(rb_world* w, size_t elems) {
     return RB_OK;
 }
 
+// ---- id-ordered host IO over spatially re-ordered rows ------------------------------------------
+static int ensure_io(rb_world* w) {
+    if (w->d_io4) return RB_OK;
+    ALLOC(w->d_io4, w->P.nb); ALLOC(w->d_io_u, w->P.nb);
+    return RB_OK;
+}
+static int read_rows_f4(rb_world* w, const float4* rows, float* host, size_t n) {
+    if (!w->d_inv) { CU(cudaMemcpyAsync(host, rows, n * 16, cudaMemcpyDeviceToHost, w->stream)); return RB_OK; }
+    int r = ensure_io(w); if (r) return r;
+    rb_launch_rows_to_ids_f4(rows, w->P.gid, w->d_io4, (uint32_t)n, w->stream); w->launches++;
+    CU(cudaMemcpyAsync(host, w->d_io4, n * 16, cudaMemcpyDeviceToHost, w->stream));
+    return RB_OK;
+}
+static int read_rows_u32(rb_world* w, const uint32_t* rows, uint32_t* host, size_t n) {
+    if (!w->d_inv) { CU(cudaMemcpyAsync(host, rows, n * 4, cudaMemcpyDeviceToHost, w->stream)); return RB_OK; }
+    int r = ensure_io(w); if (r) return r;
+    rb_launch_rows_to_ids_u32(rows, w->P.gid, w->d_io_u, (uint32_t)n, w->stream); w->launches++;
+    CU(cudaMemcpyAsync(host, w->d_io_u, n * 4, cudaMemcpyDeviceToHost, w->stream));
+    return RB_OK;
+}
+static int write_rows_f4(rb_world* w, float4* rows, uint32_t first, uint32_t count, const float* host) {
+    if (!w->d_inv) { CU(cudaMemcpyAsync(rows + first, host, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream)); return RB_OK; }
+    int r = ensure_stage(w, count); if (r) return r;
+    CU(cudaMemcpyAsync(w->d_stage, host, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    rb_launch_ids_to_rows_f4(w->d_stage, w->d_inv, rows, first, count, w->stream); w->launches++;
+    return RB_OK;
+}
+
+// K7 driver: put the body rows in the order of the last counting sort (needs a valid sort: call right
+// after a broadphase). Single-sphere, single-GPU worlds only.
+static int reorder_rows(rb_world* w) {
+    RbParams& P = w->P;
+    if (!P.single || w->d_dn || P.nb == 0) return RB_OK;
+    const size_t nb = P.nb;
+    float4** cur[RB_REORDER_MAX] = { &P.pos, &P.vel, &P.mt, &P.pt, const_cast<float4**>(&P.sph_obj), const_cast<float4**>(&P.wt), &P.force, &P.torque, &P.apos, &P.avel };
+    if (!w->d_inv) {
+        ALLOC(w->d_inv, nb); ALLOC(w->d_gid, nb); ALLOC(w->d_gid_alt, nb); ALLOC(w->d_flags_alt, nb); ALLOC(w->d_rest, 4);
+    }
+    RbReorder R; memset(&R, 0, sizeof R);
+    int slot_of[RB_REORDER_MAX];
+    for (int a = 0; a < RB_REORDER_MAX; a++) {
+        slot_of[a] = -1;
+        if (!*cur[a]) continue;
+        if (!w->alt4[a]) ALLOC(w->alt4[a], nb);
+        R.src4[R.n4] = *cur[a]; R.dst4[R.n4] = w->alt4[a]; slot_of[a] = R.n4++;
+    }
+    R.src_flags = P.flags; R.dst_flags = w->d_flags_alt;
+    R.src_gid = P.gid; R.dst_gid = P.gid == w->d_gid ? w->d_gid_alt : w->d_gid; R.inv = w->d_inv; R.rest_counter = w->d_rest;
+    CU(cudaMemsetAsync(w->d_rest, 0, 4, w->stream));
+    rb_launch_reorder(P, &R, w->stream); w->launches++;
+    CU(cudaGetLastError());
+    for (int a = 0; a < RB_REORDER_MAX; a++) if (slot_of[a] >= 0) { float4* old = *cur[a]; *cur[a] = w->alt4[a]; w->alt4[a] = old; }
+    { uint32_t* old = P.flags; P.flags = w->d_flags_alt; w->d_flags_alt = old; }
+    P.gid = R.dst_gid;
+    return RB_OK;
+}
+
+static int enqueue_broadphase(rb_world* w, int do_integrate);
 int rb_build(rb_world* w) {
     if (!w) return RB_ERR_INVALID;
     if (w->built) return fail(w, RB_ERR_INVALID, "rb_build is call-once (Physics::addEntities, SURVEY Q9)");
@@ -362,6 +422,12 @@ int rb_build(rb_world* w) {
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(w->stream));
     w->built = true;
+    if (P.single && !slab && nb > 0 && w->reorder_every > 0) {
+        // one broadphase over the initial poses, then put the body rows in that spatial order
+        int rr = enqueue_broadphase(w, 0); if (rr) return rr;
+        rr = reorder_rows(w); if (rr) return rr;
+        CU(cudaStreamSynchronize(w->stream));
+    }
     // host staging is no longer needed
     std::vector<float>().swap(w->h_tri); std::vector<float>().swap(w->h_obj); std::vector<float>().swap(w->h_W);
     std::vector<float>().swap(w->h_pos); std::vector<float>().swap(w->h_vel);
@@ -408,6 +474,7 @@ int rb_step(rb_world* w, int ms) {
     int r = enqueue_broadphase(w, 1); if (r) return r;
     r = enqueue_collide(w, true); if (r) return r;
     w->steps++;
+    if (w->reorder_every > 0 && w->steps % (uint64_t)w->reorder_every == 0) { r = reorder_rows(w); if (r) return r; }
     return RB_OK;
 }
 int rb_integrate(rb_world* w, int ms) {
@@ -499,9 +566,9 @@ int rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags) {
     if (!w || !w->built) return RB_ERR_INVALID;
     if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
     size_t nb = w->n_owned_host;
-    if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, nb * 16, cudaMemcpyDeviceToHost, w->stream));
-    if (vel4) CU(cudaMemcpyAsync(vel4, w->P.vel, nb * 16, cudaMemcpyDeviceToHost, w->stream));
-    if (flags) CU(cudaMemcpyAsync(flags, w->P.flags, nb * 4, cudaMemcpyDeviceToHost, w->stream));
+    if (pos4) { int r = read_rows_f4(w, w->P.pos, pos4, nb); if (r) return r; }
+    if (vel4) { int r = read_rows_f4(w, w->P.vel, vel4, nb); if (r) return r; }
+    if (flags) { int r = read_rows_u32(w, w->P.flags, flags, nb); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
@@ -509,8 +576,8 @@ int rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4) {
     if (!w || !w->built) return RB_ERR_INVALID;
     if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
     size_t nb = w->n_owned_host;
-    if (model_t4) CU(cudaMemcpyAsync(model_t4, w->P.mt, nb * 16, cudaMemcpyDeviceToHost, w->stream));
-    if (prev_t4) CU(cudaMemcpyAsync(prev_t4, w->P.pt, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (model_t4) { int r = read_rows_f4(w, w->P.mt, model_t4, nb); if (r) return r; }
+    if (prev_t4) { int r = read_rows_f4(w, w->P.pt, prev_t4, nb); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
@@ -518,8 +585,8 @@ int rb_get_angular(rb_world* w, float* ap4, float* av4) {
     if (!w || !w->built) return RB_ERR_INVALID;
     size_t nb = w->P.n_owned;
     if (!w->P.avel) { if (ap4) memset(ap4, 0, nb * 16); if (av4) memset(av4, 0, nb * 16); return RB_OK; }
-    if (ap4) CU(cudaMemcpyAsync(ap4, w->P.apos, nb * 16, cudaMemcpyDeviceToHost, w->stream));
-    if (av4) CU(cudaMemcpyAsync(av4, w->P.avel, nb * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (ap4) { int r = read_rows_f4(w, w->P.apos, ap4, nb); if (r) return r; }
+    if (av4) { int r = read_rows_f4(w, w->P.avel, av4, nb); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
@@ -530,8 +597,13 @@ int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
     size_t ns = w->d_dn ? w->n_owned_host : w->P.ns;
     std::vector<float> tmp(ns * 4), obj(ns * 4);
-    CU(cudaMemcpyAsync(tmp.data(), w->P.ws, ns * 16, cudaMemcpyDeviceToHost, w->stream));
-    CU(cudaMemcpyAsync(obj.data(), w->P.sph_obj, ns * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (w->P.single) {
+        int r = read_rows_f4(w, w->P.ws, tmp.data(), ns); if (r) return r;
+        r = read_rows_f4(w, w->P.sph_obj, obj.data(), ns); if (r) return r;
+    } else {
+        CU(cudaMemcpyAsync(tmp.data(), w->P.ws, ns * 16, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaMemcpyAsync(obj.data(), w->P.sph_obj, ns * 16, cudaMemcpyDeviceToHost, w->stream));
+    }
     CU(cudaStreamSynchronize(w->stream));
     for (size_t i = 0; i < ns; i++) { xyzr4[4 * i] = tmp[4 * i]; xyzr4[4 * i + 1] = tmp[4 * i + 1]; xyzr4[4 * i + 2] = tmp[4 * i + 2]; xyzr4[4 * i + 3] = obj[4 * i + 3]; }
     return RB_OK;
@@ -545,8 +617,8 @@ static int range_ok(rb_world* w, uint32_t first, uint32_t count) {
 int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4) {
     int r = range_ok(w, first, count); if (r) return r;
     if ((pos4 && !finite_all(pos4, (size_t)count * 3)) || (vel4 && !finite_all(vel4, (size_t)count * 3))) { /* w component is padding */ }
-    if (pos4) CU(cudaMemcpyAsync(w->P.pos + first, pos4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
-    if (vel4) CU(cudaMemcpyAsync(w->P.vel + first, vel4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    if (pos4) { r = write_rows_f4(w, w->P.pos, first, count, pos4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
+    if (vel4) { r = write_rows_f4(w, w->P.vel, first, count, vel4); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
@@ -555,7 +627,7 @@ int rb_set_flags(rb_world* w, uint32_t first, uint32_t count, const uint32_t* va
     if (!values) return fail(w, RB_ERR_INVALID, "values is NULL");
     r = ensure_stage_u(w, count); if (r) return r;
     CU(cudaMemcpyAsync(w->d_stage_u, values, (size_t)count * 4, cudaMemcpyHostToDevice, w->stream));
-    rb_launch_set_flags(w->P.flags, w->d_stage_u, first, count, mask & (RB_ACTIVE | RB_GRAVITY | RB_CONTACT), w->stream); w->launches++;
+    rb_launch_set_flags(w->P.flags, w->d_stage_u, w->d_inv, first, count, mask & (RB_ACTIVE | RB_GRAVITY | RB_CONTACT), w->stream); w->launches++;
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
@@ -582,7 +654,7 @@ int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4)
     r = ensure_force(w); if (r) return r;
     r = ensure_stage(w, count); if (r) return r;
     CU(cudaMemcpyAsync(w->d_stage, xyz4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
-    rb_launch_apply_force(w->P.flags, w->d_stage, w->P.force, first, count, 1, w->stream); w->launches++;
+    rb_launch_apply_force(w->P.flags, w->d_stage, w->P.force, w->d_inv, first, count, 1, w->stream); w->launches++;
     return RB_OK;
 }
 int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
@@ -591,15 +663,15 @@ int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4
     r = ensure_angular(w); if (r) return r;
     r = ensure_stage(w, count); if (r) return r;
     CU(cudaMemcpyAsync(w->d_stage, xyz4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
-    rb_launch_apply_force(w->P.flags, w->d_stage, w->P.torque, first, count, 0, w->stream); w->launches++;
+    rb_launch_apply_force(w->P.flags, w->d_stage, w->P.torque, w->d_inv, first, count, 0, w->stream); w->launches++;
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
 int rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ap4, const float* av4) {
     int r = range_ok(w, first, count); if (r) return r;
     r = ensure_angular(w); if (r) return r;
-    if (ap4) CU(cudaMemcpyAsync(w->P.apos + first, ap4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
-    if (av4) CU(cudaMemcpyAsync(w->P.avel + first, av4, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
+    if (ap4) { r = write_rows_f4(w, w->P.apos, first, count, ap4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
+    if (av4) { r = write_rows_f4(w, w->P.avel, first, count, av4); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
@@ -609,7 +681,7 @@ int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t
     int r;
     if (force4) { r = rb_set_force(w, 0, w->n_owned_host, force4); if (r) return r; }
     r = rb_step(w, ms); if (r) return r;
-    if (pos4) CU(cudaMemcpyAsync(pos4, w->P.pos, (size_t)w->n_owned_host * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (pos4) { r = read_rows_f4(w, w->P.pos, pos4, w->n_owned_host); if (r) return r; }
     CU(cudaMemcpyAsync(w->h_counters + RB_C_NCONTACT, w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     w->contacts_last = w->h_counters[RB_C_NCONTACT];
@@ -625,7 +697,7 @@ int rb_set_body_ids(rb_world* w, const uint32_t* ids, uint32_t n) {
 }
 int rb_get_body_ids(rb_world* w, uint32_t* out) {
     if (!w || !w->built || !out) return RB_ERR_INVALID;
-    if (!w->d_gid) { for (uint32_t i = 0; i < w->n_owned_host; i++) out[i] = i; return RB_OK; }
+    if (!w->d_dn) { for (uint32_t i = 0; i < w->n_owned_host; i++) out[i] = i; return RB_OK; }   // rows are reported in id order
     int r = rb_dist_refresh_counts(w); if (r) return r;
     CU(cudaMemcpy(out, w->d_gid, (size_t)w->n_owned_host * 4, cudaMemcpyDeviceToHost));
     return RB_OK;
