@@ -34,6 +34,8 @@ extern "C" int enqueue_broadphase_tail(rb_world* w);
 
 extern thread_local std::string g_create_error;
 
+#define RB_PIPE 3     // depth of the pipelined host round trip (results arrive RB_PIPE - 1 calls later)
+
 struct DevBuf { void* p = nullptr; size_t bytes = 0; };
 
 struct rb_world {
@@ -76,6 +78,12 @@ struct rb_world {
     bool profile = false;
     float kernel_ms[5] = { 0, 0, 0, 0, 0 };
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    // ---- pipelined host round trip (rb_step_host_async): copy engines overlap the tick ----
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t pe_h2d[RB_PIPE] = {}, pe_force[RB_PIPE] = {}, pe_step[RB_PIPE] = {}, pe_d2h[RB_PIPE] = {};
+    float4* p_force[RB_PIPE] = {}; float4* p_pos[RB_PIPE] = {};
+    unsigned long long* p_cnt = nullptr;     // pinned, RB_PIPE entries
+    uint64_t p_calls = 0;
     RbDist* dist = nullptr;
     rb_stats_t dist_stats;
     // ---- slab worlds (rb_dist.cu) ----

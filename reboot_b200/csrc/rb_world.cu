@@ -58,6 +58,11 @@ void rb_world_destroy(rb_world* w) {
     for (auto& b : w->allocs) cudaFree(b.p);
     if (w->h_counters) cudaFreeHost(w->h_counters);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    if (w->s_h2d) {
+        cudaStreamSynchronize(w->s_h2d); cudaStreamSynchronize(w->s_d2h);
+        for (int k = 0; k < RB_PIPE; k++) { cudaEventDestroy(w->pe_h2d[k]); cudaEventDestroy(w->pe_force[k]); cudaEventDestroy(w->pe_step[k]); cudaEventDestroy(w->pe_d2h[k]); }
+        cudaStreamDestroy(w->s_h2d); cudaStreamDestroy(w->s_d2h); cudaFreeHost(w->p_cnt);
+    }
     if (w->own_stream) cudaStreamDestroy(w->stream);
     delete w;
 }
@@ -500,6 +505,7 @@ int rb_detect(rb_world* w) {
 int rb_sync(rb_world* w) {
     if (!w) return RB_ERR_INVALID;
     CU(cudaStreamSynchronize(w->stream));
+    if (w->s_d2h) { CU(cudaStreamSynchronize(w->s_h2d)); CU(cudaStreamSynchronize(w->s_d2h)); }
     return RB_OK;
 }
 
@@ -686,6 +692,59 @@ int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t
     CU(cudaStreamSynchronize(w->stream));
     w->contacts_last = w->h_counters[RB_C_NCONTACT];
     if (n_contacts) *n_contacts = w->contacts_last;
+    return RB_OK;
+}
+
+// Pipelined per-tick host round trip: the H2D copy of this tick's forces, the tick itself and the D2H copy
+// of its positions run on three streams over a ring of RB_PIPE (3) staging buffers, so the two copy
+// engines overlap the compute of neighbouring ticks -- the reference's own threading model (its physics
+// thread produces, its render thread reads a little behind under Physics::_lock). The call returns once
+// the results of the call made RB_PIPE - 1 = 2 calls earlier have landed in the host buffers passed to
+// THAT call; callers rotate three pos4 buffers and finish with rb_sync().
+int rb_step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    const size_t nb = w->n_owned_host;
+    if (!w->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&w->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&w->s_d2h, cudaStreamNonBlocking));
+        for (int k = 0; k < RB_PIPE; k++) {
+            CU(cudaEventCreateWithFlags(&w->pe_h2d[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->pe_force[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&w->pe_step[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->pe_d2h[k], cudaEventDisableTiming));
+            ALLOC(w->p_force[k], nb); ALLOC(w->p_pos[k], nb);
+        }
+        CU(cudaMallocHost((void**)&w->p_cnt, RB_PIPE * sizeof(unsigned long long)));
+        for (int k = 0; k < RB_PIPE; k++) w->p_cnt[k] = 0;
+    }
+    const int b = (int)(w->p_calls % RB_PIPE);
+    int r;
+    if (force4) {
+        r = ensure_force(w); if (r) return r;
+        if (w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->s_h2d, w->pe_force[b], 0));   // staging b was consumed RB_PIPE calls ago
+        CU(cudaMemcpyAsync(w->p_force[b], force4, nb * 16, cudaMemcpyHostToDevice, w->s_h2d));
+        CU(cudaEventRecord(w->pe_h2d[b], w->s_h2d));
+        CU(cudaStreamWaitEvent(w->stream, w->pe_h2d[b], 0));
+        rb_launch_apply_force(w->P.flags, w->p_force[b], w->P.force, w->d_inv, 0, (uint32_t)nb, 1, w->stream); w->launches++;
+        CU(cudaEventRecord(w->pe_force[b], w->stream));
+    }
+    r = rb_step(w, ms); if (r) return r;
+    if (w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->stream, w->pe_d2h[b], 0));         // output staging b was read RB_PIPE calls ago
+    if (pos4) {
+        if (w->d_inv) { rb_launch_rows_to_ids_f4(w->P.pos, w->P.gid, w->p_pos[b], (uint32_t)nb, w->stream); w->launches++; }
+        else CU(cudaMemcpyAsync(w->p_pos[b], w->P.pos, nb * 16, cudaMemcpyDeviceToDevice, w->stream));
+    }
+    CU(cudaEventRecord(w->pe_step[b], w->stream));
+    CU(cudaStreamWaitEvent(w->s_d2h, w->pe_step[b], 0));
+    if (pos4) CU(cudaMemcpyAsync(pos4, w->p_pos[b], nb * 16, cudaMemcpyDeviceToHost, w->s_d2h));
+    CU(cudaMemcpyAsync(&w->p_cnt[b], w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->s_d2h));
+    CU(cudaEventRecord(w->pe_d2h[b], w->s_d2h));
+    // results of the call made RB_PIPE - 1 calls ago
+    if (w->p_calls >= RB_PIPE - 1) {
+        const int d = (int)((w->p_calls + 1) % RB_PIPE);
+        CU(cudaEventSynchronize(w->pe_d2h[d]));
+        if (n_contacts_done) *n_contacts_done = w->p_cnt[d];
+    } else if (n_contacts_done) *n_contacts_done = 0;
+    w->p_calls++;
     return RB_OK;
 }
 

@@ -335,3 +335,29 @@ def test_phased_kernel_bit_identical_to_first_generation_kernel(World, monkeypat
     assert s1["tests_st"] == s2["tests_st"] and s1["hits_st"] == s2["hits_st"] and s1["hits_ss"] == s2["hits_ss"] and s1["tests_ss"] == s2["tests_ss"]
     assert s2["hits_ss"] > 1000 and s2["hits_st"] > 100000
     w1.close(); w2.close()
+
+
+def test_pipelined_host_round_trip_matches_blocking(World):
+    """rb_step_host_async (3-deep ring, copies overlapping the tick) delivers, two calls later, exactly what
+    the blocking rb_step_host delivers: positions in id order and the contact count."""
+    from reboot_b200 import scenes
+    from reboot_b200._lib import ptr
+    sc = scenes.falling_spheres(30000, 120, 2.0, 0.5, (0.3, 3.0), True, 8, "pipe")
+    w1, w2 = World(sc), World(sc)
+    nb = sc.n_bodies
+    rng = np.random.default_rng(1)
+    force = np.zeros((nb, 4), np.float32); force[:, 0] = rng.uniform(-3, 3, nb); force[:, 2] = rng.uniform(-3, 3, nb)
+    p_sync = np.zeros((nb, 4), np.float32)
+    p_async = [np.zeros((nb, 4), np.float32) for _ in range(3)]
+    hist = []
+    n2 = C.c_uint64()
+    for k in range(70):
+        n1 = w1.step_host(5, force, p_sync)
+        hist.append((p_sync.copy(), n1))
+        assert w2.L.rb_step_host_async(w2.h, 5, ptr(force), ptr(p_async[k % 3]), C.byref(n2)) == 0
+        if k >= 2:
+            assert np.array_equal(bits(p_async[(k - 2) % 3]), bits(hist[k - 2][0])) and n2.value == hist[k - 2][1], k
+    w2.sync()
+    assert np.array_equal(bits(p_async[69 % 3]), bits(p_sync))
+    assert np.array_equal(bits(w1.state()["pos"]), bits(w2.state()["pos"])) and hist[-1][1] > 1000
+    w1.close(); w2.close()
