@@ -810,40 +810,78 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
         T.cand_st = 0;      // the generic walk recounts
         sphere_vs_triangles<RESOLVE>(P, S, H, T, gA, xyz(oa), oa.w, fc, frm, hit_any);
     }
-    const uint32_t nmax = __reduce_max_sync(0xffffffffu, nc);
-    float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = a4, c4 = a4;
-    uint32_t t = 0;
-    if (nc) { t = s_cand[0][threadIdx.x]; const float4* tp = P.tri + 3ull * t; a4 = __ldg(tp); b4 = __ldg(tp + 1); c4 = __ldg(tp + 2); }
-    for (uint32_t j = 0; j < nmax; ++j) {       // warp-uniform trip count, explicit reconvergence
-        // the next triangle's vertices are requested before this one is tested
-        float4 na4 = a4, nb4 = b4, nc4 = c4; uint32_t nt_ = t;
-        if (j + 1 < nc) { nt_ = s_cand[j + 1][threadIdx.x]; const float4* tp = P.tri + 3ull * nt_; na4 = __ldg(tp); nb4 = __ldg(tp + 1); nc4 = __ldg(tp + 2); }
-        if (j < nc) {
-            f3 TA = xyz(a4), TB = xyz(b4), TC = xyz(c4);
-            f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
-            T.tests_st++;
-            if (sphere_triangle_detect(c, oa.w, TA, TB, TC)) {
-                hit_any = true;
-                T.hits_st++;
-                f3 q = closest_point(c, TA, TB, TC);
-                f3 ov = sub3(c, q);
-                float dist = mag3(ov);
-                f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
-                record_hit(P, H, gA, RB_TRI_BIT | t, oa.w - dist, o, oa.w);
-                if (RESOLVE) {
-                    // triangle normal normalize((C-A)x(B-A)) is static: pre-computed at build (w lanes)
-                    f3 normal = mk3(a4.w, b4.w, c4.w);
-                    f3 delta = sub3(add3(mul3(o, oa.w * P.pushout), q), c);
-                    float ncomp = dot3(S.v, normal);
-                    f3 rv = sub3(S.v, mul3(normal, ncomp));
-                    body_set_position(S, add3(S.p, delta));
-                    S.v = rv;
-                    S.flags |= RB_F_CONTACT;
+    // Speculative, load-balanced rounds. Until a sphere is hit its pose does not change, so ALL of its
+    // remaining staged triangles can be tested at once: every round pools the remaining tests of the
+    // warp, deals them out 32 at a time (the owner's pose travels by shuffle), and each owner then takes
+    // its FIRST hit in canonical order, resolves it, and re-enters the next round with the triangles
+    // behind that hit -- exactly the sequential test/resolve sequence, without idle lanes.
+    {
+        __shared__ uint32_t s_mask[RB_BLOCK];
+        const uint32_t wbase = threadIdx.x & ~31u;
+        uint32_t j0 = 0;
+        while (true) {
+            const uint32_t rem = j0 < nc ? nc - j0 : 0;
+            if (!__any_sync(0xffffffffu, rem != 0)) break;
+            const uint32_t incl = warp_incl_scan(rem, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
+            s_mask[threadIdx.x] = 0;
+            __syncwarp();
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t item = base + lane;
+                uint32_t lo = 0;                                   // owner = number of lanes whose inclusive count is <= item
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, incl, (lo + st - 1) & 31); if (v <= item) lo += st; }
+                const uint32_t owner = lo & 31;
+                const uint32_t o_excl = __shfl_sync(0xffffffffu, incl - rem, owner), o_j0 = __shfl_sync(0xffffffffu, j0, owner);
+                const float ox = __shfl_sync(0xffffffffu, c.x, owner), oy = __shfl_sync(0xffffffffu, c.y, owner), oz = __shfl_sync(0xffffffffu, c.z, owner);
+                const float orad = __shfl_sync(0xffffffffu, oa.w, owner);
+                if (item < total) {
+                    const uint32_t k = item - o_excl;
+                    const uint32_t t = s_cand[o_j0 + k][wbase + owner];
+                    const float4* tp = P.tri + 3ull * t;
+                    float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                    if (sphere_triangle_detect(mk3(ox, oy, oz), orad, xyz(a4), xyz(b4), xyz(c4))) atomicOr(&s_mask[wbase + owner], 1u << k);
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            uint32_t m = s_mask[threadIdx.x];
+            if (rem) {
+                // sequential accounting: the tests up to and including the first hit are the ones the
+                // one-at-a-time order would have run at this pose
+                const uint32_t first = m ? (uint32_t)__ffs(m) - 1 : rem;
+                T.tests_st += (RESOLVE && m) ? first + 1 : rem;
+                if (!RESOLVE) j0 = nc; else j0 = m ? j0 + first + 1 : nc;
+                const uint32_t jbase = RESOLVE ? j0 - (m ? first + 1 : 0) : 0;
+                while (m) {                                        // RESOLVE: exactly one pass; detection: every hit
+                    const uint32_t k = (uint32_t)__ffs(m) - 1;
+                    m = RESOLVE ? 0u : (m & (m - 1));
+                    const uint32_t t = s_cand[(RESOLVE ? jbase : 0) + k][threadIdx.x];
+                    const float4* tp = P.tri + 3ull * t;
+                    float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                    f3 TA = xyz(a4), TB = xyz(b4), TC = xyz(c4);
+                    hit_any = true;
+                    T.hits_st++;
+                    f3 q = closest_point(c, TA, TB, TC);
+                    f3 ov = sub3(c, q);
+                    float dist = mag3(ov);
+                    f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
+                    record_hit(P, H, gA, RB_TRI_BIT | t, oa.w - dist, o, oa.w);
+                    if (RESOLVE) {
+                        // triangle normal normalize((C-A)x(B-A)) is static: pre-computed at build (w lanes)
+                        f3 normal = mk3(a4.w, b4.w, c4.w);
+                        f3 delta = sub3(add3(mul3(o, oa.w * P.pushout), q), c);
+                        float ncomp = dot3(S.v, normal);
+                        f3 rv = sub3(S.v, mul3(normal, ncomp));
+                        body_set_position(S, add3(S.p, delta));
+                        S.v = rv;
+                        S.flags |= RB_F_CONTACT;
+                    }
                 }
             }
+            __syncwarp();
         }
-        a4 = na4; b4 = nb4; c4 = nc4; t = nt_;
-        __syncwarp();
     }
     // ---------------- P5: flags, write-back ----------------
     if (RESOLVE && valid) {
