@@ -113,6 +113,8 @@ struct RbReorder {
     const uint32_t* src_flags; uint32_t* dst_flags;
     const uint32_t* src_gid; uint32_t* dst_gid; uint32_t* inv;
     uint32_t* rest_counter;
+    const uint32_t* owned_rank;   // slab worlds: exclusive count of owned entries in front of each sorted slot (+ total at the end)
+    uint32_t n_slots;             // capacity of owned_rank - 1
 };
 
 struct f3 { float x, y, z; };

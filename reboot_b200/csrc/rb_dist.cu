@@ -170,6 +170,14 @@ static int dist_alloc(rb_world* w) {
     return RB_OK;
 }
 
+int rb_dist_rows_moved(rb_world* w) {
+    if (!w->dist) return RB_OK;
+    RbDistParams& D = w->dist->D;
+    D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj);
+    CU(cudaMemcpyAsync(const_cast<RbDistParams*>(w->P.dp), &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
+    return RB_OK;
+}
+
 void rb_dist_destroy(RbDist* d) {
     if (!d) return;
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
@@ -312,7 +320,10 @@ static int group_collide(rb_world** ws, int n, int ms, int do_integrate, int res
         CU(cudaSetDevice(w->cfg.device));
         int r = dist_phase_b(w); if (r) return r;
         r = rb_collide_only(w, resolve != 0); if (r) return r;
-        if (do_integrate) w->steps++;
+        if (do_integrate) {
+            w->steps++;
+            if (w->reorder_every > 0 && w->steps % (uint64_t)w->reorder_every == 0) { r = rb_reorder_rows_now(w); if (r) return r; }
+        }
     }
     return RB_OK;
 }

@@ -24,12 +24,15 @@ void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* o
 void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st);
 void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st);
 void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st);
+void rb_launch_owned_flags(const RbParams& P, uint32_t* out, uint32_t n, cudaStream_t st);
 void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
 // multi-GPU (rb_dist.cu)
 struct RbDist;
 int rb_dist_step_exchange(rb_world* w, int ms);
 void rb_dist_destroy(RbDist* d);
 int rb_dist_refresh_counts(rb_world* w);
+extern "C" int rb_reorder_rows_now(rb_world* w);
+int rb_dist_rows_moved(rb_world* w);   // the per-body arrays were swapped: refresh the device copy of the halo parameters
 extern "C" int enqueue_broadphase_tail(rb_world* w);
 
 extern thread_local std::string g_create_error;
@@ -75,6 +78,7 @@ struct rb_world {
     uint32_t* d_gid_alt = nullptr; uint32_t* d_flags_alt = nullptr; uint32_t* d_rest = nullptr;
     float4* alt4[RB_REORDER_MAX] = {};
     float4* d_io4 = nullptr; uint32_t* d_io_u = nullptr;   // id-ordered staging for host IO
+    uint32_t* d_oflag = nullptr; uint32_t* d_orank = nullptr; uint8_t* d_oscan = nullptr; size_t oscan_bytes = 0;   // slab re-ordering scratch
     bool profile = false;
     float kernel_ms[5] = { 0, 0, 0, 0, 0 };
     cudaEvent_t ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };

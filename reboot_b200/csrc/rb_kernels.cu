@@ -958,17 +958,31 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_ids_to_rows_f4_kernel(const float
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB_BLOCK) rb_reorder_kernel(RbParams P, RbReorder R) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.nb) return;
+    const uint32_t n_rows = P.dn ? P.dn[0] : P.nb;
+    if (i >= n_rows) return;
     uint32_t k = P.key[i];
     uint32_t j;
-    if (k != RB_NONE) j = P.col_start[k] + P.rank[i];                                    // its slot in the last sort
-    else j = P.col_start[P.scx * P.scz] + atomicAdd(R.rest_counter, 1u);                 // not in the grid: behind
+    if (R.owned_rank) {      // slab world: ghosts share the sorted array, owned rows keep their relative order
+        const uint32_t n_sorted = P.col_start[P.scx * P.scz];
+        if (k != RB_NONE) j = R.owned_rank[P.col_start[k] + P.rank[i]];
+        else j = R.owned_rank[n_sorted] + atomicAdd(R.rest_counter, 1u);
+    } else {
+        if (k != RB_NONE) j = P.col_start[k] + P.rank[i];                                    // its slot in the last sort
+        else j = P.col_start[P.scx * P.scz] + atomicAdd(R.rest_counter, 1u);                 // not in the grid: behind
+    }
 #pragma unroll 1
     for (int a = 0; a < R.n4; ++a) R.dst4[a][j] = R.src4[a][i];
     R.dst_flags[j] = R.src_flags[i];
     uint32_t g = R.src_gid ? R.src_gid[i] : i;
     R.dst_gid[j] = g;
-    R.inv[g] = j;
+    if (R.inv) R.inv[g] = j;
+}
+// slab worlds: 1 for sorted slots holding an owned row, 0 for ghosts (and beyond the sorted range)
+__global__ void __launch_bounds__(RB_BLOCK) rb_owned_flags_kernel(RbParams P, uint32_t* out, uint32_t n) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t n_sorted = P.col_start[P.scx * P.scz];
+    out[s] = (s < n_sorted && (P.sorted_id[s] & ~RB_TRI_BIT) < P.dn[0]) ? 1u : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1036,6 +1050,9 @@ void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32
 }
 void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st) {
     if (count) rb_ids_to_rows_f4_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(in, inv, rows, first, count);
+}
+void rb_launch_owned_flags(const RbParams& P, uint32_t* out, uint32_t n, cudaStream_t st) {
+    if (n) rb_owned_flags_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(P, out, n);
 }
 void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st) {
     if (P.nb) rb_reorder_kernel<<<cdiv(P.nb, RB_BLOCK), RB_BLOCK, 0, st>>>(P, *(const RbReorder*)R);

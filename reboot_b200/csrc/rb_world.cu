@@ -265,15 +265,24 @@ static int write_rows_f4(rb_world* w, float4* rows, uint32_t first, uint32_t cou
     return RB_OK;
 }
 
+static int reorder_rows(rb_world* w);
 // K7 driver: put the body rows in the order of the last counting sort (needs a valid sort: call right
 // after a broadphase). Single-sphere, single-GPU worlds only.
+int rb_reorder_rows_now(rb_world* w) { return reorder_rows(w); }
 static int reorder_rows(rb_world* w) {
     RbParams& P = w->P;
-    if (!P.single || w->d_dn || P.nb == 0) return RB_OK;
+    if (!P.single || P.nb == 0) return RB_OK;
+    const bool slab = w->d_dn != nullptr;
     const size_t nb = P.nb;
     float4** cur[RB_REORDER_MAX] = { &P.pos, &P.vel, &P.mt, &P.pt, const_cast<float4**>(&P.sph_obj), const_cast<float4**>(&P.wt), &P.force, &P.torque, &P.apos, &P.avel };
-    if (!w->d_inv) {
-        ALLOC(w->d_inv, nb); ALLOC(w->d_gid, nb); ALLOC(w->d_gid_alt, nb); ALLOC(w->d_flags_alt, nb); ALLOC(w->d_rest, 4);
+    if (!w->d_gid_alt) {
+        if (!slab) { ALLOC(w->d_inv, nb); ALLOC(w->d_gid, nb); }
+        ALLOC(w->d_gid_alt, nb); ALLOC(w->d_flags_alt, nb); ALLOC(w->d_rest, 4);
+        if (slab) {
+            size_t tiles = rb_scan_tiles((uint32_t)nb + 1) + 1;
+            ALLOC(w->d_oflag, nb + 8); ALLOC(w->d_orank, nb + 8);
+            w->oscan_bytes = 16 + tiles * 8; ALLOC(w->d_oscan, w->oscan_bytes);
+        }
     }
     RbReorder R; memset(&R, 0, sizeof R);
     int slot_of[RB_REORDER_MAX];
@@ -284,16 +293,24 @@ static int reorder_rows(rb_world* w) {
         R.src4[R.n4] = *cur[a]; R.dst4[R.n4] = w->alt4[a]; slot_of[a] = R.n4++;
     }
     R.src_flags = P.flags; R.dst_flags = w->d_flags_alt;
-    R.src_gid = P.gid; R.dst_gid = P.gid == w->d_gid ? w->d_gid_alt : w->d_gid; R.inv = w->d_inv; R.rest_counter = w->d_rest;
+    uint32_t* gid_cur = const_cast<uint32_t*>(P.gid);
+    R.src_gid = P.gid; R.dst_gid = gid_cur == w->d_gid ? w->d_gid_alt : w->d_gid; R.inv = slab ? nullptr : w->d_inv; R.rest_counter = w->d_rest;
     CU(cudaMemsetAsync(w->d_rest, 0, 4, w->stream));
+    if (slab) {
+        // owned rows keep their relative order in the sorted array: rank = exclusive count of owned slots
+        CU(cudaMemsetAsync(w->d_oscan, 0, w->oscan_bytes, w->stream));
+        rb_launch_owned_flags(P, w->d_oflag, (uint32_t)nb, w->stream);
+        w->launches += 1 + rb_launch_scan_lookback(w->d_oflag, (uint32_t)nb, w->d_orank, (unsigned long long*)(w->d_oscan + 16), (uint32_t*)w->d_oscan, w->stream);
+        R.owned_rank = w->d_orank; R.n_slots = (uint32_t)nb;
+    }
     rb_launch_reorder(P, &R, w->stream); w->launches++;
     CU(cudaGetLastError());
     for (int a = 0; a < RB_REORDER_MAX; a++) if (slot_of[a] >= 0) { float4* old = *cur[a]; *cur[a] = w->alt4[a]; w->alt4[a] = old; }
     { uint32_t* old = P.flags; P.flags = w->d_flags_alt; w->d_flags_alt = old; }
     P.gid = R.dst_gid;
+    if (slab) { w->d_gid = R.dst_gid; w->d_gid_alt = gid_cur; rb_dist_rows_moved(w); }
     return RB_OK;
 }
-
 static int enqueue_broadphase(rb_world* w, int do_integrate);
 int rb_build(rb_world* w) {
     if (!w) return RB_ERR_INVALID;
@@ -799,6 +816,7 @@ int rb_collide_only(rb_world* w, bool resolve) { return enqueue_collide(w, resol
 #ifndef RB_HAVE_DIST
 int rb_dist_step_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 int rb_dist_refresh_counts(rb_world*) { return RB_OK; }
+int rb_dist_rows_moved(rb_world*) { return RB_OK; }
 void rb_dist_destroy(RbDist*) {}
 extern "C" int rb_dist_unique_id(const char*, uint8_t*) { g_create_error = "multi-GPU slabs not built"; return RB_ERR_INVALID; }
 extern "C" int rb_dist_init(rb_world* w, const char*, const uint8_t*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
