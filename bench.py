@@ -37,6 +37,15 @@ C3_SPHERES = 1_000_000
 C3_G = 1000
 
 
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        return float(json.load(open(p))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -315,8 +324,8 @@ def run_ours(args):
                     "note": "rb_step_host_async: every tick uploads that tick's forces from pinned host memory, runs the tick and downloads its positions + contact count; copies go through a 3-deep ring on their own streams so they overlap neighbouring ticks (blocking_ms_per_step = the same with nothing overlapped)"},
             "gpu_launches": int(l1 - l0),
             "clocks": clk,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "rb_collide_kernel<single,resolve>", "kernel_ms": collide_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic() if N == 1 else None,
+                         "kernel": "rb_collide_single_kernel<resolve>", "kernel_ms": collide_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          "kernel_ms_all": {k: v / args.steps for k, v in kms.items()}},
             "contact_tests_per_s": N * tests_step * 1000.0 / ms_step, "contact_tests_per_step": tests_step, "contacts_per_step": contacts,

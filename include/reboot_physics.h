@@ -52,7 +52,7 @@ typedef struct rb_config {
     float    friction;       /* 0.95  : math/include/StateVector.h:30 */
     float    pushout;        /* 1.0001: math/src/GeometryMath.cpp:509 */
     float    ss_damp;        /* 0.1   : math/src/GeometryMath.cpp:537,549 */
-    float    margin_cap;     /* broadphase candidate margin cap in world units (ours; 0.25) */
+    float    margin_cap;     /* broadphase candidate margin cap in world units (ours); 0 = auto: half the largest radius */
     int32_t  device;         /* CUDA device ordinal */
     void*    stream;         /* cudaStream_t to enqueue on; NULL = the world creates its own */
     uint64_t max_contacts;   /* device contact-buffer capacity; 0 = 4 per sphere + 1024 */

@@ -16,7 +16,7 @@ const char* rb_version(void) { return "reboot_b200 0.1 (sm_100a)"; }
 void rb_config_default(rb_config* c) {
     memset(c, 0, sizeof *c);
     c->world_half = 1000.0f; c->gravity = -9.8f; c->friction = 0.95f; c->pushout = 1.0001f; c->ss_damp = 0.1f;
-    c->margin_cap = 0.25f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
+    c->margin_cap = 0.0f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
     c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1; c->rm_max_hint = 0.0f;
 }
 
@@ -26,7 +26,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     if (!out) return fail(nullptr, RB_ERR_INVALID, "rb_world_create: out is NULL");
     *out = nullptr;
     rb_config c; if (cfg) c = *cfg; else rb_config_default(&c);
-    if (!(c.world_half > 0) || !(c.margin_cap >= 0) || c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks)
+    if (!(c.world_half > 0) || !(c.margin_cap >= 0.f) || c.nranks < 1 || c.rank < 0 || c.rank >= c.nranks)
         return fail(nullptr, RB_ERR_INVALID, "rb_world_create: bad config");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -329,7 +329,8 @@ int rb_build(rb_world* w) {
     if (slab) {
         float rr = 0.f; for (size_t i = 3; i < w->h_obj.size(); i += 4) rr = std::max(rr, std::fabs(w->h_obj[i]));
         rr = std::max(rr, w->cfg.rm_max_hint);
-        double frac = 2.0 * (rr + w->cfg.margin_cap) / std::max(1e-3, (double)(w->cfg.slab_hi - w->cfg.slab_lo));
+        double mc = w->cfg.margin_cap > 0.f ? w->cfg.margin_cap : 0.5 * rr;
+        double frac = 2.0 * (rr + mc) / std::max(1e-3, (double)(w->cfg.slab_hi - w->cfg.slab_lo));
         ghost_cap = (uint32_t)std::min<double>(nb / 2 + 8192.0, std::max(8192.0, 16.0 * nb * frac));
     }
     w->ghost_cap = ghost_cap;
@@ -356,6 +357,8 @@ int rb_build(rb_world* w) {
         }
     }
     if (slab && w->cfg.rm_max_hint > rmax) rmax = w->cfg.rm_max_hint;   // every rank must use the same reach
+    if (!(w->cfg.margin_cap > 0.f)) w->cfg.margin_cap = std::max(0.5f * rmax, 1e-3f);   // auto: half the largest radius
+    P.margin_cap = w->cfg.margin_cap;
     P.rm_max = rmax + w->cfg.margin_cap;
     // ---- sphere column grid geometry ----
     {

@@ -32,7 +32,7 @@ def test_struct_layouts():
     # the reference's compile-time constants (Physics.cpp:7-9, StateVector.h:28-30, GeometryMath.cpp:509,537)
     assert cfg.world_half == 1000.0 and abs(cfg.gravity + 9.8) < 1e-6 and abs(cfg.friction - 0.95) < 1e-7
     assert abs(cfg.pushout - 1.0001) < 1e-7 and abs(cfg.ss_damp - 0.1) < 1e-8
-    assert cfg.nranks == 1 and cfg.slab_lo == -1000.0 and cfg.slab_hi == 1000.0
+    assert cfg.nranks == 1 and cfg.slab_lo == -1000.0 and cfg.slab_hi == 1000.0 and cfg.margin_cap == 0.0
 
 
 def test_no_cpu_fallback_without_device():
