@@ -689,23 +689,33 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
             const bool work = i < e;
             if (!__any_sync(0xffffffffu, work)) break;
             if (work) {
-                float4 o = P.sorted[i];
-                float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
-                if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
-                    uint32_t Bl = P.sorted_id[i] & ~RB_TRI_BIT;
-                    if (Bl != A) {
-                        T.cand_ss++;
-                        uint32_t g = rb_gid(P, Bl);
-                        if (RESOLVE || g > gA) {           // detection: the lower id reports the pair
-                            npart++;
-                            // keep the RB_SSCAND_MAX smallest ids, ascending
+                // up to 4 entries of the row per iteration, all requested before the first is looked at
+                const uint32_t nb4 = min(e - i, 4u);
+                float4 ov[4];
 #pragma unroll
-                            for (int k = 0; k < RB_SSCAND_MAX; ++k)
-                                if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = Bl; g = tg; Bl = tl; }
+                for (uint32_t u = 0; u < 4; ++u) ov[u] = P.sorted[min(i + u, e - 1)];
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) {
+                    if (u < nb4) {
+                        const float4 o = ov[u];
+                        float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+                        if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
+                            uint32_t Bl = P.sorted_id[i + u] & ~RB_TRI_BIT;
+                            if (Bl != A) {
+                                T.cand_ss++;
+                                uint32_t g = rb_gid(P, Bl);
+                                if (RESOLVE || g > gA) {           // detection: the lower id reports the pair
+                                    npart++;
+                                    // keep the RB_SSCAND_MAX smallest ids, ascending
+#pragma unroll
+                                    for (int k = 0; k < RB_SSCAND_MAX; ++k)
+                                        if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = Bl; g = tg; Bl = tl; }
+                                }
+                            }
                         }
                     }
                 }
-                ++i;
+                i += nb4;
             }
             __syncwarp();
         }
@@ -744,16 +754,26 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
                 const bool work = cur[k] < end[k];
                 if (!__any_sync(0xffffffffu, work)) break;
                 if (work) {
+                    // two entries per iteration (an aligned heightfield column holds exactly two), both requested up front
+                    const uint32_t n2 = min(end[k] - cur[k], 2u);
                     const float4* ep = P.tcol_ent + 2ull * cur[k];
-                    float4 e0 = __ldg(ep), e1 = __ldg(ep + 1);          // (minx,maxx,minz,maxz) (miny,maxy,id,-)
-                    cur[k]++;
-                    T.cand_st++;
-                    bool keep = !(e0.x > fc.x + frm || e0.y < fc.x - frm) && !(e0.z > fc.z + frm || e0.w < fc.z - frm) &&
-                                !(e1.x > fc.y + frm || e1.y < fc.y - frm);
-                    if (keep) {
-                        if (nc == RB_CAND_MAX) { st_slow = true; cur[k] = end[k]; }    // too many: the generic walk takes over
-                        else s_cand[nc++][threadIdx.x] = __float_as_uint(e1.z);
+                    float4 ea0 = __ldg(ep), ea1 = __ldg(ep + 1);          // (minx,maxx,minz,maxz) (miny,maxy,id,-)
+                    float4 eb0 = ea0, eb1 = ea1;
+                    if (n2 == 2) { eb0 = __ldg(ep + 2); eb1 = __ldg(ep + 3); }
+#pragma unroll
+                    for (uint32_t u = 0; u < 2; ++u) {
+                        if (u < n2) {
+                            const float4 e0 = u ? eb0 : ea0, e1 = u ? eb1 : ea1;
+                            T.cand_st++;
+                            bool keep = !(e0.x > fc.x + frm || e0.y < fc.x - frm) && !(e0.z > fc.z + frm || e0.w < fc.z - frm) &&
+                                        !(e1.x > fc.y + frm || e1.y < fc.y - frm);
+                            if (keep) {
+                                if (nc == RB_CAND_MAX) st_slow = true;        // too many: the generic walk takes over
+                                else s_cand[nc++][threadIdx.x] = __float_as_uint(e1.z);
+                            }
+                        }
                     }
+                    cur[k] = st_slow ? end[k] : cur[k] + n2;
                 }
                 __syncwarp();
             }
