@@ -91,6 +91,10 @@ struct RbParams {
     unsigned long long contact_cap;
     unsigned long long* counters;
     unsigned long long* stripes;  // RB_STRIPES x RB_C_COUNT striped copies of the cumulative test / hit counters
+    // ---- enumerate -> resolve hand-over lists (single-sphere worlds, slot-major) ----
+    uint32_t* e_hdr;              // npart | nc << 8 | slow << 16
+    uint32_t* e_pg; uint32_t* e_pl;   // [RB_SSCAND_MAX][ns] partner global id / local row
+    uint32_t* e_cand;             // [RB_CAND_MAX][ns] staged triangle ids, ascending
     // ---- deferred commit (compound-body path) ----
     uint32_t* ch_body; float4* ch_pos; float4* ch_vel; float4* ch_mt; float4* ch_pt; uint32_t* ch_flags;
     // ---- slab ownership (multi-GPU) ----

@@ -71,7 +71,7 @@ struct rb_world {
     // ---- bookkeeping ----
     uint64_t steps = 0, launches = 0;
     uint64_t contacts_last = 0;
-    int collide_variant = 2;
+    int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)
     // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----
     int reorder_every = 32;                  // ticks between re-orderings (0 = never)
     uint32_t* d_inv = nullptr;               // body id -> row

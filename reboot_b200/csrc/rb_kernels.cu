@@ -639,8 +639,11 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
     }
 }
 
-template <bool RESOLVE>
-__global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
+// MODE 0: everything in one launch. MODE 1: enumerate only (P1 + P3) -- pure pointer chasing, compiled for
+// twice the resident warps, results parked in global lists. MODE 2: test / resolve only (P2, P4, P5) from
+// those lists. The split (default) lets each half run at its own occupancy; results are identical.
+template <bool RESOLVE, int MODE>
+__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -670,7 +673,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
 #pragma unroll
     for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
     uint32_t npart = 0;
-    {
+    if (MODE != 2) {
         // every lane walks its (up to 3) z-rows entry by entry; the loop is warp-uniform so the lanes
         // stay in lock step (independent thread scheduling would otherwise let sub-groups run ahead)
         uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0, ni = 0, ne = 0;
@@ -726,7 +729,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
     // canonical order; a triangle registered in two columns shows up twice).
     uint32_t nc = 0;
     bool st_slow = false;
-    {
+    if (MODE != 2) {
         uint32_t cur[4], end[4];
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) cur[k] = end[k] = 0;
@@ -794,6 +797,24 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_COLLIDE_MINBLOCKS) rb_collide_sin
         nc = nu;
         __syncwarp();
     }
+    if (MODE == 1) {        // park the lists (slot-major, coalesced) and stop: the resolve launch picks them up
+        if (tid < P.ns) {
+            P.e_hdr[tid] = valid ? (min(npart, 255u) | (nc << 8) | (st_slow ? 0x10000u : 0u)) : 0u;
+#pragma unroll
+            for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + tid] = pg[k]; P.e_pl[(size_t)k * P.ns + tid] = pl[k]; }
+            for (uint32_t j = 0; j < nc; ++j) P.e_cand[(size_t)j * P.ns + tid] = s_cand[j][threadIdx.x];
+        }
+        collide_epilogue(P, H, T, lane);
+        return;
+    }
+    if (MODE == 2 && valid) {
+        const uint32_t hdr = P.e_hdr[tid];
+        npart = hdr & 0xffu; nc = (hdr >> 8) & 0xffu; st_slow = (hdr & 0x10000u) != 0;
+#pragma unroll
+        for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < npart) { pg[k] = P.e_pg[(size_t)k * P.ns + tid]; pl[k] = P.e_pl[(size_t)k * P.ns + tid]; }
+        for (uint32_t j = 0; j < nc; ++j) s_cand[j][threadIdx.x] = P.e_cand[(size_t)j * P.ns + tid];
+    }
+    if (MODE == 2) __syncwarp();
     // ---------------- lazy state load ----------------
     const bool need = valid && (npart || nc || st_slow);
     if (need) {
@@ -1038,9 +1059,13 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
         if (variant == 1) {     // first-generation kernel, kept for A/B checks (RB_COLLIDE_V1=1)
             if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
             else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
-        } else {
-            if (resolve) rb_collide_single_kernel<true><<<g, RB_BLOCK, 0, st>>>(P);
-            else rb_collide_single_kernel<false><<<g, RB_BLOCK, 0, st>>>(P);
+        } else if (variant == 2 || !P.e_hdr) {     // fused phases in one launch
+            if (resolve) rb_collide_single_kernel<true, 0><<<g, RB_BLOCK, 0, st>>>(P);
+            else rb_collide_single_kernel<false, 0><<<g, RB_BLOCK, 0, st>>>(P);
+        } else {                                   // enumerate at high occupancy, then test / resolve
+            if (resolve) { rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P); rb_collide_single_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P); }
+            else { rb_collide_single_kernel<false, 1><<<g, RB_BLOCK, 0, st>>>(P); rb_collide_single_kernel<false, 2><<<g, RB_BLOCK, 0, st>>>(P); }
+            return 2;
         }
         return 1;
     }

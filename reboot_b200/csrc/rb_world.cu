@@ -44,6 +44,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     w->h_geom_start.push_back(0);
     w->h_body_start.push_back(0);
     { const char* v = getenv("RB_COLLIDE_V1"); if (v && *v == '1') w->collide_variant = 1; }
+    { const char* v = getenv("RB_COLLIDE_VARIANT"); if (v && *v) w->collide_variant = atoi(v); }
     { const char* v = getenv("RB_SCAN_V1"); if (v && *v == '1') w->scan_variant = 1; }
     { const char* v = getenv("RB_REORDER_EVERY"); if (v && *v) w->reorder_every = atoi(v); }
     *out = w;
@@ -428,6 +429,11 @@ int rb_build(rb_world* w) {
         uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
         ALLOC(cb, nb); ALLOC(c1, nb); ALLOC(c2, nb); ALLOC(c3, nb); ALLOC(c4, nb); ALLOC(cf, nb);
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
+    }
+    if (P.single && P.ns) {     // enumerate -> resolve hand-over lists
+        uint32_t *eh, *eg, *el, *ec;
+        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4); ALLOC(ec, (size_t)P.ns * 12);
+        P.e_hdr = eh; P.e_pg = eg; P.e_pl = el; P.e_cand = ec;
     }
     // ---- contacts + counters ----
     P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(slab ? cap : ns) * 4 + 1024;
