@@ -16,15 +16,64 @@
 #pragma once
 #include "../reboot_physics.h"
 
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <functional>
 #include <map>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
 namespace reboot {
+
+// engine/include/MasterClock.h:30-31
+const int KINEMATICS_TIME = 5;   // kinematics time in milliseconds
+
+// MasterClock (engine/include/MasterClock.h:33-74, engine/src/MasterClock.cpp:31-61, 127-131): the fixed-rate
+// physics thread. Subscribers are called in subscription order every KINEMATICS_TIME ms with the tick length;
+// the remainder of the tick is slept, an overrun is printed like the reference does. With the B200 path the
+// per-Entity _updateKinematics subscriptions disappear: Physics::run() subscribes ONE function, the tick.
+class MasterClock {
+    std::vector<std::function<void(int)>> _kinematicsRateFuncs;
+    std::mutex _kinematicsRateLock;
+    std::thread* _physicsThread = nullptr;
+    std::atomic<bool> _running{false};
+    std::atomic<unsigned long> _ticks{0}, _overruns{0};
+    bool _reportOverruns = true;
+    void _physicsProcess() {
+        while (_running) {
+            auto start = std::chrono::high_resolution_clock::now();
+            {
+                std::lock_guard<std::mutex> g(_kinematicsRateLock);
+                for (auto& func : _kinematicsRateFuncs) if (func) func(KINEMATICS_TIME);
+            }
+            _ticks++;
+            auto end = std::chrono::high_resolution_clock::now();
+            double milliseconds = std::chrono::duration<double, std::milli>(end - start).count();
+            double left = static_cast<double>(KINEMATICS_TIME) - milliseconds;
+            if (left > 0) std::this_thread::sleep_for(std::chrono::duration<double, std::milli>(left));
+            else if (left < 0) { _overruns++; if (_reportOverruns) std::printf("Extra time being used on physics calculations: %f\n", -left); }
+        }
+    }
+public:
+    MasterClock() = default;
+    ~MasterClock() { stop(); }
+    static MasterClock* instance() { static MasterClock c; return &c; }
+    // Physics clock time update (MasterClock.cpp:127-131)
+    void subscribeKinematicsRate(std::function<void(int)> func) { std::lock_guard<std::mutex> g(_kinematicsRateLock); _kinematicsRateFuncs.push_back(func); }
+    void clearKinematicsSubscribers() { std::lock_guard<std::mutex> g(_kinematicsRateLock); _kinematicsRateFuncs.clear(); }
+    // Kicks off the physics thread (MasterClock.cpp:23-29 starts three threads; only the physics one is on this path)
+    void run() { if (_running.exchange(true)) return; _physicsThread = new std::thread(&MasterClock::_physicsProcess, this); }
+    void stop() { if (!_running.exchange(false)) return; _physicsThread->join(); delete _physicsThread; _physicsThread = nullptr; }
+    void reportOverruns(bool on) { _reportOverruns = on; }
+    unsigned long ticks() const { return _ticks; }
+    unsigned long overruns() const { return _overruns; }
+};
 
 class Vector4 {
     float _vec[4];
@@ -167,9 +216,10 @@ public:
         ck(_w, rb_build(_w));
         _built = true;
     }
-    // Physics::run -- physics/src/Physics.cpp:18-24 subscribes _physicsProcess to the 5 ms kinematics
-    // tick; here the caller (or a MasterClock-style thread) drives tick() itself.
-    void run() {}
+    // Physics::run -- physics/src/Physics.cpp:18-24: subscribe the step to the 5 ms kinematics tick of a
+    // MasterClock (NULL: the caller drives tick() itself). One subscription replaces every Entity's
+    // _updateKinematics subscription plus _physicsProcess.
+    void run(MasterClock* clock = nullptr) { if (clock) clock->subscribeKinematicsRate([this](int ms) { tick(ms); }); }
     // one kinematics tick: every Entity::_updateKinematics(ms) then Physics::_physicsProcess(ms)
     void tick(int milliseconds = 5) { ck(_w, rb_step(_w, milliseconds)); }
     // refresh every Entity's StateVector / model translations from the device

@@ -156,6 +156,13 @@ int         rb_contact_count(rb_world* w, uint64_t* n);
 int         rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags);
 /* Entity::getMVP / getPrevMVP model-matrix translations ([3],[7],[11]) as n_bodies * 4 floats */
 int         rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4);
+/* Entity::getMVP()->getModelBuffer() / getPrevMVP()->getModelBuffer() (model/include/Entity.h:66-68,
+ * model/src/Entity.cpp:134-140, 388-390): the full row-major 4x4 model matrices translation(p) * W of every
+ * body, current and previous (motion blur), n_bodies * 16 floats each, in body-id order. Either may be NULL. */
+int         rb_get_model_matrices(rb_world* w, float* model16, float* prev16);
+/* The same buffers left on the device for a renderer to map (CUDA-GL/Vulkan interop): device pointers to
+ * n_bodies * 16 floats each, refreshed by this call, valid until the next call or rb_world_destroy. */
+int         rb_export_model_matrices(rb_world* w, const float** model16_dev, const float** prev16_dev);
 /* angular state, n_bodies * 4 floats each */
 int         rb_get_angular(rb_world* w, float* ang_pos4, float* ang_vel4);
 /* world-space spheres as Sphere::getPosition/getRadius see them: n_spheres * 4 floats */

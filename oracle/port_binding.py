@@ -54,6 +54,7 @@ def lib():
         L.orc_reset_counters.argtypes = [C.c_void_p]
         L.orc_leaf_count.argtypes = [C.c_void_p]
         L.orc_get_state.argtypes = [C.c_void_p, _f32p, _f32p, _i32p, _f32p, _f32p]
+        L.orc_get_model_matrices.argtypes = [C.c_void_p, _f32p, _f32p]
         L.orc_get_angular.argtypes = [C.c_void_p, _f32p, _f32p]
         L.orc_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_flags.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -160,6 +161,12 @@ class OrcWorld:
         pt = np.zeros((n, 3), np.float32)
         self.L.orc_get_state(self.h, pos, vel, fl, mt, pt)
         return dict(pos=pos, vel=vel, flags=fl, model_t=mt, prev_t=pt)
+
+    def model_matrices(self):
+        cur = np.zeros((self.n_bodies, 16), np.float32)
+        prev = np.zeros((self.n_bodies, 16), np.float32)
+        self.L.orc_get_model_matrices(self.h, cur, prev)
+        return cur.reshape(-1, 4, 4), prev.reshape(-1, 4, 4)
 
     def angular(self):
         ap = np.zeros((self.n_bodies, 3), np.float32)

@@ -691,6 +691,14 @@ void orc_get_state(orc_world* w, float* pos, float* vel, int32_t* flags, float* 
         if (prev_t) { prev_t[3*b] = e->prev_model.m[3]; prev_t[3*b+1] = e->prev_model.m[7]; prev_t[3*b+2] = e->prev_model.m[11]; }
     }
 }
+/* Entity::getMVP()->getModelBuffer() / getPrevMVP()->getModelBuffer(): first 16 floats, row-major */
+void orc_get_model_matrices(orc_world* w, float* cur16, float* prev16) {
+    for (int b = 0; b < w->n_bodies; b++) {
+        entity_t* e = &w->ent[w->n_geoms + b];
+        memcpy(cur16 + 16 * b, e->model.m, sizeof(float) * 16);
+        memcpy(prev16 + 16 * b, e->prev_model.m, sizeof(float) * 16);
+    }
+}
 void orc_get_angular(orc_world* w, float* apos, float* avel) {
     for (int b = 0; b < w->n_bodies; b++) {
         entity_t* e = &w->ent[w->n_geoms + b];

@@ -49,6 +49,7 @@ def lib():
         L.ref_reset_counters.argtypes = [C.c_void_p]
         L.ref_entity_count.argtypes = [C.c_void_p]
         L.ref_get_state.argtypes = [C.c_void_p, _f32p, _f32p, _i32p, _f32p, _f32p]
+        L.ref_get_model_matrices.argtypes = [C.c_void_p, _f32p, _f32p]
         L.ref_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_set_flags.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.ref_set_force.argtypes = [C.c_void_p, C.c_int, _f32p]
@@ -174,6 +175,14 @@ class RefWorld:
         self.L.ref_get_state(self.h, pos, vel, fl, mt, pt)
         g = self.n_geoms
         return dict(pos=pos[g:], vel=vel[g:], flags=fl[g:], model_t=mt[g:], prev_t=pt[g:])
+
+    def model_matrices(self):
+        n = self.L.ref_entity_count(self.h)
+        cur = np.zeros((n, 16), np.float32)
+        prev = np.zeros((n, 16), np.float32)
+        self.L.ref_get_model_matrices(self.h, cur, prev)
+        g = self.n_geoms
+        return cur[g:].reshape(-1, 4, 4), prev[g:].reshape(-1, 4, 4)
 
     def set_state(self, body, pos=None, vel=None):
         p = None if pos is None else np.ascontiguousarray(pos, np.float32)

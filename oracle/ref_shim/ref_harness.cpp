@@ -275,6 +275,14 @@ void ref_get_state(void* wp, float* pos, float* vel, int32_t* flags, float* mode
         if (prev_t) { prev_t[3*i] = pm[3]; prev_t[3*i+1] = pm[7]; prev_t[3*i+2] = pm[11]; }
     }
 }
+/* full model matrices (first 16 floats of Matrix::getFlatBuffer) of every entity */
+void ref_get_model_matrices(void* wp, float* cur16, float* prev16) {
+    RefWorld* w = (RefWorld*)wp;
+    for (size_t i = 0; i < w->entities.size(); i++) {
+        memcpy(cur16 + 16 * i, w->entities[i]->getMVP()->getModelBuffer(), sizeof(float) * 16);
+        memcpy(prev16 + 16 * i, w->entities[i]->getPrevMVP()->getModelBuffer(), sizeof(float) * 16);
+    }
+}
 void ref_set_state(void* wp, int i, const float* pos3, const float* vel3) {
     StateVector* s = ((RefWorld*)wp)->entities[i]->getStateVector();
     if (pos3) s->setLinearPosition(Vector4(pos3[0], pos3[1], pos3[2], 1.0f));

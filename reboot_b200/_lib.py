@@ -66,6 +66,8 @@ SIGNATURES = {
     "rb_contact_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "rb_get_state": (C.c_int, [_P, _P, _P, _P]),
     "rb_get_model_translations": (C.c_int, [_P, _P, _P]),
+    "rb_get_model_matrices": (C.c_int, [_P, _P, _P]),
+    "rb_export_model_matrices": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
     "rb_get_angular": (C.c_int, [_P, _P, _P]),
     "rb_get_world_spheres": (C.c_int, [_P, _P]),
     "rb_set_state": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),

@@ -25,6 +25,7 @@ void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32
 void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st);
 void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st);
 void rb_launch_owned_flags(const RbParams& P, uint32_t* out, uint32_t n, cudaStream_t st);
+void rb_launch_model_matrices(const float4* w3, const uint32_t* gid, const float4* mt, const float4* pt, float4* cur, float4* prev, uint32_t n, int prev_is_default, cudaStream_t st);
 void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
 // multi-GPU (rb_dist.cu)
 struct RbDist;
@@ -70,6 +71,7 @@ struct rb_world {
     unsigned long long* h_counters = nullptr;               // pinned mirror
     // ---- bookkeeping ----
     uint64_t steps = 0, launches = 0;
+    uint64_t pose_updates = 0;              // ticks / integrations / collisions so far (model-matrix export: _prevMVP default)
     uint64_t contacts_last = 0;
     int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)
     // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----
@@ -78,6 +80,7 @@ struct rb_world {
     uint32_t* d_gid_alt = nullptr; uint32_t* d_flags_alt = nullptr; uint32_t* d_rest = nullptr;
     float4* alt4[RB_REORDER_MAX] = {};
     float4* d_io4 = nullptr; uint32_t* d_io_u = nullptr;   // id-ordered staging for host IO
+    float4* d_w3 = nullptr; float4* d_mm_cur = nullptr; float4* d_mm_prev = nullptr; bool any_w3 = false;   // model-matrix export
     uint32_t* d_oflag = nullptr; uint32_t* d_orank = nullptr; uint8_t* d_oscan = nullptr; size_t oscan_bytes = 0;   // slab re-ordering scratch
     bool profile = false;
     float kernel_ms[5] = { 0, 0, 0, 0, 0 };

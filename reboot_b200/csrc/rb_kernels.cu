@@ -992,6 +992,25 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_ids_to_rows_f4_kernel(const float
     if (i < count) rows[inv[first + i]] = in[i];
 }
 
+// K8: model-matrix export. total = translation(p) * W keeps W's 3x3 and carries the translation the step
+// maintains (mt / pt), so the renderer-facing 4x4 row-major matrices of Entity::_mvp / _prevMVP
+// (model/src/Entity.cpp:134-140, 388-390) are composed here, in body-id order.
+__global__ void __launch_bounds__(RB_BLOCK) rb_model_matrix_kernel(const float4* __restrict__ w3, const uint32_t* __restrict__ gid,
+                                                                  const float4* __restrict__ mt, const float4* __restrict__ pt,
+                                                                  float4* __restrict__ cur, float4* __restrict__ prev, uint32_t n, int prev_is_default) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const uint32_t id = gid ? gid[r] : r;
+    float4 r0 = make_float4(1.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 1.f, 0.f, 0.f), r2 = make_float4(0.f, 0.f, 1.f, 0.f);
+    if (w3) { r0 = w3[3ull * id]; r1 = w3[3ull * id + 1]; r2 = w3[3ull * id + 2]; }      // static, stored in id order
+    const float4 m = mt[r], p = pt[r];
+    float4* c = cur + 4ull * id; float4* q = prev + 4ull * id;
+    c[0] = make_float4(r0.x, r0.y, r0.z, m.x); c[1] = make_float4(r1.x, r1.y, r1.z, m.y); c[2] = make_float4(r2.x, r2.y, r2.z, m.z); c[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+    // before the first tick _prevMVP still holds MVP()'s default model matrix: identity (math/src/Matrix.cpp:7-16)
+    if (prev_is_default) { r0 = make_float4(1.f, 0.f, 0.f, 0.f); r1 = make_float4(0.f, 1.f, 0.f, 0.f); r2 = make_float4(0.f, 0.f, 1.f, 0.f); }
+    q[0] = make_float4(r0.x, r0.y, r0.z, p.x); q[1] = make_float4(r1.x, r1.y, r1.z, p.y); q[2] = make_float4(r2.x, r2.y, r2.z, p.z); q[3] = make_float4(0.f, 0.f, 0.f, 1.f);
+}
+
 // ------------------------------------------------------------------------------------------
 // K7: spatial re-ordering of the body rows (single-sphere worlds). Bodies are gathered and scattered by
 // body row all over the step; keeping the rows in the order of the last counting sort turns those random
@@ -1095,6 +1114,9 @@ void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32
 }
 void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st) {
     if (count) rb_ids_to_rows_f4_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(in, inv, rows, first, count);
+}
+void rb_launch_model_matrices(const float4* w3, const uint32_t* gid, const float4* mt, const float4* pt, float4* cur, float4* prev, uint32_t n, int prev_is_default, cudaStream_t st) {
+    if (n) rb_model_matrix_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(w3, gid, mt, pt, cur, prev, n, prev_is_default);
 }
 void rb_launch_owned_flags(const RbParams& P, uint32_t* out, uint32_t n, cudaStream_t st) {
     if (n) rb_owned_flags_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(P, out, n);

@@ -435,6 +435,18 @@ int rb_build(rb_world* w) {
         ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4); ALLOC(ec, (size_t)P.ns * 12);
         P.e_hdr = eh; P.e_pg = eg; P.e_pl = el; P.e_cand = ec;
     }
+    {   // static 3x3 of every _worldSpaceTransform, kept only when some body is not identity (model-matrix export)
+        bool any = false;
+        for (uint32_t b = 0; b < nb && !any; b++) { const float* W = &w->h_W[(size_t)b * 12]; any = !(W[0] == 1.f && W[1] == 0.f && W[2] == 0.f && W[3] == 0.f && W[4] == 1.f && W[5] == 0.f && W[6] == 0.f && W[7] == 0.f && W[8] == 1.f); }
+        if (any) {
+            std::vector<float> w3((size_t)nb * 12, 0.f);
+            for (uint32_t b = 0; b < nb; b++) for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) w3[(size_t)b * 12 + r * 4 + c] = w->h_W[(size_t)b * 12 + r * 3 + c];
+            ALLOC(w->d_w3, (size_t)nb * 3);
+            CU(cudaMemcpyAsync(w->d_w3, w3.data(), w3.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
+            CU(cudaStreamSynchronize(w->stream));
+            w->any_w3 = true;
+        }
+    }
     // ---- contacts + counters ----
     P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(slab ? cap : ns) * 4 + 1024;
     RbContactRec* d_c; ALLOC(d_c, (size_t)P.contact_cap); P.contacts = d_c;
@@ -504,7 +516,7 @@ int rb_step(rb_world* w, int ms) {
     w->P.dt = (float)ms / 1000.0f;                     // StateVector.cpp:19
     int r = enqueue_broadphase(w, 1); if (r) return r;
     r = enqueue_collide(w, true); if (r) return r;
-    w->steps++;
+    w->steps++; w->pose_updates++;
     if (w->reorder_every > 0 && w->steps % (uint64_t)w->reorder_every == 0) { r = reorder_rows(w); if (r) return r; }
     return RB_OK;
 }
@@ -513,6 +525,7 @@ int rb_integrate(rb_world* w, int ms) {
     CU(cudaSetDevice(w->cfg.device));
     w->P.dt = (float)ms / 1000.0f;
     rb_launch_integrate_bin(w->P, 1, 0, w->stream); w->launches++;
+    w->pose_updates++;
     CU(cudaGetLastError());
     return RB_OK;
 }
@@ -610,6 +623,26 @@ int rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4) {
     size_t nb = w->n_owned_host;
     if (model_t4) { int r = read_rows_f4(w, w->P.mt, model_t4, nb); if (r) return r; }
     if (prev_t4) { int r = read_rows_f4(w, w->P.pt, prev_t4, nb); if (r) return r; }
+    CU(cudaStreamSynchronize(w->stream));
+    return RB_OK;
+}
+int rb_export_model_matrices(rb_world* w, const float** cur_dev, const float** prev_dev) {
+    if (!w || !w->built) return RB_ERR_INVALID;
+    if (w->d_dn) return fail(w, RB_ERR_INVALID, "model-matrix export is not available on slab worlds yet");
+    CU(cudaSetDevice(w->cfg.device));
+    const size_t nb = w->n_owned_host;
+    if (!w->d_mm_cur) { ALLOC(w->d_mm_cur, std::max<size_t>(nb, 1) * 4); ALLOC(w->d_mm_prev, std::max<size_t>(nb, 1) * 4); }
+    rb_launch_model_matrices(w->d_w3, w->d_inv ? w->P.gid : nullptr, w->P.mt, w->P.pt, w->d_mm_cur, w->d_mm_prev, (uint32_t)nb, w->pose_updates == 0 ? 1 : 0, w->stream); w->launches++;
+    CU(cudaGetLastError());
+    if (cur_dev) *cur_dev = (const float*)w->d_mm_cur;
+    if (prev_dev) *prev_dev = (const float*)w->d_mm_prev;
+    return RB_OK;
+}
+int rb_get_model_matrices(rb_world* w, float* model16, float* prev16) {
+    int r = rb_export_model_matrices(w, nullptr, nullptr); if (r) return r;
+    const size_t nb = w->n_owned_host;
+    if (model16) CU(cudaMemcpyAsync(model16, w->d_mm_cur, nb * 64, cudaMemcpyDeviceToHost, w->stream));
+    if (prev16) CU(cudaMemcpyAsync(prev16, w->d_mm_prev, nb * 64, cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }

@@ -183,6 +183,14 @@ class World:
         self._ck(self.L.rb_get_model_translations(self.h, ptr(mt), ptr(pt)))
         return dict(pos=pos[:, :3].copy(), vel=vel[:, :3].copy(), flags=fl.astype(np.int32), model_t=mt[:, :3].copy(), prev_t=pt[:, :3].copy())
 
+    def model_matrices(self):
+        """(model[n,4,4], prev_model[n,4,4]) -- Entity::getMVP / getPrevMVP model buffers, row-major."""
+        n = self.stats()["n_bodies"]
+        cur = np.zeros((n, 16), np.float32)
+        prev = np.zeros((n, 16), np.float32)
+        self._ck(self.L.rb_get_model_matrices(self.h, ptr(cur), ptr(prev)))
+        return cur.reshape(n, 4, 4), prev.reshape(n, 4, 4)
+
     def angular(self):
         n = self.stats()["n_bodies"]
         ap = np.zeros((n, 4), np.float32)

@@ -26,6 +26,19 @@ def test_facade_compiles_and_fails_loudly_without_gpu(tmp_path):
         assert r.returncode != 0 and "no CPU path" in r.stderr
 
 
+def test_master_clock_tick_driver(tmp_path):
+    """MasterClock facade (5 ms kinematics tick, subscription order, overrun accounting) -- no GPU involved."""
+    exe = str(tmp_path / "clock_test")
+    lib = os.path.join(ROOT, "reboot_b200", "csrc")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "clock_test.cpp"),
+                           "-L" + lib, "-lreboot_b200", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()
+    ticks, calls, ms, alternating = int(out[1]), int(out[3]), int(out[5]), int(out[7])
+    assert 25 <= ticks <= 45 and calls == ticks and ms == 5 and alternating == 1      # 210 ms / 5 ms, scheduler slack allowed
+    slow_ticks, slow_over = int(out[12]), int(out[14])
+    assert 4 <= slow_ticks <= 9 and slow_over == slow_ticks
+
+
 @pytest.mark.gpu
 def test_facade_matches_c_abi(tmp_path):
     import torch

@@ -361,3 +361,34 @@ def test_pipelined_host_round_trip_matches_blocking(World):
     assert np.array_equal(bits(p_async[69 % 3]), bits(p_sync))
     assert np.array_equal(bits(w1.state()["pos"]), bits(w2.state()["pos"])) and hist[-1][1] > 1000
     w1.close(); w2.close()
+
+
+def test_model_matrix_export_matches_oracle(World, port):
+    """Entity::getMVP / getPrevMVP model buffers (the step's only product the renderer consumes): full 4x4
+    row-major matrices, incl. W = scale and W with a translation, before the first tick and after ticks."""
+    from reboot_b200 import scenes
+    tris, _ = scenes.terrain_triangles(24, 2.0, 2)
+    w = World(); o = port.OrcWorld()
+    w.add_static_geometry(tris); o.L.orc_add_geom(o.h, tris.shape[0], tris); o.n_geoms = 1
+    rng = np.random.default_rng(3)
+    for k in range(40):
+        X = np.eye(4, dtype=np.float32)
+        if k % 3 == 1:
+            X[0, 0] = X[1, 1] = X[2, 2] = np.float32(1.5)
+        if k % 3 == 2:
+            X[0, 3], X[1, 3], X[2, 3] = np.float32(0.25), np.float32(-0.125), np.float32(0.5)
+        obj = np.array([[0, 0, 0, 0.4]], np.float32)
+        # bodies whose W carries a translation stay airborne here: every resolution teleports them by W.t
+        # (quirk Q1), further than any candidate margin -- that regime is counted in margin_overflow instead
+        p = np.array([rng.uniform(-20, 20), rng.uniform(1.5, 4.0) + (30.0 if k % 3 == 2 else 0.0), rng.uniform(-20, 20)], np.float32)
+        w.add_model(obj, p, (0, 0, 0), 3, X)
+        o.L.orc_add_body(o.h, 1, obj, np.ascontiguousarray(X).ctypes.data_as(C.c_void_p), p, np.zeros(3, np.float32), 1, 1); o.n_bodies += 1
+    w.build(); o.build(False)
+    for nsteps in (0, 1, 60):
+        for _ in range(nsteps):
+            w.step(5); o.step(5, port.ORDER_CANONICAL)
+        a, b = w.model_matrices(), o.model_matrices()
+        assert np.array_equal(bits(a[0].reshape(-1, 16)), bits(b[0].reshape(-1, 16))), nsteps
+        assert np.array_equal(bits(a[1].reshape(-1, 16)), bits(b[1].reshape(-1, 16))), nsteps
+    assert (w.state()["flags"] & 4).any() and w.stats()["margin_overflow"] == 0
+    w.close()

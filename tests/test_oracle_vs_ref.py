@@ -60,3 +60,6 @@ def test_world_transform_scale_and_visualize_channel(ref, port):
     assert set(map(tuple, viz)) >= set((int(r[1]), int(r[3]), int(r[4])) for r in st)
     s1, s2 = w.state(), o.state()
     assert np.allclose(s1["pos"], s2["pos"], rtol=1e-5, atol=1e-5)
+    m1, m2 = w.model_matrices(), o.model_matrices()      # Entity::getMVP / getPrevMVP model buffers
+    assert np.array_equal(bits(m1[0].reshape(-1, 16)), bits(m2[0].reshape(-1, 16))) and np.array_equal(bits(m1[1].reshape(-1, 16)), bits(m2[1].reshape(-1, 16)))
+    assert m1[0][0, 0, 0] == 2.0 and m1[0][0, 3, 3] == 1.0
