@@ -220,7 +220,11 @@ def run_ours(args):
     w.build()
     if N > 1:
         from reboot_b200 import dist as rbdist
-        rbdist.init_world(w, rank, N)
+        halo = os.environ.get("RB_HALO", "p2p")
+        if halo == "nccl":
+            rbdist.init_world(w, rank, N)            # baseline transport: ncclSend / ncclRecv per tick
+        else:
+            rbdist.init_world_p2p(w, rank, N)        # K1 stores into the neighbours' memory over NVLink + flag handshake
 
     def timed(nsteps):
         barrier()
@@ -315,7 +319,7 @@ def run_ours(args):
             "n_gpus": N, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": ("C3: 1,000,000 spheres r=0.5 vs 2,000,000-triangle procedural heightfield (sphere-triangle + sphere-sphere + integration)"
-                                    if N == 1 else f"C3 weak-scaled x{N}: {N}x1M spheres r={sc.meta['r']:.4f} on a {sc.meta['G']}^2-cell terrain ({sc.n_tris} tris replicated), x-slabs + NCCL halo"),
+                                    if N == 1 else f"C3 weak-scaled x{N}: {N}x1M spheres r={sc.meta['r']:.4f} on a {sc.meta['G']}^2-cell terrain ({sc.n_tris} tris replicated), x-slabs, halo = " + os.environ.get("RB_HALO", "p2p") + ""),
                        "regime": f"settled ({args.settle} untimed ticks first)", "dt_ms": DT_MS,
                        "l2": "working set > L2: state + sorted spheres + grids + triangles ~ 0.3 GB per GPU, no flush needed",
                        "unit_note": "value = n_gpus x ticks/s (each tick advances n_gpus C3-sized units)"},

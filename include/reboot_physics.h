@@ -211,6 +211,14 @@ int         rb_dist_unique_id(const char* nccl_lib_path, uint8_t id[RB_NCCL_ID_B
 /* join the communicator; cfg.rank/nranks/slab_lo/slab_hi say which slab this world owns */
 int         rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t id[RB_NCCL_ID_BYTES]);
 
+/* Fused compute + communication halo transport: instead of NCCL send/recv, the integrate kernel stores the
+ * ghost / migrant records straight into the neighbour's buffer over NVLink (CUDA IPC peer memory) and a
+ * flag handshake replaces the collective. Every rank exports its handle, the host passes each rank the
+ * handles of its left / right neighbour (NULL at the world edge). Use instead of rb_dist_init. */
+#define RB_IPC_HANDLE_BYTES 64
+int         rb_dist_p2p_export(rb_world* w, uint8_t handle[RB_IPC_HANDLE_BYTES]);
+int         rb_dist_p2p_connect(rb_world* w, const uint8_t* left_handle, const uint8_t* right_handle);
+
 /* global body ids of a slab world: set before rb_build (default: local insertion index), read back for
  * the bodies currently owned, in the same order as rb_get_state's rows (ownership migrates) */
 int         rb_set_body_ids(rb_world* w, const uint32_t* ids, uint32_t n);

@@ -14,6 +14,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "reboot_physics.h"
 RB_OK, RB_ERR_INVALID, RB_ERR_OOM, RB_ERR_CAPACITY, RB_ERR_CUDA, RB_ERR_NCCL, RB_ERR_NO_DEVICE = range(7)
 RB_ACTIVE, RB_GRAVITY, RB_CONTACT = 1, 2, 4
 RB_NCCL_ID_BYTES = 128
+RB_IPC_HANDLE_BYTES = 64
 
 
 class RbConfig(C.Structure):
@@ -83,6 +84,8 @@ SIGNATURES = {
     "rb_launch_count": (C.c_uint64, [_P]),
     "rb_dist_unique_id": (C.c_int, [C.c_char_p, _P]),
     "rb_dist_init": (C.c_int, [_P, C.c_char_p, _P]),
+    "rb_dist_p2p_export": (C.c_int, [_P, _P]),
+    "rb_dist_p2p_connect": (C.c_int, [_P, _P, _P]),
     "rb_set_body_ids": (C.c_int, [_P, _P, C.c_uint32]),
     "rb_get_body_ids": (C.c_int, [_P, _P]),
     "rb_dist_attach_peers": (C.c_int, [_P, _P, _P]),

@@ -57,15 +57,63 @@ static int load_nccl(rb_world* w, const char* path) {
 }
 #define NC(call) do { int r_ = (call); if (r_ != 0) return fail(w, RB_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
 
+// Exchange transports:
+//   RB_X_NCCL   ncclSend/ncclRecv of the out buffers into the neighbours' in buffers (baseline)
+//   RB_X_P2P    fused compute + communication: K1 stores ghost / migrant records straight into the neighbour's
+//               in buffer through a CUDA-IPC peer pointer (NVLink stores); a one-thread signal kernel then
+//               copies the 16-B header over and raises the neighbour's arrival flag (release, system scope),
+//               the neighbour's wait kernel acquires it. In buffers are double-buffered by tick parity.
+//   RB_X_LOCAL  the same peer stores between slab worlds of one process (tests on one GPU; the host
+//               sequences the phases, so no flag wait)
+enum { RB_X_NONE = 0, RB_X_NCCL = 1, RB_X_P2P = 2, RB_X_LOCAL = 3 };
+
 struct RbDist {
+    int mode = RB_X_NONE;
     ncclComm_t comm = nullptr;
     rb_world* peer[2] = { nullptr, nullptr };       // in-process neighbours (left, right)
-    RbHaloBuf out[2], in[2];
-    RbDistParams D;
+    RbHaloBuf out[2];                                // local staging (NCCL) and local headers (all modes)
+    uint8_t* blob = nullptr; size_t blob_bytes = 0;  // in[side][parity] buffers + arrival flags, one cudaMalloc (IPC-exportable)
+    size_t buf_bytes = 0;
+    uint8_t* peer_blob[2] = { nullptr, nullptr };    // neighbours' blobs (IPC-opened or same-process pointers)
+    bool peer_opened[2] = { false, false };
+    RbDistParams D;                                  // parameters of the current tick (host copy)
+    RbDistParams* d_dp[2] = { nullptr, nullptr };    // device copies, one per parity
     uint32_t ghost_cap = 0, migr_cap = 0;
+    uint32_t halo_step = 0;
     uint32_t* h_dn = nullptr;                        // pinned
     RbHaloHeader* h_hdr = nullptr;                   // pinned, 4 headers (out L/R, in L/R)
+    RbHaloBuf in_buf(int side, int parity) const { RbHaloBuf b; b.base = blob + (size_t)(side * 2 + parity) * buf_bytes; b.bytes = buf_bytes; return b; }
+    static RbHaloBuf buf_at(uint8_t* blob_base, size_t buf_bytes, int side, int parity) { RbHaloBuf b; b.base = blob_base + (size_t)(side * 2 + parity) * buf_bytes; b.bytes = buf_bytes; return b; }
+    uint32_t* arrive(int side) const { return (uint32_t*)(blob + 4 * buf_bytes) + 4 * side; }
+    static uint32_t* arrive_at(uint8_t* blob_base, size_t buf_bytes, int side) { return (uint32_t*)(blob_base + 4 * buf_bytes) + 4 * side; }
+    uint32_t* timeout_flag() const { return (uint32_t*)(blob + 4 * buf_bytes) + 8; }
 };
+
+// header + arrival flag to the neighbour: the records are already there (K1 stored them remotely)
+__global__ void rb_halo_signal_kernel(const RbHaloHeader* out_hdr0, const RbHaloHeader* out_hdr1, RbHaloHeader* peer_hdr0, RbHaloHeader* peer_hdr1,
+                                      uint32_t* peer_arrive0, uint32_t* peer_arrive1, uint32_t step) {
+    if (threadIdx.x || blockIdx.x) return;
+    if (peer_hdr0) *peer_hdr0 = *out_hdr0;
+    if (peer_hdr1) *peer_hdr1 = *out_hdr1;
+    __threadfence_system();
+    if (peer_arrive0) *(volatile uint32_t*)peer_arrive0 = step + 1;
+    if (peer_arrive1) *(volatile uint32_t*)peer_arrive1 = step + 1;
+}
+// wait until both neighbours have delivered this tick (bounded: a dead neighbour raises the timeout flag instead of hanging)
+__global__ void rb_halo_wait_kernel(const uint32_t* arrive0, const uint32_t* arrive1, uint32_t step, uint32_t* timeout_flag) {
+    if (threadIdx.x || blockIdx.x) return;
+    const long long t0 = clock64();
+    const long long limit = 4000000000ll;      // ~2 s of SM clocks
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t* a = side ? arrive1 : arrive0;
+        if (!a) continue;
+        while (*(volatile const uint32_t*)a < step + 1) {
+            if (clock64() - t0 > limit) { *timeout_flag = 1u; break; }
+            __nanosleep(200);
+        }
+    }
+    __threadfence_system();
+}
 
 // K6a (pack ghosts and migrants) is fused into rb_integrate_bin_kernel (rb_kernels.cu).
 
@@ -142,11 +190,16 @@ static int dist_alloc(rb_world* w) {
     d->ghost_cap = w->ghost_cap;
     d->migr_cap = std::max<uint32_t>(1024u, w->ghost_cap / 8);
     size_t bytes = sizeof(RbHaloHeader) + (size_t)d->ghost_cap * sizeof(RbGhostRec) + (size_t)d->migr_cap * sizeof(RbMigrRec);
+    bytes = (bytes + 255) / 256 * 256;
+    d->buf_bytes = bytes;
     for (int k = 0; k < 2; k++) {
-        uint8_t *o, *i; ALLOC(o, bytes); ALLOC(i, bytes);
-        CU(cudaMemsetAsync(o, 0, bytes, w->stream)); CU(cudaMemsetAsync(i, 0, bytes, w->stream));
-        d->out[k].base = o; d->out[k].bytes = bytes; d->in[k].base = i; d->in[k].bytes = bytes;
+        uint8_t* o; ALLOC(o, bytes);
+        CU(cudaMemsetAsync(o, 0, bytes, w->stream));
+        d->out[k].base = o; d->out[k].bytes = bytes;
     }
+    d->blob_bytes = 4 * bytes + 256;
+    ALLOC(d->blob, d->blob_bytes);
+    CU(cudaMemsetAsync(d->blob, 0, d->blob_bytes, w->stream));
     RbGhostRec* sg; uint32_t *em, *cnts; ALLOC(sg, d->ghost_cap); ALLOC(em, d->migr_cap * 2 + 16); ALLOC(cnts, 4);
     CU(cudaMemsetAsync(cnts, 0, 16, w->stream));
     CU(cudaMallocHost((void**)&d->h_dn, 4 * sizeof(uint32_t)));
@@ -155,17 +208,19 @@ static int dist_alloc(rb_world* w) {
     memset(&D, 0, sizeof D);
     for (int k = 0; k < 2; k++) {
         D.out_hdr[k] = d->out[k].hdr(); D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap);
-        D.in_hdr[k] = d->in[k].hdr(); D.in_ghost[k] = d->in[k].ghosts(); D.in_migr[k] = d->in[k].migr(d->ghost_cap);
+        RbHaloBuf ib = d->in_buf(k, 0);
+        D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
     }
     D.self_ghost = sg; D.self_cnt = cnts; D.emig = em; D.emig_cnt = cnts + 1;
     D.ghost_cap = d->ghost_cap; D.migr_cap = d->migr_cap; D.cap_local = w->cap_local;
     D.slab_lo = w->cfg.slab_lo; D.slab_hi = w->cfg.slab_hi;
     D.has_left = w->cfg.rank > 0; D.has_right = w->cfg.rank < w->cfg.nranks - 1;
     D.dn = w->d_dn; D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj); D.counters = w->P.counters;
-    RbDistParams* d_dp; ALLOC(d_dp, 1);
-    CU(cudaMemcpyAsync(d_dp, &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
+    ALLOC(d->d_dp[0], 1); ALLOC(d->d_dp[1], 1);
+    CU(cudaMemcpyAsync(d->d_dp[0], &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d->d_dp[1], &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
     CU(cudaStreamSynchronize(w->stream));
-    w->P.dp = d_dp;
+    w->P.dp = d->d_dp[0];
     w->dist = d;
     return RB_OK;
 }
@@ -174,13 +229,13 @@ int rb_dist_rows_moved(rb_world* w) {
     if (!w->dist) return RB_OK;
     RbDistParams& D = w->dist->D;
     D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj);
-    CU(cudaMemcpyAsync(const_cast<RbDistParams*>(w->P.dp), &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
-    return RB_OK;
+    return RB_OK;      // the per-tick parameter upload (dist_set_tick_params) carries the new pointers
 }
 
 void rb_dist_destroy(RbDist* d) {
     if (!d) return;
     if (d->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(d->comm);
+    for (int k = 0; k < 2; k++) if (d->peer_opened[k] && d->peer_blob[k]) cudaIpcCloseMemHandle(d->peer_blob[k]);
     if (d->h_dn) cudaFreeHost(d->h_dn);
     if (d->h_hdr) cudaFreeHost(d->h_hdr);
     delete d;
@@ -196,8 +251,13 @@ int rb_dist_refresh_counts(rb_world* w) {
         RbDist* d = w->dist;
         CU(cudaMemcpy(&d->h_hdr[0], d->out[0].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&d->h_hdr[1], d->out[1].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(&d->h_hdr[2], d->in[0].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(&d->h_hdr[3], d->in[1].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        const int lp = (d->mode == RB_X_P2P || d->mode == RB_X_LOCAL) ? (int)((d->halo_step + 1) & 1) : 0;   // parity of the last tick
+        CU(cudaMemcpy(&d->h_hdr[2], d->in_buf(0, lp).base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&d->h_hdr[3], d->in_buf(1, lp).base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        if (d->mode == RB_X_P2P) {
+            uint32_t to = 0; CU(cudaMemcpy(&to, d->timeout_flag(), 4, cudaMemcpyDeviceToHost));
+            if (to) return fail(w, RB_ERR_NCCL, "halo exchange timed out waiting for a neighbour's arrival flag");
+        }
         w->dist_stats.halo_sent_last = d->h_hdr[0].n_ghost + d->h_hdr[1].n_ghost;
         w->dist_stats.halo_recv_last = (w->dist->D.has_left ? d->h_hdr[2].n_ghost : 0) + (w->dist->D.has_right ? d->h_hdr[3].n_ghost : 0);
         w->dist_stats.migrated_out_last = d->h_hdr[0].n_migr + d->h_hdr[1].n_migr;
@@ -208,9 +268,29 @@ int rb_dist_refresh_counts(rb_world* w) {
     return RB_OK;
 }
 
-// phase A: integrate + pack (everything before the exchange)
+// parameters of this tick: where K1 stores the records (local staging, or the neighbour's in buffer of this
+// tick's parity) and which in buffers the unpack kernels read
+static int dist_set_tick_params(rb_world* w) {
+    RbDist* d = w->dist; RbDistParams& D = d->D;
+    const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
+    const int p = remote ? (int)(d->halo_step & 1) : 0;
+    for (int k = 0; k < 2; k++) {
+        if (remote && d->mode == RB_X_LOCAL && d->peer[k] && !d->peer_blob[k]) d->peer_blob[k] = d->peer[k]->dist->blob;
+        if (remote && d->peer_blob[k]) {
+            RbHaloBuf pb = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p);      // my left neighbour receives on ITS right side
+            D.out_ghost[k] = pb.ghosts(); D.out_migr[k] = pb.migr(d->ghost_cap);
+        } else { D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap); }
+        RbHaloBuf ib = d->in_buf(k, p);
+        D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
+    }
+    CU(cudaMemcpyAsync(d->d_dp[p], &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
+    w->P.dp = d->d_dp[p];
+    return RB_OK;
+}
+// phase A: integrate + bin + halo pack (everything before the exchange)
 static int dist_phase_a(rb_world* w, int do_integrate) {
     RbDist* d = w->dist; RbParams& P = w->P;
+    int r = dist_set_tick_params(w); if (r) return r;
     CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));
     CU(cudaMemsetAsync(w->d_dn + 1, 0, sizeof(uint32_t), w->stream));                       // n_ghost
     CU(cudaMemsetAsync(d->D.self_cnt, 0, 2 * sizeof(uint32_t), w->stream));                 // self ghosts + emigrants
@@ -219,38 +299,44 @@ static int dist_phase_a(rb_world* w, int do_integrate) {
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;     // integrate + bin + halo pack
     if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));
+    if (d->mode == RB_X_P2P || d->mode == RB_X_LOCAL) {
+        const int p = (int)(d->halo_step & 1);
+        RbHaloHeader* ph[2] = { nullptr, nullptr }; uint32_t* pa[2] = { nullptr, nullptr };
+        for (int k = 0; k < 2; k++) if (d->peer_blob[k]) { ph[k] = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p).hdr(); pa[k] = RbDist::arrive_at(d->peer_blob[k], d->buf_bytes, 1 - k); }
+        rb_halo_signal_kernel<<<1, 32, 0, w->stream>>>(d->out[0].hdr(), d->out[1].hdr(), ph[0], ph[1], pa[0], pa[1], d->halo_step); w->launches++;
+    }
     return RB_OK;
 }
-// phase B: unpack + bin + scan + scatter (everything after the exchange)
+// phase B: unpack + scan + scatter (everything after the exchange)
 static int dist_phase_b(rb_world* w) {
     RbDist* d = w->dist; RbParams& P = w->P;
+    if (d->mode == RB_X_P2P) {
+        rb_halo_wait_kernel<<<1, 32, 0, w->stream>>>(d->peer_blob[0] ? d->arrive(0) : nullptr, d->peer_blob[1] ? d->arrive(1) : nullptr, d->halo_step, d->timeout_flag()); w->launches++;
+    }
     rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->D);
     rb_halo_immigrate_kernel<<<cdiv(2 * d->migr_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
     rb_halo_ghost_kernel<<<cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
     w->launches += 3;
     CU(cudaGetLastError());
-    int r = enqueue_broadphase_tail(w);
-    if (w->profile) {   // halo time = pack .. bin, reported as family 4
-        // ev[5] = before pack, ev[1] = before scan (recorded by the tail)
-    }
-    return r;
+    d->halo_step++;
+    return enqueue_broadphase_tail(w);
 }
 
 static int dist_exchange_nccl(rb_world* w) {
     RbDist* d = w->dist;
     int rank = w->cfg.rank, n = w->cfg.nranks;
     NC(g_nccl.GroupStart());
-    if (rank > 0) { NC(g_nccl.Send(d->out[0].base, d->out[0].bytes, NCCL_UINT8, rank - 1, d->comm, w->stream)); NC(g_nccl.Recv(d->in[0].base, d->in[0].bytes, NCCL_UINT8, rank - 1, d->comm, w->stream)); }
-    if (rank < n - 1) { NC(g_nccl.Send(d->out[1].base, d->out[1].bytes, NCCL_UINT8, rank + 1, d->comm, w->stream)); NC(g_nccl.Recv(d->in[1].base, d->in[1].bytes, NCCL_UINT8, rank + 1, d->comm, w->stream)); }
+    if (rank > 0) { NC(g_nccl.Send(d->out[0].base, d->out[0].bytes, NCCL_UINT8, rank - 1, d->comm, w->stream)); NC(g_nccl.Recv(d->in_buf(0, 0).base, d->buf_bytes, NCCL_UINT8, rank - 1, d->comm, w->stream)); }
+    if (rank < n - 1) { NC(g_nccl.Send(d->out[1].base, d->out[1].bytes, NCCL_UINT8, rank + 1, d->comm, w->stream)); NC(g_nccl.Recv(d->in_buf(1, 0).base, d->buf_bytes, NCCL_UINT8, rank + 1, d->comm, w->stream)); }
     NC(g_nccl.GroupEnd());
     return RB_OK;
 }
 
 int rb_dist_step_exchange(rb_world* w, int do_integrate) {
     RbDist* d = w->dist;
-    if (!d->comm) return fail(w, RB_ERR_INVALID, "this slab world has in-process neighbours: step it with rb_step_group");
+    if (d->mode != RB_X_NCCL && d->mode != RB_X_P2P) return fail(w, RB_ERR_INVALID, "this slab world has in-process neighbours: step it with rb_step_group");
     int r = dist_phase_a(w, do_integrate); if (r) return r;
-    r = dist_exchange_nccl(w); if (r) return r;
+    if (d->mode == RB_X_NCCL) { r = dist_exchange_nccl(w); if (r) return r; }
     return dist_phase_b(w);
 }
 
@@ -272,6 +358,7 @@ int rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t id[RB_NCC
     r = dist_alloc(w); if (r) return r;
     ncclUniqueId_t u; memcpy(&u, id, RB_NCCL_ID_BYTES);
     NC(g_nccl.CommInitRank(&w->dist->comm, w->cfg.nranks, u, w->cfg.rank));
+    w->dist->mode = RB_X_NCCL;
     return RB_OK;
 }
 
@@ -283,6 +370,34 @@ int rb_dist_attach_peers(rb_world* w, rb_world* left, rb_world* right) {
     CU(cudaSetDevice(w->cfg.device));
     int r = dist_alloc(w); if (r) return r;
     w->dist->peer[0] = left; w->dist->peer[1] = right;
+    w->dist->mode = RB_X_LOCAL;
+    return RB_OK;
+}
+
+// Fused compute + communication transport (RB_X_P2P): every rank exports the IPC handle of its halo blob,
+// the host hands each rank its neighbours' handles, and from then on K1 stores straight into them.
+int rb_dist_p2p_export(rb_world* w, uint8_t handle[RB_IPC_HANDLE_BYTES]) {
+    if (!w || !handle) return RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    int r = dist_alloc(w); if (r) return r;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, w->dist->blob));
+    static_assert(sizeof(h) == RB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    memcpy(handle, &h, sizeof h);
+    return RB_OK;
+}
+int rb_dist_p2p_connect(rb_world* w, const uint8_t* left_handle, const uint8_t* right_handle) {
+    if (!w || !w->dist) return w ? fail(w, RB_ERR_INVALID, "rb_dist_p2p_connect before rb_dist_p2p_export") : RB_ERR_INVALID;
+    CU(cudaSetDevice(w->cfg.device));
+    const uint8_t* hs[2] = { left_handle, right_handle };
+    for (int k = 0; k < 2; k++) {
+        if (!hs[k]) continue;
+        cudaIpcMemHandle_t h; memcpy(&h, hs[k], sizeof h);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        w->dist->peer_blob[k] = (uint8_t*)p; w->dist->peer_opened[k] = true;
+    }
+    w->dist->mode = RB_X_P2P;
     return RB_OK;
 }
 
@@ -304,17 +419,7 @@ static int group_collide(rb_world** ws, int n, int ms, int do_integrate, int res
         int r = dist_phase_a(w, do_integrate); if (r) return r;
     }
     for (int i = 0; i < n; i++) { rb_world* w = ws[i]; CU(cudaSetDevice(w->cfg.device)); CU(cudaStreamSynchronize(w->stream)); }
-    for (int i = 0; i < n; i++) {          // exchange: my out[right] -> right's in[left], my out[left] -> left's in[right]
-        rb_world* w = ws[i]; RbDist* d = w->dist;
-        CU(cudaSetDevice(w->cfg.device));
-        for (int k = 0; k < 2; k++) {
-            rb_world* p = d->peer[k];
-            if (!p) continue;
-            RbHaloBuf& dst = p->dist->in[1 - k];
-            CU(cudaMemcpyAsync(dst.base, d->out[k].base, d->out[k].bytes, cudaMemcpyDefault, w->stream));
-        }
-    }
-    for (int i = 0; i < n; i++) { rb_world* w = ws[i]; CU(cudaSetDevice(w->cfg.device)); CU(cudaStreamSynchronize(w->stream)); }
+    // (the records and headers already sit in the neighbours' in buffers: K1 and the signal kernel stored them there)
     for (int i = 0; i < n; i++) {
         rb_world* w = ws[i];
         CU(cudaSetDevice(w->cfg.device));

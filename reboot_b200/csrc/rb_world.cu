@@ -864,5 +864,7 @@ extern "C" int rb_dist_unique_id(const char*, uint8_t*) { g_create_error = "mult
 extern "C" int rb_dist_init(rb_world* w, const char*, const uint8_t*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 extern "C" int rb_dist_attach_peers(rb_world* w, rb_world*, rb_world*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 extern "C" int rb_step_group(rb_world**, int, int) { return RB_ERR_INVALID; }
+extern "C" int rb_dist_p2p_export(rb_world* w, uint8_t*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+extern "C" int rb_dist_p2p_connect(rb_world* w, const uint8_t*, const uint8_t*) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 extern "C" int rb_detect_group(rb_world**, int) { return RB_ERR_INVALID; }
 #endif

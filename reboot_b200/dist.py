@@ -94,6 +94,26 @@ def init_world(w: World, rank: int, nranks: int):
     w._ck(L.rb_dist_init(w.h, path, buf))
 
 
+def init_world_p2p(w: World, rank: int, nranks: int):
+    """Join the slab ring with the fused compute+communication transport: every rank exports the CUDA-IPC
+    handle of its halo blob, handles are all-gathered with torch.distributed, each rank opens its left /
+    right neighbour's blob; from then on the integrate kernel stores ghost / migrant records straight into
+    the neighbour's memory over NVLink (call after w.build())."""
+    import torch
+    import torch.distributed as dist
+    L = w.L
+    buf = (C.c_uint8 * _lib.RB_IPC_HANDLE_BYTES)()
+    w._ck(L.rb_dist_p2p_export(w.h, buf))
+    mine = torch.from_numpy(np.frombuffer(bytes(buf), dtype=np.uint8).copy()).to(torch.device("cuda", torch.cuda.current_device()))
+    allh = [torch.zeros_like(mine) for _ in range(nranks)]
+    dist.all_gather(allh, mine)
+    hs = [t.cpu().numpy().tobytes() for t in allh]
+    left = (C.c_uint8 * _lib.RB_IPC_HANDLE_BYTES).from_buffer_copy(hs[rank - 1]) if rank > 0 else None
+    right = (C.c_uint8 * _lib.RB_IPC_HANDLE_BYTES).from_buffer_copy(hs[rank + 1]) if rank < nranks - 1 else None
+    w._ck(L.rb_dist_p2p_connect(w.h, left, right))
+    dist.barrier()
+
+
 class SlabGroup:
     """N slab worlds of one scene in one process, stepped in lockstep."""
 
