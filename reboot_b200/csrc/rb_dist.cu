@@ -76,7 +76,9 @@ struct RbDist {
     size_t buf_bytes = 0;
     uint8_t* peer_blob[2] = { nullptr, nullptr };    // neighbours' blobs (IPC-opened or same-process pointers)
     bool peer_opened[2] = { false, false };
-    RbDistParams D;                                  // parameters of the current tick (host copy)
+    RbDistParams D;                                  // parity-independent parameters (host copy)
+    RbDistParams Dp[2];                              // per-parity parameters (host copies of d_dp)
+    bool params_valid = false;
     RbDistParams* d_dp[2] = { nullptr, nullptr };    // device copies, one per parity
     uint32_t ghost_cap = 0, migr_cap = 0;
     uint32_t halo_step = 0;
@@ -99,9 +101,8 @@ __global__ void rb_halo_signal_kernel(const RbHaloHeader* out_hdr0, const RbHalo
     if (peer_arrive0) *(volatile uint32_t*)peer_arrive0 = step + 1;
     if (peer_arrive1) *(volatile uint32_t*)peer_arrive1 = step + 1;
 }
-// wait until both neighbours have delivered this tick (bounded: a dead neighbour raises the timeout flag instead of hanging)
-__global__ void rb_halo_wait_kernel(const uint32_t* arrive0, const uint32_t* arrive1, uint32_t step, uint32_t* timeout_flag) {
-    if (threadIdx.x || blockIdx.x) return;
+// bounded wait for the neighbours' arrival flags (a dead neighbour raises the timeout flag instead of hanging)
+__device__ __forceinline__ void halo_wait(const uint32_t* arrive0, const uint32_t* arrive1, uint32_t step, uint32_t* timeout_flag) {
     const long long t0 = clock64();
     const long long limit = 4000000000ll;      // ~2 s of SM clocks
     for (int side = 0; side < 2; ++side) {
@@ -109,7 +110,7 @@ __global__ void rb_halo_wait_kernel(const uint32_t* arrive0, const uint32_t* arr
         if (!a) continue;
         while (*(volatile const uint32_t*)a < step + 1) {
             if (clock64() - t0 > limit) { *timeout_flag = 1u; break; }
-            __nanosleep(200);
+            __nanosleep(100);
         }
     }
     __threadfence_system();
@@ -118,8 +119,9 @@ __global__ void rb_halo_wait_kernel(const uint32_t* arrive0, const uint32_t* arr
 // K6a (pack ghosts and migrants) is fused into rb_integrate_bin_kernel (rb_kernels.cu).
 
 // ---- K6b: swap-remove the emigrants (few per tick; one thread keeps it simple and ordered) --------
-__global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D) {
+__global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t* arrive0, const uint32_t* arrive1, uint32_t step, uint32_t* timeout_flag) {
     if (threadIdx.x || blockIdx.x) return;
+    if (arrive0 || arrive1) halo_wait(arrive0, arrive1, step, timeout_flag);     // fused-transport ticks: the neighbours' records must have landed
     uint32_t m = *D.emig_cnt;
     uint32_t n = D.dn[0];
     // descending order so that the element moved into a hole is never itself a pending hole
@@ -137,40 +139,41 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D) {
     D.counters[RB_C_MIGRATED] = m;
 }
 
-// ---- K6c: immigrants become owned bodies -----------------------------------------------------------
-__global__ void __launch_bounds__(RB_BLOCK) rb_halo_immigrate_kernel(RbParams P, RbDistParams D) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n0 = min(D.in_hdr[0] ? D.in_hdr[0]->n_migr : 0u, D.migr_cap);
-    uint32_t n1 = min(D.in_hdr[1] ? D.in_hdr[1]->n_migr : 0u, D.migr_cap);
-    if (t >= n0 + n1) return;
-    const RbMigrRec m = t < n0 ? D.in_migr[0][t] : D.in_migr[1][t - n0];
-    uint32_t i = atomicAdd(&D.dn[0], 1u);
-    if (i >= D.cap_local) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_OVERFLOW], 1ull); return; }
-    P.pos[i] = m.pos; P.vel[i] = m.vel; P.mt[i] = m.mt; P.pt[i] = m.pt; P.flags[i] = m.flags;
-    D.sph_obj_w[i] = m.obj; D.gid[i] = m.gid;
-    // same world sphere K1 computed on the old owner (same state, same formula)
-    f3 c = mk3(m.obj.x + m.mt.x, m.obj.y + m.mt.y, m.obj.z + m.mt.z);
-    float speed = mag3(xyz(m.vel));
-    float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * P.dt + 0.01f * m.obj.w, 1e-3f));
-    P.ws[i] = make_float4(c.x, c.y, c.z, m.obj.w + margin);
-    uint32_t k = RB_NONE;
-    if ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) {
-        k = rb_col(c.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
-        P.rank[i] = atomicAdd(&P.col_count[k], 1u);
+// ---- K6c: one launch unpacks both kinds. Blocks [0, imm_blocks): immigrants become owned rows (appended
+// behind the owned rows); the other blocks: ghosts, stored from the END of the arrays downwards so that they
+// do not depend on the final owned count. Both are binned on the way. -----------------------------------
+__global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, RbDistParams D, uint32_t imm_blocks) {
+    const uint32_t ghost_floor = D.cap_local - 3u * D.ghost_cap;      // rows [ghost_floor, cap) are reserved for ghosts
+    if (blockIdx.x < imm_blocks) {
+        uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t n0 = min(D.in_hdr[0]->n_migr, D.migr_cap);
+        uint32_t n1 = min(D.in_hdr[1]->n_migr, D.migr_cap);
+        if (t >= n0 + n1) return;
+        const RbMigrRec m = t < n0 ? D.in_migr[0][t] : D.in_migr[1][t - n0];
+        uint32_t i = atomicAdd(&D.dn[0], 1u);
+        if (i >= ghost_floor) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_OVERFLOW], 1ull); return; }
+        P.pos[i] = m.pos; P.vel[i] = m.vel; P.mt[i] = m.mt; P.pt[i] = m.pt; P.flags[i] = m.flags;
+        D.sph_obj_w[i] = m.obj; D.gid[i] = m.gid;
+        // same world sphere K1 computed on the old owner (same state, same formula)
+        f3 c = mk3(m.obj.x + m.mt.x, m.obj.y + m.mt.y, m.obj.z + m.mt.z);
+        float speed = mag3(xyz(m.vel));
+        float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * P.dt + 0.01f * m.obj.w, 1e-3f));
+        P.ws[i] = make_float4(c.x, c.y, c.z, m.obj.w + margin);
+        uint32_t k = RB_NONE;
+        if ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) {
+            k = rb_col(c.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
+            P.rank[i] = atomicAdd(&P.col_count[k], 1u);
+        }
+        P.key[i] = k;
+        return;
     }
-    P.key[i] = k;
-}
-
-// ---- K6d: ghosts go behind the owned bodies ---------------------------------------------------------
-__global__ void __launch_bounds__(RB_BLOCK) rb_halo_ghost_kernel(RbParams P, RbDistParams D) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t n0 = min(D.in_hdr[0] ? D.in_hdr[0]->n_ghost : 0u, D.ghost_cap);
-    uint32_t n1 = min(D.in_hdr[1] ? D.in_hdr[1]->n_ghost : 0u, D.ghost_cap);
+    uint32_t t = (blockIdx.x - imm_blocks) * blockDim.x + threadIdx.x;
+    uint32_t n0 = min(D.in_hdr[0]->n_ghost, D.ghost_cap);
+    uint32_t n1 = min(D.in_hdr[1]->n_ghost, D.ghost_cap);
     uint32_t n2 = min(*D.self_cnt, D.ghost_cap);
     if (t >= n0 + n1 + n2) return;
     const RbGhostRec q = t < n0 ? D.in_ghost[0][t] : (t < n0 + n1 ? D.in_ghost[1][t - n0] : D.self_ghost[t - n0 - n1]);
-    uint32_t i = D.dn[0] + atomicAdd(&D.dn[1], 1u);
-    if (i >= D.cap_local) { atomicSub(&D.dn[1], 1u); atomicAdd(&D.counters[RB_C_OVERFLOW], 1ull); return; }
+    uint32_t i = D.cap_local - 1u - atomicAdd(&D.dn[1], 1u);
     P.ws[i] = q.ws;
     D.sph_obj_w[i] = make_float4(0.f, 0.f, 0.f, q.r);
     D.gid[i] = q.gid;
@@ -200,14 +203,15 @@ static int dist_alloc(rb_world* w) {
     d->blob_bytes = 4 * bytes + 256;
     ALLOC(d->blob, d->blob_bytes);
     CU(cudaMemsetAsync(d->blob, 0, d->blob_bytes, w->stream));
-    RbGhostRec* sg; uint32_t *em, *cnts; ALLOC(sg, d->ghost_cap); ALLOC(em, d->migr_cap * 2 + 16); ALLOC(cnts, 4);
-    CU(cudaMemsetAsync(cnts, 0, 16, w->stream));
+    // per-tick counters sit behind {n_owned, n_ghost} so ONE memset clears them: [2] self ghosts, [3] emigrants, [4..7] / [8..11] out headers
+    RbGhostRec* sg; uint32_t *em; ALLOC(sg, d->ghost_cap); ALLOC(em, d->migr_cap * 2 + 16);
+    uint32_t* cnts = w->d_dn + 2;
     CU(cudaMallocHost((void**)&d->h_dn, 4 * sizeof(uint32_t)));
     CU(cudaMallocHost((void**)&d->h_hdr, 4 * sizeof(RbHaloHeader)));
     RbDistParams& D = d->D;
     memset(&D, 0, sizeof D);
     for (int k = 0; k < 2; k++) {
-        D.out_hdr[k] = d->out[k].hdr(); D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap);
+        D.out_hdr[k] = (RbHaloHeader*)(w->d_dn + 4 + 4 * k); D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap);
         RbHaloBuf ib = d->in_buf(k, 0);
         D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
     }
@@ -229,7 +233,8 @@ int rb_dist_rows_moved(rb_world* w) {
     if (!w->dist) return RB_OK;
     RbDistParams& D = w->dist->D;
     D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj);
-    return RB_OK;      // the per-tick parameter upload (dist_set_tick_params) carries the new pointers
+    w->dist->params_valid = false;
+    return RB_OK;
 }
 
 void rb_dist_destroy(RbDist* d) {
@@ -249,8 +254,7 @@ int rb_dist_refresh_counts(rb_world* w) {
     w->n_owned_host = tmp[0];
     if (w->dist) {
         RbDist* d = w->dist;
-        CU(cudaMemcpy(&d->h_hdr[0], d->out[0].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(&d->h_hdr[1], d->out[1].base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&d->h_hdr[0], w->d_dn + 4, 2 * sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));      // both out headers (tick block)
         const int lp = (d->mode == RB_X_P2P || d->mode == RB_X_LOCAL) ? (int)((d->halo_step + 1) & 1) : 0;   // parity of the last tick
         CU(cudaMemcpy(&d->h_hdr[2], d->in_buf(0, lp).base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(&d->h_hdr[3], d->in_buf(1, lp).base, sizeof(RbHaloHeader), cudaMemcpyDeviceToHost));
@@ -268,55 +272,60 @@ int rb_dist_refresh_counts(rb_world* w) {
     return RB_OK;
 }
 
-// parameters of this tick: where K1 stores the records (local staging, or the neighbour's in buffer of this
-// tick's parity) and which in buffers the unpack kernels read
-static int dist_set_tick_params(rb_world* w) {
-    RbDist* d = w->dist; RbDistParams& D = d->D;
+// device parameter blocks, one per tick parity: where K1 stores the records (local staging, or the neighbour's
+// in buffer of that parity) and which in buffers the unpack kernel reads. Rebuilt only when the transport
+// connects or the body rows move.
+static int dist_upload_params(rb_world* w) {
+    RbDist* d = w->dist;
     const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
-    const int p = remote ? (int)(d->halo_step & 1) : 0;
-    for (int k = 0; k < 2; k++) {
-        if (remote && d->mode == RB_X_LOCAL && d->peer[k] && !d->peer_blob[k]) d->peer_blob[k] = d->peer[k]->dist->blob;
-        if (remote && d->peer_blob[k]) {
-            RbHaloBuf pb = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p);      // my left neighbour receives on ITS right side
-            D.out_ghost[k] = pb.ghosts(); D.out_migr[k] = pb.migr(d->ghost_cap);
-        } else { D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap); }
-        RbHaloBuf ib = d->in_buf(k, p);
-        D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
+    for (int p = 0; p < 2; p++) {
+        RbDistParams D = d->D;
+        for (int k = 0; k < 2; k++) {
+            if (remote && d->mode == RB_X_LOCAL && d->peer[k] && !d->peer_blob[k]) d->peer_blob[k] = d->peer[k]->dist->blob;
+            if (remote && d->peer_blob[k]) {
+                RbHaloBuf pb = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p);      // my left neighbour receives on ITS right side
+                D.out_ghost[k] = pb.ghosts(); D.out_migr[k] = pb.migr(d->ghost_cap);
+            } else { D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap); }
+            RbHaloBuf ib = d->in_buf(k, remote ? p : 0);
+            D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
+        }
+        d->Dp[p] = D;
+        CU(cudaMemcpyAsync(d->d_dp[p], &d->Dp[p], sizeof D, cudaMemcpyHostToDevice, w->stream));
     }
-    CU(cudaMemcpyAsync(d->d_dp[p], &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
-    w->P.dp = d->d_dp[p];
+    d->params_valid = true;
     return RB_OK;
 }
 // phase A: integrate + bin + halo pack (everything before the exchange)
 static int dist_phase_a(rb_world* w, int do_integrate) {
     RbDist* d = w->dist; RbParams& P = w->P;
-    int r = dist_set_tick_params(w); if (r) return r;
+    if (!d->params_valid) { int r = dist_upload_params(w); if (r) return r; }
+    const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
+    const int p = remote ? (int)(d->halo_step & 1) : 0;
+    P.dp = d->d_dp[p];
     CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));
-    CU(cudaMemsetAsync(w->d_dn + 1, 0, sizeof(uint32_t), w->stream));                       // n_ghost
-    CU(cudaMemsetAsync(d->D.self_cnt, 0, 2 * sizeof(uint32_t), w->stream));                 // self ghosts + emigrants
-    CU(cudaMemsetAsync(d->out[0].base, 0, sizeof(RbHaloHeader), w->stream));
-    CU(cudaMemsetAsync(d->out[1].base, 0, sizeof(RbHaloHeader), w->stream));
+    CU(cudaMemsetAsync(w->d_dn + 1, 0, 11 * sizeof(uint32_t), w->stream));    // n_ghost, self ghosts, emigrants, both out headers
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;     // integrate + bin + halo pack
     if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));
-    if (d->mode == RB_X_P2P || d->mode == RB_X_LOCAL) {
-        const int p = (int)(d->halo_step & 1);
-        RbHaloHeader* ph[2] = { nullptr, nullptr }; uint32_t* pa[2] = { nullptr, nullptr };
-        for (int k = 0; k < 2; k++) if (d->peer_blob[k]) { ph[k] = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p).hdr(); pa[k] = RbDist::arrive_at(d->peer_blob[k], d->buf_bytes, 1 - k); }
-        rb_halo_signal_kernel<<<1, 32, 0, w->stream>>>(d->out[0].hdr(), d->out[1].hdr(), ph[0], ph[1], pa[0], pa[1], d->halo_step); w->launches++;
+    // headers (and, on the fused transport, the arrival flags) go out
+    RbHaloHeader* ph[2] = { d->out[0].hdr(), d->out[1].hdr() }; uint32_t* pa[2] = { nullptr, nullptr };
+    if (remote) for (int k = 0; k < 2; k++) {
+        ph[k] = nullptr;
+        if (d->peer_blob[k]) { ph[k] = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p).hdr(); pa[k] = RbDist::arrive_at(d->peer_blob[k], d->buf_bytes, 1 - k); }
     }
+    rb_halo_signal_kernel<<<1, 32, 0, w->stream>>>(d->Dp[p].out_hdr[0], d->Dp[p].out_hdr[1], ph[0], ph[1], pa[0], pa[1], d->halo_step); w->launches++;
     return RB_OK;
 }
 // phase B: unpack + scan + scatter (everything after the exchange)
 static int dist_phase_b(rb_world* w) {
     RbDist* d = w->dist; RbParams& P = w->P;
-    if (d->mode == RB_X_P2P) {
-        rb_halo_wait_kernel<<<1, 32, 0, w->stream>>>(d->peer_blob[0] ? d->arrive(0) : nullptr, d->peer_blob[1] ? d->arrive(1) : nullptr, d->halo_step, d->timeout_flag()); w->launches++;
-    }
-    rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->D);
-    rb_halo_immigrate_kernel<<<cdiv(2 * d->migr_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
-    rb_halo_ghost_kernel<<<cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->D);
-    w->launches += 3;
+    const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
+    const int p = remote ? (int)(d->halo_step & 1) : 0;
+    const bool wait = d->mode == RB_X_P2P;
+    rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->Dp[p], wait && d->peer_blob[0] ? d->arrive(0) : nullptr, wait && d->peer_blob[1] ? d->arrive(1) : nullptr, d->halo_step, d->timeout_flag());
+    const uint32_t imm_blocks = cdiv(2 * d->migr_cap, RB_BLOCK);
+    rb_halo_unpack_kernel<<<imm_blocks + cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->Dp[p], imm_blocks);
+    w->launches += 2;
     CU(cudaGetLastError());
     d->halo_step++;
     return enqueue_broadphase_tail(w);

@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scan_lookback_kernel(const uint32
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= rb_n_local(P)) return;
+    if (P.dn) { if (s >= P.nb || (s >= P.dn[0] && s < P.nb - P.dn[1])) return; }     // slab worlds: owned rows in front, ghosts at the end
+    else if (s >= P.ns) return;
     uint32_t k = P.key[s];
     if (k == RB_NONE) return;
     uint32_t slot = P.col_start[k] + P.rank[s];

@@ -388,8 +388,8 @@ int rb_build(rb_world* w) {
     ALLOC(d_pos, nba); ALLOC(d_vel, nba); ALLOC(d_mt, nba); ALLOC(d_pt, nba); ALLOC(d_flags, nba);
     ALLOC(d_sph, nsa); ALLOC(d_ws, nsa); ALLOC(d_key, nsa); ALLOC(d_rank, nsa); ALLOC(d_sorted, nsa); ALLOC(d_sid, nsa);
     if (slab) {
-        ALLOC(w->d_dn, 4); ALLOC(w->d_gid, nba);
-        uint32_t dn0[4] = { nb, 0, 0, 0 };
+        ALLOC(w->d_dn, 16); ALLOC(w->d_gid, nba);
+        uint32_t dn0[16] = { nb, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
         CU(cudaMemcpyAsync(w->d_dn, dn0, sizeof dn0, cudaMemcpyHostToDevice, w->stream));
         std::vector<uint32_t> ids(nb);
         for (uint32_t i = 0; i < nb; i++) ids[i] = i < w->h_gid.size() ? w->h_gid[i] : i;
