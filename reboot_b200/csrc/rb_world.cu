@@ -505,6 +505,10 @@ static int enqueue_collide(rb_world* w, bool resolve) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
         for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, w->ev[k], w->ev[k + 1])); w->kernel_ms[k] += ms; }
+        if (w->dist) {                                  // slab worlds: split K1 from the halo step (signal, wait, remove, unpack) that follows it
+            float ms = 0; CU(cudaEventElapsedTime(&ms, w->ev[5], w->ev[1]));
+            w->kernel_ms[0] -= ms; w->kernel_ms[4] += ms;
+        }
     }
     CU(cudaGetLastError());
     return RB_OK;
