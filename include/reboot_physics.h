@@ -95,6 +95,11 @@ typedef struct rb_stats_t {
     uint64_t device_bytes;        /* HBM held by this world */
     uint32_t halo_sent_last, halo_recv_last; /* multi-GPU: boundary spheres exchanged in the last step */
     uint32_t migrated_out_last, migrated_in_last;
+    uint32_t list_ticks, list_rebuilds;      /* persistent candidate lists: ticks stepped from lists / ticks that rebuilt them */
+    float    list_skin;                      /* the skin the lists are built with (0: lists not in use) */
+    uint32_t list_hot_last;                  /* bodies that stepped without their list in the last tick (fast movers, crowded bodies) */
+    uint32_t list_rebuild_reason;            /* most recent rebuild: 1 a body entered/left the grid | 2 too many hot bodies | 4 requested by the host side */
+    uint32_t reserved0;
 } rb_stats_t;
 
 void        rb_config_default(rb_config* cfg);

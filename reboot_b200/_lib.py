@@ -44,7 +44,9 @@ class RbStats(C.Structure):
                 ("n_bodies", C.c_uint32), ("n_spheres", C.c_uint32), ("n_geoms", C.c_uint32), ("n_tris", C.c_uint32),
                 ("sphere_cols_x", C.c_uint32), ("sphere_cols_z", C.c_uint32), ("tri_cols_x", C.c_uint32), ("tri_cols_z", C.c_uint32),
                 ("device_bytes", C.c_uint64), ("halo_sent_last", C.c_uint32), ("halo_recv_last", C.c_uint32),
-                ("migrated_out_last", C.c_uint32), ("migrated_in_last", C.c_uint32)]
+                ("migrated_out_last", C.c_uint32), ("migrated_in_last", C.c_uint32),
+                ("list_ticks", C.c_uint32), ("list_rebuilds", C.c_uint32), ("list_skin", C.c_float), ("list_hot_last", C.c_uint32),
+                ("list_rebuild_reason", C.c_uint32), ("reserved0", C.c_uint32)]
 
 
 # every symbol include/reboot_physics.h declares: name -> (restype, argtypes)

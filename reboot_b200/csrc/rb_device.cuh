@@ -14,6 +14,15 @@
 #define RB_F_CONTACT 4u
 #define RB_NONE 0xFFFFFFFFu
 #define RB_TRI_BIT 0x80000000u
+#define RB_HOT_BIT 0x80000000u   // in RbParams::key: the body steps without its list this tick
+
+// words of RbParams::vl
+#define RB_VL_REBUILD 0   // this tick rebuilds the lists (set by K1, cleared by the resolve kernel)
+#define RB_VL_WHY     1   // why: 1 a body entered / left the grid, 2 hot table full, 4 host (first tick, rows moved, state edited)
+#define RB_VL_WHY_LAST 4  // the reasons of the most recent rebuild
+#define RB_VL_NFAST   5   // per-tick kernel only: bodies whose one-tick margin alone exceeds the skin (saturates at hot_cap)
+#define RB_VL_NREBUILD 2  // rebuild ticks so far
+#define RB_VL_NTICK   3   // list ticks so far
 
 // device contact record, 32 B (two 16-B stores)
 struct __align__(16) RbContactRec {
@@ -91,10 +100,22 @@ struct RbParams {
     unsigned long long contact_cap;
     unsigned long long* counters;
     unsigned long long* stripes;  // RB_STRIPES x RB_C_COUNT striped copies of the cumulative test / hit counters
-    // ---- enumerate -> resolve hand-over lists (single-sphere worlds, slot-major) ----
+    // ---- candidate lists, indexed by body row (single-sphere worlds, slot-major) ----
     uint32_t* e_hdr;              // npart | nc << 8 | slow << 16
     uint32_t* e_pg; uint32_t* e_pl;   // [RB_SSCAND_MAX][ns] partner global id / local row
     uint32_t* e_cand;             // [RB_CAND_MAX][ns] staged triangle ids, ascending
+    // ---- persistent lists ("Verlet lists"): the lists above are built for spheres grown by vl_skin and
+    // reused until some body has used its skin up; the sort and the enumeration only run on those ticks ----
+    uint32_t* vl;                 // device words, see RB_VL_*
+    volatile uint32_t* vl_host;   // mapped host copy of {rebuilds, ticks} (heuristics only)
+    float4* ws_build;             // frozen sphere of every row at the last rebuild
+    float vl_skin;
+    // "hot" bodies have used their skin up (fast movers): they enumerate for themselves every tick (triangles
+    // from the static grid, cold partners from the sort of the last rebuild, which is off by less than the
+    // skin) and are published in a coarse (x,z) cell table so that cold bodies and other hot bodies find them
+    uint32_t* hot_head;           // [hcn * hcn] chain heads (index + 1, 0 = empty), then the hot counter word
+    uint32_t* hot_row; uint32_t* hot_next; uint32_t hot_cap;
+    uint32_t hcn; float hc_inv_w;
     // ---- deferred commit (compound-body path) ----
     uint32_t* ch_body; float4* ch_pos; float4* ch_vel; float4* ch_mt; float4* ch_pt; uint32_t* ch_flags;
     // ---- slab ownership (multi-GPU) ----
@@ -108,6 +129,17 @@ struct RbParams {
 
 __device__ __forceinline__ uint32_t rb_n_owned(const RbParams& P) { return P.dn ? P.dn[0] : P.n_owned; }
 __device__ __forceinline__ uint32_t rb_n_local(const RbParams& P) { return P.dn ? P.dn[0] + P.dn[1] : P.ns; }
+// non-binding L1 prefetch of the line holding p (no register, no scoreboard entry)
+#ifndef RB_PREFETCH_LEVEL
+#define RB_PREFETCH_LEVEL 1
+#endif
+__device__ __forceinline__ void rb_prefetch(const void* p) {
+#if RB_PREFETCH_LEVEL == 1
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#elif RB_PREFETCH_LEVEL == 2
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
 __device__ __forceinline__ uint32_t rb_gid(const RbParams& P, uint32_t local) { return P.gid ? P.gid[local] : local; }
 
 // K7 arguments: every per-body array pair (current rows -> re-ordered rows)

@@ -18,6 +18,10 @@ uint32_t rb_scan_tiles(uint32_t n);
 int rb_launch_scan_lookback(const uint32_t* in, uint32_t n, uint32_t* out, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_scatter(const RbParams& P, cudaStream_t st);
 int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st);
+void rb_launch_vl_bin(const RbParams& P, cudaStream_t st);
+void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
+void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st);
 void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, const uint32_t* inv, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
 void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t* inv, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
 void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st);
@@ -73,6 +77,14 @@ struct rb_world {
     uint64_t steps = 0, launches = 0;
     uint64_t pose_updates = 0;              // ticks / integrations / collisions so far (model-matrix export: _prevMVP default)
     uint64_t contacts_last = 0;
+    // persistent candidate lists (single worlds of single-sphere bodies, rb_step only; RB_VERLET=0 turns them off)
+    bool vl_on = false;                      // decided at rb_build
+    bool vl_force = true;                    // the next list tick must rebuild (first tick, rows moved, state edited behind the lists' back)
+    float vl_skin_cfg = 0.0f;                // 0 = auto
+    // adaptive: while the lists get rebuilt on most ticks (free fall, violent scenes) the per-tick kernel is cheaper
+    bool vl_active = true; uint64_t vl_resume_at = 0; uint32_t vl_backoff = 32; uint32_t vl_seen_r = 0, vl_seen_t = 0;
+    int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
+    uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}
     int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)
     // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----
     int reorder_every = 32;                  // ticks between re-orderings (0 = never)

@@ -25,6 +25,13 @@
 // with the translation matrix of :326-338), so a world sphere centre is
 // ((W00*ox + W01*oy) + W02*oz) + (W03 + px): the bracket is pre-summed on the host (sph_obj.xyz).
 // ------------------------------------------------------------------------------------------
+// raise the rebuild flag (many threads may want to in the same tick: only the first few actually store)
+__device__ __forceinline__ void vl_request_rebuild(const RbParams& P, uint32_t why) {
+    volatile uint32_t* v = P.vl;
+    if (!v[RB_VL_REBUILD]) v[RB_VL_REBUILD] = 1u;
+    if (!(v[RB_VL_WHY] & why)) atomicOr(&P.vl[RB_VL_WHY], why);
+}
+
 __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_owned = rb_n_owned(P);
@@ -114,8 +121,37 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
                 uint32_t cx = rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
                 uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
                 k = cz * P.scx + cx;
-                P.rank[s] = atomicAdd(&P.col_count[k], 1u);
+                if (do_bin == 1) P.rank[s] = atomicAdd(&P.col_count[k], 1u);
             } else k = 0;
+            // lists switched off for now (the host sits out a phase of constant rebuilding on the per-tick kernel):
+            // keep reporting how many bodies outrun the skin within one tick, so that it knows when to come back
+            if (do_bin == 1 && P.vl && !(8.0f * speed * dt + 0.01f * r <= P.vl_skin)) {        // a list would not last it ~6 ticks
+                volatile uint32_t* nf = P.vl + RB_VL_NFAST;
+                if (*nf < P.hot_cap) atomicAdd(&P.vl[RB_VL_NFAST], 1u);
+            }
+        }
+        if (do_bin >= 2) {
+            // persistent lists stay valid while every sphere stays inside the skin it was enumerated with:
+            // displacement since the rebuild + this tick's margin <= skin, and nobody entered or left the grid
+            const uint32_t k_prev = P.key[s];
+            const float4 wb = P.ws_build[s];
+            const float ddx = c.x - wb.x, ddy = c.y - wb.y, ddz = c.z - wb.z;
+            const float moved = sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz);
+            if (do_bin == 3) { /* the host asked for a rebuild: nothing to classify */ }
+            else if ((k_prev == RB_NONE) != (k == RB_NONE)) vl_request_rebuild(P, 1u);
+            else if (k != RB_NONE && (!(moved + margin <= P.vl_skin) || wb.w < 0.f)) {      // w < 0: more partners than a list holds
+                // hot: steps without its list this tick. Too many of them and rebuilding is cheaper
+                // (once the table is full nobody queues up on the counter any more).
+                uint32_t* nhot = P.hot_head + P.hcn * P.hcn;
+                const uint32_t h = (*(volatile uint32_t*)nhot >= P.hot_cap) ? P.hot_cap : atomicAdd(nhot, 1u);
+                if (h < P.hot_cap) {
+                    const uint32_t cell = rb_col(c.z, P.half, P.hc_inv_w, P.hcn) * P.hcn + rb_col(c.x, P.half, P.hc_inv_w, P.hcn);
+                    P.hot_row[h] = s;
+                    P.hot_next[h] = atomicExch(&P.hot_head[cell], h + 1u);
+                } else vl_request_rebuild(P, 2u);
+                k |= RB_HOT_BIT;
+            }
+            if (s == 0 && do_bin == 3) { P.vl[RB_VL_REBUILD] = 1u; P.vl[RB_VL_WHY] |= 4u; }
         }
         P.key[s] = k;
     }
@@ -196,9 +232,12 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scan_apply_kernel(const uint32_t*
 // tile aggregate available, 2 = inclusive prefix available. Tile ids are handed out by an atomic ticket
 // so that a tile only ever waits on tiles that are already running. ticket + status are zeroed by the
 // same memset that clears the histogram (they sit right behind it).
-__global__ void __launch_bounds__(RB_BLOCK) rb_scan_lookback_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
-                                                                    unsigned long long* status, uint32_t* ticket) {
+// `cond` (optional): the kernel returns at once unless *cond is set; with `clear_in` the histogram is zeroed as
+// it is read (persistent-list ticks: no per-tick memset, the next rebuild finds a clean histogram).
+__global__ void __launch_bounds__(RB_BLOCK) rb_scan_lookback_kernel(uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out,
+                                                                    unsigned long long* status, uint32_t* ticket, const uint32_t* cond, int clear_in) {
     __shared__ uint32_t s_tile, s_total, s_prefix;
+    if (cond && !*cond) return;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -206,12 +245,13 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scan_lookback_kernel(const uint32
     uint32_t v[RB_SCAN_ITEMS];
     uint32_t sum = 0;
     if (base + RB_SCAN_ITEMS <= n) {
-        const uint4* p = reinterpret_cast<const uint4*>(in + base);
+        uint4* p = reinterpret_cast<uint4*>(in + base);
         uint4 a = p[0], b = p[1];
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        if (clear_in) { p[0] = make_uint4(0u, 0u, 0u, 0u); p[1] = make_uint4(0u, 0u, 0u, 0u); }
     } else {
 #pragma unroll
-        for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) v[i] = (base + i < n) ? in[base + i] : 0;
+        for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) { v[i] = (base + i < n) ? in[base + i] : 0; if (clear_in && base + i < n) in[base + i] = 0; }
     }
 #pragma unroll
     for (uint32_t i = 0; i < RB_SCAN_ITEMS; ++i) sum += v[i];
@@ -261,18 +301,39 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scan_lookback_kernel(const uint32
 // ------------------------------------------------------------------------------------------
 // K3: counting-sort scatter into column order.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P) {
+// vl != 0: persistent-list rebuild tick -- conditional on the rebuild flag, spheres are stored grown by the
+// skin, and the scan's ticket / tile status words are reset for the next rebuild.
+__global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P, int vl, unsigned long long* scan_status, uint32_t* scan_ticket, uint32_t scan_tiles) {
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (vl) {
+        if (!P.vl[RB_VL_REBUILD]) return;
+        for (uint32_t t = s; t < scan_tiles; t += gridDim.x * blockDim.x) scan_status[t] = 0ull;
+        if (s == 0) *scan_ticket = 0u;
+    }
     if (P.dn) { if (s >= P.nb || (s >= P.dn[0] && s < P.nb - P.dn[1])) return; }     // slab worlds: owned rows in front, ghosts at the end
     else if (s >= P.ns) return;
     uint32_t k = P.key[s];
     if (k == RB_NONE) return;
+    k &= ~RB_HOT_BIT;
     uint32_t slot = P.col_start[k] + P.rank[s];
-    P.sorted[slot] = P.ws[s];
+    float4 wsv = P.ws[s];
+    if (vl) wsv.w += P.vl_skin;
+    P.sorted[slot] = wsv;
     // bit 31: the body's contact flag, so that the collide kernel needs no per-body gather for bodies
     // that touch nothing this tick (Physics.cpp:201-207 only needs "was in contact")
     uint32_t body = P.single ? s : P.sph_body[s];
     P.sorted_id[slot] = s | ((P.flags[body] & RB_F_CONTACT) ? RB_TRI_BIT : 0u);
+}
+
+// K1b (persistent lists, rebuild ticks only): histogram rank of every binned row + the poses the new lists
+// are built for. `cond` kernels return at once on the ticks whose lists are still valid.
+__global__ void __launch_bounds__(RB_BLOCK) rb_vl_bin_kernel(RbParams P) {
+    if (!P.vl[RB_VL_REBUILD]) return;
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.ns) return;
+    P.ws_build[s] = P.ws[s];
+    uint32_t k = P.key[s];
+    if (k != RB_NONE) P.rank[s] = atomicAdd(&P.col_count[k & ~RB_HOT_BIT], 1u);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -470,6 +531,27 @@ __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 
     }
 }
 
+// the same over the coarse table of hot bodies (persistent lists, reuse ticks)
+__device__ __forceinline__ void scan_hot_partners(const RbParams& P, uint32_t A, f3 fc, float frm, uint32_t lo,
+                                                  uint32_t& best, uint32_t& best_local, uint32_t& eligible) {
+    const float reach = frm + P.rm_max;
+    const uint32_t hx0 = rb_col(fc.x - reach, P.half, P.hc_inv_w, P.hcn), hx1 = rb_col(fc.x + reach, P.half, P.hc_inv_w, P.hcn);
+    const uint32_t hz0 = rb_col(fc.z - reach, P.half, P.hc_inv_w, P.hcn), hz1 = rb_col(fc.z + reach, P.half, P.hc_inv_w, P.hcn);
+    for (uint32_t hz = hz0; hz <= hz1; ++hz)
+        for (uint32_t hx = hx0; hx <= hx1; ++hx)
+            for (uint32_t h = P.hot_head[hz * P.hcn + hx]; h; h = P.hot_next[h - 1u]) {
+                const uint32_t Bl = P.hot_row[h - 1u];
+                if (Bl == A) continue;
+                const float4 o = P.ws[Bl];
+                float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+                if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
+                const uint32_t B = rb_gid(P, Bl);
+                if (B < lo) continue;
+                eligible++;
+                if (B < best) { best = B; best_local = Bl; }
+            }
+}
+
 template <bool SINGLE, bool RESOLVE>
 __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -614,6 +696,9 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
 #ifndef RB_COLLIDE_MINBLOCKS
 #define RB_COLLIDE_MINBLOCKS 3
 #endif
+#ifndef RB_COLLIDE_MINBLOCKS_LISTS
+#define RB_COLLIDE_MINBLOCKS_LISTS 4      // stepping from lists is lighter: 64 registers, 4 blocks per SM measured faster (3 for the fused kernel)
+#endif
 
 template <bool RESOLVE>
 __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, HitBuf& H, Tally& T,
@@ -644,41 +729,62 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
 // twice the resident warps, results parked in global lists. MODE 2: test / resolve only (P2, P4, P5) from
 // those lists. The split (default) lets each half run at its own occupancy; results are identical.
 template <bool RESOLVE, int MODE>
-__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
+__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : (MODE == 2) ? RB_COLLIDE_MINBLOCKS_LISTS : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
     HitBuf H; H.n = 0;
-    const uint32_t n_sorted = P.col_start[P.scx * P.scz];
-    bool valid = tid < n_sorted;
-    uint32_t A = 0;
+    if (MODE == 1 && P.vl && !P.vl[RB_VL_REBUILD]) return;       // persistent lists still valid: nothing to enumerate
+    bool valid;
+    uint32_t A = 0, keyA = RB_NONE;
     float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
     bool had_contact = false;
-    if (valid) {
-        f0 = P.sorted[tid];
-        uint32_t sid = P.sorted_id[tid];
-        A = sid & ~RB_TRI_BIT; had_contact = (sid & RB_TRI_BIT) != 0;
-        valid = A < rb_n_owned(P);
+    if (MODE == 2) {
+        // one thread per body ROW: the lists are indexed by row and may be older than this tick's poses,
+        // so the frozen sphere comes from K1's world-sphere array, not from a sort
+        A = tid;
+        if (tid < rb_n_owned(P)) keyA = P.key[tid];
+        valid = keyA != RB_NONE;
+        if (valid) { f0 = P.ws[tid]; had_contact = (P.flags[tid] & RB_F_CONTACT) != 0; }
+    } else {
+        const uint32_t n_sorted = P.col_start[P.scx * P.scz];
+        valid = tid < n_sorted;
+        if (valid) {
+            f0 = P.sorted[tid];
+            uint32_t sid = P.sorted_id[tid];
+            A = sid & ~RB_TRI_BIT; had_contact = (sid & RB_TRI_BIT) != 0;
+            valid = A < rb_n_owned(P);
+        }
     }
     // body state is loaded lazily: a body with no partner and no staged triangle needs none of it
+    // (a body that was in contact last tick will almost surely need it: start the gathers now)
+    if (MODE != 1 && valid && had_contact) {
+        rb_prefetch(P.pos + A); rb_prefetch(P.vel + A); rb_prefetch(P.mt + A); rb_prefetch(P.pt + A); rb_prefetch(P.sph_obj + A);
+    }
     BodyState S; S.changed = false; S.flags = 0;
     S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
     float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t gA = valid ? rb_gid(P, A) : 0u;
     const f3 fc = xyz(f0);
     const float frm = f0.w;
+    // persistent lists, reuse tick (warp-uniform): cold bodies step from their lists; hot bodies (they have
+    // used their skin up) enumerate for themselves -- partners from the sort of the last rebuild, whose
+    // entries are off by less than the skin they were grown by, and triangles from the static grid
+    const bool reuse = MODE == 2 && P.vl && !P.vl[RB_VL_REBUILD];
+    const bool hot = reuse && valid && (keyA & RB_HOT_BIT) != 0;
+    const bool enu = (MODE != 2) ? valid : hot;      // lanes that enumerate in this launch
 
     // ---------------- P1: partner scan ----------------
     uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
 #pragma unroll
     for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
     uint32_t npart = 0;
-    if (MODE != 2) {
+    if (MODE != 2 || reuse) {
         // every lane walks its (up to 3) z-rows entry by entry; the loop is warp-uniform so the lanes
         // stay in lock step (independent thread scheduling would otherwise let sub-groups run ahead)
         uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0, ni = 0, ne = 0;
-        if (valid) {
+        if (enu) {
             float reach = frm + P.rm_max;
             cx0 = rb_col(fc.x - reach, -P.s_x0, P.s_inv_w, P.scx); cx1 = rb_col(fc.x + reach, -P.s_x0, P.s_inv_w, P.scx);
             cz = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz); cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
@@ -724,17 +830,64 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOC
             __syncwarp();
         }
     }
+    uint32_t hdr = 0;
+    if (MODE == 2 && valid && !hot) {          // cold (or every body of a launch that follows an enumeration): partners from the list
+        hdr = P.e_hdr[A];
+        npart = hdr & 0xffu;
+#pragma unroll
+        for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < min(npart, (uint32_t)RB_SSCAND_MAX)) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
+    }
+    if (MODE == 2 && reuse) {
+        // hot bodies are nobody's list: everybody looks them up in the coarse cell table (<= 2 x 2 cells)
+        uint32_t hcell[4] = { 0, 0, 0, 0 }, hn = 0;
+        if (valid) {
+            const float reach = frm + P.rm_max;
+            const uint32_t hx0 = rb_col(fc.x - reach, P.half, P.hc_inv_w, P.hcn), hx1 = rb_col(fc.x + reach, P.half, P.hc_inv_w, P.hcn);
+            const uint32_t hz0 = rb_col(fc.z - reach, P.half, P.hc_inv_w, P.hcn), hz1 = rb_col(fc.z + reach, P.half, P.hc_inv_w, P.hcn);
+            hcell[0] = hz0 * P.hcn + hx0; hn = 1;
+            if (hx1 != hx0) hcell[hn++] = hz0 * P.hcn + hx1;
+            if (hz1 != hz0) { hcell[hn++] = hz1 * P.hcn + hx0; if (hx1 != hx0) hcell[hn++] = hz1 * P.hcn + hx1; }
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            uint32_t h = (q < hn) ? __ldg(P.hot_head + hcell[q]) : 0u;
+            while (true) {
+                if (!__any_sync(0xffffffffu, h != 0u)) break;
+                if (h) {
+                    const uint32_t Bl = P.hot_row[h - 1u];
+                    h = P.hot_next[h - 1u];
+                    if (Bl != A) {
+                        const float4 o = P.ws[Bl];
+                        float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+                        if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
+                            uint32_t g = rb_gid(P, Bl), bl = Bl;
+                            bool dup = false;
+#pragma unroll
+                            for (int k = 0; k < RB_SSCAND_MAX; ++k) dup |= (pg[k] == g);
+                            if (!dup) {
+                                T.cand_ss++; npart++;
+#pragma unroll
+                                for (int k = 0; k < RB_SSCAND_MAX; ++k)
+                                    if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = bl; g = tg; bl = tl; }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
     // ---------------- P3: stage sphere-triangle candidates ----------------
     // Column entries carry the triangle's box (32 B, contiguous per column), so the prune needs no
     // vertex gather: survivors are staged, then sorted + de-duplicated (ascending global id = the
     // canonical order; a triangle registered in two columns shows up twice).
     uint32_t nc = 0;
     bool st_slow = false;
-    if (MODE != 2) {
+    if (MODE != 2 || reuse) {
         uint32_t cur[4], end[4];
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) cur[k] = end[k] = 0;
-        if (valid && P.nt) {
+        if (enu && P.nt) {
             uint32_t cx0 = rb_col(fc.x - frm, P.half, P.t_inv_w, P.tcx), cx1 = rb_col(fc.x + frm, P.half, P.t_inv_w, P.tcx);
             uint32_t cz0 = rb_col(fc.z - frm, P.half, P.t_inv_w, P.tcz), cz1 = rb_col(fc.z + frm, P.half, P.t_inv_w, P.tcz);
             uint32_t nx = cx1 - cx0 + 1, ncol = nx * (cz1 - cz0 + 1);
@@ -773,7 +926,11 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOC
                                         !(e1.x > fc.y + frm || e1.y < fc.y - frm);
                             if (keep) {
                                 if (nc == RB_CAND_MAX) st_slow = true;        // too many: the generic walk takes over
-                                else s_cand[nc++][threadIdx.x] = __float_as_uint(e1.z);
+                                else {
+                                    const uint32_t tcand = __float_as_uint(e1.z);
+                                    s_cand[nc++][threadIdx.x] = tcand;
+                                    rb_prefetch(P.tri + 3ull * tcand); rb_prefetch(P.tri + 3ull * tcand + 2);     // the exact test gathers these 48 B later
+                                }
                             }
                         }
                     }
@@ -798,22 +955,20 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOC
         nc = nu;
         __syncwarp();
     }
-    if (MODE == 1) {        // park the lists (slot-major, coalesced) and stop: the resolve launch picks them up
-        if (tid < P.ns) {
-            P.e_hdr[tid] = valid ? (min(npart, 255u) | (nc << 8) | (st_slow ? 0x10000u : 0u)) : 0u;
+    if (MODE == 1) {        // park the lists by body row (slot-major; rows follow the sort order closely) and stop
+        if (valid) {
+            P.e_hdr[A] = min(npart, 255u) | (nc << 8) | (st_slow ? 0x10000u : 0u);
 #pragma unroll
-            for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + tid] = pg[k]; P.e_pl[(size_t)k * P.ns + tid] = pl[k]; }
-            for (uint32_t j = 0; j < nc; ++j) P.e_cand[(size_t)j * P.ns + tid] = s_cand[j][threadIdx.x];
+            for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + A] = pg[k]; P.e_pl[(size_t)k * P.ns + A] = pl[k]; }
+            for (uint32_t j = 0; j < nc; ++j) P.e_cand[(size_t)j * P.ns + A] = s_cand[j][threadIdx.x];
+            if (P.vl && npart > RB_SSCAND_MAX) P.ws_build[A].w = -1.0f;     // crowded: no list can hold its partners, it enumerates every tick (hot)
         }
         collide_epilogue(P, H, T, lane);
         return;
     }
-    if (MODE == 2 && valid) {
-        const uint32_t hdr = P.e_hdr[tid];
-        npart = hdr & 0xffu; nc = (hdr >> 8) & 0xffu; st_slow = (hdr & 0x10000u) != 0;
-#pragma unroll
-        for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < npart) { pg[k] = P.e_pg[(size_t)k * P.ns + tid]; pl[k] = P.e_pl[(size_t)k * P.ns + tid]; }
-        for (uint32_t j = 0; j < nc; ++j) s_cand[j][threadIdx.x] = P.e_cand[(size_t)j * P.ns + tid];
+    if (MODE == 2 && valid && !hot) {
+        nc = (hdr >> 8) & 0xffu; st_slow = (hdr & 0x10000u) != 0;
+        for (uint32_t j = 0; j < nc; ++j) s_cand[j][threadIdx.x] = P.e_cand[(size_t)j * P.ns + A];
     }
     if (MODE == 2) __syncwarp();
     // ---------------- lazy state load ----------------
@@ -839,6 +994,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOC
         while (true) {
             uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
             scan_partners<true>(P, A, fc, frm, lo, best, best_local, eligible, T);
+            if (reuse) scan_hot_partners(P, A, fc, frm, lo, best, best_local, eligible);
             if (best == RB_NONE) break;
             ss_pair_single<RESOLVE>(P, S, H, T, A, gA, oa, best_local, best);
             lo = best + 1;
@@ -943,6 +1099,15 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : RB_COLLIDE_MINBLOC
         }
     }
     collide_epilogue(P, H, T, lane);
+    if (MODE == 0 && P.vl && P.vl_host && tid == 0) P.vl_host[2] = P.vl[RB_VL_NFAST];     // lists switched off: K1's count of fast movers
+    if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping, flag down for the next K1
+        const uint32_t f = P.vl[RB_VL_REBUILD];
+        P.vl[RB_VL_REBUILD] = 0u;
+        if (f) { P.vl[RB_VL_WHY_LAST] = P.vl[RB_VL_WHY]; P.vl[RB_VL_WHY] = 0u; }
+        const uint32_t nr = P.vl[RB_VL_NREBUILD] + (f ? 1u : 0u), nt = P.vl[RB_VL_NTICK] + 1u;
+        P.vl[RB_VL_NREBUILD] = nr; P.vl[RB_VL_NTICK] = nt;
+        if (P.vl_host) { P.vl_host[0] = nr; P.vl_host[1] = nt; }
+    }
 }
 
 // K5: deferred commit for compound bodies
@@ -1022,6 +1187,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_reorder_kernel(RbParams P, RbReor
     const uint32_t n_rows = P.dn ? P.dn[0] : P.nb;
     if (i >= n_rows) return;
     uint32_t k = P.key[i];
+    if (k != RB_NONE) k &= ~RB_HOT_BIT;
     uint32_t j;
     if (R.owned_rank) {      // slab world: ghosts share the sorted array, owned rows keep their relative order
         const uint32_t n_sorted = P.col_start[P.scx * P.scz];
@@ -1066,11 +1232,29 @@ int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile
 uint32_t rb_scan_tiles(uint32_t n) { return cdiv(n, RB_SCAN_TILE); }
 // single launch; status/ticket must have been zeroed (they live behind the histogram, see rb_build)
 int rb_launch_scan_lookback(const uint32_t* in, uint32_t n, uint32_t* out, unsigned long long* status, uint32_t* ticket, cudaStream_t st) {
-    rb_scan_lookback_kernel<<<cdiv(n, RB_SCAN_TILE), RB_BLOCK, 0, st>>>(in, n, out, status, ticket);
+    rb_scan_lookback_kernel<<<cdiv(n, RB_SCAN_TILE), RB_BLOCK, 0, st>>>(const_cast<uint32_t*>(in), n, out, status, ticket, nullptr, 0);
     return 1;
 }
 void rb_launch_scatter(const RbParams& P, cudaStream_t st) {
-    if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
+    if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P, 0, nullptr, nullptr, 0);
+}
+// persistent lists: the rebuild chain (bin -> scan -> scatter -> enumerate), every kernel conditional on the
+// device-side rebuild flag, followed by the unconditional test / resolve kernel over the lists
+void rb_launch_vl_bin(const RbParams& P, cudaStream_t st) {
+    if (P.ns) rb_vl_bin_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
+}
+void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st) {
+    rb_scan_lookback_kernel<<<cdiv(ncols, RB_SCAN_TILE), RB_BLOCK, 0, st>>>(P.col_count, ncols, P.col_start, status, ticket, P.vl + RB_VL_REBUILD, 1);
+}
+void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st) {
+    if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P, 1, status, ticket, cdiv(ncols, RB_SCAN_TILE));
+}
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st) {
+    if (!P.nb) return 0;
+    const uint32_t g = cdiv(P.ns, RB_BLOCK);
+    rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
+    rb_collide_single_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P);
+    return 2;
 }
 int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st) {
     if (!P.nb) return 0;

@@ -45,6 +45,9 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     w->h_body_start.push_back(0);
     { const char* v = getenv("RB_COLLIDE_V1"); if (v && *v == '1') w->collide_variant = 1; }
     { const char* v = getenv("RB_COLLIDE_VARIANT"); if (v && *v) w->collide_variant = atoi(v); }
+    { const char* v = getenv("RB_VERLET"); w->vl_on = !(v && *v == '0'); }          // persistent candidate lists (default on where they apply)
+    { const char* v = getenv("RB_VERLET_SKIN"); if (v && *v) w->vl_skin_cfg = (float)atof(v); }
+    { const char* v = getenv("RB_VERLET_HOT"); if (v && *v) w->vl_hot_cfg = atoi(v); }
     { const char* v = getenv("RB_SCAN_V1"); if (v && *v == '1') w->scan_variant = 1; }
     { const char* v = getenv("RB_REORDER_EVERY"); if (v && *v) w->reorder_every = atoi(v); }
     *out = w;
@@ -58,6 +61,7 @@ void rb_world_destroy(rb_world* w) {
     if (w->dist) rb_dist_destroy(w->dist);
     for (auto& b : w->allocs) cudaFree(b.p);
     if (w->h_counters) cudaFreeHost(w->h_counters);
+    if (w->vl_host) cudaFreeHost(w->vl_host);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->s_h2d) {
         cudaStreamSynchronize(w->s_h2d); cudaStreamSynchronize(w->s_d2h);
@@ -361,6 +365,14 @@ int rb_build(rb_world* w) {
     if (!(w->cfg.margin_cap > 0.f)) w->cfg.margin_cap = std::max(0.5f * rmax, 1e-3f);   // auto: half the largest radius
     P.margin_cap = w->cfg.margin_cap;
     P.rm_max = rmax + w->cfg.margin_cap;
+    // persistent candidate lists: single worlds of single-sphere bodies stepped by rb_step with the default kernel
+    w->vl_on = w->vl_on && !slab && P.single && ns > 0 && w->collide_variant == 2;
+    if (w->vl_on) {
+        float rmin = rmax;
+        for (size_t i = 3; i < sph.size() && i < (size_t)ns * 4; i += 4) rmin = std::min(rmin, std::fabs(sph[i]));
+        P.vl_skin = w->vl_skin_cfg > 0.f ? w->vl_skin_cfg : std::max(0.1f * rmin, 4e-3f);   // auto: a tenth of the smallest radius
+        P.rm_max += P.vl_skin;               // the largest grown radius any enumeration can meet
+    }
     // ---- sphere column grid geometry ----
     {
         float wcol = std::max(2.0f * P.rm_max, 2.0f * P.half / 4096.0f);
@@ -429,6 +441,24 @@ int rb_build(rb_world* w) {
         uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
         ALLOC(cb, nb); ALLOC(c1, nb); ALLOC(c2, nb); ALLOC(c3, nb); ALLOC(c4, nb); ALLOC(cf, nb);
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
+    }
+    if (w->vl_on) {
+        uint32_t* v; float4* wb;
+        ALLOC(v, 8); CU(cudaMemsetAsync(v, 0, 8 * sizeof(uint32_t), w->stream));
+        ALLOC(wb, ns); CU(cudaMemsetAsync(wb, 0, (size_t)ns * 16, w->stream));
+        CU(cudaMemsetAsync(d_key, 0xff, (size_t)ns * 4, w->stream));                 // "not in the grid" until the first K1
+        CU(cudaHostAlloc((void**)&w->vl_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
+        w->vl_host[0] = w->vl_host[1] = w->vl_host[2] = w->vl_host[3] = 0;
+        uint32_t* dv = nullptr; CU(cudaHostGetDevicePointer((void**)&dv, w->vl_host, 0));
+        P.vl = v; P.ws_build = wb; P.vl_host = dv;
+        // coarse cell table of the hot bodies: cells wide enough that any reach box touches at most 2 x 2 of them
+        const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 256.0f);
+        P.hcn = (uint32_t)std::max(1L, (long)std::floor(2.0 * P.half / lc));
+        P.hc_inv_w = (float)P.hcn / (2.0f * P.half);
+        P.hot_cap = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(256u, ns / 128u);
+        uint32_t *hh, *hr, *hn;
+        ALLOC(hh, (size_t)P.hcn * P.hcn + 1); ALLOC(hr, P.hot_cap); ALLOC(hn, P.hot_cap);
+        P.hot_head = hh; P.hot_row = hr; P.hot_next = hn;
     }
     if (P.single && P.ns) {     // enumerate -> resolve hand-over lists
         uint32_t *eh, *eg, *el, *ec;
@@ -514,18 +544,74 @@ static int enqueue_collide(rb_world* w, bool resolve) {
     return RB_OK;
 }
 
+// One tick with persistent candidate lists. K1 integrates, checks whether every sphere is still inside the
+// skin its list was built with, and raises the device-side rebuild flag if not; bin -> scan -> scatter ->
+// enumerate follow as launches that return at once while the flag is down (the host never has to look), and
+// the test / resolve kernel runs every tick from the lists. Results are the ones of the per-tick enumeration:
+// the lists are supersets of it and every decision is taken by the same exact tests in the same order.
+static int enqueue_list_tick(rb_world* w, bool reorder_due) {
+    RbParams& P = w->P;
+    const bool force = w->vl_force || reorder_due;
+    if (force) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));   // other paths may have left counts behind
+    CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 1) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter
+    CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
+    if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
+    rb_launch_integrate_bin(P, 1, force ? 3 : 2, w->stream);
+    rb_launch_vl_bin(P, w->stream);
+    if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
+    rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
+    if (w->profile) CU(cudaEventRecord(w->ev[2], w->stream));
+    rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
+    if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
+    w->launches += 4 + rb_launch_vl_collide(P, w->stream);
+    if (w->profile) {
+        CU(cudaEventRecord(w->ev[4], w->stream));
+        CU(cudaEventSynchronize(w->ev[4]));
+        for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, w->ev[k], w->ev[k + 1])); w->kernel_ms[k] += ms; }
+    }
+    CU(cudaGetLastError());
+    w->vl_force = false;
+    return RB_OK;
+}
+
 int rb_step(rb_world* w, int ms) {
     if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_step before rb_build") : RB_ERR_INVALID;
     CU(cudaSetDevice(w->cfg.device));
     w->P.dt = (float)ms / 1000.0f;                     // StateVector.cpp:19
-    int r = enqueue_broadphase(w, 1); if (r) return r;
-    r = enqueue_collide(w, true); if (r) return r;
+    const bool reorder_due = w->reorder_every > 0 && (w->steps + 1) % (uint64_t)w->reorder_every == 0;
+    int r;
+    if (w->vl_on) {
+        // the device reports {rebuild ticks, list ticks} through mapped host memory; the host only looks at it
+        // (never waits for it) to notice phases in which nearly every tick rebuilds, and sits those out on the
+        // per-tick kernel. Both paths give the same results, so the switch is invisible.
+        if (w->vl_active) {
+            const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
+            if (nt - w->vl_seen_t >= 16u) {
+                const bool mostly_rebuilding = 2u * (nr - w->vl_seen_r) > (nt - w->vl_seen_t);
+                w->vl_seen_r = nr; w->vl_seen_t = nt;
+                if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
+                else w->vl_backoff = 32;
+            }
+        } else if (w->steps >= w->vl_resume_at) {
+            // come back once few enough bodies outrun the skin (the per-tick kernel keeps counting them)
+            if (w->vl_host[2] < w->P.hot_cap / 4u) { w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1]; }
+            else w->vl_resume_at = w->steps + 16;
+        }
+    }
+    if (w->vl_on && w->vl_active) { r = enqueue_list_tick(w, reorder_due); if (r) return r; }      // a re-ordering tick rebuilds: it needs a fresh sort
+    else {
+        if (w->vl_on) CU(cudaMemsetAsync(w->P.vl + RB_VL_NFAST, 0, 4, w->stream));
+        r = enqueue_broadphase(w, 1); if (r) return r;
+        r = enqueue_collide(w, true); if (r) return r;
+        w->vl_force = true;
+    }
     w->steps++; w->pose_updates++;
-    if (w->reorder_every > 0 && w->steps % (uint64_t)w->reorder_every == 0) { r = reorder_rows(w); if (r) return r; }
+    if (reorder_due) { r = reorder_rows(w); if (r) return r; w->vl_force = true; }                // rows moved: the lists are stale
     return RB_OK;
 }
 int rb_integrate(rb_world* w, int ms) {
     if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_integrate before rb_build") : RB_ERR_INVALID;
+    w->vl_force = true;
     CU(cudaSetDevice(w->cfg.device));
     w->P.dt = (float)ms / 1000.0f;
     rb_launch_integrate_bin(w->P, 1, 0, w->stream); w->launches++;
@@ -535,12 +621,14 @@ int rb_integrate(rb_world* w, int ms) {
 }
 int rb_collide(rb_world* w) {
     if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_collide before rb_build") : RB_ERR_INVALID;
+    w->vl_force = true;
     CU(cudaSetDevice(w->cfg.device));
     int r = enqueue_broadphase(w, 0); if (r) return r;
     return enqueue_collide(w, true);
 }
 int rb_detect(rb_world* w) {
     if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_detect before rb_build") : RB_ERR_INVALID;
+    w->vl_force = true;
     CU(cudaSetDevice(w->cfg.device));
     int r = enqueue_broadphase(w, 0); if (r) return r;
     return enqueue_collide(w, false);
@@ -661,6 +749,7 @@ int rb_get_angular(rb_world* w, float* ap4, float* av4) {
 }
 int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     if (!w || !w->built || !xyzr4) return RB_ERR_INVALID;
+    w->vl_force = true;
     // recompute from the current model translations (no integration, no binning side effects on state)
     CU(cudaMemsetAsync(w->P.col_count, 0, w->hist_clear_bytes, w->stream));
     rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
@@ -685,6 +774,7 @@ static int range_ok(rb_world* w, uint32_t first, uint32_t count) {
 }
 int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4) {
     int r = range_ok(w, first, count); if (r) return r;
+    w->vl_force = true;
     if ((pos4 && !finite_all(pos4, (size_t)count * 3)) || (vel4 && !finite_all(vel4, (size_t)count * 3))) { /* w component is padding */ }
     if (pos4) { r = write_rows_f4(w, w->P.pos, first, count, pos4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
     if (vel4) { r = write_rows_f4(w, w->P.vel, first, count, vel4); if (r) return r; }
@@ -693,6 +783,7 @@ int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4,
 }
 int rb_set_flags(rb_world* w, uint32_t first, uint32_t count, const uint32_t* values, uint32_t mask) {
     int r = range_ok(w, first, count); if (r) return r;
+    w->vl_force = true;
     if (!values) return fail(w, RB_ERR_INVALID, "values is NULL");
     r = ensure_stage_u(w, count); if (r) return r;
     CU(cudaMemcpyAsync(w->d_stage_u, values, (size_t)count * 4, cudaMemcpyHostToDevice, w->stream));
@@ -837,6 +928,14 @@ int rb_get_stats(rb_world* w, rb_stats_t* out) {
         out->contacts_dropped = c[RB_C_DROPPED]; out->margin_overflow = c[RB_C_OVERFLOW];
     }
     if (w->built && w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
+    if (w->built && w->vl_on) {
+        uint32_t v[8], nh = 0;
+        CU(cudaMemcpyAsync(v, w->P.vl, sizeof v, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaMemcpyAsync(&nh, w->P.hot_head + (size_t)w->P.hcn * w->P.hcn, 4, cudaMemcpyDeviceToHost, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        out->list_rebuilds = v[RB_VL_NREBUILD]; out->list_ticks = v[RB_VL_NTICK]; out->list_skin = w->P.vl_skin;
+        out->list_hot_last = nh; out->list_rebuild_reason = v[RB_VL_WHY_LAST];
+    }
     out->n_bodies = w->built ? w->n_owned_host : (uint32_t)w->h_flags.size();
     out->n_spheres = w->d_dn ? w->n_owned_host : w->P.ns; out->n_geoms = (uint32_t)w->h_geom_start.size() - 1; out->n_tris = w->P.nt;
     out->sphere_cols_x = w->P.scx; out->sphere_cols_z = w->P.scz; out->tri_cols_x = w->P.tcx; out->tri_cols_z = w->P.tcz;

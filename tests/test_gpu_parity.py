@@ -323,18 +323,92 @@ def test_phased_kernel_bit_identical_to_first_generation_kernel(World, monkeypat
     monkeypatch.setenv("RB_COLLIDE_V1", "1")
     w1 = World(sc)
     monkeypatch.delenv("RB_COLLIDE_V1")
+    monkeypatch.setenv("RB_VERLET", "0")          # the phased kernel enumerating every tick
     w2 = World(sc)
+    monkeypatch.delenv("RB_VERLET")
+    w3 = World(sc)                                # default: the same kernel stepping from persistent lists
     for k in range(200):
-        w1.step(5); w2.step(5)
-    a, b = w1.state(), w2.state()
+        w1.step(5); w2.step(5); w3.step(5)
+    a, b, c = w1.state(), w2.state(), w3.state()
     for key in ("pos", "vel", "model_t", "prev_t"):
         assert np.array_equal(bits(a[key]), bits(b[key])), key
-    assert np.array_equal(a["flags"], b["flags"])
-    assert np.array_equal(w1.contacts(), w2.contacts())
-    s1, s2 = w1.stats(), w2.stats()
+        assert np.array_equal(bits(a[key]), bits(c[key])), key
+    assert np.array_equal(a["flags"], b["flags"]) and np.array_equal(a["flags"], c["flags"])
+    assert np.array_equal(w1.contacts(), w2.contacts()) and np.array_equal(w1.contacts(), w3.contacts())
+    s1, s2, s3 = w1.stats(), w2.stats(), w3.stats()
     assert s1["tests_st"] == s2["tests_st"] and s1["hits_st"] == s2["hits_st"] and s1["hits_ss"] == s2["hits_ss"] and s1["tests_ss"] == s2["tests_ss"]
+    assert s3["hits_st"] == s2["hits_st"] and s3["hits_ss"] == s2["hits_ss"]      # lists are supersets: more tests, the same hits
     assert s2["hits_ss"] > 1000 and s2["hits_st"] > 100000
-    w1.close(); w2.close()
+    assert s2["list_ticks"] == 0 and 0 < s3["list_rebuilds"] <= s3["list_ticks"] <= 200   # (the host may sit out rebuild-heavy phases on the per-tick kernel)
+    w1.close(); w2.close(); w3.close()
+
+
+def test_persistent_lists_survive_host_edits(World, monkeypatch):
+    """Persistent candidate lists (default) against per-tick enumeration (RB_VERLET=0) over a run that settles
+    (lists get reused for many ticks) and is disturbed from the host: teleports, velocity kicks, bodies
+    switched off and on, per-tick forces, interleaved rb_detect / rb_integrate + rb_collide calls.
+    Bit-identical state, flags and contact sets at every checkpoint."""
+    from reboot_b200 import scenes
+    sc = scenes.falling_spheres(20000, 100, 2.0, 0.5, (0.3, 2.0), True, 33, "vl")
+    monkeypatch.setenv("RB_VERLET", "0")
+    wa = World(sc)
+    monkeypatch.delenv("RB_VERLET")
+    wb = World(sc)
+    rng = np.random.default_rng(5)
+    nb = sc.n_bodies
+
+    def same(tag):
+        a, b = wa.state(), wb.state()
+        for key in ("pos", "vel", "model_t", "prev_t"):
+            assert np.array_equal(bits(a[key]), bits(b[key])), (tag, key)
+        assert np.array_equal(a["flags"], b["flags"]), tag
+        assert np.array_equal(wa.contacts(), wb.contacts()), tag
+
+    for k in range(400):
+        wa.step(5); wb.step(5)
+        if k % 50 == 49: same(("settle", k))
+    st = wb.stats()
+    assert 100 < st["list_ticks"] <= 400 and st["list_rebuilds"] < st["list_ticks"] - 50, st       # lists were reused once the pile settled
+    settled_rebuilds = st["list_rebuilds"]
+    # teleport a block of bodies on top of others, kick some velocities
+    ids = rng.choice(nb, 500, replace=False)
+    s = wa.state()
+    pos = np.zeros((nb, 4), np.float32); pos[:, :3] = s["pos"]; pos[:, 3] = 1
+    vel = np.zeros((nb, 4), np.float32); vel[:, :3] = s["vel"]
+    pos[ids[:250], :3] = pos[ids[250:], :3] + np.float32(0.3)
+    vel[ids[250:], :3] += rng.normal(0, 3, (250, 3)).astype(np.float32)
+    for w in (wa, wb):
+        w.set_state(0, pos[:, :3], vel[:, :3])
+    for k in range(60):
+        wa.step(5); wb.step(5)
+    same("teleport")
+    # switch bodies off and on
+    off = np.zeros(nb, np.uint32); on = np.full(nb, 1, np.uint32)
+    for w in (wa, wb):
+        w.set_flags(0, off[:3000], 1)
+    for k in range(20):
+        wa.step(5); wb.step(5)
+    same("off")
+    for w in (wa, wb):
+        w.set_flags(0, on[:3000], 1)
+    for k in range(20):
+        wa.step(5); wb.step(5)
+    same("on")
+    # per-tick forces through the host call, and the stand-alone phases in between
+    f = np.zeros((nb, 4), np.float32); f[:, 0] = rng.normal(0, 40, nb); f[:, 2] = rng.normal(0, 40, nb); f[:, 3] = 1
+    p4 = np.zeros((nb, 4), np.float32)
+    for k in range(40):
+        wa.step_host(5, f, p4); wb.step_host(5, f, p4)
+        if k == 10:
+            wa.detect(); wb.detect()
+            assert np.array_equal(wa.contacts(), wb.contacts())
+        if k == 20:
+            for w in (wa, wb):
+                w.integrate(5); w.collide()
+    same("forces")
+    assert wb.stats()["list_rebuilds"] > settled_rebuilds
+    assert wa.stats()["margin_overflow"] == wb.stats()["margin_overflow"]
+    wa.close(); wb.close()
 
 
 def test_pipelined_host_round_trip_matches_blocking(World):
