@@ -110,6 +110,7 @@ struct RbParams {
     volatile uint32_t* vl_host;   // mapped host copy of {rebuilds, ticks} (heuristics only)
     float4* ws_build;             // frozen sphere of every row at the last rebuild
     float vl_skin;
+    float vl_slack;               // added to the grown radius when a list is pruned with the exact predicate (>> its rounding error)
     // "hot" bodies have used their skin up (fast movers): they enumerate for themselves every tick (triangles
     // from the static grid, cold partners from the sort of the last rebuild, which is off by less than the
     // skin) and are published in a coarse (x,z) cell table so that cold bodies and other hot bodies find them

@@ -696,6 +696,9 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
 #ifndef RB_COLLIDE_MINBLOCKS
 #define RB_COLLIDE_MINBLOCKS 3
 #endif
+#ifndef RB_COLLIDE_MINBLOCKS_ENUM
+#define RB_COLLIDE_MINBLOCKS_ENUM 4
+#endif
 #ifndef RB_COLLIDE_MINBLOCKS_LISTS
 #define RB_COLLIDE_MINBLOCKS_LISTS 4      // stepping from lists is lighter: 64 registers, 4 blocks per SM measured faster (3 for the fused kernel)
 #endif
@@ -729,7 +732,7 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
 // twice the resident warps, results parked in global lists. MODE 2: test / resolve only (P2, P4, P5) from
 // those lists. The split (default) lets each half run at its own occupancy; results are identical.
 template <bool RESOLVE, int MODE>
-__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : (MODE == 2) ? RB_COLLIDE_MINBLOCKS_LISTS : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
+__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : (MODE == 2) ? RB_COLLIDE_MINBLOCKS_LISTS : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
@@ -954,6 +957,45 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? 6 : (MODE == 2) ? RB_C
         }
         nc = nu;
         __syncwarp();
+    }
+    if (MODE == 1 && P.vl) {
+        // Persistent lists keep only the triangles the sphere can actually reach while its list lives: the
+        // exact predicate, run once at the build pose with the radius grown by the skin (a body steps from
+        // its list only while displacement + margin <= skin, and the distance to a triangle is 1-Lipschitz
+        // in the centre) plus a slack far above the predicate's rounding error. What is dropped here could
+        // not have tested positive, so the hits -- and with them every result -- are unchanged.
+        // Pooled over the warp like P4 (no idle lanes).
+        __shared__ uint32_t s_keep[RB_BLOCK];
+        const uint32_t wbase = threadIdx.x & ~31u;
+        const uint32_t incl = warp_incl_scan(nc, lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const float prad = frm + P.vl_slack;
+        s_keep[threadIdx.x] = 0;
+        __syncwarp();
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t item = base + lane;
+            uint32_t lo = 0;
+#pragma unroll
+            for (int st = 16; st >= 1; st >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, incl, (lo + st - 1) & 31); if (v <= item) lo += st; }
+            const uint32_t owner = lo & 31;
+            const uint32_t o_excl = __shfl_sync(0xffffffffu, incl - nc, owner);
+            const float ox = __shfl_sync(0xffffffffu, fc.x, owner), oy = __shfl_sync(0xffffffffu, fc.y, owner), oz = __shfl_sync(0xffffffffu, fc.z, owner);
+            const float orad = __shfl_sync(0xffffffffu, prad, owner);
+            if (item < total) {
+                const uint32_t k = item - o_excl;
+                const uint32_t t = s_cand[k][wbase + owner];
+                const float4* tp = P.tri + 3ull * t;
+                float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                if (sphere_triangle_detect(mk3(ox, oy, oz), orad, xyz(a4), xyz(b4), xyz(c4))) atomicOr(&s_keep[wbase + owner], 1u << k);
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        const uint32_t m = s_keep[threadIdx.x];
+        uint32_t nu = 0;
+        for (uint32_t j = 0; j < nc; ++j) if ((m >> j) & 1u) s_cand[nu++][threadIdx.x] = s_cand[j][threadIdx.x];
+        T.tests_st += nc;
+        nc = nu;
     }
     if (MODE == 1) {        // park the lists by body row (slot-major; rows follow the sort order closely) and stop
         if (valid) {

@@ -372,6 +372,7 @@ int rb_build(rb_world* w) {
         for (size_t i = 3; i < sph.size() && i < (size_t)ns * 4; i += 4) rmin = std::min(rmin, std::fabs(sph[i]));
         P.vl_skin = w->vl_skin_cfg > 0.f ? w->vl_skin_cfg : std::max(0.1f * rmin, 4e-3f);   // auto: a tenth of the smallest radius
         P.rm_max += P.vl_skin;               // the largest grown radius any enumeration can meet
+        P.vl_slack = std::max(1e-2f, 1e-5f * P.half);   // FP32 rounding of the predicate in sphere-centred coordinates is ~1e-4 at |x| = 1000
     }
     // ---- sphere column grid geometry ----
     {
