@@ -144,12 +144,14 @@ __device__ __forceinline__ void rb_prefetch(const void* p) {
 __device__ __forceinline__ uint32_t rb_gid(const RbParams& P, uint32_t local) { return P.gid ? P.gid[local] : local; }
 
 // K7 arguments: every per-body array pair (current rows -> re-ordered rows)
-#define RB_REORDER_MAX 10
+#define RB_REORDER_MAX 12
 struct RbReorder {
     const float4* src4[RB_REORDER_MAX]; float4* dst4[RB_REORDER_MAX]; int n4;
     const uint32_t* src_flags; uint32_t* dst_flags;
     const uint32_t* src_gid; uint32_t* dst_gid; uint32_t* inv;
     uint32_t* rest_counter;
+    const uint32_t* src_key; uint32_t* dst_key;   // in-tick re-ordering (between the sort and the enumeration of a list rebuild):
+    uint32_t* sorted_id_fix;                      // keys travel with the rows and the sorted ids are rewritten to the new rows
     const uint32_t* owned_rank;   // slab worlds: exclusive count of owned entries in front of each sorted slot (+ total at the end)
     uint32_t n_slots;             // capacity of owned_rank - 1
 };

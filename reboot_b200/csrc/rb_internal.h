@@ -89,7 +89,7 @@ struct rb_world {
     // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----
     int reorder_every = 32;                  // ticks between re-orderings (0 = never)
     uint32_t* d_inv = nullptr;               // body id -> row
-    uint32_t* d_gid_alt = nullptr; uint32_t* d_flags_alt = nullptr; uint32_t* d_rest = nullptr;
+    uint32_t* d_gid_alt = nullptr; uint32_t* d_flags_alt = nullptr; uint32_t* d_rest = nullptr; uint32_t* d_key_alt = nullptr;
     float4* alt4[RB_REORDER_MAX] = {};
     float4* d_io4 = nullptr; uint32_t* d_io_u = nullptr;   // id-ordered staging for host IO
     float4* d_w3 = nullptr; float4* d_mm_cur = nullptr; float4* d_mm_prev = nullptr; bool any_w3 = false;   // model-matrix export

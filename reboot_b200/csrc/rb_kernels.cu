@@ -1241,7 +1241,12 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_reorder_kernel(RbParams P, RbReor
     }
 #pragma unroll 1
     for (int a = 0; a < R.n4; ++a) R.dst4[a][j] = R.src4[a][i];
-    R.dst_flags[j] = R.src_flags[i];
+    const uint32_t fl = R.src_flags[i];
+    R.dst_flags[j] = fl;
+    if (R.dst_key) {
+        R.dst_key[j] = R.src_key[i];
+        if (k != RB_NONE) R.sorted_id_fix[j] = j | ((fl & RB_F_CONTACT) ? RB_TRI_BIT : 0u);      // slot j now holds row j
+    }
     uint32_t g = R.src_gid ? R.src_gid[i] : i;
     R.dst_gid[j] = g;
     if (R.inv) R.inv[g] = j;

@@ -270,16 +270,19 @@ static int write_rows_f4(rb_world* w, float4* rows, uint32_t first, uint32_t cou
     return RB_OK;
 }
 
-static int reorder_rows(rb_world* w);
+static int reorder_rows(rb_world* w, bool intick = false);
 // K7 driver: put the body rows in the order of the last counting sort (needs a valid sort: call right
 // after a broadphase). Single-sphere, single-GPU worlds only.
 int rb_reorder_rows_now(rb_world* w) { return reorder_rows(w); }
-static int reorder_rows(rb_world* w) {
+static int reorder_rows(rb_world* w, bool intick) {
     RbParams& P = w->P;
     if (!P.single || P.nb == 0) return RB_OK;
     const bool slab = w->d_dn != nullptr;
     const size_t nb = P.nb;
-    float4** cur[RB_REORDER_MAX] = { &P.pos, &P.vel, &P.mt, &P.pt, const_cast<float4**>(&P.sph_obj), const_cast<float4**>(&P.wt), &P.force, &P.torque, &P.apos, &P.avel };
+    // intick: between the sort and the enumeration of a list-rebuild tick -- K1's per-row outputs (world spheres,
+    // build poses, keys) travel too and the sorted ids are rewritten, so the lists are built for the new rows
+    float4** cur[RB_REORDER_MAX] = { &P.pos, &P.vel, &P.mt, &P.pt, const_cast<float4**>(&P.sph_obj), const_cast<float4**>(&P.wt), &P.force, &P.torque, &P.apos, &P.avel,
+                                     intick ? &P.ws : nullptr, intick ? &P.ws_build : nullptr };
     if (!w->d_gid_alt) {
         if (!slab) { ALLOC(w->d_inv, nb); ALLOC(w->d_gid, nb); }
         ALLOC(w->d_gid_alt, nb); ALLOC(w->d_flags_alt, nb); ALLOC(w->d_rest, 4);
@@ -293,11 +296,15 @@ static int reorder_rows(rb_world* w) {
     int slot_of[RB_REORDER_MAX];
     for (int a = 0; a < RB_REORDER_MAX; a++) {
         slot_of[a] = -1;
-        if (!*cur[a]) continue;
+        if (!cur[a] || !*cur[a]) continue;
         if (!w->alt4[a]) ALLOC(w->alt4[a], nb);
         R.src4[R.n4] = *cur[a]; R.dst4[R.n4] = w->alt4[a]; slot_of[a] = R.n4++;
     }
     R.src_flags = P.flags; R.dst_flags = w->d_flags_alt;
+    if (intick) {
+        if (!w->d_key_alt) ALLOC(w->d_key_alt, nb);
+        R.src_key = P.key; R.dst_key = w->d_key_alt; R.sorted_id_fix = P.sorted_id;
+    }
     uint32_t* gid_cur = const_cast<uint32_t*>(P.gid);
     R.src_gid = P.gid; R.dst_gid = gid_cur == w->d_gid ? w->d_gid_alt : w->d_gid; R.inv = slab ? nullptr : w->d_inv; R.rest_counter = w->d_rest;
     CU(cudaMemsetAsync(w->d_rest, 0, 4, w->stream));
@@ -312,6 +319,7 @@ static int reorder_rows(rb_world* w) {
     CU(cudaGetLastError());
     for (int a = 0; a < RB_REORDER_MAX; a++) if (slot_of[a] >= 0) { float4* old = *cur[a]; *cur[a] = w->alt4[a]; w->alt4[a] = old; }
     { uint32_t* old = P.flags; P.flags = w->d_flags_alt; w->d_flags_alt = old; }
+    if (intick) { uint32_t* old = P.key; P.key = w->d_key_alt; w->d_key_alt = old; }
     P.gid = R.dst_gid;
     if (slab) { w->d_gid = R.dst_gid; w->d_gid_alt = gid_cur; rb_dist_rows_moved(w); }
     return RB_OK;
@@ -563,6 +571,7 @@ static int enqueue_list_tick(rb_world* w, bool reorder_due) {
     rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[2], w->stream));
     rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
+    if (reorder_due) { int r = reorder_rows(w, true); if (r) return r; }     // rows into sort order before the lists are built for them
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
     w->launches += 4 + rb_launch_vl_collide(P, w->stream);
     if (w->profile) {
@@ -607,7 +616,7 @@ int rb_step(rb_world* w, int ms) {
         w->vl_force = true;
     }
     w->steps++; w->pose_updates++;
-    if (reorder_due) { r = reorder_rows(w); if (r) return r; w->vl_force = true; }                // rows moved: the lists are stale
+    if (reorder_due && !(w->vl_on && w->vl_active)) { r = reorder_rows(w); if (r) return r; }      // (list ticks re-order inside the tick)
     return RB_OK;
 }
 int rb_integrate(rb_world* w, int ms) {
