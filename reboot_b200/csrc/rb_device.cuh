@@ -101,9 +101,9 @@ struct RbParams {
     unsigned long long* counters;
     unsigned long long* stripes;  // RB_STRIPES x RB_C_COUNT striped copies of the cumulative test / hit counters
     // ---- candidate lists, indexed by body row (single-sphere worlds, slot-major) ----
-    uint32_t* e_hdr;              // npart | nc << 8 | slow << 16
+    uint4* e_rec;                 // per row: { npart | nc << 8 | slow << 16, first three triangle ids }
     uint32_t* e_pg; uint32_t* e_pl;   // [RB_SSCAND_MAX][ns] partner global id / local row
-    uint32_t* e_cand;             // [RB_CAND_MAX][ns] staged triangle ids, ascending
+    uint32_t* e_cand;             // [RB_CAND_MAX - 3][ns] the triangle ids beyond the third, ascending
     // ---- persistent lists ("Verlet lists"): the lists above are built for spheres grown by vl_skin and
     // reused until some body has used its skin up; the sort and the enumeration only run on those ticks ----
     uint32_t* vl;                 // device words, see RB_VL_*

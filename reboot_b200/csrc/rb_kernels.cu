@@ -728,28 +728,42 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
     }
 }
 
-// MODE 0: everything in one launch. MODE 1: enumerate only (P1 + P3) -- pure pointer chasing, compiled for
-// twice the resident warps, results parked in global lists. MODE 2: test / resolve only (P2, P4, P5) from
-// those lists. The split (default) lets each half run at its own occupancy; results are identical.
+// MODE 0: everything in one launch (per-tick enumeration). MODE 1: enumerate only (P1 + P3, plus the exact-predicate
+// pruning of persistent lists), results parked in global lists indexed by body row. MODE 2: test / resolve only
+// (P2, P4, P5), one thread per row, from those lists. MODE 3: the hot bodies of a list-reuse tick, one thread each,
+// enumerating for themselves like MODE 0 but against the sort of the last rebuild + the hot-body table.
+// All modes run the same tests in the same canonical order: results are bit-identical.
 template <bool RESOLVE, int MODE>
-__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : (MODE == 2) ? RB_COLLIDE_MINBLOCKS_LISTS : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(RbParams P) {
+__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : (MODE == 2) ? RB_COLLIDE_MINBLOCKS_LISTS : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(const RbParams P) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
     HitBuf H; H.n = 0;
     if (MODE == 1 && P.vl && !P.vl[RB_VL_REBUILD]) return;       // persistent lists still valid: nothing to enumerate
+    if (MODE == 3 && P.vl[RB_VL_REBUILD]) return;                // rebuild tick: everybody steps from the fresh lists
     bool valid;
     uint32_t A = 0, keyA = RB_NONE;
     float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     bool had_contact = false;
     if (MODE == 2) {
         // one thread per body ROW: the lists are indexed by row and may be older than this tick's poses,
         // so the frozen sphere comes from K1's world-sphere array, not from a sort
         A = tid;
-        if (tid < rb_n_owned(P)) keyA = P.key[tid];
+        uint32_t fl = 0;
+        if (tid < rb_n_owned(P)) { keyA = P.key[tid]; rec = P.e_rec[tid]; f0 = P.ws[tid]; fl = P.flags[tid]; }    // all in flight together
         valid = keyA != RB_NONE;
-        if (valid) { f0 = P.ws[tid]; had_contact = (P.flags[tid] & RB_F_CONTACT) != 0; }
+        had_contact = valid && (fl & RB_F_CONTACT) != 0;
+        // hot bodies (they have used their skin up) step in their own launch (MODE 3) on reuse ticks
+        if (P.vl && !P.vl[RB_VL_REBUILD] && (keyA & RB_HOT_BIT)) valid = false;
+    } else if (MODE == 3) {
+        // one thread per hot body of this tick (K1's table): it enumerates for itself -- partners from the sort of
+        // the last rebuild, whose entries are off by less than the skin they were grown by, plus the other hot
+        // bodies, triangles from the static grid -- and then steps exactly like the fused kernel
+        const uint32_t nh = min(P.hot_head[P.hcn * P.hcn], P.hot_cap);
+        valid = tid < nh;
+        if (valid) { A = P.hot_row[tid]; f0 = P.ws[A]; had_contact = (P.flags[A] & RB_F_CONTACT) != 0; }
     } else {
         const uint32_t n_sorted = P.col_start[P.scx * P.scz];
         valid = tid < n_sorted;
@@ -771,19 +785,16 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     const uint32_t gA = valid ? rb_gid(P, A) : 0u;
     const f3 fc = xyz(f0);
     const float frm = f0.w;
-    // persistent lists, reuse tick (warp-uniform): cold bodies step from their lists; hot bodies (they have
-    // used their skin up) enumerate for themselves -- partners from the sort of the last rebuild, whose
-    // entries are off by less than the skin they were grown by, and triangles from the static grid
-    const bool reuse = MODE == 2 && P.vl && !P.vl[RB_VL_REBUILD];
-    const bool hot = reuse && valid && (keyA & RB_HOT_BIT) != 0;
-    const bool enu = (MODE != 2) ? valid : hot;      // lanes that enumerate in this launch
+    // reuse tick of the persistent lists (warp-uniform): hot bodies are in nobody's list, everybody looks them up
+    const bool reuse = MODE == 3 || (MODE == 2 && P.vl && !P.vl[RB_VL_REBUILD]);
+    const bool enu = MODE != 2 && valid;      // lanes that enumerate in this launch
 
     // ---------------- P1: partner scan ----------------
     uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
 #pragma unroll
     for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
     uint32_t npart = 0;
-    if (MODE != 2 || reuse) {
+    if (MODE != 2) {
         // every lane walks its (up to 3) z-rows entry by entry; the loop is warp-uniform so the lanes
         // stay in lock step (independent thread scheduling would otherwise let sub-groups run ahead)
         uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0, ni = 0, ne = 0;
@@ -833,14 +844,15 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
             __syncwarp();
         }
     }
-    uint32_t hdr = 0;
-    if (MODE == 2 && valid && !hot) {          // cold (or every body of a launch that follows an enumeration): partners from the list
-        hdr = P.e_hdr[A];
+    const uint32_t hdr = rec.x;
+    if (MODE == 2 && valid) {                  // partners from the list
         npart = hdr & 0xffu;
+        if (npart) {
 #pragma unroll
-        for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < min(npart, (uint32_t)RB_SSCAND_MAX)) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
+            for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < min(npart, (uint32_t)RB_SSCAND_MAX)) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
+        }
     }
-    if (MODE == 2 && reuse) {
+    if ((MODE == 2 || MODE == 3) && reuse) {
         // hot bodies are nobody's list: everybody looks them up in the coarse cell table (<= 2 x 2 cells)
         uint32_t hcell[4] = { 0, 0, 0, 0 }, hn = 0;
         if (valid) {
@@ -886,7 +898,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     // canonical order; a triangle registered in two columns shows up twice).
     uint32_t nc = 0;
     bool st_slow = false;
-    if (MODE != 2 || reuse) {
+    if (MODE != 2) {
         uint32_t cur[4], end[4];
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) cur[k] = end[k] = 0;
@@ -999,18 +1011,27 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     }
     if (MODE == 1) {        // park the lists by body row (slot-major; rows follow the sort order closely) and stop
         if (valid) {
-            P.e_hdr[A] = min(npart, 255u) | (nc << 8) | (st_slow ? 0x10000u : 0u);
+            // one 16-B record per row: header + the first three triangles (most bodies have no more); the rest
+            // and the partners go to slot-major arrays
+            uint4 r4;
+            r4.x = min(npart, 255u) | (nc << 8) | (st_slow ? 0x10000u : 0u);
+            r4.y = nc > 0 ? s_cand[0][threadIdx.x] : 0u; r4.z = nc > 1 ? s_cand[1][threadIdx.x] : 0u; r4.w = nc > 2 ? s_cand[2][threadIdx.x] : 0u;
+            P.e_rec[A] = r4;
 #pragma unroll
             for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + A] = pg[k]; P.e_pl[(size_t)k * P.ns + A] = pl[k]; }
-            for (uint32_t j = 0; j < nc; ++j) P.e_cand[(size_t)j * P.ns + A] = s_cand[j][threadIdx.x];
+            for (uint32_t j = 3; j < nc; ++j) P.e_cand[(size_t)(j - 3) * P.ns + A] = s_cand[j][threadIdx.x];
             if (P.vl && npart > RB_SSCAND_MAX) P.ws_build[A].w = -1.0f;     // crowded: no list can hold its partners, it enumerates every tick (hot)
         }
         collide_epilogue(P, H, T, lane);
         return;
     }
-    if (MODE == 2 && valid && !hot) {
+    if (MODE == 2 && valid) {
         nc = (hdr >> 8) & 0xffu; st_slow = (hdr & 0x10000u) != 0;
-        for (uint32_t j = 0; j < nc; ++j) s_cand[j][threadIdx.x] = P.e_cand[(size_t)j * P.ns + A];
+        // the exact tests gather these 48-B triangles a little later: start the loads now
+        if (nc > 0) { s_cand[0][threadIdx.x] = rec.y; rb_prefetch(P.tri + 3ull * rec.y); rb_prefetch(P.tri + 3ull * rec.y + 2); }
+        if (nc > 1) { s_cand[1][threadIdx.x] = rec.z; rb_prefetch(P.tri + 3ull * rec.z); rb_prefetch(P.tri + 3ull * rec.z + 2); }
+        if (nc > 2) { s_cand[2][threadIdx.x] = rec.w; rb_prefetch(P.tri + 3ull * rec.w); rb_prefetch(P.tri + 3ull * rec.w + 2); }
+        for (uint32_t j = 3; j < nc; ++j) s_cand[j][threadIdx.x] = P.e_cand[(size_t)(j - 3) * P.ns + A];
     }
     if (MODE == 2) __syncwarp();
     // ---------------- lazy state load ----------------
@@ -1142,9 +1163,8 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     }
     collide_epilogue(P, H, T, lane);
     if (MODE == 0 && P.vl && P.vl_host && tid == 0) P.vl_host[2] = P.vl[RB_VL_NFAST];     // lists switched off: K1's count of fast movers
-    if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping, flag down for the next K1
-        const uint32_t f = P.vl[RB_VL_REBUILD];
-        P.vl[RB_VL_REBUILD] = 0u;
+    if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping
+        const uint32_t f = P.vl[RB_VL_REBUILD];      // (cleared by the next tick's memset: other blocks of this launch still read it)
         if (f) { P.vl[RB_VL_WHY_LAST] = P.vl[RB_VL_WHY]; P.vl[RB_VL_WHY] = 0u; }
         const uint32_t nr = P.vl[RB_VL_NREBUILD] + (f ? 1u : 0u), nt = P.vl[RB_VL_NTICK] + 1u;
         P.vl[RB_VL_NREBUILD] = nr; P.vl[RB_VL_NTICK] = nt;
@@ -1296,12 +1316,19 @@ void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* st
 void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st) {
     if (P.ns) rb_scatter_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P, 1, status, ticket, cdiv(ncols, RB_SCAN_TILE));
 }
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st) {
+// The hot bodies' launch is small and latency-bound (a few warps walking dependent loads): it runs on a side
+// stream next to the big list kernel. Both only write the bodies they own and read frozen data of the others.
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
     if (!P.nb) return 0;
     const uint32_t g = cdiv(P.ns, RB_BLOCK);
     rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
-    rb_collide_single_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P);
-    return 2;
+    cudaEventRecord(fork, st);
+    cudaStreamWaitEvent(side, fork, 0);
+    rb_collide_single_kernel<true, 3><<<cdiv(P.hot_cap, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies (reuse ticks)
+    cudaEventRecord(join, side);
+    rb_collide_single_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P);                              // everybody else, from the lists
+    cudaStreamWaitEvent(st, join, 0);
+    return 3;
 }
 int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st) {
     if (!P.nb) return 0;
@@ -1310,7 +1337,7 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
         if (variant == 1) {     // first-generation kernel, kept for A/B checks (RB_COLLIDE_V1=1)
             if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
             else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
-        } else if (variant == 2 || !P.e_hdr) {     // fused phases in one launch
+        } else if (variant == 2 || !P.e_rec) {     // fused phases in one launch
             if (resolve) rb_collide_single_kernel<true, 0><<<g, RB_BLOCK, 0, st>>>(P);
             else rb_collide_single_kernel<false, 0><<<g, RB_BLOCK, 0, st>>>(P);
         } else {                                   // enumerate at high occupancy, then test / resolve

@@ -62,6 +62,7 @@ void rb_world_destroy(rb_world* w) {
     for (auto& b : w->allocs) cudaFree(b.p);
     if (w->h_counters) cudaFreeHost(w->h_counters);
     if (w->vl_host) cudaFreeHost(w->vl_host);
+    if (w->vl_side) { cudaStreamDestroy(w->vl_side); cudaEventDestroy(w->vl_fork); cudaEventDestroy(w->vl_join); }
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->s_h2d) {
         cudaStreamSynchronize(w->s_h2d); cudaStreamSynchronize(w->s_d2h);
@@ -452,27 +453,33 @@ int rb_build(rb_world* w) {
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
     }
     if (w->vl_on) {
-        uint32_t* v; float4* wb;
-        ALLOC(v, 8); CU(cudaMemsetAsync(v, 0, 8 * sizeof(uint32_t), w->stream));
+        float4* wb;
         ALLOC(wb, ns); CU(cudaMemsetAsync(wb, 0, (size_t)ns * 16, w->stream));
         CU(cudaMemsetAsync(d_key, 0xff, (size_t)ns * 4, w->stream));                 // "not in the grid" until the first K1
         CU(cudaHostAlloc((void**)&w->vl_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
         w->vl_host[0] = w->vl_host[1] = w->vl_host[2] = w->vl_host[3] = 0;
         uint32_t* dv = nullptr; CU(cudaHostGetDevicePointer((void**)&dv, w->vl_host, 0));
-        P.vl = v; P.ws_build = wb; P.vl_host = dv;
+        P.ws_build = wb; P.vl_host = dv;
+        CU(cudaStreamCreateWithFlags(&w->vl_side, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&w->vl_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_join, cudaEventDisableTiming));
         // coarse cell table of the hot bodies: cells wide enough that any reach box touches at most 2 x 2 of them
         const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 256.0f);
         P.hcn = (uint32_t)std::max(1L, (long)std::floor(2.0 * P.half / lc));
         P.hc_inv_w = (float)P.hcn / (2.0f * P.half);
         P.hot_cap = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(256u, ns / 128u);
+        // one blob: cell heads | hot counter | list words. The per-tick memset clears the heads, the counter and the
+        // first list word (the rebuild flag) in one go; the words behind it persist.
         uint32_t *hh, *hr, *hn;
-        ALLOC(hh, (size_t)P.hcn * P.hcn + 1); ALLOC(hr, P.hot_cap); ALLOC(hn, P.hot_cap);
-        P.hot_head = hh; P.hot_row = hr; P.hot_next = hn;
+        const size_t ncell = (size_t)P.hcn * P.hcn;
+        ALLOC(hh, ncell + 1 + 8); ALLOC(hr, P.hot_cap); ALLOC(hn, P.hot_cap);
+        CU(cudaMemsetAsync(hh, 0, (ncell + 1 + 8) * sizeof(uint32_t), w->stream));
+        P.hot_head = hh; P.hot_row = hr; P.hot_next = hn; P.vl = hh + ncell + 1;
+        static_assert(RB_VL_REBUILD == 0, "the rebuild flag must be the first list word");
     }
     if (P.single && P.ns) {     // enumerate -> resolve hand-over lists
-        uint32_t *eh, *eg, *el, *ec;
-        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4); ALLOC(ec, (size_t)P.ns * 12);
-        P.e_hdr = eh; P.e_pg = eg; P.e_pl = el; P.e_cand = ec;
+        uint4* eh; uint32_t *eg, *el, *ec;
+        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4); ALLOC(ec, (size_t)P.ns * 9);
+        P.e_rec = eh; P.e_pg = eg; P.e_pl = el; P.e_cand = ec;
     }
     {   // static 3x3 of every _worldSpaceTransform, kept only when some body is not identity (model-matrix export)
         bool any = false;
@@ -562,7 +569,7 @@ static int enqueue_list_tick(rb_world* w, bool reorder_due) {
     RbParams& P = w->P;
     const bool force = w->vl_force || reorder_due;
     if (force) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));   // other paths may have left counts behind
-    CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 1) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter
+    CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter + rebuild flag
     CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, 1, force ? 3 : 2, w->stream);
@@ -573,7 +580,7 @@ static int enqueue_list_tick(rb_world* w, bool reorder_due) {
     rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (reorder_due) { int r = reorder_rows(w, true); if (r) return r; }     // rows into sort order before the lists are built for them
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
-    w->launches += 4 + rb_launch_vl_collide(P, w->stream);
+    w->launches += 4 + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join);
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
