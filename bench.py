@@ -280,26 +280,37 @@ def run_ours(args):
     step_bytes = st1["n_bodies"] * 64 + st1["n_tris"] * 36 + contacts * 24
     # ---- e2e: the per-tick host round trip through the C ABI with pinned HOST buffers ----
     nb = st1["n_bodies"]
-    force = [torch.zeros((nb, 4), dtype=torch.float32).pin_memory() for _ in range(3)]
-    pos = [torch.zeros((nb, 4), dtype=torch.float32).pin_memory() for _ in range(3)]
+    RING = 4          # RB_HOST_PIPE_DEPTH of include/reboot_physics.h: results land three calls later
+    force = [torch.zeros((nb, 4), dtype=torch.float32).pin_memory() for _ in range(RING)]
+    pos = [torch.zeros((nb, 4), dtype=torch.float32).pin_memory() for _ in range(RING)]
+    force3 = [torch.zeros((nb, 3), dtype=torch.float32).pin_memory() for _ in range(RING)]
+    pos3 = [torch.zeros((nb, 3), dtype=torch.float32).pin_memory() for _ in range(RING)]
     e2e_steps = max(20, min(args.steps, 200))
 
-    def host_tick(k):
+    def host_tick(k, packed=True):
         # one reference-style tick through the C ABI with HOST buffers: this tick's forces go up from pinned
-        # memory, the tick runs, its positions + contact count come back (double-buffered, see rb_step_host_async)
-        rc = w.L.rb_step_host_async(w.h, DT_MS, force[k % 3].data_ptr(), pos[k % 3].data_ptr(), None)
+        # memory, the tick runs, its positions + contact count come back (4-deep ring, see rb_step_host_async).
+        # packed: xyz arrays, 12 B per body each way (rb_step_host_async3); else float4 arrays
+        if packed:
+            rc = w.L.rb_step_host_async3(w.h, DT_MS, force3[k % RING].data_ptr(), pos3[k % RING].data_ptr(), None)
+        else:
+            rc = w.L.rb_step_host_async(w.h, DT_MS, force[k % RING].data_ptr(), pos[k % RING].data_ptr(), None)
         assert rc == 0, w.L.rb_last_error(w.h)
 
-    for k in range(6):
-        host_tick(k)
-    w.sync()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        host_tick(k)
-    w.sync()          # the last tick's positions have landed
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1000 / e2e_steps
+    def time_host_ticks(packed):
+        for k in range(6):
+            host_tick(k, packed)
+        w.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            host_tick(k, packed)
+        w.sync()          # the last tick's positions have landed
+        barrier()
+        return (time.perf_counter() - t0) * 1000 / e2e_steps
+
+    e2e_xyzw_ms = time_host_ticks(False)
+    e2e_ms = time_host_ticks(True)
     # blocking variant (upload, tick, download, sync -- nothing overlapped), for the record
     for _ in range(3):
         w.L.rb_step_host(w.h, DT_MS, force[0].data_ptr(), pos[0].data_ptr(), None)
@@ -323,19 +334,20 @@ def run_ours(args):
                        "regime": f"settled ({args.settle} untimed ticks first)", "dt_ms": DT_MS,
                        "l2": "working set > L2: state + sorted spheres + grids + triangles ~ 0.3 GB per GPU, no flush needed",
                        "unit_note": "value = n_gpus x ticks/s (each tick advances n_gpus C3-sized units)"},
-            "e2e": {"value": N * 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": nb * 16, "d2h_bytes_per_step": nb * 16 + 8, "ms_per_step": e2e_ms,
-                    "blocking_ms_per_step": e2e_blocking_ms,
-                    "note": "rb_step_host_async: every tick uploads that tick's forces from pinned host memory, runs the tick and downloads its positions + contact count; copies go through a 3-deep ring on their own streams so they overlap neighbouring ticks (blocking_ms_per_step = the same with nothing overlapped)"},
+            "e2e": {"value": N * 1000.0 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": nb * 12, "d2h_bytes_per_step": nb * 12 + 8, "ms_per_step": e2e_ms,
+                    "xyzw_ms_per_step": e2e_xyzw_ms, "blocking_ms_per_step": e2e_blocking_ms,
+                    "note": "rb_step_host_async3: every tick uploads that tick's forces (xyz per body) from pinned host memory, runs the tick and downloads its positions (xyz) + contact count; copies go through a 4-deep ring on their own streams so they overlap neighbouring ticks. The round trip is PCIe-bound: xyzw_ms_per_step = the same with float4 arrays (16 B per body each way, rb_step_host_async), blocking_ms_per_step = float4 with nothing overlapped (rb_step_host)"},
             "gpu_launches": int(l1 - l0),
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic() if N == 1 else None,
-                         "kernel": "rb_collide_single_kernel<resolve>", "kernel_ms": collide_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
+                         "kernel": "rb_collide_single_kernel<resolve, lists> (+ the amortised list rebuilds)" if final.get("list_ticks") else "rb_collide_single_kernel<resolve>", "kernel_ms": collide_ms, "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "step_algorithmic_bytes": step_bytes, "step_frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          "kernel_ms_all": {k: v / args.steps for k, v in kms.items()}},
             "contact_tests_per_s": N * tests_step * 1000.0 / ms_step, "contact_tests_per_step": tests_step, "contacts_per_step": contacts,
             "free_fall": {"ms_per_step": ff_ms, "steps_per_s": N * 1000.0 / ff_ms, "contact_tests_per_step": ff_tests},
             "audit": {"contacts_dropped": final["contacts_dropped"], "margin_overflow": final["margin_overflow"],
-                      "halo_sent_last": final["halo_sent_last"], "halo_recv_last": final["halo_recv_last"], "device_bytes": final["device_bytes"]},
+                      "halo_sent_last": final["halo_sent_last"], "halo_recv_last": final["halo_recv_last"], "device_bytes": final["device_bytes"],
+                      "list_ticks": final["list_ticks"], "list_rebuilds": final["list_rebuilds"], "list_hot_last": final["list_hot_last"], "list_skin": final["list_skin"]},
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

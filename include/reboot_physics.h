@@ -192,12 +192,17 @@ int         rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const fl
  * nullable) and the contact count, and synchronise. */
 int         rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts);
 /* The same round trip, pipelined: the H2D copy of this tick's forces, the tick, and the D2H copy of its
- * positions run on three streams over a ring of 3 staging buffers so both copy engines overlap
+ * positions run on three streams over a ring of 4 staging buffers so both copy engines overlap
  * neighbouring ticks -- the reference's own model (physics thread produces, render thread reads a little
  * behind under Physics::_lock, physics/include/Physics.h:44). Returns when the pos4 buffer and contact
- * count of the call made TWO calls earlier are complete; rotate three pinned pos4 buffers and finish
- * with rb_sync(). */
+ * count of the call made THREE calls earlier are complete; rotate four pinned pos4 (and force4) buffers
+ * and finish with rb_sync(). On ticks stepped from the persistent candidate lists the forces are taken
+ * and the positions are left by the tick's own kernels (no extra pass over the bodies). */
+#define RB_HOST_PIPE_DEPTH 4
 int         rb_step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done);
+/* The same with packed xyz arrays (3 floats per body each way; masses keep their values): the pipelined
+ * round trip is bound by the PCIe copies, so 12 instead of 16 bytes per body is a quarter less time. */
+int         rb_step_host_async3(rb_world* w, int ms, const float* force3, float* pos3, uint64_t* n_contacts_done);
 
 int         rb_get_stats(rb_world* w, rb_stats_t* out);
 /* cumulative CUDA-event time (ms) of each kernel family since the last reset, when profiling is on:

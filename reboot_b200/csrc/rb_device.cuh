@@ -100,6 +100,10 @@ struct RbParams {
     unsigned long long contact_cap;
     unsigned long long* counters;
     unsigned long long* stripes;  // RB_STRIPES x RB_C_COUNT striped copies of the cumulative test / hit counters
+    // ---- host round trip fused into the tick (list ticks of rb_step_host_async*): K1 takes this tick's forces
+    // straight from the uploaded id-ordered array, the resolve kernels leave the final positions in id order ----
+    const float* force_in; uint32_t force_in_stride;   // NULL: forces come from P.force as usual
+    float* pos_out; uint32_t pos_out_stride;            // NULL: nobody asked
     // ---- candidate lists, indexed by body row (single-sphere worlds, slot-major) ----
     uint4* e_rec;                 // per row: { npart | nc << 8 | slow << 16, first three triangle ids }
     uint32_t* e_pg; uint32_t* e_pl;   // [RB_SSCAND_MAX][ns] partner global id / local row

@@ -25,6 +25,8 @@ int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, 
 void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, const uint32_t* inv, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
 void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t* inv, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
 void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st);
+void rb_launch_apply_force3(const uint32_t* flags, const float* in3, float4* out, const uint32_t* inv, uint32_t count, cudaStream_t st);
+void rb_launch_rows_to_ids_f3(const float4* rows, const uint32_t* gid, float* out3, uint32_t n, cudaStream_t st);
 void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st);
 void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st);
 void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st);
@@ -37,12 +39,15 @@ int rb_dist_step_exchange(rb_world* w, int ms);
 void rb_dist_destroy(RbDist* d);
 int rb_dist_refresh_counts(rb_world* w);
 extern "C" int rb_reorder_rows_now(rb_world* w);
+extern "C" bool rb_step_will_use_lists(rb_world* w);
 int rb_dist_rows_moved(rb_world* w);   // the per-body arrays were swapped: refresh the device copy of the halo parameters
 extern "C" int enqueue_broadphase_tail(rb_world* w);
 
 extern thread_local std::string g_create_error;
 
-#define RB_PIPE 3     // depth of the pipelined host round trip (results arrive RB_PIPE - 1 calls later)
+#ifndef RB_PIPE
+#define RB_PIPE 4     // depth of the pipelined host round trip (results arrive RB_PIPE - 1 calls later; 3 left the copy
+#endif                // engines no slack: a tick's upload was only queued once the download two ticks back had finished)
 
 struct DevBuf { void* p = nullptr; size_t bytes = 0; };
 
@@ -82,6 +87,7 @@ struct rb_world {
     bool vl_force = true;                    // the next list tick must rebuild (first tick, rows moved, state edited behind the lists' back)
     float vl_skin_cfg = 0.0f;                // 0 = auto
     // adaptive: while the lists get rebuilt on most ticks (free fall, violent scenes) the per-tick kernel is cheaper
+    uint64_t vl_decided_for = 0;             // step number (1-based) the use-lists decision below was taken for
     bool vl_active = true; uint64_t vl_resume_at = 0; uint32_t vl_backoff = 32; uint32_t vl_seen_r = 0, vl_seen_t = 0;
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
     uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}

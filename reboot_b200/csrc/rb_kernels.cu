@@ -41,10 +41,21 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
     f3 p = xyz(p4), v = xyz(v4);
     const float dt = P.dt;
     if (do_integrate) {
+        float4 F = make_float4(0.f, 0.f, 0.f, 1.0f);
+        if (P.force && b < n_owned) {
+            F = P.force[b];
+            if (P.force_in) {
+                // StateVector::setForce for this tick, fused: gated by the contact / gravity flags as they stand before
+                // the integration (math/src/StateVector.cpp:147-157); the array is in body-id order
+                const float* fi = P.force_in + (size_t)P.force_in_stride * (P.gid ? P.gid[b] : b);
+                if ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) F = make_float4(fi[0], fi[1], fi[2], F.w);
+                else F = make_float4(0.f, 0.f, 0.f, F.w);
+                P.force[b] = F;
+            }
+        }
         if ((f & RB_F_ACTIVE) && b < n_owned) {
-            f3 frc = mk3(0.f, 0.f, 0.f);
-            float mass = 1.0f;
-            if (P.force) { float4 F = P.force[b]; frc = xyz(F); mass = F.w; }
+            f3 frc = xyz(F);
+            float mass = F.w;
             f3 la = mk3(frc.x / mass, frc.y / mass, frc.z / mass);
             float g = (f & RB_F_GRAVITY) ? P.gravity : 0.0f;
             f3 dv = mk3(la.x * dt, (la.y + g) * dt, la.z * dt);
@@ -1161,6 +1172,18 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
             atomicAnd(&P.flags[A], ~RB_F_CONTACT);       // touched nothing: lose the contact flag, no state gather
         }
     }
+    if ((MODE == 2 || MODE == 3) && P.pos_out) {
+        // the host asked for this tick's positions in id order: every row is written exactly once, by the launch that
+        // owns it this tick (hot rows by MODE 3 on reuse ticks, everything else by MODE 2)
+        const bool mine = MODE == 3 ? valid : (tid < rb_n_owned(P) && !(P.vl && !P.vl[RB_VL_REBUILD] && keyA != RB_NONE && (keyA & RB_HOT_BIT)));
+        if (mine) {
+            f3 pf = S.p;
+            if (!need) pf = xyz(P.pos[A]);
+            float* po = P.pos_out + (size_t)P.pos_out_stride * rb_gid(P, A);
+            po[0] = pf.x; po[1] = pf.y; po[2] = pf.z;
+            if (P.pos_out_stride == 4) po[3] = 1.0f;
+        }
+    }
     collide_epilogue(P, H, T, lane);
     if (MODE == 0 && P.vl && P.vl_host && tid == 0) P.vl_host[2] = P.vl[RB_VL_NFAST];     // lists switched off: K1's count of fast movers
     if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping
@@ -1210,6 +1233,24 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_fill_f4_kernel(float4* p, uint32_
 __global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_f4_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ gid, float4* __restrict__ out, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[gid[i]] = rows[i];
+}
+// packed xyz variants of the host round trip (12 B per body each way instead of 16: the round trip is PCIe-bound)
+__global__ void __launch_bounds__(RB_BLOCK) rb_apply_force3_kernel(const uint32_t* __restrict__ flags, const float* __restrict__ in3,
+                                                                  float4* __restrict__ out, const uint32_t* __restrict__ inv, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    uint32_t row = inv ? inv[i] : i;
+    uint32_t f = flags[row];
+    float w = out[row].w;
+    if ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) out[row] = make_float4(in3[3ull * i], in3[3ull * i + 1], in3[3ull * i + 2], w);
+    else out[row] = make_float4(0.f, 0.f, 0.f, w);
+}
+__global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_f3_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ gid, float* __restrict__ out3, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 v = rows[i];
+    const size_t o = 3ull * (gid ? gid[i] : i);
+    out3[o] = v.x; out3[o + 1] = v.y; out3[o + 2] = v.z;
 }
 __global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_u32_kernel(const uint32_t* __restrict__ rows, const uint32_t* __restrict__ gid, uint32_t* __restrict__ out, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1367,6 +1408,12 @@ void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st) {
 }
 void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st) {
     if (n) rb_rows_to_ids_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n);
+}
+void rb_launch_apply_force3(const uint32_t* flags, const float* in3, float4* out, const uint32_t* inv, uint32_t count, cudaStream_t st) {
+    if (count) rb_apply_force3_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, in3, out, inv, count);
+}
+void rb_launch_rows_to_ids_f3(const float4* rows, const uint32_t* gid, float* out3, uint32_t n, cudaStream_t st) {
+    if (n) rb_rows_to_ids_f3_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out3, n);
 }
 void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st) {
     if (n) rb_rows_to_ids_u32_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n);

@@ -591,30 +591,37 @@ static int enqueue_list_tick(rb_world* w, bool reorder_due) {
     return RB_OK;
 }
 
+// Will the next rb_step run from the persistent lists? (decided once per step)
+// The device reports {rebuild ticks, list ticks} through mapped host memory; the host only looks at it (never
+// waits for it) to notice phases in which nearly every tick rebuilds, and sits those out on the per-tick
+// kernel. Both paths give the same results, so the switch is invisible.
+bool rb_step_will_use_lists(rb_world* w) {
+    if (!w->vl_on) return false;
+    if (w->vl_decided_for == w->steps + 1) return w->vl_active;
+    w->vl_decided_for = w->steps + 1;
+    if (w->vl_active) {
+        const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
+        if (nt - w->vl_seen_t >= 16u) {
+            const bool mostly_rebuilding = 2u * (nr - w->vl_seen_r) > (nt - w->vl_seen_t);
+            w->vl_seen_r = nr; w->vl_seen_t = nt;
+            if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
+            else w->vl_backoff = 32;
+        }
+    } else if (w->steps >= w->vl_resume_at) {
+        // come back once few enough bodies outrun the skin (the per-tick kernel keeps counting them)
+        if (w->vl_host[2] < w->P.hot_cap / 4u) { w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1]; }
+        else w->vl_resume_at = w->steps + 16;
+    }
+    return w->vl_active;
+}
+
 int rb_step(rb_world* w, int ms) {
     if (!w || !w->built) return w ? fail(w, RB_ERR_INVALID, "rb_step before rb_build") : RB_ERR_INVALID;
     CU(cudaSetDevice(w->cfg.device));
     w->P.dt = (float)ms / 1000.0f;                     // StateVector.cpp:19
     const bool reorder_due = w->reorder_every > 0 && (w->steps + 1) % (uint64_t)w->reorder_every == 0;
     int r;
-    if (w->vl_on) {
-        // the device reports {rebuild ticks, list ticks} through mapped host memory; the host only looks at it
-        // (never waits for it) to notice phases in which nearly every tick rebuilds, and sits those out on the
-        // per-tick kernel. Both paths give the same results, so the switch is invisible.
-        if (w->vl_active) {
-            const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
-            if (nt - w->vl_seen_t >= 16u) {
-                const bool mostly_rebuilding = 2u * (nr - w->vl_seen_r) > (nt - w->vl_seen_t);
-                w->vl_seen_r = nr; w->vl_seen_t = nt;
-                if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
-                else w->vl_backoff = 32;
-            }
-        } else if (w->steps >= w->vl_resume_at) {
-            // come back once few enough bodies outrun the skin (the per-tick kernel keeps counting them)
-            if (w->vl_host[2] < w->P.hot_cap / 4u) { w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1]; }
-            else w->vl_resume_at = w->steps + 16;
-        }
-    }
+    rb_step_will_use_lists(w);
     if (w->vl_on && w->vl_active) { r = enqueue_list_tick(w, reorder_due); if (r) return r; }      // a re-ordering tick rebuilds: it needs a fresh sort
     else {
         if (w->vl_on) CU(cudaMemsetAsync(w->P.vl + RB_VL_NFAST, 0, 4, w->stream));
@@ -867,12 +874,16 @@ int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t
 }
 
 // Pipelined per-tick host round trip: the H2D copy of this tick's forces, the tick itself and the D2H copy
-// of its positions run on three streams over a ring of RB_PIPE (3) staging buffers, so the two copy
+// of its positions run on three streams over a ring of RB_PIPE (4) staging buffers, so the two copy
 // engines overlap the compute of neighbouring ticks -- the reference's own threading model (its physics
 // thread produces, its render thread reads a little behind under Physics::_lock). The call returns once
-// the results of the call made RB_PIPE - 1 = 2 calls earlier have landed in the host buffers passed to
-// THAT call; callers rotate three pos4 buffers and finish with rb_sync().
-int rb_step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done) {
+// the results of the call made RB_PIPE - 1 = 3 calls earlier have landed in the host buffers passed to
+// THAT call; callers rotate four pos4 buffers and finish with rb_sync().
+static_assert(RB_PIPE == RB_HOST_PIPE_DEPTH, "header and implementation disagree on the ring depth");
+static int step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done, int stride);
+int rb_step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done) { return step_host_async(w, ms, force4, pos4, n_contacts_done, 4); }
+int rb_step_host_async3(rb_world* w, int ms, const float* force3, float* pos3, uint64_t* n_contacts_done) { return step_host_async(w, ms, force3, pos3, n_contacts_done, 3); }
+static int step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done, int stride) {
     if (!w || !w->built) return RB_ERR_INVALID;
     CU(cudaSetDevice(w->cfg.device));
     const size_t nb = w->n_owned_host;
@@ -889,24 +900,40 @@ int rb_step_host_async(rb_world* w, int ms, const float* force4, float* pos4, ui
     }
     const int b = (int)(w->p_calls % RB_PIPE);
     int r;
+    // list ticks take the forces and leave the positions themselves (no extra pass over the bodies);
+    // whether this tick will be one is rb_step's decision, so it is asked first
+    const bool fused_io = rb_step_will_use_lists(w);
     if (force4) {
         r = ensure_force(w); if (r) return r;
         if (w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->s_h2d, w->pe_force[b], 0));   // staging b was consumed RB_PIPE calls ago
-        CU(cudaMemcpyAsync(w->p_force[b], force4, nb * 16, cudaMemcpyHostToDevice, w->s_h2d));
+        CU(cudaMemcpyAsync(w->p_force[b], force4, nb * 4 * stride, cudaMemcpyHostToDevice, w->s_h2d));
         CU(cudaEventRecord(w->pe_h2d[b], w->s_h2d));
         CU(cudaStreamWaitEvent(w->stream, w->pe_h2d[b], 0));
-        rb_launch_apply_force(w->P.flags, w->p_force[b], w->P.force, w->d_inv, 0, (uint32_t)nb, 1, w->stream); w->launches++;
-        CU(cudaEventRecord(w->pe_force[b], w->stream));
+        if (fused_io) { w->P.force_in = (const float*)w->p_force[b]; w->P.force_in_stride = (uint32_t)stride; }
+        else {
+            if (stride == 4) rb_launch_apply_force(w->P.flags, w->p_force[b], w->P.force, w->d_inv, 0, (uint32_t)nb, 1, w->stream);
+            else rb_launch_apply_force3(w->P.flags, (const float*)w->p_force[b], w->P.force, w->d_inv, (uint32_t)nb, w->stream);
+            w->launches++;
+            CU(cudaEventRecord(w->pe_force[b], w->stream));
+        }
     }
-    r = rb_step(w, ms); if (r) return r;
-    if (w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->stream, w->pe_d2h[b], 0));         // output staging b was read RB_PIPE calls ago
-    if (pos4) {
-        if (w->d_inv) { rb_launch_rows_to_ids_f4(w->P.pos, w->P.gid, w->p_pos[b], (uint32_t)nb, w->stream); w->launches++; }
+    if (fused_io && pos4) {
+        if (w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->stream, w->pe_d2h[b], 0));     // output staging b was read RB_PIPE calls ago
+        w->P.pos_out = (float*)w->p_pos[b]; w->P.pos_out_stride = (uint32_t)stride;
+    }
+    r = rb_step(w, ms);
+    w->P.force_in = nullptr; w->P.pos_out = nullptr;
+    if (r) return r;
+    if (fused_io && force4) CU(cudaEventRecord(w->pe_force[b], w->stream));
+    if (!fused_io && w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->stream, w->pe_d2h[b], 0));         // output staging b was read RB_PIPE calls ago
+    if (pos4 && !fused_io) {
+        if (stride == 3) { rb_launch_rows_to_ids_f3(w->P.pos, w->d_inv ? w->P.gid : nullptr, (float*)w->p_pos[b], (uint32_t)nb, w->stream); w->launches++; }
+        else if (w->d_inv) { rb_launch_rows_to_ids_f4(w->P.pos, w->P.gid, w->p_pos[b], (uint32_t)nb, w->stream); w->launches++; }
         else CU(cudaMemcpyAsync(w->p_pos[b], w->P.pos, nb * 16, cudaMemcpyDeviceToDevice, w->stream));
     }
     CU(cudaEventRecord(w->pe_step[b], w->stream));
     CU(cudaStreamWaitEvent(w->s_d2h, w->pe_step[b], 0));
-    if (pos4) CU(cudaMemcpyAsync(pos4, w->p_pos[b], nb * 16, cudaMemcpyDeviceToHost, w->s_d2h));
+    if (pos4) CU(cudaMemcpyAsync(pos4, w->p_pos[b], nb * 4 * stride, cudaMemcpyDeviceToHost, w->s_d2h));
     CU(cudaMemcpyAsync(&w->p_cnt[b], w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->s_d2h));
     CU(cudaEventRecord(w->pe_d2h[b], w->s_d2h));
     // results of the call made RB_PIPE - 1 calls ago

@@ -412,29 +412,38 @@ def test_persistent_lists_survive_host_edits(World, monkeypatch):
 
 
 def test_pipelined_host_round_trip_matches_blocking(World):
-    """rb_step_host_async (3-deep ring, copies overlapping the tick) delivers, two calls later, exactly what
+    """rb_step_host_async (4-deep ring, copies overlapping the tick) delivers, three calls later, exactly what
     the blocking rb_step_host delivers: positions in id order and the contact count."""
     from reboot_b200 import scenes
     from reboot_b200._lib import ptr
     sc = scenes.falling_spheres(30000, 120, 2.0, 0.5, (0.3, 3.0), True, 8, "pipe")
-    w1, w2 = World(sc), World(sc)
+    w1, w2, w3 = World(sc), World(sc), World(sc)
     nb = sc.n_bodies
     rng = np.random.default_rng(1)
     force = np.zeros((nb, 4), np.float32); force[:, 0] = rng.uniform(-3, 3, nb); force[:, 2] = rng.uniform(-3, 3, nb)
+    force3 = np.ascontiguousarray(force[:, :3])
     p_sync = np.zeros((nb, 4), np.float32)
-    p_async = [np.zeros((nb, 4), np.float32) for _ in range(3)]
+    D = 4                                                             # RB_HOST_PIPE_DEPTH: results arrive D - 1 calls later
+    p_async = [np.zeros((nb, 4), np.float32) for _ in range(D)]
+    p_async3 = [np.zeros((nb, 3), np.float32) for _ in range(D)]      # rb_step_host_async3: packed xyz both ways
     hist = []
-    n2 = C.c_uint64()
+    n2, n3 = C.c_uint64(), C.c_uint64()
     for k in range(70):
+        if k == 40:       # the forces change mid-run (they are taken from the uploaded array of each tick)
+            force[:, 0] = rng.uniform(-30, 30, nb); force3 = np.ascontiguousarray(force[:, :3])
         n1 = w1.step_host(5, force, p_sync)
         hist.append((p_sync.copy(), n1))
-        assert w2.L.rb_step_host_async(w2.h, 5, ptr(force), ptr(p_async[k % 3]), C.byref(n2)) == 0
-        if k >= 2:
-            assert np.array_equal(bits(p_async[(k - 2) % 3]), bits(hist[k - 2][0])) and n2.value == hist[k - 2][1], k
-    w2.sync()
-    assert np.array_equal(bits(p_async[69 % 3]), bits(p_sync))
+        assert w2.L.rb_step_host_async(w2.h, 5, ptr(force), ptr(p_async[k % D]), C.byref(n2)) == 0
+        assert w3.L.rb_step_host_async3(w3.h, 5, ptr(force3), ptr(p_async3[k % D]), C.byref(n3)) == 0
+        if k >= D - 1:
+            j = k - (D - 1)
+            assert np.array_equal(bits(p_async[j % D]), bits(hist[j][0])) and n2.value == hist[j][1], k
+            assert np.array_equal(bits(p_async3[j % D]), bits(hist[j][0][:, :3].copy())) and n3.value == hist[j][1], k
+    w2.sync(); w3.sync()
+    assert np.array_equal(bits(p_async[69 % D]), bits(p_sync)) and np.array_equal(bits(p_async3[69 % D]), bits(p_sync[:, :3].copy()))
     assert np.array_equal(bits(w1.state()["pos"]), bits(w2.state()["pos"])) and hist[-1][1] > 1000
-    w1.close(); w2.close()
+    assert np.array_equal(bits(w1.state()["pos"]), bits(w3.state()["pos"])) and np.array_equal(bits(w1.state()["vel"]), bits(w3.state()["vel"]))
+    w1.close(); w2.close(); w3.close()
 
 
 def test_model_matrix_export_matches_oracle(World, port):
