@@ -142,7 +142,10 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
 // ---- K6c: one launch unpacks both kinds. Blocks [0, imm_blocks): immigrants become owned rows (appended
 // behind the owned rows); the other blocks: ghosts, stored from the END of the arrays downwards so that they
 // do not depend on the final owned count. Both are binned on the way. -----------------------------------
-__global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, RbDistParams D, uint32_t imm_blocks) {
+// list_tick: persistent-list ticks -- immigrants only get their column (the conditional bin kernel ranks them) and
+// force a list rebuild; ghosts are not binned at all but linked into the hot-body cell table behind the own hot
+// bodies (entry hot_cap + ghost index), where every owned body looks them up.
+__global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, RbDistParams D, uint32_t imm_blocks, int list_tick) {
     const uint32_t ghost_floor = D.cap_local - 3u * D.ghost_cap;      // rows [ghost_floor, cap) are reserved for ghosts
     if (blockIdx.x < imm_blocks) {
         uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,9 +165,10 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
         uint32_t k = RB_NONE;
         if ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) {
             k = rb_col(c.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
-            P.rank[i] = atomicAdd(&P.col_count[k], 1u);
+            if (!list_tick) P.rank[i] = atomicAdd(&P.col_count[k], 1u);
         }
         P.key[i] = k;
+        if (list_tick) { P.vl[RB_VL_REBUILD] = 1u; atomicOr(&P.vl[RB_VL_WHY], 8u); }      // new row: the lists are stale
         return;
     }
     uint32_t t = (blockIdx.x - imm_blocks) * blockDim.x + threadIdx.x;
@@ -173,11 +177,20 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
     uint32_t n2 = min(*D.self_cnt, D.ghost_cap);
     if (t >= n0 + n1 + n2) return;
     const RbGhostRec q = t < n0 ? D.in_ghost[0][t] : (t < n0 + n1 ? D.in_ghost[1][t - n0] : D.self_ghost[t - n0 - n1]);
-    uint32_t i = D.cap_local - 1u - atomicAdd(&D.dn[1], 1u);
+    const uint32_t gi = atomicAdd(&D.dn[1], 1u);
+    uint32_t i = D.cap_local - 1u - gi;
     P.ws[i] = q.ws;
     D.sph_obj_w[i] = make_float4(0.f, 0.f, 0.f, q.r);
     D.gid[i] = q.gid;
     P.flags[i] = RB_F_ACTIVE;
+    if (list_tick) {
+        const uint32_t h = P.hot_cap + gi;
+        const uint32_t cell = rb_col(q.ws.z, P.half, P.hc_inv_w, P.hcn) * P.hcn + rb_col(q.ws.x, P.half, P.hc_inv_w, P.hcn);
+        P.hot_row[h] = i;
+        P.hot_next[h] = atomicExch(&P.hot_head[cell], h + 1u);
+        P.key[i] = RB_NONE;
+        return;
+    }
     uint32_t k = rb_col(q.ws.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(q.ws.x, -P.s_x0, P.s_inv_w, P.scx);
     P.key[i] = k;
     P.rank[i] = atomicAdd(&P.col_count[k], 1u);
@@ -296,16 +309,18 @@ static int dist_upload_params(rb_world* w) {
     return RB_OK;
 }
 // phase A: integrate + bin + halo pack (everything before the exchange)
-static int dist_phase_a(rb_world* w, int do_integrate) {
+// list_mode: 0 = per-tick enumeration (K1 bins), 2 = persistent-list tick, 3 = the same with a rebuild forced by the host
+static int dist_phase_a(rb_world* w, int do_integrate, int list_mode) {
     RbDist* d = w->dist; RbParams& P = w->P;
     if (!d->params_valid) { int r = dist_upload_params(w); if (r) return r; }
     const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
     const int p = remote ? (int)(d->halo_step & 1) : 0;
     P.dp = d->d_dp[p];
-    CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));
+    if (list_mode != 2) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));      // (list ticks leave the histogram clean themselves)
+    if (list_mode) CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter + rebuild flag
     CU(cudaMemsetAsync(w->d_dn + 1, 0, 11 * sizeof(uint32_t), w->stream));    // n_ghost, self ghosts, emigrants, both out headers
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
-    rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;     // integrate + bin + halo pack
+    rb_launch_integrate_bin(P, do_integrate, list_mode ? list_mode : 1, w->stream); w->launches++;     // integrate + bin + halo pack
     if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));
     // headers (and, on the fused transport, the arrival flags) go out
     RbHaloHeader* ph[2] = { d->out[0].hdr(), d->out[1].hdr() }; uint32_t* pa[2] = { nullptr, nullptr };
@@ -317,18 +332,18 @@ static int dist_phase_a(rb_world* w, int do_integrate) {
     return RB_OK;
 }
 // phase B: unpack + scan + scatter (everything after the exchange)
-static int dist_phase_b(rb_world* w) {
+static int dist_phase_b(rb_world* w, int list_mode) {
     RbDist* d = w->dist; RbParams& P = w->P;
     const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
     const int p = remote ? (int)(d->halo_step & 1) : 0;
     const bool wait = d->mode == RB_X_P2P;
     rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->Dp[p], wait && d->peer_blob[0] ? d->arrive(0) : nullptr, wait && d->peer_blob[1] ? d->arrive(1) : nullptr, d->halo_step, d->timeout_flag());
     const uint32_t imm_blocks = cdiv(2 * d->migr_cap, RB_BLOCK);
-    rb_halo_unpack_kernel<<<imm_blocks + cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->Dp[p], imm_blocks);
+    rb_halo_unpack_kernel<<<imm_blocks + cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->Dp[p], imm_blocks, list_mode ? 1 : 0);
     w->launches += 2;
     CU(cudaGetLastError());
     d->halo_step++;
-    return enqueue_broadphase_tail(w);
+    return list_mode ? RB_OK : enqueue_broadphase_tail(w);       // (list ticks: the caller continues with the conditional rebuild chain)
 }
 
 static int dist_exchange_nccl(rb_world* w) {
@@ -344,9 +359,17 @@ static int dist_exchange_nccl(rb_world* w) {
 int rb_dist_step_exchange(rb_world* w, int do_integrate) {
     RbDist* d = w->dist;
     if (d->mode != RB_X_NCCL && d->mode != RB_X_P2P) return fail(w, RB_ERR_INVALID, "this slab world has in-process neighbours: step it with rb_step_group");
-    int r = dist_phase_a(w, do_integrate); if (r) return r;
+    int r = dist_phase_a(w, do_integrate, 0); if (r) return r;
     if (d->mode == RB_X_NCCL) { r = dist_exchange_nccl(w); if (r) return r; }
-    return dist_phase_b(w);
+    return dist_phase_b(w, 0);
+}
+// the halo part of a persistent-list tick (K1 with the list checks + pack, exchange, remove + unpack)
+int rb_dist_list_exchange(rb_world* w, int list_mode) {
+    RbDist* d = w->dist;
+    if (d->mode != RB_X_NCCL && d->mode != RB_X_P2P) return fail(w, RB_ERR_INVALID, "this slab world has in-process neighbours: step it with rb_step_group");
+    int r = dist_phase_a(w, 1, list_mode); if (r) return r;
+    if (d->mode == RB_X_NCCL) { r = dist_exchange_nccl(w); if (r) return r; }
+    return dist_phase_b(w, list_mode);
 }
 
 extern "C" {
@@ -425,15 +448,29 @@ static int group_collide(rb_world** ws, int n, int ms, int do_integrate, int res
         if (!w || !w->dist) return w ? fail(w, RB_ERR_INVALID, "rb_step_group: world %d has no peers attached", i) : RB_ERR_INVALID;
         CU(cudaSetDevice(w->cfg.device));
         if (do_integrate) w->P.dt = (float)ms / 1000.0f;
-        int r = dist_phase_a(w, do_integrate); if (r) return r;
+        // persistent-list tick? (decided per world; stepping only)
+        w->group_list_mode = 0;
+        if (do_integrate && resolve && rb_step_will_use_lists(w)) {
+            const bool reorder_due = w->reorder_every > 0 && (w->steps + 1) % (uint64_t)w->reorder_every == 0;
+            w->group_list_mode = (w->vl_force || reorder_due) ? 3 : 2;
+        }
+        if (w->vl_on && !w->group_list_mode) CU(cudaMemsetAsync(w->P.vl + RB_VL_NFAST, 0, 4, w->stream));     // K1 counts the fast movers while the lists sit a phase out
+        int r = dist_phase_a(w, do_integrate, w->group_list_mode); if (r) return r;
     }
     for (int i = 0; i < n; i++) { rb_world* w = ws[i]; CU(cudaSetDevice(w->cfg.device)); CU(cudaStreamSynchronize(w->stream)); }
     // (the records and headers already sit in the neighbours' in buffers: K1 and the signal kernel stored them there)
     for (int i = 0; i < n; i++) {
         rb_world* w = ws[i];
         CU(cudaSetDevice(w->cfg.device));
-        int r = dist_phase_b(w); if (r) return r;
+        int r = dist_phase_b(w, w->group_list_mode); if (r) return r;
+        if (w->group_list_mode) {
+            const bool reorder_due = w->reorder_every > 0 && (w->steps + 1) % (uint64_t)w->reorder_every == 0;
+            r = rb_list_tick_tail(w, reorder_due); if (r) return r;
+            w->steps++; w->pose_updates++;
+            continue;
+        }
         r = rb_collide_only(w, resolve != 0); if (r) return r;
+        if (w->vl_on) w->vl_force = true;
         if (do_integrate) {
             w->steps++;
             if (w->reorder_every > 0 && w->steps % (uint64_t)w->reorder_every == 0) { r = rb_reorder_rows_now(w); if (r) return r; }

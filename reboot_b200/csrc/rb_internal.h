@@ -36,6 +36,8 @@ void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st);
 // multi-GPU (rb_dist.cu)
 struct RbDist;
 int rb_dist_step_exchange(rb_world* w, int ms);
+int rb_dist_list_exchange(rb_world* w, int list_mode);
+extern "C" int rb_list_tick_tail(rb_world* w, bool reorder_due);
 void rb_dist_destroy(RbDist* d);
 int rb_dist_refresh_counts(rb_world* w);
 extern "C" int rb_reorder_rows_now(rb_world* w);
@@ -87,6 +89,7 @@ struct rb_world {
     bool vl_force = true;                    // the next list tick must rebuild (first tick, rows moved, state edited behind the lists' back)
     float vl_skin_cfg = 0.0f;                // 0 = auto
     // adaptive: while the lists get rebuilt on most ticks (free fall, violent scenes) the per-tick kernel is cheaper
+    int group_list_mode = 0;                 // rb_step_group: this tick's mode of the world (0 per-tick enumeration, 2 lists, 3 lists + forced rebuild)
     uint64_t vl_decided_for = 0;             // step number (1-based) the use-lists decision below was taken for
     bool vl_active = true; uint64_t vl_resume_at = 0; uint32_t vl_backoff = 32; uint32_t vl_seen_r = 0, vl_seen_t = 0;
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P, int vl
         for (uint32_t t = s; t < scan_tiles; t += gridDim.x * blockDim.x) scan_status[t] = 0ull;
         if (s == 0) *scan_ticket = 0u;
     }
-    if (P.dn) { if (s >= P.nb || (s >= P.dn[0] && s < P.nb - P.dn[1])) return; }     // slab worlds: owned rows in front, ghosts at the end
+    if (P.dn) { if (s >= P.nb || (s >= P.dn[0] && (vl || s < P.nb - P.dn[1]))) return; }     // slab worlds: owned rows in front, ghosts at the end (not sorted on list ticks)
     else if (s >= P.ns) return;
     uint32_t k = P.key[s];
     if (k == RB_NONE) return;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P, int vl
 __global__ void __launch_bounds__(RB_BLOCK) rb_vl_bin_kernel(RbParams P) {
     if (!P.vl[RB_VL_REBUILD]) return;
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.ns) return;
+    if (s >= (P.dn ? P.dn[0] : P.ns)) return;       // slab worlds: owned rows only (ghosts never enter the sort of a list tick)
     P.ws_build[s] = P.ws[s];
     uint32_t k = P.key[s];
     if (k != RB_NONE) P.rank[s] = atomicAdd(&P.col_count[k & ~RB_HOT_BIT], 1u);
@@ -544,7 +544,7 @@ __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 
 
 // the same over the coarse table of hot bodies (persistent lists, reuse ticks)
 __device__ __forceinline__ void scan_hot_partners(const RbParams& P, uint32_t A, f3 fc, float frm, uint32_t lo,
-                                                  uint32_t& best, uint32_t& best_local, uint32_t& eligible) {
+                                                  uint32_t& best, uint32_t& best_local, uint32_t& eligible, bool ghosts_only) {
     const float reach = frm + P.rm_max;
     const uint32_t hx0 = rb_col(fc.x - reach, P.half, P.hc_inv_w, P.hcn), hx1 = rb_col(fc.x + reach, P.half, P.hc_inv_w, P.hcn);
     const uint32_t hz0 = rb_col(fc.z - reach, P.half, P.hc_inv_w, P.hcn), hz1 = rb_col(fc.z + reach, P.half, P.hc_inv_w, P.hcn);
@@ -552,7 +552,7 @@ __device__ __forceinline__ void scan_hot_partners(const RbParams& P, uint32_t A,
         for (uint32_t hx = hx0; hx <= hx1; ++hx)
             for (uint32_t h = P.hot_head[hz * P.hcn + hx]; h; h = P.hot_next[h - 1u]) {
                 const uint32_t Bl = P.hot_row[h - 1u];
-                if (Bl == A) continue;
+                if (Bl == A || (ghosts_only && h - 1u < P.hot_cap)) continue;
                 const float4 o = P.ws[Bl];
                 float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
                 if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
@@ -863,7 +863,10 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
             for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < min(npart, (uint32_t)RB_SSCAND_MAX)) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
         }
     }
-    if ((MODE == 2 || MODE == 3) && reuse) {
+    // slab worlds: the neighbours' ghosts are in nobody's list either (their rows change every tick); they sit in
+    // the same cell table behind the own hot bodies (entries >= hot_cap) and are looked up on EVERY list tick
+    const bool ghosts_only = (MODE == 2 || MODE == 3) && !reuse;
+    if ((MODE == 2 || MODE == 3) && (reuse || P.dn)) {
         // hot bodies are nobody's list: everybody looks them up in the coarse cell table (<= 2 x 2 cells)
         uint32_t hcell[4] = { 0, 0, 0, 0 }, hn = 0;
         if (valid) {
@@ -881,8 +884,9 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
                 if (!__any_sync(0xffffffffu, h != 0u)) break;
                 if (h) {
                     const uint32_t Bl = P.hot_row[h - 1u];
+                    const bool skip = ghosts_only && h - 1u < P.hot_cap;     // rebuild tick: own hot bodies are in the fresh lists
                     h = P.hot_next[h - 1u];
-                    if (Bl != A) {
+                    if (Bl != A && !skip) {
                         const float4 o = P.ws[Bl];
                         float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
                         if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
@@ -1068,7 +1072,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         while (true) {
             uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
             scan_partners<true>(P, A, fc, frm, lo, best, best_local, eligible, T);
-            if (reuse) scan_hot_partners(P, A, fc, frm, lo, best, best_local, eligible);
+            if (reuse || P.dn) scan_hot_partners(P, A, fc, frm, lo, best, best_local, eligible, ghosts_only);
             if (best == RB_NONE) break;
             ss_pair_single<RESOLVE>(P, S, H, T, A, gA, oa, best_local, best);
             lo = best + 1;
@@ -1288,7 +1292,15 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_model_matrix_kernel(const float4*
 __global__ void __launch_bounds__(RB_BLOCK) rb_reorder_kernel(RbParams P, RbReorder R) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_rows = P.dn ? P.dn[0] : P.nb;
-    if (i >= n_rows) return;
+    if (i >= n_rows) {
+        // in-tick re-ordering of a slab world: this tick's ghost rows (end of the arrays) move to the new buffers as they are
+        if (R.dst_key && P.dn && i < P.nb && i >= P.nb - P.dn[1]) {
+#pragma unroll 1
+            for (int a = 0; a < R.n4; ++a) R.dst4[a][i] = R.src4[a][i];
+            R.dst_flags[i] = R.src_flags[i]; R.dst_key[i] = R.src_key[i]; R.dst_gid[i] = R.src_gid[i];
+        }
+        return;
+    }
     uint32_t k = P.key[i];
     if (k != RB_NONE) k &= ~RB_HOT_BIT;
     uint32_t j;

@@ -309,7 +309,7 @@ static int reorder_rows(rb_world* w, bool intick) {
     uint32_t* gid_cur = const_cast<uint32_t*>(P.gid);
     R.src_gid = P.gid; R.dst_gid = gid_cur == w->d_gid ? w->d_gid_alt : w->d_gid; R.inv = slab ? nullptr : w->d_inv; R.rest_counter = w->d_rest;
     CU(cudaMemsetAsync(w->d_rest, 0, 4, w->stream));
-    if (slab) {
+    if (slab && !intick) {
         // owned rows keep their relative order in the sorted array: rank = exclusive count of owned slots
         CU(cudaMemsetAsync(w->d_oscan, 0, w->oscan_bytes, w->stream));
         rb_launch_owned_flags(P, w->d_oflag, (uint32_t)nb, w->stream);
@@ -375,7 +375,7 @@ int rb_build(rb_world* w) {
     P.margin_cap = w->cfg.margin_cap;
     P.rm_max = rmax + w->cfg.margin_cap;
     // persistent candidate lists: single worlds of single-sphere bodies stepped by rb_step with the default kernel
-    w->vl_on = w->vl_on && !slab && P.single && ns > 0 && w->collide_variant == 2;
+    w->vl_on = w->vl_on && P.single && ns > 0 && w->collide_variant == 2;
     if (w->vl_on) {
         float rmin = rmax;
         for (size_t i = 3; i < sph.size() && i < (size_t)ns * 4; i += 4) rmin = std::min(rmin, std::fabs(sph[i]));
@@ -454,8 +454,8 @@ int rb_build(rb_world* w) {
     }
     if (w->vl_on) {
         float4* wb;
-        ALLOC(wb, ns); CU(cudaMemsetAsync(wb, 0, (size_t)ns * 16, w->stream));
-        CU(cudaMemsetAsync(d_key, 0xff, (size_t)ns * 4, w->stream));                 // "not in the grid" until the first K1
+        ALLOC(wb, nsa); CU(cudaMemsetAsync(wb, 0, (size_t)nsa * 16, w->stream));
+        CU(cudaMemsetAsync(d_key, 0xff, (size_t)nsa * 4, w->stream));                 // "not in the grid" until the first K1
         CU(cudaHostAlloc((void**)&w->vl_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
         w->vl_host[0] = w->vl_host[1] = w->vl_host[2] = w->vl_host[3] = 0;
         uint32_t* dv = nullptr; CU(cudaHostGetDevicePointer((void**)&dv, w->vl_host, 0));
@@ -466,12 +466,12 @@ int rb_build(rb_world* w) {
         const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 256.0f);
         P.hcn = (uint32_t)std::max(1L, (long)std::floor(2.0 * P.half / lc));
         P.hc_inv_w = (float)P.hcn / (2.0f * P.half);
-        P.hot_cap = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(256u, ns / 128u);
+        P.hot_cap = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(1024u, ns / 128u);
         // one blob: cell heads | hot counter | list words. The per-tick memset clears the heads, the counter and the
         // first list word (the rebuild flag) in one go; the words behind it persist.
         uint32_t *hh, *hr, *hn;
         const size_t ncell = (size_t)P.hcn * P.hcn;
-        ALLOC(hh, ncell + 1 + 8); ALLOC(hr, P.hot_cap); ALLOC(hn, P.hot_cap);
+        ALLOC(hh, ncell + 1 + 8); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
         CU(cudaMemsetAsync(hh, 0, (ncell + 1 + 8) * sizeof(uint32_t), w->stream));
         P.hot_head = hh; P.hot_row = hr; P.hot_next = hn; P.vl = hh + ncell + 1;
         static_assert(RB_VL_REBUILD == 0, "the rebuild flag must be the first list word");
@@ -565,14 +565,11 @@ static int enqueue_collide(rb_world* w, bool resolve) {
 // enumerate follow as launches that return at once while the flag is down (the host never has to look), and
 // the test / resolve kernel runs every tick from the lists. Results are the ones of the per-tick enumeration:
 // the lists are supersets of it and every decision is taken by the same exact tests in the same order.
-static int enqueue_list_tick(rb_world* w, bool reorder_due) {
+// second half of a list tick: the conditional rebuild chain and the resolve launches (slab worlds get here after their
+// halo exchange; K1 ran before it)
+int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     RbParams& P = w->P;
-    const bool force = w->vl_force || reorder_due;
-    if (force) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));   // other paths may have left counts behind
-    CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter + rebuild flag
     CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
-    if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
-    rb_launch_integrate_bin(P, 1, force ? 3 : 2, w->stream);
     rb_launch_vl_bin(P, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
     rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
@@ -585,10 +582,26 @@ static int enqueue_list_tick(rb_world* w, bool reorder_due) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
         for (int k = 0; k < 4; k++) { float ms = 0; CU(cudaEventElapsedTime(&ms, w->ev[k], w->ev[k + 1])); w->kernel_ms[k] += ms; }
+        if (w->dist) {                                  // slab worlds: split K1 from the halo step that follows it
+            float ms = 0; CU(cudaEventElapsedTime(&ms, w->ev[5], w->ev[1]));
+            w->kernel_ms[0] -= ms; w->kernel_ms[4] += ms;
+        }
     }
     CU(cudaGetLastError());
     w->vl_force = false;
     return RB_OK;
+}
+static int enqueue_list_tick(rb_world* w, bool reorder_due) {
+    RbParams& P = w->P;
+    const bool force = w->vl_force || reorder_due;
+    if (w->dist) { int r = rb_dist_list_exchange(w, force ? 3 : 2); if (r) return r; }      // K1 (+ pack), exchange, remove + unpack
+    else {
+        if (force) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));   // other paths may have left counts behind
+        CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter + rebuild flag
+        if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
+        rb_launch_integrate_bin(P, 1, force ? 3 : 2, w->stream);
+    }
+    return rb_list_tick_tail(w, reorder_due);
 }
 
 // Will the next rb_step run from the persistent lists? (decided once per step)
@@ -609,7 +622,7 @@ bool rb_step_will_use_lists(rb_world* w) {
         }
     } else if (w->steps >= w->vl_resume_at) {
         // come back once few enough bodies outrun the skin (the per-tick kernel keeps counting them)
-        if (w->vl_host[2] < w->P.hot_cap / 4u) { w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1]; }
+        if (w->vl_host[2] < w->P.hot_cap / 2u) { w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1]; }
         else w->vl_resume_at = w->steps + 16;
     }
     return w->vl_active;
@@ -902,7 +915,7 @@ static int step_host_async(rb_world* w, int ms, const float* force4, float* pos4
     int r;
     // list ticks take the forces and leave the positions themselves (no extra pass over the bodies);
     // whether this tick will be one is rb_step's decision, so it is asked first
-    const bool fused_io = rb_step_will_use_lists(w);
+    const bool fused_io = rb_step_will_use_lists(w) && !w->d_dn;      // (slab worlds hand out rows, not ids)
     if (force4) {
         r = ensure_force(w); if (r) return r;
         if (w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->s_h2d, w->pe_force[b], 0));   // staging b was consumed RB_PIPE calls ago
@@ -1004,6 +1017,7 @@ int rb_collide_only(rb_world* w, bool resolve) { return enqueue_collide(w, resol
 // ---- multi-GPU placeholders until rb_dist.cu lands ---------------------------------------------
 #ifndef RB_HAVE_DIST
 int rb_dist_step_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
+int rb_dist_list_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 int rb_dist_refresh_counts(rb_world*) { return RB_OK; }
 int rb_dist_rows_moved(rb_world*) { return RB_OK; }
 void rb_dist_destroy(RbDist*) {}

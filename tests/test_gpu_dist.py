@@ -64,3 +64,41 @@ def test_slab_group_bit_identical_to_single_world(mods, nslabs):
     sa, sb = single.contact_sets(), group.contact_sets()
     assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
     single.close(); group.close()
+
+
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_slab_group_steps_from_persistent_lists(mods, nslabs):
+    """Slab worlds stepping from persistent candidate lists: a scene that comes to rest around the slab faces
+    (so the lists get reused for many ticks, the neighbours' ghosts are looked up through the hot-body table,
+    and a few bodies still migrate), against a single world -- bit-identical at every checkpoint."""
+    World, dist, scenes = mods
+    n = 6000
+    sc = scenes.falling_spheres(n, 400, 2.0, 0.5, (0.3, 1.5), True, 11, "rest")
+    rng = np.random.default_rng(11)
+    sc.body_vel[:, 0] = rng.uniform(-1.5, 1.5, n).astype(np.float32)
+    k = (3 * n) // 4
+    faces = [0.0] if nslabs == 2 else [-500.0, 0.0, 500.0]
+    sc.body_pos[:k, 0] = (rng.choice([-200.0, 0.0, 200.0] if nslabs == 4 else faces, k) + rng.uniform(-40, 40, k)).astype(np.float32)
+    single = World(sc)
+    group = dist.SlabGroup(sc, nslabs)
+    migrated = 0
+    for t in range(500):
+        single.step(5)
+        group.step(5)
+        if t % 25 == 24:
+            a = single.state(); b = group.state(sc.n_bodies)
+            assert (b["owner"] >= 0).all(), "a body was lost in migration"
+            for key in ("pos", "vel", "model_t", "prev_t"):
+                assert np.array_equal(bits(a[key]), bits(b[key])), (t, key)
+            assert np.array_equal(a["flags"], b["flags"]), t
+            sa, sb = single.contact_sets(), group.contact_sets()
+            assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1]), t
+            migrated += sum(w.stats()["migrated_out_last"] for w in group.worlds)
+    st = [w.stats() for w in group.worlds]
+    assert sum(s["halo_recv_last"] for s in st) > 0, "ghosts must be in play"
+    busy = [s for s in st if s["n_bodies"] > 100]
+    ss = single.stats()
+    info = [(s["n_bodies"], s["list_ticks"], s["list_rebuilds"], s["list_hot_last"], s["list_rebuild_reason"]) for s in st + [ss]]
+    assert busy and all(s["list_ticks"] > 200 and s["list_rebuilds"] < s["list_ticks"] // 2 for s in busy), info
+    assert len(sa[0]) > 50, "sphere-sphere contacts (some across a face) must be in play"
+    single.close(); group.close()
