@@ -20,6 +20,7 @@
 #define RB_VL_REBUILD 0   // this tick rebuilds the lists (set by K1, cleared by the resolve kernel)
 #define RB_VL_WHY     1   // why: 1 a body entered / left the grid (or emigrated), 2 hot table full, 4 host (first tick, rows moved, state edited), 8 immigrants
 #define RB_VL_WHY_LAST 4  // the reasons of the most recent rebuild
+#define RB_VL_STORM   6   // the previous list tick rebuilt too
 #define RB_VL_NFAST   5   // per-tick kernel only: bodies whose one-tick margin alone exceeds the skin (saturates at hot_cap)
 #define RB_VL_NREBUILD 2  // rebuild ticks so far
 #define RB_VL_NTICK   3   // list ticks so far

@@ -985,7 +985,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         nc = nu;
         __syncwarp();
     }
-    if (MODE == 1 && P.vl) {
+    if (MODE == 1 && P.vl && !P.vl[RB_VL_STORM]) {     // (not while every tick rebuilds: those lists die young, pruning them is wasted work)
         // Persistent lists keep only the triangles the sphere can actually reach while its list lives: the
         // exact predicate, run once at the build pose with the radius grown by the skin (a body steps from
         // its list only while displacement + margin <= skin, and the distance to a triangle is 1-Lipschitz
@@ -1193,6 +1193,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping
         const uint32_t f = P.vl[RB_VL_REBUILD];      // (cleared by the next tick's memset: other blocks of this launch still read it)
         if (f) { P.vl[RB_VL_WHY_LAST] = P.vl[RB_VL_WHY]; P.vl[RB_VL_WHY] = 0u; }
+        P.vl[RB_VL_STORM] = f;                       // the next rebuild, if it comes right away, skips the list pruning
         const uint32_t nr = P.vl[RB_VL_NREBUILD] + (f ? 1u : 0u), nt = P.vl[RB_VL_NTICK] + 1u;
         P.vl[RB_VL_NREBUILD] = nr; P.vl[RB_VL_NTICK] = nt;
         if (P.vl_host) { P.vl_host[0] = nr; P.vl_host[1] = nt; }
