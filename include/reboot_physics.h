@@ -99,6 +99,7 @@ typedef struct rb_stats_t {
     float    list_skin;                      /* the skin the lists are built with (0: lists not in use) */
     uint32_t list_hot_last;                  /* bodies that stepped without their list in the last tick (fast movers, crowded bodies) */
     uint32_t list_rebuild_reason;            /* most recent rebuild: 1 a body entered/left the grid | 2 too many hot bodies | 4 requested by the host side */
+    uint32_t list_rebuilds_by_reason[4];     /* rebuild ticks by reason: a body entered/left the grid or emigrated, hot table full, host side (first tick, scheduled re-ordering, state edited), immigrants */
     uint32_t reserved0;
 } rb_stats_t;
 

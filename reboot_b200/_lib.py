@@ -46,7 +46,7 @@ class RbStats(C.Structure):
                 ("device_bytes", C.c_uint64), ("halo_sent_last", C.c_uint32), ("halo_recv_last", C.c_uint32),
                 ("migrated_out_last", C.c_uint32), ("migrated_in_last", C.c_uint32),
                 ("list_ticks", C.c_uint32), ("list_rebuilds", C.c_uint32), ("list_skin", C.c_float), ("list_hot_last", C.c_uint32),
-                ("list_rebuild_reason", C.c_uint32), ("reserved0", C.c_uint32)]
+                ("list_rebuild_reason", C.c_uint32), ("list_rebuilds_by_reason", C.c_uint32 * 4), ("reserved0", C.c_uint32)]
 
 
 # every symbol include/reboot_physics.h declares: name -> (restype, argtypes)

@@ -20,6 +20,8 @@
 #define RB_VL_REBUILD 0   // this tick rebuilds the lists (set by K1, cleared by the resolve kernel)
 #define RB_VL_WHY     1   // why: 1 a body entered / left the grid (or emigrated), 2 hot table full, 4 host (first tick, rows moved, state edited), 8 immigrants
 #define RB_VL_WHY_LAST 4  // the reasons of the most recent rebuild
+#define RB_VL_NWHY    8   // 4 words: rebuilds so far by reason bit (grid entry/exit, hot table full, host, immigrants)
+#define RB_VL_WORDS   16
 #define RB_VL_STORM   6   // the previous list tick rebuilt too
 #define RB_VL_NFAST   5   // per-tick kernel only: bodies whose one-tick margin alone exceeds the skin (saturates at hot_cap)
 #define RB_VL_NREBUILD 2  // rebuild ticks so far
@@ -51,6 +53,7 @@ struct RbDistParams {
     uint32_t* emig; uint32_t* emig_cnt;             // local indices of emigrants
     uint32_t ghost_cap, migr_cap, cap_local;
     float slab_lo, slab_hi; int has_left, has_right;
+    float mig_band;               // list ticks: a body up to this far beyond a face stays with its owner until the next scheduled rebuild
     uint32_t* dn;                                   // {n_owned, n_ghost}
     uint32_t* gid; float4* sph_obj_w; unsigned long long* counters;
 };

@@ -232,6 +232,7 @@ static int dist_alloc(rb_world* w) {
     D.ghost_cap = d->ghost_cap; D.migr_cap = d->migr_cap; D.cap_local = w->cap_local;
     D.slab_lo = w->cfg.slab_lo; D.slab_hi = w->cfg.slab_hi;
     D.has_left = w->cfg.rank > 0; D.has_right = w->cfg.rank < w->cfg.nranks - 1;
+    D.mig_band = w->vl_on ? w->P.margin_cap : 0.0f;
     D.dn = w->d_dn; D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj); D.counters = w->P.counters;
     ALLOC(d->d_dp[0], 1); ALLOC(d->d_dp[1], 1);
     CU(cudaMemcpyAsync(d->d_dp[0], &D, sizeof D, cudaMemcpyHostToDevice, w->stream));

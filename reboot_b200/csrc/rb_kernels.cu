@@ -104,6 +104,11 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
             const RbDistParams& D = *P.dp;
             int dir = -1;
             if (c.x < D.slab_lo && D.has_left) dir = 0; else if (c.x >= D.slab_hi && D.has_right) dir = 1;
+            // Persistent lists: a migration moves rows, i.e. costs both ranks a list rebuild (and, in lockstep, everybody a
+            // wait). A body that has only just crossed the face therefore stays with its owner -- it is the neighbour's
+            // ghost either way, and the ghost reach below is wider by the same band -- until the next rebuild the host
+            // schedules anyway (do_bin == 3) or until it is further out than the band. Ownership never shows in results.
+            if (dir >= 0 && do_bin == 2 && (dir == 0 ? D.slab_lo - c.x : c.x - D.slab_hi) <= D.mig_band) dir = -1;
             if (dir >= 0) {
                 uint32_t kk = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
                 if (kk < D.migr_cap) {
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
                     in_grid = false;        // leaves this slab: not binned here
                 } else atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u);   // stays owned here one more tick
             } else if (in_grid) {
-                float reach = r + margin + P.rm_max;   // own grown radius + the largest grown radius anywhere
+                float reach = r + margin + P.rm_max + D.mig_band;   // own grown radius + the largest grown radius anywhere (+ how far a neighbour's body may sit on our side)
                 RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0;
                 if (D.has_left && c.x - reach < D.slab_lo) {
                     uint32_t kk = atomicAdd(&D.out_hdr[0]->n_ghost, 1u);
@@ -1192,7 +1197,12 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     if (MODE == 0 && P.vl && P.vl_host && tid == 0) P.vl_host[2] = P.vl[RB_VL_NFAST];     // lists switched off: K1's count of fast movers
     if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping
         const uint32_t f = P.vl[RB_VL_REBUILD];      // (cleared by the next tick's memset: other blocks of this launch still read it)
-        if (f) { P.vl[RB_VL_WHY_LAST] = P.vl[RB_VL_WHY]; P.vl[RB_VL_WHY] = 0u; }
+        if (f) {
+            const uint32_t why = P.vl[RB_VL_WHY];
+            P.vl[RB_VL_WHY_LAST] = why; P.vl[RB_VL_WHY] = 0u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) if (why & (1u << b)) P.vl[RB_VL_NWHY + b]++;      // rebuilds by reason (several may apply)
+        }
         P.vl[RB_VL_STORM] = f;                       // the next rebuild, if it comes right away, skips the list pruning
         const uint32_t nr = P.vl[RB_VL_NREBUILD] + (f ? 1u : 0u), nt = P.vl[RB_VL_NTICK] + 1u;
         P.vl[RB_VL_NREBUILD] = nr; P.vl[RB_VL_NTICK] = nt;

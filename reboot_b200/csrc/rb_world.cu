@@ -471,8 +471,8 @@ int rb_build(rb_world* w) {
         // first list word (the rebuild flag) in one go; the words behind it persist.
         uint32_t *hh, *hr, *hn;
         const size_t ncell = (size_t)P.hcn * P.hcn;
-        ALLOC(hh, ncell + 1 + 8); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
-        CU(cudaMemsetAsync(hh, 0, (ncell + 1 + 8) * sizeof(uint32_t), w->stream));
+        ALLOC(hh, ncell + 1 + RB_VL_WORDS); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
+        CU(cudaMemsetAsync(hh, 0, (ncell + 1 + RB_VL_WORDS) * sizeof(uint32_t), w->stream));
         P.hot_head = hh; P.hot_row = hr; P.hot_next = hn; P.vl = hh + ncell + 1;
         static_assert(RB_VL_REBUILD == 0, "the rebuild flag must be the first list word");
     }
@@ -986,12 +986,13 @@ int rb_get_stats(rb_world* w, rb_stats_t* out) {
     }
     if (w->built && w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
     if (w->built && w->vl_on) {
-        uint32_t v[8], nh = 0;
+        uint32_t v[RB_VL_WORDS], nh = 0;
         CU(cudaMemcpyAsync(v, w->P.vl, sizeof v, cudaMemcpyDeviceToHost, w->stream));
         CU(cudaMemcpyAsync(&nh, w->P.hot_head + (size_t)w->P.hcn * w->P.hcn, 4, cudaMemcpyDeviceToHost, w->stream));
         CU(cudaStreamSynchronize(w->stream));
         out->list_rebuilds = v[RB_VL_NREBUILD]; out->list_ticks = v[RB_VL_NTICK]; out->list_skin = w->P.vl_skin;
         out->list_hot_last = nh; out->list_rebuild_reason = v[RB_VL_WHY_LAST];
+        for (int b = 0; b < 4; b++) out->list_rebuilds_by_reason[b] = v[RB_VL_NWHY + b];
     }
     out->n_bodies = w->built ? w->n_owned_host : (uint32_t)w->h_flags.size();
     out->n_spheres = w->d_dn ? w->n_owned_host : w->P.ns; out->n_geoms = (uint32_t)w->h_geom_start.size() - 1; out->n_tris = w->P.nt;

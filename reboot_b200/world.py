@@ -239,7 +239,7 @@ class World:
     def stats(self) -> dict:
         s = RbStats()
         self._ck(self.L.rb_get_stats(self.h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in RbStats._fields_}
+        return {k: (list(getattr(s, k)) if k == "list_rebuilds_by_reason" else getattr(s, k)) for k, _ in RbStats._fields_}
 
     def profile(self, on: bool):
         self._ck(self.L.rb_profile(self.h, 1 if on else 0))

@@ -53,9 +53,13 @@ def test_slab_group_bit_identical_to_single_world(mods, nslabs):
         migrated += sum(w.stats()["migrated_out_last"] for w in group.worlds)
     assert migrated > 0, "the scene must exercise migration"
     assert sum(w.stats()["halo_sent_last"] for w in group.worlds) > 0
-    # ownership follows position
+    # ownership follows position (list ticks keep a body that has only just crossed a face with its owner until the
+    # next scheduled rebuild: up to margin_cap = half the largest radius beyond the face)
     b = group.state(sc.n_bodies)
-    assert np.array_equal(b["owner"], dist.owner_of(b["pos"][:, 0], nslabs))
+    own = dist.owner_of(b["pos"][:, 0], nslabs)
+    off = np.nonzero(b["owner"] != own)[0]
+    faces = -1000.0 + 2000.0 * np.arange(1, nslabs) / nslabs
+    assert all(np.abs(b["pos"][i, 0] - faces).min() <= 0.25 + 1e-4 and abs(int(b["owner"][i]) - int(own[i])) == 1 for i in off), off[:10]
     # frozen detection through the group path
     single.integrate(5)
     for w in group.worlds:
