@@ -215,8 +215,12 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     sc, slab = c3_weak_scene(N, rank)
     ids = (np.arange(sc.n_bodies, dtype=np.uint32) + np.uint32(rank * C3_SPHERES)) if N > 1 else None
+    cap = 0
+    if N > 1:
+        from reboot_b200 import dist as rbdist
+        cap = rbdist.common_ghost_cap(sc.n_bodies, float(sc.meta["r"]), slab[1] - slab[0])      # one halo buffer layout on every rank
     w = World(sc, device=local_rank, stream=stream.cuda_stream, slab=slab, rank=rank, nranks=N,
-              max_contacts=8 * sc.n_spheres, build=False, ids=ids, rm_max_hint=float(sc.meta["r"]))
+              max_contacts=8 * sc.n_spheres, build=False, ids=ids, rm_max_hint=float(sc.meta["r"]), halo_ghost_cap=cap)
     w.build()
     if N > 1:
         from reboot_b200 import dist as rbdist

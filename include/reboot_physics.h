@@ -60,6 +60,10 @@ typedef struct rb_config {
     float    slab_lo, slab_hi;
     int32_t  rank, nranks;
     float    rm_max_hint;    /* multi-GPU: largest world-space sphere radius over ALL ranks (0 = this rank's own) */
+    uint32_t halo_ghost_cap; /* multi-GPU: capacity (records) of each halo buffer. It fixes the buffer layout the neighbours
+                              * store into, so it must be the SAME on every rank: pass the maximum over the ranks of
+                              * rb_halo_ghost_cap_auto(). 0 = this rank's own auto value (fine when all ranks hold
+                              * equally many bodies; connecting ranks with different layouts is refused). */
 } rb_config;
 
 /* initial state of a body: StateVector setters, math/include/StateVector.h:48-60 */
@@ -226,9 +230,13 @@ int         rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t i
  * ghost / migrant records straight into the neighbour's buffer over NVLink (CUDA IPC peer memory) and a
  * flag handshake replaces the collective. Every rank exports its handle, the host passes each rank the
  * handles of its left / right neighbour (NULL at the world edge). Use instead of rb_dist_init. */
-#define RB_IPC_HANDLE_BYTES 64
+#define RB_IPC_HANDLE_BYTES 80   /* cudaIpcMemHandle_t (64) + the exporting rank's halo buffer layout (checked on connect) */
 int         rb_dist_p2p_export(rb_world* w, uint8_t handle[RB_IPC_HANDLE_BYTES]);
 int         rb_dist_p2p_connect(rb_world* w, const uint8_t* left_handle, const uint8_t* right_handle);
+
+/* the halo capacity a rank would pick by itself for n_bodies bodies of radius <= r_max in a slab of the given width
+ * (pure function; see rb_config.halo_ghost_cap) */
+uint32_t    rb_halo_ghost_cap_auto(uint32_t n_bodies, float r_max, float margin_cap, float slab_width);
 
 /* global body ids of a slab world: set before rb_build (default: local insertion index), read back for
  * the bodies currently owned, in the same order as rb_get_state's rows (ownership migrates) */

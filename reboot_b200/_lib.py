@@ -14,14 +14,14 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "reboot_physics.h"
 RB_OK, RB_ERR_INVALID, RB_ERR_OOM, RB_ERR_CAPACITY, RB_ERR_CUDA, RB_ERR_NCCL, RB_ERR_NO_DEVICE = range(7)
 RB_ACTIVE, RB_GRAVITY, RB_CONTACT = 1, 2, 4
 RB_NCCL_ID_BYTES = 128
-RB_IPC_HANDLE_BYTES = 64
+RB_IPC_HANDLE_BYTES = 80
 
 
 class RbConfig(C.Structure):
     _fields_ = [("world_half", C.c_float), ("gravity", C.c_float), ("friction", C.c_float), ("pushout", C.c_float),
                 ("ss_damp", C.c_float), ("margin_cap", C.c_float), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("max_contacts", C.c_uint64), ("slab_lo", C.c_float), ("slab_hi", C.c_float),
-                ("rank", C.c_int32), ("nranks", C.c_int32), ("rm_max_hint", C.c_float)]
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("rm_max_hint", C.c_float), ("halo_ghost_cap", C.c_uint32)]
 
 
 class RbBodyInit(C.Structure):
@@ -89,6 +89,7 @@ SIGNATURES = {
     "rb_dist_init": (C.c_int, [_P, C.c_char_p, _P]),
     "rb_dist_p2p_export": (C.c_int, [_P, _P]),
     "rb_dist_p2p_connect": (C.c_int, [_P, _P, _P]),
+    "rb_halo_ghost_cap_auto": (C.c_uint32, [C.c_uint32, C.c_float, C.c_float, C.c_float]),
     "rb_set_body_ids": (C.c_int, [_P, _P, C.c_uint32]),
     "rb_get_body_ids": (C.c_int, [_P, _P]),
     "rb_dist_attach_peers": (C.c_int, [_P, _P, _P]),

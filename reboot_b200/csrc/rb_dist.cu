@@ -403,6 +403,9 @@ int rb_dist_attach_peers(rb_world* w, rb_world* left, rb_world* right) {
     CU(cudaSetDevice(w->cfg.device));
     int r = dist_alloc(w); if (r) return r;
     w->dist->peer[0] = left; w->dist->peer[1] = right;
+    for (rb_world* pw : { left, right })
+        if (pw && pw->ghost_cap != w->ghost_cap)
+            return fail(w, RB_ERR_INVALID, "halo buffer layouts differ between slab worlds (ghost capacity %u vs %u): pass the same rb_config.halo_ghost_cap to all of them", w->ghost_cap, pw->ghost_cap);
     w->dist->mode = RB_X_LOCAL;
     return RB_OK;
 }
@@ -415,8 +418,11 @@ int rb_dist_p2p_export(rb_world* w, uint8_t handle[RB_IPC_HANDLE_BYTES]) {
     int r = dist_alloc(w); if (r) return r;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, w->dist->blob));
-    static_assert(sizeof(h) == RB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    static_assert(sizeof(h) + 16 == RB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
     memcpy(handle, &h, sizeof h);
+    // the layout the neighbours will store into: they must have computed the same one
+    const uint32_t caps[2] = { w->dist->ghost_cap, w->dist->migr_cap }; const uint64_t bb = w->dist->buf_bytes;
+    memcpy(handle + sizeof h, caps, 8); memcpy(handle + sizeof h + 8, &bb, 8);
     return RB_OK;
 }
 int rb_dist_p2p_connect(rb_world* w, const uint8_t* left_handle, const uint8_t* right_handle) {
@@ -426,6 +432,10 @@ int rb_dist_p2p_connect(rb_world* w, const uint8_t* left_handle, const uint8_t* 
     for (int k = 0; k < 2; k++) {
         if (!hs[k]) continue;
         cudaIpcMemHandle_t h; memcpy(&h, hs[k], sizeof h);
+        uint32_t caps[2]; uint64_t bb; memcpy(caps, hs[k] + sizeof h, 8); memcpy(&bb, hs[k] + sizeof h + 8, 8);
+        if (caps[0] != w->dist->ghost_cap || caps[1] != w->dist->migr_cap || bb != w->dist->buf_bytes)
+            return fail(w, RB_ERR_INVALID, "halo buffer layouts differ between ranks (ghost capacity %u here, %u at the %s neighbour): pass the same rb_config.halo_ghost_cap on every rank",
+                        w->dist->ghost_cap, caps[0], k ? "right" : "left");
         void* p = nullptr;
         CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
         w->dist->peer_blob[k] = (uint8_t*)p; w->dist->peer_opened[k] = true;

@@ -13,11 +13,17 @@ extern "C" {
 
 const char* rb_version(void) { return "reboot_b200 0.1 (sm_100a)"; }
 
+// ghosts per face ~ n * reach / slab width; 16x headroom (overflow is detected and reported)
+uint32_t rb_halo_ghost_cap_auto(uint32_t n_bodies, float r_max, float margin_cap, float slab_width) {
+    double mc = margin_cap > 0.f ? margin_cap : 0.5 * r_max;
+    double frac = 2.0 * (r_max + mc) / std::max(1e-3, (double)slab_width);
+    return (uint32_t)std::min<double>(n_bodies / 2 + 8192.0, std::max(8192.0, 16.0 * n_bodies * frac));
+}
 void rb_config_default(rb_config* c) {
     memset(c, 0, sizeof *c);
     c->world_half = 1000.0f; c->gravity = -9.8f; c->friction = 0.95f; c->pushout = 1.0001f; c->ss_damp = 0.1f;
     c->margin_cap = 0.0f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
-    c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1; c->rm_max_hint = 0.0f;
+    c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1; c->rm_max_hint = 0.0f; c->halo_ghost_cap = 0;
 }
 
 const char* rb_last_error(const rb_world* w) { return w ? w->err.c_str() : g_create_error.c_str(); }
@@ -343,9 +349,7 @@ int rb_build(rb_world* w) {
     if (slab) {
         float rr = 0.f; for (size_t i = 3; i < w->h_obj.size(); i += 4) rr = std::max(rr, std::fabs(w->h_obj[i]));
         rr = std::max(rr, w->cfg.rm_max_hint);
-        double mc = w->cfg.margin_cap > 0.f ? w->cfg.margin_cap : 0.5 * rr;
-        double frac = 2.0 * (rr + mc) / std::max(1e-3, (double)(w->cfg.slab_hi - w->cfg.slab_lo));
-        ghost_cap = (uint32_t)std::min<double>(nb / 2 + 8192.0, std::max(8192.0, 16.0 * nb * frac));
+        ghost_cap = w->cfg.halo_ghost_cap ? w->cfg.halo_ghost_cap : rb_halo_ghost_cap_auto(nb, rr, w->cfg.margin_cap, w->cfg.slab_hi - w->cfg.slab_lo);
     }
     w->ghost_cap = ghost_cap;
     const uint32_t cap = slab ? nb + std::max<uint32_t>(nb / 4, 4096u) + 3 * ghost_cap : nb;

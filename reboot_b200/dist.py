@@ -94,6 +94,18 @@ def init_world(w: World, rank: int, nranks: int):
     w._ck(L.rb_dist_init(w.h, path, buf))
 
 
+def common_ghost_cap(n_local_bodies: int, r_max: float, slab_width: float, margin_cap: float = 0.0) -> int:
+    """The halo capacity every rank must pass as World(halo_ghost_cap=...): the maximum over the ranks of the value
+    each would pick by itself (torch.distributed all-reduce; call before building the worlds)."""
+    import torch
+    import torch.distributed as dist
+    cap = int(_lib.load().rb_halo_ghost_cap_auto(int(n_local_bodies), float(r_max), float(margin_cap), float(slab_width)))
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.tensor([cap], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
 def init_world_p2p(w: World, rank: int, nranks: int):
     """Join the slab ring with the fused compute+communication transport: every rank exports the CUDA-IPC
     handle of its halo blob, handles are all-gathered with torch.distributed, each rank opens its left /
@@ -120,9 +132,11 @@ class SlabGroup:
     def __init__(self, scene, nslabs: int, device: int = 0, **kw):
         self.L = _lib.load()
         self.worlds = []
-        for r in range(nslabs):
-            sub, ids, slab, rmax = partition_scene(scene, nslabs, r)
-            w = World(sub, device=device, slab=slab, rank=r, nranks=nslabs, ids=ids, rm_max_hint=rmax, **kw)
+        parts = [partition_scene(scene, nslabs, r) for r in range(nslabs)]
+        # one halo buffer layout for everybody: the largest capacity any slab would pick by itself
+        cap = max(int(self.L.rb_halo_ghost_cap_auto(sub.n_bodies, float(rmax), 0.0, float(slab[1] - slab[0]))) for sub, _, slab, rmax in parts)
+        for r, (sub, ids, slab, rmax) in enumerate(parts):
+            w = World(sub, device=device, slab=slab, rank=r, nranks=nslabs, ids=ids, rm_max_hint=rmax, halo_ghost_cap=cap, **kw)
             self.worlds.append(w)
         for r, w in enumerate(self.worlds):
             left = self.worlds[r - 1].h if r > 0 else None
