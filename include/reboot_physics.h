@@ -234,6 +234,39 @@ int         rb_dist_init(rb_world* w, const char* nccl_lib_path, const uint8_t i
 int         rb_dist_p2p_export(rb_world* w, uint8_t handle[RB_IPC_HANDLE_BYTES]);
 int         rb_dist_p2p_connect(rb_world* w, const uint8_t* left_handle, const uint8_t* right_handle);
 
+/* ---- callers either side of the step ---------------------------------------------------------
+ * Frustum culling on the spatial structure. rb_frustum_planes = GeometryMath::getFrustumPlanes
+ * (math/src/GeometryMath.cpp:630-731): six planes (left, right, far, near, bottom, top) x (nx, ny, nz, d) from the
+ * inverse view-projection the reference builds as view.inverse() * projection.inverse() (physics/src/OSP.cpp:129-130),
+ * row-major 4x4. Pure host function, bit-identical to the reference. */
+int         rb_frustum_planes(const float inv_view_proj[16], float planes24[24]);
+/* OSP::getVisibleFrustumCulling (physics/src/OSP.cpp:125-180) for n caller-supplied boxes in the reference's Cube form
+ * (centre xyz, length = x, height = y, width = z; e.g. the leaves of the caller's render octree): GeometryMath::
+ * frustumAABBDetection (math/src/GeometryMath.cpp:733-757) on the device, then the 0-based indices of the boxes that
+ * meet the frustum, front to back by |centre| like the reference (equal distances in index order; the reference's
+ * std::sort leaves them unspecified). *n_visible receives the count; RB_ERR_CAPACITY if cap is too small. */
+int         rb_frustum_cull_cubes(rb_world* w, const float planes24[24], uint32_t n, const float* cubes6,
+                                  uint32_t* visible, uint32_t cap, uint32_t* n_visible);
+/* the same over the world's own static structure: ids of the non-empty cells of the triangle column grid that meet
+ * the frustum, front to back (a renderer draws the triangles registered there). rb_get_static_cells describes the
+ * cells: boxes6 = (min xyz, max xyz), ntri = triangles registered, tri_cols_x * tri_cols_z cells (rb_stats_t). */
+int         rb_frustum_cull_static(rb_world* w, const float inv_view_proj[16], uint32_t* cells, uint32_t cap, uint32_t* n_visible);
+int         rb_get_static_cells(rb_world* w, float* boxes6, uint32_t* ntri);
+
+/* Collider ingest: FbxLoader::_buildGeometryData (model/src/FbxLoader.cpp:1109-1216) for a neutral indexed mesh
+ * (xyz3 vertices, idx). trs9 = node translation, rotation in degrees (x, y, z), scale: the node transform is
+ * translation * rotX * rotY * rotZ * scale (:1114-1131). Pure host functions, bit-identical to the reference's
+ * arithmetic.
+ *   rb_ingest_mesh_triangles  static model (GeometryType::Triangle, :1133-1160): nidx / 3 world-space triangles with
+ *                             the TRS baked in -> rb_add_static_geometry (rb_ingest_static_mesh does both)
+ *   rb_ingest_mesh_sphere     animated model (GeometryType::Sphere, :1161-1215): ONE sphere per collider mesh,
+ *                             r = (max.x - min.x) / 2, centre = min + r on all three axes (sic), max starting at
+ *                             FLT_MIN (sic) -> an object-space sphere for rb_add_model */
+int         rb_ingest_trs_matrix(const float trs9[9], float out16[16]);
+int         rb_ingest_mesh_triangles(uint32_t nverts, const float* xyz3, uint32_t nidx, const uint32_t* idx, const float trs9[9], float* out_xyz9);
+int         rb_ingest_mesh_sphere(uint32_t nverts, const float* xyz3, uint32_t nidx, const uint32_t* idx, const float trs9[9], float sphere4[4]);
+int         rb_ingest_static_mesh(rb_world* w, uint32_t nverts, const float* xyz3, uint32_t nidx, const uint32_t* idx, const float trs9[9], uint32_t* geom_id);
+
 /* the halo capacity a rank would pick by itself for n_bodies bodies of radius <= r_max in a slab of the given width
  * (pure function; see rb_config.halo_ghost_cap) */
 uint32_t    rb_halo_ghost_cap_auto(uint32_t n_bodies, float r_max, float margin_cap, float slab_width);

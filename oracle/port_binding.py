@@ -67,6 +67,14 @@ def lib():
         L.orc_pred_triangle_cube.argtypes = [C.c_long, _f32p, _f32p, _i32p]
         L.orc_closest_point.argtypes = [C.c_long, _f32p, _f32p, _f32p]
         L.orc_state_update.argtypes = [C.c_long, _f32p, _i32p, C.c_int, C.c_int]
+        L.orc_frustum_planes.argtypes = [_f32p, _f32p]
+        L.orc_frustum_aabb.argtypes = [C.c_long, _f32p, _f32p, _f32p, _i32p]
+        L.orc_cube_box.argtypes = [_f32p, _f32p, _f32p, _f32p]
+        L.orc_visible_frustum_culling.argtypes = [C.c_void_p, _f32p, _i32p, C.c_long]
+        L.orc_visible_frustum_culling.restype = C.c_long
+        L.orc_trs_matrix.argtypes = [_f32p, _f32p]
+        L.orc_ingest_triangles.argtypes = [C.c_long, _f32p, _i32p, _f32p, _f32p]
+        L.orc_ingest_sphere.argtypes = [C.c_long, _f32p, _i32p, _f32p, _f32p]
         _lib = L
     return _lib
 
@@ -244,3 +252,54 @@ def state_update(io18, flags, ms=5, nsteps=1):
     fl = np.ascontiguousarray(np.broadcast_to(np.asarray(flags, np.int32), (io.shape[0],)))
     lib().orc_state_update(io.shape[0], io, fl, ms, nsteps)
     return io
+
+
+# ---- frustum culling and collider ingest ----
+def frustum_planes(inv_vp):
+    out = np.zeros(24, np.float32)
+    lib().orc_frustum_planes(np.ascontiguousarray(inv_vp, np.float32).reshape(-1), out)
+    return out.reshape(6, 4)
+
+
+def frustum_aabb(planes, mins, maxs):
+    mins = np.ascontiguousarray(mins, np.float32).reshape(-1, 3); maxs = np.ascontiguousarray(maxs, np.float32).reshape(-1, 3)
+    out = np.zeros(mins.shape[0], np.int32)
+    lib().orc_frustum_aabb(mins.shape[0], np.ascontiguousarray(planes, np.float32).reshape(-1), mins, maxs, out)
+    return out
+
+
+def cube_boxes(cubes6):
+    """(centre, length, height, width) -> mins, maxs, |centre| exactly as OSP::getVisibleFrustumCulling forms them"""
+    c = np.ascontiguousarray(cubes6, np.float32).reshape(-1, 6)
+    mn = np.zeros((c.shape[0], 3), np.float32); mx = np.zeros((c.shape[0], 3), np.float32); key = np.zeros(c.shape[0], np.float32)
+    k1 = np.zeros(1, np.float32)
+    for i in range(c.shape[0]):
+        lib().orc_cube_box(c[i], mn[i], mx[i], k1); key[i] = k1[0]
+    return mn, mx, key
+
+
+def visible_frustum_culling(world, inv_vp):
+    n = world.leaf_count()
+    out = np.zeros(max(n, 1), np.int32)
+    k = lib().orc_visible_frustum_culling(world.h, np.ascontiguousarray(inv_vp, np.float32).reshape(-1), out, n)
+    return out[:k]
+
+
+def trs_matrix(trs9):
+    out = np.zeros(16, np.float32)
+    lib().orc_trs_matrix(np.ascontiguousarray(trs9, np.float32), out)
+    return out.reshape(4, 4)
+
+
+def ingest_triangles(xyz3, idx, trs9):
+    idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
+    out = np.zeros((idx.shape[0] // 3, 9), np.float32)
+    lib().orc_ingest_triangles(idx.shape[0], np.ascontiguousarray(xyz3, np.float32).reshape(-1), idx, np.ascontiguousarray(trs9, np.float32), out.reshape(-1))
+    return out
+
+
+def ingest_sphere(xyz3, idx, trs9):
+    idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
+    out = np.zeros(4, np.float32)
+    lib().orc_ingest_sphere(idx.shape[0], np.ascontiguousarray(xyz3, np.float32).reshape(-1), idx, np.ascontiguousarray(trs9, np.float32), out)
+    return out

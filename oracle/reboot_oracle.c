@@ -761,3 +761,130 @@ void orc_state_update(long n, float* io18, const int32_t* flags, int ms, int nst
         p[6] = s.ang_pos.x; p[7] = s.ang_pos.y; p[8] = s.ang_pos.z; p[9] = s.ang_vel.x; p[10] = s.ang_vel.y; p[11] = s.ang_vel.z;
     }
 }
+
+/* ======================================================================================== */
+/* frustum culling on the spatial structure                              */
+/* ======================================================================================== */
+/* GeometryMath::getFrustumPlanes (math/src/GeometryMath.cpp:630-731). Planes come out in the reference's
+ * order left, right, far, near, bottom, top as (nx, ny, nz, d), all four divided by |n| (Vector4::normalize,
+ * Vector4.cpp:128-136). Point = M * p (Matrix.cpp:124-134) then / w (Vector4.cpp:40-47). */
+void orc_frustum_planes(const float* inv_vp16, float* planes24) {
+    static const float ndc[8][3] = { { -1, -1, 1 }, { -1, 1, 1 }, { -1, -1, -1 }, { -1, 1, -1 }, { 1, -1, 1 }, { 1, 1, 1 }, { 1, -1, -1 }, { 1, 1, -1 } };
+    /* (origin, A = pa - origin, B = pb - origin) per plane, GeometryMath.cpp:648-730 */
+    static const int pl[6][3] = { { 0, 2, 1 }, { 4, 5, 6 }, { 6, 3, 2 }, { 4, 0, 1 }, { 0, 4, 2 }, { 5, 1, 3 } };
+    v3 pt[8];
+    const float* m = inv_vp16;
+    for (int i = 0; i < 8; i++) {
+        float px = ndc[i][0], py = ndc[i][1], pz = ndc[i][2], pw = 1.0f;   /* Vector4(x,y,z) has w = 1 (Vector4.h default) */
+        float x = m[0] * px + m[1] * py + m[2] * pz + m[3] * pw;
+        float y = m[4] * px + m[5] * py + m[6] * pz + m[7] * pw;
+        float z = m[8] * px + m[9] * py + m[10] * pz + m[11] * pw;
+        float w = m[12] * px + m[13] * py + m[14] * pz + m[15] * pw;
+        pt[i] = v3_make(x / w, y / w, z / w);
+    }
+    for (int p = 0; p < 6; p++) {
+        v3 o = pt[pl[p][0]];
+        v3 A = v3_sub(pt[pl[p][1]], o), B = v3_sub(pt[pl[p][2]], o);
+        v3 C = v3_cross(B, A);
+        float d = -(C.x * -o.x + C.y * -o.y + C.z * -o.z);
+        float mag = v3_mag(C);
+        planes24[4 * p] = C.x / mag; planes24[4 * p + 1] = C.y / mag; planes24[4 * p + 2] = C.z / mag; planes24[4 * p + 3] = d / mag;
+    }
+}
+/* GeometryMath::frustumAABBDetection (math/src/GeometryMath.cpp:733-757): a box is culled iff all 8 corners are on the
+ * positive side of some plane; "distance" is the plane's w, pointOnPlane = n * w (Vector4.cpp:49-56) */
+static int frustum_aabb(const float* planes24, v3 mn, v3 mx) {
+    const v3 c[8] = { { mn.x, mn.y, mn.z }, { mn.x, mn.y, mx.z }, { mn.x, mx.y, mx.z }, { mx.x, mx.y, mx.z },
+                      { mx.x, mx.y, mn.z }, { mx.x, mn.y, mn.z }, { mx.x, mn.y, mx.z }, { mn.x, mx.y, mn.z } };
+    int outside = 0;
+    for (int p = 0; p < 6; p++) {
+        v3 n = v3_make(planes24[4 * p], planes24[4 * p + 1], planes24[4 * p + 2]);
+        float dist = planes24[4 * p + 3];
+        v3 on = v3_mulf(n, dist);
+        int cnt = 0;
+        for (int k = 0; k < 8; k++) if (v3_dot(n, v3_sub(c[k], on)) > 0) cnt++;
+        if (cnt == 8) outside = 1;
+    }
+    return !outside;
+}
+void orc_frustum_aabb(long n, const float* planes24, const float* mins3, const float* maxs3, int32_t* out) {
+    for (long i = 0; i < n; i++)
+        out[i] = frustum_aabb(planes24, v3_make(mins3[3 * i], mins3[3 * i + 1], mins3[3 * i + 2]), v3_make(maxs3[3 * i], maxs3[3 * i + 1], maxs3[3 * i + 2]));
+}
+/* the box of a cube exactly as OSP::getVisibleFrustumCulling forms it (physics/src/OSP.cpp:147-156), and its sort key
+ * |centre| (:160) */
+void orc_cube_box(const float* cube6, float* mins3, float* maxs3, float* key) {
+    mins3[0] = cube6[0] - cube6[3] / 2.0f; mins3[1] = cube6[1] - cube6[4] / 2.0f; mins3[2] = cube6[2] - cube6[5] / 2.0f;
+    maxs3[0] = cube6[0] + cube6[3] / 2.0f; maxs3[1] = cube6[1] + cube6[4] / 2.0f; maxs3[2] = cube6[2] + cube6[5] / 2.0f;
+    *key = v3_mag(v3_make(cube6[0], cube6[1], cube6[2]));
+}
+/* OSP::getVisibleFrustumCulling (physics/src/OSP.cpp:125-180) on this world's octree: 1-based offsets of the visible
+ * triangle-bearing leaves, front to back by |leaf centre| (ties: leaf order -- the reference's std::sort leaves them
+ * unspecified). inv_vp16 = view.inverse() * projection.inverse(), computed by the caller. */
+long orc_visible_frustum_culling(orc_world* w, const float* inv_vp16, int32_t* out, long cap) {
+    float planes[24];
+    orc_frustum_planes(inv_vp16, planes);
+    long n = 0;
+    float* keys = (float*)malloc(sizeof(float) * (size_t)(w->n_leaves > 0 ? w->n_leaves : 1));
+    int32_t* ids = (int32_t*)malloc(sizeof(int32_t) * (size_t)(w->n_leaves > 0 ? w->n_leaves : 1));
+    for (int li = 0; li < w->n_leaves; li++) {
+        node_t* leaf = w->leaves[li];
+        if (leaf->tris.n == 0) continue;
+        float c6[6] = { leaf->cube.c.x, leaf->cube.c.y, leaf->cube.c.z, leaf->cube.length, leaf->cube.height, leaf->cube.width };
+        float mn[3], mx[3], key;
+        orc_cube_box(c6, mn, mx, &key);
+        if (frustum_aabb(planes, v3_make(mn[0], mn[1], mn[2]), v3_make(mx[0], mx[1], mx[2]))) { keys[n] = key; ids[n] = li + 1; n++; }
+    }
+    for (long i = 1; i < n; i++) {      /* stable insertion sort by key */
+        float k = keys[i]; int32_t id = ids[i]; long j = i - 1;
+        while (j >= 0 && keys[j] > k) { keys[j + 1] = keys[j]; ids[j + 1] = ids[j]; j--; }
+        keys[j + 1] = k; ids[j + 1] = id;
+    }
+    for (long i = 0; i < n && i < cap; i++) out[i] = ids[i];
+    free(keys); free(ids);
+    return n;
+}
+
+/* ======================================================================================== */
+/* collider ingest, FbxLoader::_buildGeometryData (model/src/FbxLoader.cpp:1109-1216)   */
+/* ======================================================================================== */
+#define ORC_PI_OVER_180 (3.14159265f / 180.0f)           /* math/include/Matrix.h:27-28 */
+/* translation * (rotX * rotY * rotZ) * scale, angles in degrees (FbxLoader.cpp:1114-1131; Matrix.cpp:261-376).
+ * cos / sin are the float overloads (Matrix.cpp is compiled with `using namespace std`). */
+static mat4 trs_matrix(const float* trs9) {
+    float tx = trs9[3] * ORC_PI_OVER_180, ty = trs9[4] * ORC_PI_OVER_180, tz = trs9[5] * ORC_PI_OVER_180;
+    mat4 rx = mat_identity(), ry = mat_identity(), rz = mat_identity(), sc = mat_identity();
+    rx.m[5] = cosf(tx); rx.m[6] = sinf(tx); rx.m[9] = -sinf(tx); rx.m[10] = cosf(tx);
+    ry.m[0] = cosf(ty); ry.m[2] = -sinf(ty); ry.m[8] = sinf(ty); ry.m[10] = cosf(ty);
+    rz.m[0] = cosf(tz); rz.m[1] = sinf(tz); rz.m[4] = -sinf(tz); rz.m[5] = cosf(tz);
+    sc.m[0] = trs9[6]; sc.m[5] = trs9[7]; sc.m[10] = trs9[8];
+    mat4 t = mat_translation(trs9[0], trs9[1], trs9[2]);
+    mat4 rxy = mat_mul(&rx, &ry), rot = mat_mul(&rxy, &rz);
+    mat4 tr = mat_mul(&t, &rot);
+    return mat_mul(&tr, &sc);
+}
+void orc_trs_matrix(const float* trs9, float* out16) { mat4 m = trs_matrix(trs9); memcpy(out16, m.m, sizeof m.m); }
+/* GeometryType::Triangle (:1133-1160) */
+void orc_ingest_triangles(long nidx, const float* xyz3, const int32_t* idx, const float* trs9, float* out_xyz9) {
+    mat4 m = trs_matrix(trs9);
+    for (long t = 0; t < nidx / 3; t++)
+        for (int k = 0; k < 3; k++) {
+            const float* v = xyz3 + 3 * (long)idx[3 * t + k];
+            v3 q = mat_mulv(&m, v3_make(v[0], v[1], v[2]), 1.0f);
+            out_xyz9[9 * t + 3 * k] = q.x; out_xyz9[9 * t + 3 * k + 1] = q.y; out_xyz9[9 * t + 3 * k + 2] = q.z;
+        }
+}
+/* GeometryType::Sphere (:1161-1215): r = (max.x - min.x) / 2, centre = min + r on ALL axes; max starts at FLT_MIN
+ * (numeric_limits<float>::min(), the smallest positive float), so a mesh entirely at negative x keeps max.x = FLT_MIN */
+void orc_ingest_sphere(long nidx, const float* xyz3, const int32_t* idx, const float* trs9, float* out4) {
+    mat4 m = trs_matrix(trs9);
+    float mn[3] = { 3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f }, mx[3] = { 1.175494351e-38f, 1.175494351e-38f, 1.175494351e-38f };
+    for (long i = 0; i < nidx; i++) {
+        const float* v = xyz3 + 3 * (long)idx[i];
+        v3 q = mat_mulv(&m, v3_make(v[0], v[1], v[2]), 1.0f);
+        float p[3] = { q.x, q.y, q.z };
+        for (int a = 0; a < 3; a++) { if (p[a] < mn[a]) mn[a] = p[a]; if (p[a] > mx[a]) mx[a] = p[a]; }
+    }
+    float radius = (mx[0] - mn[0]) / 2.0f;
+    out4[0] = mn[0] + radius; out4[1] = mn[1] + radius; out4[2] = mn[2] + radius; out4[3] = radius;
+}

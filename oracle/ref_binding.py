@@ -67,6 +67,14 @@ def lib():
         L.ref_state_update.argtypes = [_f32p, C.c_int, C.c_int, C.c_int]
         L.ref_bench.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.ref_bench.restype = C.c_double
+        L.ref_frustum_planes.argtypes = [_f32p, _f32p]
+        L.ref_frustum_aabb.argtypes = [C.c_long, _f32p, _f32p, _f32p, _i32p]
+        L.ref_inverse_view_projection.argtypes = [_f32p, _f32p, _f32p]
+        L.ref_visible_frustum_culling.argtypes = [C.c_void_p, _f32p, _f32p, _i32p, C.c_long]
+        L.ref_visible_frustum_culling.restype = C.c_long
+        L.ref_trs_matrix.argtypes = [_f32p, _f32p]
+        L.ref_ingest_triangles.argtypes = [C.c_long, _f32p, _i32p, _f32p, _f32p]
+        L.ref_ingest_sphere.argtypes = [C.c_long, _f32p, _i32p, _f32p, _f32p]
         _lib = L
     return _lib
 
@@ -268,3 +276,51 @@ def state_update(io18, flags, ms=5, nsteps=1):
     for i in range(io.shape[0]):
         L.ref_state_update(io[i], int(flags[i]), ms, nsteps)
     return io
+
+
+# ---- frustum culling and collider ingest through the reference's own arithmetic ----
+def frustum_planes(inv_vp):
+    out = np.zeros(24, np.float32)
+    lib().ref_frustum_planes(np.ascontiguousarray(inv_vp, np.float32).reshape(-1), out)
+    return out.reshape(6, 4)
+
+
+def frustum_aabb(planes, mins, maxs):
+    mins = np.ascontiguousarray(mins, np.float32).reshape(-1, 3); maxs = np.ascontiguousarray(maxs, np.float32).reshape(-1, 3)
+    out = np.zeros(mins.shape[0], np.int32)
+    lib().ref_frustum_aabb(mins.shape[0], np.ascontiguousarray(planes, np.float32).reshape(-1), mins, maxs, out)
+    return out
+
+
+def inverse_view_projection(view, proj):
+    out = np.zeros(16, np.float32)
+    lib().ref_inverse_view_projection(np.ascontiguousarray(view, np.float32).reshape(-1), np.ascontiguousarray(proj, np.float32).reshape(-1), out)
+    return out.reshape(4, 4)
+
+
+def visible_frustum_culling(world, view, proj):
+    """OSP::getVisibleFrustumCulling on a RefWorld's octree: 1-based visible leaf offsets, front to back."""
+    n = world.L.ref_leaf_count(world.h)
+    out = np.zeros(max(n, 1), np.int32)
+    k = lib().ref_visible_frustum_culling(world.h, np.ascontiguousarray(view, np.float32).reshape(-1), np.ascontiguousarray(proj, np.float32).reshape(-1), out, n)
+    return out[:k]
+
+
+def trs_matrix(trs9):
+    out = np.zeros(16, np.float32)
+    lib().ref_trs_matrix(np.ascontiguousarray(trs9, np.float32), out)
+    return out.reshape(4, 4)
+
+
+def ingest_triangles(xyz3, idx, trs9):
+    idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
+    out = np.zeros((idx.shape[0] // 3, 9), np.float32)
+    lib().ref_ingest_triangles(idx.shape[0], np.ascontiguousarray(xyz3, np.float32).reshape(-1), idx, np.ascontiguousarray(trs9, np.float32), out.reshape(-1))
+    return out
+
+
+def ingest_sphere(xyz3, idx, trs9):
+    idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
+    out = np.zeros(4, np.float32)
+    lib().ref_ingest_sphere(idx.shape[0], np.ascontiguousarray(xyz3, np.float32).reshape(-1), idx, np.ascontiguousarray(trs9, np.float32), out)
+    return out

@@ -1,7 +1,9 @@
-/* Shim: only OSP::getVisibleFrustumCulling (out of scope) uses the view manager. */
+/* Shim: only OSP::getVisibleFrustumCulling uses the view manager. The harness sets the two matrices
+ * (ref_visible_frustum_culling) before calling the unmodified reference function. */
 #pragma once
 #include "Matrix.h"
 struct ViewEventDistributor {
-    Matrix getFrustumView() { return Matrix(); }
-    Matrix getFrustumProjection() { return Matrix(); }
+    Matrix view, proj;
+    Matrix getFrustumView() { return view; }
+    Matrix getFrustumProjection() { return proj; }
 };

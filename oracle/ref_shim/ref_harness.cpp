@@ -82,6 +82,8 @@ static int tri_index(Entity* e, Triangle* t) {
     return (int)(t - v->data());
 }
 
+#include <limits>
+#include "ModelBroker.h"
 extern "C" {
 /* mangled: GeometryMath::sphereSphereDetection(Sphere&, Sphere&) etc. */
 bool __real__ZN12GeometryMath21sphereSphereDetectionER6SphereS1_(Sphere*, Sphere*);
@@ -378,6 +380,74 @@ void ref_state_update(float* io18, int flags, int ms, int nsteps) {
     io18[9] = av.getx(); io18[10] = av.gety(); io18[11] = av.getz();
 }
 /* times nsteps reference ticks; returns seconds */
+/* ---- frustum culling: the reference's own functions ------------------------------ */
+static Matrix mat16(const float* m16) { float b[MATRIX_SIZE] = {0}; for (int i = 0; i < 16; i++) b[i] = m16[i]; b[24] = 1.0f; return Matrix(b); }
+/* GeometryMath::getFrustumPlanes (math/src/GeometryMath.cpp:630-731): 6 planes (left,right,far,near,bottom,top) x (nx,ny,nz,d) */
+void ref_frustum_planes(const float* inv_vp16, float* planes24) {
+    std::vector<Vector4> planes;
+    GeometryMath::getFrustumPlanes(mat16(inv_vp16), planes);
+    for (int p = 0; p < 6; p++) { float* f = planes[p].getFlatBuffer(); for (int k = 0; k < 4; k++) planes24[4*p+k] = f[k]; }
+}
+/* GeometryMath::frustumAABBDetection (math/src/GeometryMath.cpp:733-757) over n boxes */
+void ref_frustum_aabb(long n, const float* planes24, const float* mins3, const float* maxs3, int32_t* out) {
+    std::vector<Vector4> planes;
+    for (int p = 0; p < 6; p++) planes.push_back(Vector4(planes24[4*p], planes24[4*p+1], planes24[4*p+2], planes24[4*p+3]));
+    for (long i = 0; i < n; i++) {
+        Vector4 mn(mins3[3*i], mins3[3*i+1], mins3[3*i+2]), mx(maxs3[3*i], maxs3[3*i+1], maxs3[3*i+2]);
+        out[i] = GeometryMath::frustumAABBDetection(planes, mn, mx) ? 1 : 0;
+    }
+}
+/* inverseViewProjection exactly as OSP::getVisibleFrustumCulling builds it (physics/src/OSP.cpp:129-130) */
+void ref_inverse_view_projection(const float* view16, const float* proj16, float* out16) {
+    Matrix r = mat16(view16).inverse() * mat16(proj16).inverse();
+    for (int i = 0; i < 16; i++) out16[i] = r.getFlatBuffer()[i];
+}
+/* OSP::getVisibleFrustumCulling (physics/src/OSP.cpp:125-180), unmodified, on the world's physics octree:
+ * 1-based leaf offsets of the visible triangle-bearing leaves, front to back by |leaf centre| */
+long ref_visible_frustum_culling(void* wp, const float* view16, const float* proj16, int32_t* out, long cap) {
+    ModelBroker::getViewManager()->view = mat16(view16);
+    ModelBroker::getViewManager()->proj = mat16(proj16);
+    std::vector<int> v = ((RefWorld*)wp)->phys->_octalSpacePartioner.getVisibleFrustumCulling();
+    for (size_t i = 0; i < v.size() && (long)i < cap; i++) out[i] = v[i];
+    return (long)v.size();
+}
+
+/* ---- collider ingest: FbxLoader::_buildGeometryData (model/src/FbxLoader.cpp:1109-1216) cannot be
+ * compiled (FBX SDK), so its loops are restated here on top of the reference's own Matrix / Vector4 arithmetic ---- */
+static Matrix trs_matrix(const float* trs9) {
+    Matrix rotation = Matrix::rotationAroundX(trs9[3]) * Matrix::rotationAroundY(trs9[4]) * Matrix::rotationAroundZ(trs9[5]);   /* :1118-1120 */
+    Matrix translation = Matrix::translation(trs9[0], trs9[1], trs9[2]);                                                          /* :1122-1124 */
+    Matrix scale = Matrix::scale(trs9[6], trs9[7], trs9[8]);                                                                      /* :1126-1128 */
+    return translation * rotation * scale;                                                                                        /* :1131 */
+}
+void ref_trs_matrix(const float* trs9, float* out16) { Matrix m = trs_matrix(trs9); for (int i = 0; i < 16; i++) out16[i] = m.getFlatBuffer()[i]; }
+/* GeometryType::Triangle branch (:1133-1160): every index triple becomes a triangle with the node TRS baked in */
+void ref_ingest_triangles(long nidx, const float* xyz3, const int32_t* idx, const float* trs9, float* out_xyz9) {
+    Matrix transformation = trs_matrix(trs9);
+    for (long t = 0; t < nidx / 3; t++)
+        for (int k = 0; k < 3; k++) {
+            const float* v = xyz3 + 3 * (long)idx[3*t+k];
+            Vector4 P(v[0], v[1], v[2], 1.0);
+            Vector4 q = transformation * P;
+            out_xyz9[9*t+3*k] = q.getx(); out_xyz9[9*t+3*k+1] = q.gety(); out_xyz9[9*t+3*k+2] = q.getz();
+        }
+}
+/* GeometryType::Sphere branch (:1161-1215): one sphere per collider mesh, r = x-extent / 2, centre = min + r on all axes
+ * (max starts at numeric_limits<float>::min(), the smallest POSITIVE float, as in the reference) */
+void ref_ingest_sphere(long nidx, const float* xyz3, const int32_t* idx, const float* trs9, float* out4) {
+    Matrix transformation = trs_matrix(trs9);
+    float mn[3] = { (std::numeric_limits<float>::max)(), (std::numeric_limits<float>::max)(), (std::numeric_limits<float>::max)() };
+    float mx[3] = { (std::numeric_limits<float>::min)(), (std::numeric_limits<float>::min)(), (std::numeric_limits<float>::min)() };
+    for (long i = 0; i < nidx; i++) {
+        const float* v = xyz3 + 3 * (long)idx[i];
+        Vector4 vert = transformation * Vector4(v[0], v[1], v[2], 1.0f);
+        float p[3] = { vert.getx(), vert.gety(), vert.getz() };
+        for (int a = 0; a < 3; a++) { if (p[a] < mn[a]) mn[a] = p[a]; if (p[a] > mx[a]) mx[a] = p[a]; }
+    }
+    float radius = (mx[0] - mn[0]) / 2.0f;
+    out4[0] = mn[0] + radius; out4[1] = mn[1] + radius; out4[2] = mn[2] + radius; out4[3] = radius;
+}
+
 double ref_bench(void* wp, int ms, int nsteps) {
     auto t0 = std::chrono::steady_clock::now();
     for (int k = 0; k < nsteps; k++) ref_step(wp, ms);

@@ -89,6 +89,14 @@ SIGNATURES = {
     "rb_dist_init": (C.c_int, [_P, C.c_char_p, _P]),
     "rb_dist_p2p_export": (C.c_int, [_P, _P]),
     "rb_dist_p2p_connect": (C.c_int, [_P, _P, _P]),
+    "rb_frustum_planes": (C.c_int, [_P, _P]),
+    "rb_frustum_cull_cubes": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "rb_frustum_cull_static": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
+    "rb_get_static_cells": (C.c_int, [_P, _P, _P]),
+    "rb_ingest_trs_matrix": (C.c_int, [_P, _P]),
+    "rb_ingest_mesh_triangles": (C.c_int, [C.c_uint32, _P, C.c_uint32, _P, _P, _P]),
+    "rb_ingest_mesh_sphere": (C.c_int, [C.c_uint32, _P, C.c_uint32, _P, _P, _P]),
+    "rb_ingest_static_mesh": (C.c_int, [_P, C.c_uint32, _P, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "rb_halo_ghost_cap_auto": (C.c_uint32, [C.c_uint32, C.c_float, C.c_float, C.c_float]),
     "rb_set_body_ids": (C.c_int, [_P, _P, C.c_uint32]),
     "rb_get_body_ids": (C.c_int, [_P, _P]),

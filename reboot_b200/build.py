@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["rb_kernels.cu", "rb_world.cu", "rb_dist.cu"]
+SOURCES = ["rb_kernels.cu", "rb_world.cu", "rb_dist.cu", "rb_extras.cu"]
 OUT = os.path.join(CSRC, "libreboot_b200.so")
 
 NVCC_FLAGS = [

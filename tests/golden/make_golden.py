@@ -145,9 +145,56 @@ def scene_golden(sc, checkpoints, prefix):
     return out
 
 
+def extras_golden():
+    """SURVEY 8(f) ranks 2 and 4: frustum planes / AABB culling / the full OSP::getVisibleFrustumCulling on the C1
+    octree, and FbxLoader::_buildGeometryData's two branches, all through the reference's own arithmetic."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cams
+    rng = np.random.default_rng(105)
+    out = {}
+    views, projs, invs, planes, mins, maxs, flags = [], [], [], [], [], [], []
+    for k in range(40):
+        V = cams.view_matrix(rng.uniform(-300, 300, 3), rng.uniform(0, 6.28), rng.uniform(-1, 1))
+        P = cams.projection(rng.uniform(30, 100), rng.uniform(1, 2), 0.1, rng.uniform(50, 3000))
+        inv = rb.inverse_view_projection(V, P)
+        pl = rb.frustum_planes(inv)
+        mn = rng.uniform(-1000, 900, (300, 3)).astype(f32); mx = (mn + rng.uniform(1, 400, (300, 3))).astype(f32)
+        views.append(V); projs.append(P); invs.append(inv); planes.append(pl); mins.append(mn); maxs.append(mx); flags.append(rb.frustum_aabb(pl, mn, mx))
+    out.update(fr_view=np.array(views), fr_proj=np.array(projs), fr_inv=np.array(invs), fr_planes=np.array(planes),
+               fr_mins=np.array(mins), fr_maxs=np.array(maxs), fr_flags=np.array(flags))
+    w = rb.RefWorld(scenes.config1())
+    cube, ntri, _ = w.leaves()
+    vis = []
+    cv, cp = [], []
+    for k in range(12):
+        V = cams.view_matrix(rng.uniform(-60, 60, 3) * [1, 0.3, 1], rng.uniform(0, 6.28), rng.uniform(-0.6, 0.2))
+        P = cams.projection(60, 1.6, 0.1, rng.uniform(30, 400))
+        v = rb.visible_frustum_culling(w, V, P)
+        cv.append(V); cp.append(P); vis.append(np.concatenate([v, np.full(len(cube) - len(v), -1, np.int32)]))
+    out.update(c1_leaf_cubes=cube, c1_leaf_ntri=ntri.astype(np.int32), c1_cull_view=np.array(cv), c1_cull_proj=np.array(cp),
+               c1_cull_inv=np.array([rb.inverse_view_projection(a, b) for a, b in zip(cv, cp)]), c1_cull_visible=np.array(vis))
+    # ingest: meshes of 3..60 vertices under random node transforms; every fifth entirely at negative x (the FLT_MIN quirk)
+    xs, ids, trss, tris, sphs, mats = [], [], [], [], [], []
+    for k in range(60):
+        nv = 64; xyz = rng.uniform(-5, 5, (nv, 3)).astype(f32); idx = rng.integers(0, nv, 96).astype(np.int32)
+        trs = np.concatenate([rng.uniform(-100, 100, 3), rng.uniform(-180, 180, 3), rng.uniform(0.2, 4, 3)]).astype(f32)
+        if k % 5 == 0:
+            xyz[:, 0] -= 100; trs[:6] = 0
+        xs.append(xyz); ids.append(idx); trss.append(trs)
+        mats.append(rb.trs_matrix(trs)); tris.append(rb.ingest_triangles(xyz, idx, trs)); sphs.append(rb.ingest_sphere(xyz, idx, trs))
+    out.update(in_xyz=np.array(xs), in_idx=np.array(ids), in_trs=np.array(trss), in_mat=np.array(mats), in_tris=np.array(tris), in_sphere=np.array(sphs))
+    return out
+
+
 def main():
     if not rb.available():
         raise SystemExit("oracle/_ref/libref_physics.so missing: run `make -C oracle ref` (needs /root/reference)")
+    ex = extras_golden()
+    np.savez_compressed(os.path.join(OUT, "extras.npz"), **ex)
+    print("extras.npz", {k: v.shape for k, v in ex.items()})
+    if "--extras-only" in sys.argv:
+        return
+
     micro = {}
     micro.update(micro_sphere_triangle()); micro.update(micro_sphere_sphere()); micro.update(micro_cubes()); micro.update(micro_state())
     np.savez_compressed(os.path.join(OUT, "micro.npz"), **micro)
