@@ -129,7 +129,6 @@ M4 trs_matrix(const float* trs9) {
     return m_mul(m_mul(t, m_mul(m_mul(rx, ry), rz)), sc);
 }
 bool idx_ok(uint32_t nverts, uint32_t nidx, const uint32_t* idx) { for (uint32_t i = 0; i < nidx; i++) if (idx[i] >= nverts) return false; return true; }
-thread_local std::string g_extras_error;
 }
 
 extern "C" {
