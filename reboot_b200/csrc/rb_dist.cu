@@ -317,9 +317,12 @@ static int dist_phase_a(rb_world* w, int do_integrate, int list_mode) {
     const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
     const int p = remote ? (int)(d->halo_step & 1) : 0;
     P.dp = d->d_dp[p];
-    if (list_mode != 2) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));      // (list ticks leave the histogram clean themselves)
-    if (list_mode) CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter + rebuild flag
-    CU(cudaMemsetAsync(w->d_dn + 1, 0, 11 * sizeof(uint32_t), w->stream));    // n_ghost, self ghosts, emigrants, both out headers
+    // clears as kernels (a memset may land on a copy engine and queue behind a host transfer)
+    if (list_mode != 2) { rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++; }      // (list ticks leave the histogram clean themselves)
+    if (list_mode) {   // hot cell table + hot counter + rebuild flag | the tick block, and below the per-step counters
+        rb_launch_clear(P.hot_head, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->d_dn + 1, 11, w->stream); w->launches++;
+        rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
+    } else { rb_launch_clear(nullptr, 0, w->d_dn + 1, 11, w->stream); w->launches++; }    // n_ghost, self ghosts, emigrants, both out headers
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, list_mode ? list_mode : 1, w->stream); w->launches++;     // integrate + bin + halo pack
     if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));

@@ -341,6 +341,17 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P, int vl
     P.sorted_id[slot] = s | ((P.flags[body] & RB_F_CONTACT) ? RB_TRI_BIT : 0u);
 }
 
+// Per-tick clears run as a kernel, not as cudaMemsetAsync: a memset may be executed by a copy engine, and then it
+// queues behind whatever transfer that engine is busy with -- with the pipelined host round trip that stalled the
+// tick for a good part of every 12-MB copy (measured: +60 us per tick).
+__global__ void __launch_bounds__(RB_BLOCK) rb_clear_kernel(uint4* __restrict__ a, uint32_t n16a, uint32_t* __restrict__ a_tail, uint32_t ntail,
+                                                           uint32_t* __restrict__ b, uint32_t nb4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n16a) a[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < ntail) a_tail[i] = 0u;         // the (< 4) words behind the last full 16 bytes: never a byte more than asked
+    if (i < nb4) b[i] = 0u;
+}
+
 // K1b (persistent lists, rebuild ticks only): histogram rank of every binned row + the poses the new lists
 // are built for. `cond` kernels return at once on the ticks whose lists are still valid.
 __global__ void __launch_bounds__(RB_BLOCK) rb_vl_bin_kernel(RbParams P) {
@@ -1371,6 +1382,12 @@ void rb_launch_scatter(const RbParams& P, cudaStream_t st) {
 }
 // persistent lists: the rebuild chain (bin -> scan -> scatter -> enumerate), every kernel conditional on the
 // device-side rebuild flag, followed by the unconditional test / resolve kernel over the lists
+// zero exactly `bytes_a` bytes at a (16-byte aligned, a multiple of 4 bytes) and `words_b` 32-bit words at b (either may be empty)
+void rb_launch_clear(void* a, size_t bytes_a, uint32_t* b, uint32_t words_b, cudaStream_t st) {
+    const uint32_t n16 = (uint32_t)(bytes_a / 16), ntail = (uint32_t)((bytes_a % 16) / 4);
+    const uint32_t n = n16 > words_b ? (n16 > ntail ? n16 : ntail) : (words_b > ntail ? words_b : ntail);
+    if (n) rb_clear_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>((uint4*)a, n16, (uint32_t*)a + 4ull * n16, ntail, b, words_b);
+}
 void rb_launch_vl_bin(const RbParams& P, cudaStream_t st) {
     if (P.ns) rb_vl_bin_kernel<<<cdiv(P.ns, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
 }

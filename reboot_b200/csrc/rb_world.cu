@@ -541,7 +541,7 @@ int enqueue_broadphase_tail(rb_world* w) {
 static int enqueue_broadphase(rb_world* w, int do_integrate) {
     RbParams& P = w->P;
     if (w->dist) return rb_dist_step_exchange(w, do_integrate);
-    CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));
+    rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++;      // histogram + scan ticket / status
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;
     return enqueue_broadphase_tail(w);
@@ -549,7 +549,7 @@ static int enqueue_broadphase(rb_world* w, int do_integrate) {
 static int enqueue_collide(rb_world* w, bool resolve) {
     RbParams& P = w->P;
     // per-step counters: contact count + changed count
-    CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
+    rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
     w->launches += rb_launch_collide(P, resolve, w->collide_variant, w->stream);
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
@@ -573,7 +573,6 @@ static int enqueue_collide(rb_world* w, bool resolve) {
 // halo exchange; K1 ran before it)
 int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     RbParams& P = w->P;
-    CU(cudaMemsetAsync(P.counters + RB_C_NCONTACT, 0, 2 * sizeof(unsigned long long), w->stream));
     rb_launch_vl_bin(P, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
     rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
@@ -600,8 +599,9 @@ static int enqueue_list_tick(rb_world* w, bool reorder_due) {
     const bool force = w->vl_force || reorder_due;
     if (w->dist) { int r = rb_dist_list_exchange(w, force ? 3 : 2); if (r) return r; }      // K1 (+ pack), exchange, remove + unpack
     else {
-        if (force) CU(cudaMemsetAsync(P.col_count, 0, w->hist_clear_bytes, w->stream));   // other paths may have left counts behind
-        CU(cudaMemsetAsync(P.hot_head, 0, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->stream));   // hot cell table + hot counter + rebuild flag
+        if (force) { rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++; }   // other paths may have left counts behind
+        // hot cell table + hot counter + rebuild flag, and the per-step contact / changed counters, in one launch
+        rb_launch_clear(P.hot_head, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
         if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
         rb_launch_integrate_bin(P, 1, force ? 3 : 2, w->stream);
     }
