@@ -251,8 +251,36 @@ public:
         for (uint64_t i = 0; i < n; i++) if (c[i].kind == 1) _triangleIntersectionList[_bodies[c[i].body]].insert({_geoms[c[i].other], c[i].other_prim});
         return _triangleIntersectionList;
     }
+    // OSP::getVisibleFrustumCulling -- physics/src/OSP.cpp:125-180, over this world's own static structure: ids of the
+    // non-empty static cells that meet the frustum, front to back. inverseViewProjection is what the reference builds
+    // as view.inverse() * projection.inverse() (:129-130).
+    std::vector<uint32_t> getVisibleFrustumCulling(const Matrix& inverseViewProjection) {
+        rb_stats_t st; ck(_w, rb_get_stats(_w, &st));
+        std::vector<uint32_t> cells((size_t)st.tri_cols_x * st.tri_cols_z + 1); uint32_t n = 0;
+        ck(_w, rb_frustum_cull_static(_w, inverseViewProjection.data(), cells.data(), (uint32_t)cells.size(), &n));
+        cells.resize(n);
+        return cells;
+    }
     rb_world* handle() { return _w; }
 };
+
+// FbxLoader::_buildGeometryData -- model/src/FbxLoader.cpp:1109-1216 for a neutral indexed mesh: fills the model's
+// Geometry exactly like the reference (static model: one triangle per index triple with the node TRS baked in;
+// animated model: ONE sphere per collider mesh, r = x-extent / 2, centre = min + r on all axes).
+// trs9 = LclTranslation, LclRotation (degrees), LclScaling of the node.
+inline void buildGeometryData(Model* model, const std::vector<float>& xyz3, const std::vector<uint32_t>& indices, const float trs9[9]) {
+    const uint32_t nv = (uint32_t)(xyz3.size() / 3), ni = (uint32_t)indices.size();
+    if (model->getGeometryType() == GeometryType::Triangle) {
+        std::vector<float> t((size_t)(ni / 3) * 9);
+        if (rb_ingest_mesh_triangles(nv, xyz3.data(), ni, indices.data(), trs9, t.data())) throw std::runtime_error("reboot_b200: bad mesh");
+        for (size_t k = 0; k + 8 < t.size(); k += 9)
+            model->getGeometry()->addTriangle(Triangle(Vector4(t[k], t[k + 1], t[k + 2]), Vector4(t[k + 3], t[k + 4], t[k + 5]), Vector4(t[k + 6], t[k + 7], t[k + 8])));
+    } else {
+        float s[4];
+        if (rb_ingest_mesh_sphere(nv, xyz3.data(), ni, indices.data(), trs9, s)) throw std::runtime_error("reboot_b200: bad mesh");
+        model->getGeometry()->addSphere(Sphere(s[3], Vector4(s[0], s[1], s[2])));
+    }
+}
 
 inline void StateVector::push_pos() {
     if (!_owner || !_owner->_built) return;

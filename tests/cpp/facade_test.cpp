@@ -45,6 +45,18 @@ int main(int argc, char** argv) {
         printf("%zu %.9g %.9g %.9g %.9g %.9g %.9g %d\n", i - 1, p.getx(), p.gety(), p.getz(), v.getx(), v.gety(), v.getz(), (int)s->getContact());
     }
     printf("hits %zu\n", hits);
+    // callers either side of the step: culling over the world's static cells (identity inverse view-projection = the
+    // NDC cube itself: the four cells around the origin) and collider ingest (FbxLoader::_buildGeometryData)
+    std::vector<uint32_t> vis = physics->getVisibleFrustumCulling(Matrix());
+    Model collider(GeometryType::Sphere), prop(GeometryType::Triangle);
+    const std::vector<float> mesh = { -1, 0, 0,  3, 0.5f, 0,  0, 2, 1,  1, -1, -2 };
+    const std::vector<uint32_t> mi = { 0, 1, 2, 0, 2, 3 };
+    const float trs[9] = { 10, 0, 0, 0, 0, 0, 2, 2, 2 };
+    buildGeometryData(&collider, mesh, mi, trs);
+    buildGeometryData(&prop, mesh, mi, trs);
+    const Sphere& cs = (*collider.getGeometry()->getSpheres())[0];
+    fprintf(stderr, "extras: visible %zu sphere r %.6g cx %.6g cy %.6g tris %zu\n", vis.size(), cs.getObjectRadius(), cs.getObjectPosition().getx(),
+            cs.getObjectPosition().gety(), prop.getGeometry()->getTriangles()->size());
     delete physics;
     return 0;
 }

@@ -46,7 +46,11 @@ def test_facade_matches_c_abi(tmp_path):
         pytest.skip("no CUDA device")
     from reboot_b200 import World
     exe = _build(tmp_path)
-    out = subprocess.run([exe, "6", "120"], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    run = subprocess.run([exe, "6", "120"], capture_output=True, text=True, check=True)
+    # culling over the static cells + collider ingest through the facade: x-extent of the scaled mesh is 8 -> r = 4,
+    # centre = min + r on every axis (min = (8, -2, -4)); the NDC cube meets the four cells around the origin
+    assert "extras: visible 4 sphere r 4 cx 12 cy 2 tris 2" in run.stderr, run.stderr
+    out = run.stdout.strip().splitlines()
     rows = np.array([[float(x) for x in ln.split()] for ln in out[:-1]])
     assert int(out[-1].split()[1]) > 0
     # same scene through the ctypes mirror
