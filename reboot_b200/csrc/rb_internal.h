@@ -95,6 +95,7 @@ struct rb_world {
     bool vl_active = true; uint64_t vl_resume_at = 0; uint32_t vl_backoff = 32; uint32_t vl_seen_r = 0, vl_seen_t = 0;
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
     uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}
+    cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)
     cudaStream_t vl_side = nullptr; cudaEvent_t vl_fork = nullptr, vl_join = nullptr;   // the hot bodies' launch runs next to the list kernel
     int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)
     // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----

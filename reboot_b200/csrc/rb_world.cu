@@ -69,6 +69,7 @@ void rb_world_destroy(rb_world* w) {
     if (w->h_counters) cudaFreeHost(w->h_counters);
     if (w->vl_host) cudaFreeHost(w->vl_host);
     if (w->vl_side) { cudaStreamDestroy(w->vl_side); cudaEventDestroy(w->vl_fork); cudaEventDestroy(w->vl_join); }
+    if (w->vl_pace[0]) { cudaEventDestroy(w->vl_pace[0]); cudaEventDestroy(w->vl_pace[1]); }
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     if (w->s_h2d) {
         cudaStreamSynchronize(w->s_h2d); cudaStreamSynchronize(w->s_d2h);
@@ -648,6 +649,16 @@ int rb_step(rb_world* w, int ms) {
     }
     w->steps++; w->pose_updates++;
     if (reorder_due && !(w->vl_on && w->vl_active)) { r = reorder_rows(w); if (r) return r; }      // (list ticks re-order inside the tick)
+    if (w->vl_on && (w->steps & 15u) == 0) {
+        // bounded run-ahead: the use-lists decision above feeds on what the device reports, so a host that enqueues
+        // hundreds of ticks ahead would decide blind. Every 16 ticks wait for the tick enqueued 16 ticks earlier:
+        // the device always has 16+ ticks queued (no bubble), the host is never more than 32 ahead.
+        const int k = (int)((w->steps >> 4) & 1u);
+        if (!w->vl_pace[0]) { CU(cudaEventCreateWithFlags(&w->vl_pace[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_pace[1], cudaEventDisableTiming)); }
+        CU(cudaEventRecord(w->vl_pace[k], w->stream));
+        if (w->vl_pace_armed[k ^ 1]) CU(cudaEventSynchronize(w->vl_pace[k ^ 1]));
+        w->vl_pace_armed[k] = true;
+    }
     return RB_OK;
 }
 int rb_integrate(rb_world* w, int ms) {
