@@ -106,3 +106,21 @@ def test_slab_group_steps_from_persistent_lists(mods, nslabs):
     assert busy and all(s["list_ticks"] > 200 and s["list_rebuilds"] < s["list_ticks"] // 2 for s in busy), info
     assert len(sa[0]) > 50, "sphere-sphere contacts (some across a face) must be in play"
     single.close(); group.close()
+
+
+def test_mismatched_halo_layouts_are_refused(mods):
+    """The neighbours store straight into a rank's halo buffers, so their layout (rb_config.halo_ghost_cap) must agree:
+    attaching peers whose capacities differ fails loudly instead of corrupting memory."""
+    World, dist, scenes = mods
+    sc = _crossing_scene(scenes, n=600)
+    parts = [dist.partition_scene(sc, 2, r) for r in range(2)]
+    ws = []
+    for r, (sub, ids, slab, rmax) in enumerate(parts):
+        ws.append(World(sub, slab=slab, rank=r, nranks=2, ids=ids, rm_max_hint=rmax, halo_ghost_cap=8192 + 1024 * r))
+    rc = ws[0].L.rb_dist_attach_peers(ws[0].h, None, ws[1].h)
+    assert rc != 0 and b"halo buffer layouts differ" in ws[0].L.rb_last_error(ws[0].h)
+    for w in ws:
+        w.close()
+    # and the helper picks one layout for uneven partitions (the bug this guards against: per-rank auto values)
+    L = ws[0].L
+    assert L.rb_halo_ghost_cap_auto(500_000, 0.5, 0.0, 1000.0) != L.rb_halo_ghost_cap_auto(505_000, 0.5, 0.0, 1000.0)
