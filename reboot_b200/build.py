@@ -17,6 +17,7 @@ NVCC_FLAGS = [
     "-fmad=false",                      # parity: no FMA contraction (reference is x86 SSE without FMA)
     "-Xcompiler", "-fPIC,-ffp-contract=off",
     "-DRB_HAVE_DIST",
+    "-DRB_HAVE_CDP",                    # a second, relocatable pass over rb_kernels.cu provides the device-launched list rebuild
 ]
 
 
@@ -35,6 +36,33 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     flags = list(NVCC_FLAGS)
     if not os.path.exists(os.path.join(CSRC, "rb_dist.cu")):
         flags.remove("-DRB_HAVE_DIST")
-    cmd = [nvcc_path()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + srcs + ["-ldl"]
-    subprocess.check_call(cmd, cwd=CSRC)
+    link_library(flags, srcs, OUT, verbose)
     return OUT
+
+
+def link_library(flags, srcs, out, verbose=False, tag=""):
+    """normal pass over every source + the relocatable chain pass over rb_kernels.cu (gate kernel and the kernels it
+    tail-launches), device-linked against cudadevrt, all into one shared library"""
+    nv = nvcc_path()
+    cflags = [f for f in flags if f != "-shared"]
+    objdir = os.path.join(CSRC, "build" + tag)
+    os.makedirs(objdir, exist_ok=True)
+    v = ["-Xptxas", "-v"] if verbose else []
+    objs = []
+    procs = []
+    for s in srcs:
+        o = os.path.join(objdir, os.path.basename(s) + ".o")
+        objs.append(o)
+        procs.append(subprocess.Popen([nv] + cflags + v + ["-c", s, "-o", o], cwd=CSRC))
+    extra = []
+    if "-DRB_HAVE_CDP" in flags:
+        chain_o = os.path.join(objdir, "rb_kernels.chain.o"); dlink_o = os.path.join(objdir, "rb_kernels.chain.dlink.o")
+        p = subprocess.Popen([nv] + cflags + v + ["-rdc=true", "-DRB_CHAIN_TU", "-c", os.path.join(CSRC, "rb_kernels.cu"), "-o", chain_o], cwd=CSRC)
+        if p.wait():
+            raise subprocess.CalledProcessError(p.returncode, "nvcc (chain pass)")
+        subprocess.check_call([nv, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-dlink", chain_o, "-o", dlink_o, "-lcudadevrt"], cwd=CSRC)
+        extra = [chain_o, dlink_o]
+    for p in procs:
+        if p.wait():
+            raise subprocess.CalledProcessError(p.returncode, "nvcc")
+    subprocess.check_call([nv, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-o", out] + objs + extra + ["-ldl", "-lcudadevrt"], cwd=CSRC)

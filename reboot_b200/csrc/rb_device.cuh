@@ -118,6 +118,7 @@ struct RbParams {
     volatile uint32_t* vl_host;   // mapped host copy of {rebuilds, ticks} (heuristics only)
     float4* ws_build;             // frozen sphere of every row at the last rebuild
     float vl_skin;
+    unsigned long long* scan_status; uint32_t* scan_ticket; uint32_t ncols;     // the scan's work words (device-launched rebuild chain)
     float vl_slack;               // added to the grown radius when a list is pruned with the exact predicate (>> its rounding error)
     // "hot" bodies have used their skin up (fast movers): they enumerate for themselves every tick (triangles
     // from the static grid, cold partners from the sort of the last rebuild, which is off by less than the

@@ -22,7 +22,9 @@ void rb_launch_clear(void* a, size_t bytes_a, uint32_t* b, uint32_t words_b, cud
 void rb_launch_vl_bin(const RbParams& P, cudaStream_t st);
 void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join);
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate);
+bool rb_have_device_launch();
+void rb_launch_vl_gate(const RbParams& P, cudaStream_t st);
 void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, const uint32_t* inv, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
 void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t* inv, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
 void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st);
@@ -93,6 +95,8 @@ struct rb_world {
     int group_list_mode = 0;                 // rb_step_group: this tick's mode of the world (0 per-tick enumeration, 2 lists, 3 lists + forced rebuild)
     uint64_t vl_decided_for = 0;             // step number (1-based) the use-lists decision below was taken for
     bool vl_active = true; uint64_t vl_resume_at = 0; uint32_t vl_backoff = 32; uint32_t vl_seen_r = 0, vl_seen_t = 0;
+    bool vl_gate_ok = true;                  // recent rebuild rate is low enough for the device-launched chain (else the host enqueues it)
+    bool vl_cdp = false;                     // K1 launches the rebuild chain from the device (library built with -rdc=true)
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
     uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}
     cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)

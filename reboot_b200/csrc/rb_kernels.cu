@@ -13,6 +13,18 @@
 // All kernels are HBM/L2-bound integer + FP32 work: no tensor cores (nothing here is a contraction).
 #include "rb_device.cuh"
 
+// This file is compiled twice. The normal pass holds every kernel and the host launchers. The second pass
+// (-rdc=true -DRB_CHAIN_TU, device-linked against cudadevrt) holds only the gate kernel of the persistent-list tick
+// and ITS OWN copies of the rebuild-chain kernels it tail-launches (CUDA dynamic parallelism needs relocatable device
+// code, and relocatable code made the big per-tick kernels measurably slower: 0.241 -> 0.262 ms per tick), so the
+// kernels that run every tick stay in the normal pass.
+#ifdef RB_CHAIN_TU
+#define RB_KNS rbk_chain
+#else
+#define RB_KNS rbk
+#endif
+namespace RB_KNS {
+
 #define RB_BLOCK 256
 #define RB_MAXLOCAL 6   // contacts a thread buffers before the warp-aggregated append
 
@@ -32,7 +44,7 @@ __device__ __forceinline__ void vl_request_rebuild(const RbParams& P, uint32_t w
     if (!(v[RB_VL_WHY] & why)) atomicOr(&P.vl[RB_VL_WHY], why);
 }
 
-__global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
+__device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const int do_integrate, const int do_bin) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_owned = rb_n_owned(P);
     if (b >= (P.dn ? n_owned : P.nb)) return;
@@ -172,6 +184,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, 
         P.key[s] = k;
     }
 }
+
 
 // ------------------------------------------------------------------------------------------
 // K2: exclusive scan of col_count[0..n) into col_start[0..n], three launches.
@@ -1221,6 +1234,25 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     }
 }
 
+// do_bin: 0 integrate only, 1 integrate + bin (per-tick enumeration), 2 list tick, 3 list tick with a rebuild forced by the host
+__global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
+    rb_integrate_bin_body(P, do_integrate, do_bin);
+}
+#ifdef RB_CHAIN_TU
+// The gate of a list tick (one thread, right behind K1): if K1 raised the rebuild flag it tail-launches
+// bin -> scan -> scatter -> enumerate (CUDA dynamic parallelism: tail launches run after this grid and before the next
+// kernel of the stream, in order). On the other ticks -- nearly all of them -- the rebuild chain costs this one
+// 2-us launch instead of four full-grid launches that return at once.
+__global__ void rb_vl_gate_kernel(RbParams P) {
+    if (threadIdx.x || blockIdx.x || !P.vl[RB_VL_REBUILD]) return;
+    const uint32_t g = (P.ns + RB_BLOCK - 1) / RB_BLOCK, tiles = (P.ncols + RB_SCAN_TILE - 1) / RB_SCAN_TILE;
+    rb_vl_bin_kernel<<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P);
+    rb_scan_lookback_kernel<<<tiles, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P.col_count, P.ncols, P.col_start, P.scan_status, P.scan_ticket, P.vl + RB_VL_REBUILD, 1);
+    rb_scatter_kernel<<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P, 1, P.scan_status, P.scan_ticket, tiles);
+    rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P);
+}
+#endif
+
 // K5: deferred commit for compound bodies
 __global__ void __launch_bounds__(RB_BLOCK) rb_commit_kernel(RbParams P) {
     uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1354,12 +1386,25 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_owned_flags_kernel(RbParams P, ui
     out[s] = (s < n_sorted && (P.sorted_id[s] & ~RB_TRI_BIT) < P.dn[0]) ? 1u : 0u;
 }
 
+} // namespace RB_KNS
+using namespace RB_KNS;
+
 // ------------------------------------------------------------------------------------------
 // host-callable launchers (called from rb_world.cu)
 // ------------------------------------------------------------------------------------------
 static inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
+#ifdef RB_CHAIN_TU
 extern "C++" {
+void rb_launch_vl_gate(const RbParams& P, cudaStream_t st) { rb_vl_gate_kernel<<<1, 32, 0, st>>>(P); }
+bool rb_have_device_launch() { return true; }
+}
+#else
+extern "C++" {
+#ifndef RB_HAVE_CDP      /* built without the relocatable pass: the host always enqueues the rebuild chain itself */
+void rb_launch_vl_gate(const RbParams&, cudaStream_t) {}
+bool rb_have_device_launch() { return false; }
+#endif
 void rb_launch_integrate_bin(const RbParams& P, int do_integrate, int do_bin, cudaStream_t st) {
     if (P.nb) rb_integrate_bin_kernel<<<cdiv(P.nb, RB_BLOCK), RB_BLOCK, 0, st>>>(P, do_integrate, do_bin);
 }
@@ -1399,10 +1444,10 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 }
 // The hot bodies' launch is small and latency-bound (a few warps walking dependent loads): it runs on a side
 // stream next to the big list kernel. Both only write the bodies they own and read frozen data of the others.
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate) {
     if (!P.nb) return 0;
     const uint32_t g = cdiv(P.ns, RB_BLOCK);
-    rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
+    if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
     cudaEventRecord(fork, st);
     cudaStreamWaitEvent(side, fork, 0);
     rb_collide_single_kernel<true, 3><<<cdiv(P.hot_cap, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies (reuse ticks)
@@ -1471,3 +1516,4 @@ void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st) {
     if (P.nb) rb_reorder_kernel<<<cdiv(P.nb, RB_BLOCK), RB_BLOCK, 0, st>>>(P, *(const RbReorder*)R);
 }
 }
+#endif // RB_CHAIN_TU

@@ -54,6 +54,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     { const char* v = getenv("RB_VERLET"); w->vl_on = !(v && *v == '0'); }          // persistent candidate lists (default on where they apply)
     { const char* v = getenv("RB_VERLET_SKIN"); if (v && *v) w->vl_skin_cfg = (float)atof(v); }
     { const char* v = getenv("RB_VERLET_HOT"); if (v && *v) w->vl_hot_cfg = atoi(v); }
+    { const char* v = getenv("RB_VERLET_CDP"); w->vl_cdp = rb_have_device_launch() && !(v && *v == '0'); }
     { const char* v = getenv("RB_SCAN_V1"); if (v && *v == '1') w->scan_variant = 1; }
     { const char* v = getenv("RB_REORDER_EVERY"); if (v && *v) w->reorder_every = atoi(v); }
     *out = w;
@@ -479,6 +480,7 @@ int rb_build(rb_world* w) {
         ALLOC(hh, ncell + 1 + RB_VL_WORDS); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
         CU(cudaMemsetAsync(hh, 0, (ncell + 1 + RB_VL_WORDS) * sizeof(uint32_t), w->stream));
         P.hot_head = hh; P.hot_row = hr; P.hot_next = hn; P.vl = hh + ncell + 1;
+        P.scan_status = w->d_scan_status; P.scan_ticket = w->d_scan_ticket; P.ncols = w->ncols;      // for the device-launched rebuild chain
         static_assert(RB_VL_REBUILD == 0, "the rebuild flag must be the first list word");
     }
     if (P.single && P.ns) {     // enumerate -> resolve hand-over lists
@@ -573,15 +575,20 @@ static int enqueue_collide(rb_world* w, bool resolve) {
 // second half of a list tick: the conditional rebuild chain and the resolve launches (slab worlds get here after their
 // halo exchange; K1 ran before it)
 int rb_list_tick_tail(rb_world* w, bool reorder_due) {
+    const bool tail_forced = w->vl_force || reorder_due;
     RbParams& P = w->P;
-    rb_launch_vl_bin(P, w->stream);
+    // built with device-side launches: a one-thread gate kernel tail-launches bin -> scan -> scatter -> enumerate when the
+    // rebuild flag is up (rb_kernels.cu), so the host only enqueues the chain itself on the ticks it forces
+    const bool chain = !w->vl_cdp || tail_forced || !w->vl_gate_ok;
+    if (!chain) rb_launch_vl_gate(P, w->stream);
+    if (chain) rb_launch_vl_bin(P, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
-    rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
+    if (chain) rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[2], w->stream));
-    rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
+    if (chain) rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (reorder_due) { int r = reorder_rows(w, true); if (r) return r; }     // rows into sort order before the lists are built for them
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
-    w->launches += 4 + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join);
+    w->launches += (chain ? 4 : 2) + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join, chain);
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
@@ -621,6 +628,7 @@ bool rb_step_will_use_lists(rb_world* w) {
         const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
         if (nt - w->vl_seen_t >= 16u) {
             const bool mostly_rebuilding = 2u * (nr - w->vl_seen_r) > (nt - w->vl_seen_t);
+            w->vl_gate_ok = 8u * (nr - w->vl_seen_r) <= (nt - w->vl_seen_t);     // device-launched rebuilds pay off while rebuilds are rare
             w->vl_seen_r = nr; w->vl_seen_t = nt;
             if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
             else w->vl_backoff = 32;

@@ -9,5 +9,5 @@ name, extra = sys.argv[1], sys.argv[2:]
 out_dir = os.path.join(ROOT, "variants"); os.makedirs(out_dir, exist_ok=True)
 out = os.path.join(out_dir, f"lib_{name}.so")
 srcs = [os.path.join(B.CSRC, s) for s in B.SOURCES]
-subprocess.check_call([B.nvcc_path()] + B.NVCC_FLAGS + extra + ["-o", out] + srcs + ["-ldl"], cwd=B.CSRC)
+B.link_library(B.NVCC_FLAGS + extra, srcs, out, tag="_" + name)
 print(out)
