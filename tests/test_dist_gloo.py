@@ -1,5 +1,5 @@
 """CPU suite, world_size 2 over gloo: the host-side logic of the multi-GPU path -- slab ownership,
-scene partitioning, and the unique-id rendezvous -- without any GPU."""
+scene partitioning, the unique-id rendezvous and the agreement on the halo buffer layout -- without any GPU."""
 import os
 import sys
 
@@ -32,6 +32,16 @@ def _worker(rank, world_size, port, q):
     # unique-id rendezvous: rank 0's bytes arrive everywhere
     uid = rbdist.broadcast_unique_id(lambda: bytes(range(128)), rank)
     ok &= uid.tobytes() == bytes(range(128))
+    # one halo buffer layout for every rank: the maximum of what each would pick for its own (uneven) body count
+    from reboot_b200 import _lib
+    L = _lib.load()
+    n_fake = 400_000 + 150_000 * rank                      # uneven partition: the per-rank values differ ...
+    mine = int(L.rb_halo_ghost_cap_auto(n_fake, 0.5, 0.0, 1000.0))
+    cap = rbdist.common_ghost_cap(n_fake, 0.5, 1000.0)
+    caps = [torch.zeros(1, dtype=torch.int64) for _ in range(world_size)]
+    dist.all_gather(caps, torch.tensor([cap], dtype=torch.int64))
+    ok &= all(int(c) == cap for c in caps) and cap >= mine   # ... the agreed one is the same everywhere and covers everybody
+    ok &= cap == int(L.rb_halo_ghost_cap_auto(400_000 + 150_000 * (world_size - 1), 0.5, 0.0, 1000.0))
     q.put((rank, ok, len(ids)))
     dist.destroy_process_group()
 
