@@ -170,12 +170,18 @@ static int cull_common(rb_world* w, const float planes24[24], int mode, uint32_t
     CU(cudaSetDevice(w->cfg.device));
     *n_visible = 0;
     if (n == 0) return RB_OK;
-    float* d_cubes = nullptr; RbCullOut* d_out = nullptr; uint32_t* d_cnt = nullptr;
+    // scratch lives with the world and only grows: culling is a per-frame call of a renderer
     cudaError_t e = cudaSuccess;
-    if (mode == 0) { e = cudaMalloc(&d_cubes, (size_t)n * 6 * sizeof(float)); if (e == cudaSuccess) e = cudaMemcpyAsync(d_cubes, cubes6_host, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, w->stream); }
-    if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)n * sizeof(RbCullOut));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cnt, sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t), w->stream);
+    if (w->cull_cap < n) {
+        cudaFree(w->d_cull_out); cudaFree(w->d_cull_cubes); w->d_cull_out = nullptr; w->d_cull_cubes = nullptr; w->cull_cap = 0;
+        e = cudaMalloc(&w->d_cull_out, (size_t)n * sizeof(RbCullOut));
+        if (e == cudaSuccess) e = cudaMalloc(&w->d_cull_cubes, (size_t)n * 6 * sizeof(float));
+        if (e == cudaSuccess && !w->d_cull_cnt) e = cudaMalloc(&w->d_cull_cnt, sizeof(uint32_t));
+        if (e == cudaSuccess) w->cull_cap = n;
+    }
+    float* d_cubes = (float*)w->d_cull_cubes; RbCullOut* d_out = (RbCullOut*)w->d_cull_out; uint32_t* d_cnt = w->d_cull_cnt;
+    if (e == cudaSuccess && mode == 0) e = cudaMemcpyAsync(d_cubes, cubes6_host, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, w->stream);
+    if (e == cudaSuccess) { rb_launch_clear(nullptr, 0, d_cnt, 1, w->stream); w->launches++; }
     std::vector<RbCullOut> h;
     uint32_t cnt = 0;
     if (e == cudaSuccess) {
@@ -187,7 +193,6 @@ static int cull_common(rb_world* w, const float planes24[24], int mode, uint32_t
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
         if (e == cudaSuccess && cnt) { h.resize(cnt); e = cudaMemcpy(h.data(), d_out, (size_t)cnt * sizeof(RbCullOut), cudaMemcpyDeviceToHost); }
     }
-    cudaFree(d_cubes); cudaFree(d_out); cudaFree(d_cnt);
     if (e != cudaSuccess) return fail(w, RB_ERR_CUDA, "frustum culling: %s", cudaGetErrorString(e));
     // front to back by |centre| (OSP.cpp:166-178); equal keys in index order (the reference's std::sort leaves ties unspecified)
     std::sort(h.begin(), h.end(), [](const RbCullOut& a, const RbCullOut& b) { return a.key < b.key || (a.key == b.key && a.idx < b.idx); });

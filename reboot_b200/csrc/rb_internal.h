@@ -99,6 +99,7 @@ struct rb_world {
     bool vl_cdp = false;                     // K1 launches the rebuild chain from the device (library built with -rdc=true)
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
     uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}
+    void* d_cull_out = nullptr; void* d_cull_cubes = nullptr; uint32_t* d_cull_cnt = nullptr; uint32_t cull_cap = 0;   // frustum-culling scratch (rb_extras.cu)
     cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)
     cudaStream_t vl_side = nullptr; cudaEvent_t vl_fork = nullptr, vl_join = nullptr;   // the hot bodies' launch runs next to the list kernel
     int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)

@@ -69,6 +69,7 @@ void rb_world_destroy(rb_world* w) {
     for (auto& b : w->allocs) cudaFree(b.p);
     if (w->h_counters) cudaFreeHost(w->h_counters);
     if (w->vl_host) cudaFreeHost(w->vl_host);
+    cudaFree(w->d_cull_out); cudaFree(w->d_cull_cubes); cudaFree(w->d_cull_cnt);
     if (w->vl_side) { cudaStreamDestroy(w->vl_side); cudaEventDestroy(w->vl_fork); cudaEventDestroy(w->vl_join); }
     if (w->vl_pace[0]) { cudaEventDestroy(w->vl_pace[0]); cudaEventDestroy(w->vl_pace[1]); }
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
