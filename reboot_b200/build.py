@@ -36,7 +36,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     flags = list(NVCC_FLAGS)
     if not os.path.exists(os.path.join(CSRC, "rb_dist.cu")):
         flags.remove("-DRB_HAVE_DIST")
-    link_library(flags, srcs, OUT, verbose)
+    try:
+        link_library(flags, srcs, OUT, verbose)
+    except (subprocess.CalledProcessError, OSError) as e:
+        if "-DRB_HAVE_CDP" not in flags:
+            raise
+        # the relocatable pass (device-side launches, needs libcudadevrt) is an optimisation, not a requirement:
+        # without it the host enqueues the list-rebuild chain itself
+        print(f"[build] relocatable pass failed ({e}); building without device-side launches")
+        link_library([f for f in flags if f != "-DRB_HAVE_CDP"], srcs, OUT, verbose)
     return OUT
 
 
