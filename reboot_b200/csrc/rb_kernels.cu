@@ -817,7 +817,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     // body state is loaded lazily: a body with no partner and no staged triangle needs none of it
     // (a body that was in contact last tick will almost surely need it: start the gathers now)
     if (MODE != 1 && valid && had_contact) {
-        rb_prefetch(P.pos + A); rb_prefetch(P.vel + A); rb_prefetch(P.mt + A); rb_prefetch(P.pt + A); rb_prefetch(P.sph_obj + A);
+        rb_prefetch(P.pos + A); rb_prefetch(P.vel + A); rb_prefetch(P.mt + A); rb_prefetch(P.sph_obj + A);
     }
     BodyState S; S.changed = false; S.flags = 0;
     S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
@@ -1081,7 +1081,8 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     // ---------------- lazy state load ----------------
     const bool need = valid && (npart || nc || st_slow);
     if (need) {
-        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]);
+        if (npart) S.pt = xyz(P.pt[A]);      // only a sphere-sphere hit reads the previous pose (snap-back); every other path overwrites it first
         if (P.wt) S.wt = xyz(P.wt[A]);
         S.flags = P.flags[A];
         oa = P.sph_obj[A];
