@@ -1,16 +1,19 @@
 // rb_kernels.cu -- hand-written sm_100a kernels of the ReBoot physics step.
 //
-//   K1 integrate_bin   StateVector::update + Entity::_updateKinematics + sphere world transform,
-//                      fused with the broadphase key build and the counting-sort histogram
-//   K2 scan_*          exclusive scan of the column histogram (3 small launches)
-//   K3 scatter         counting-sort scatter of world spheres into column order (SoA float4)
-//   K4 collide         per-body canonical-order narrowphase + resolution:
-//                        sphere-sphere over the sorted float4 sphere grid (vectorised 16-B loads),
-//                        sphere-triangle by a k-way merge over the static triangle column grid,
-//                        fused integrate-side bookkeeping (contact flags, model translations)
-//   K5 commit          deferred state commit for compound bodies
+//   K1  integrate_bin    StateVector::update + Entity::_updateKinematics + sphere world transform, fused with the
+//                        broadphase key build (and, per-tick enumeration, the counting-sort histogram); in slab
+//                        worlds the halo pack; on list ticks the per-body validity check of the persistent lists
+//   K1b vl_bin           list-rebuild ticks: histogram rank + build poses
+//   K2  scan_lookback    single-pass exclusive scan of the column histogram (decoupled look-back)
+//   K3  scatter          counting-sort scatter of world spheres into column order (SoA float4)
+//   K4  collide_single   canonical-order narrowphase + resolution for single-sphere bodies, four modes:
+//                        0 everything per tick, 1 enumerate + prune -> lists, 2 step from lists, 3 hot bodies
+//   K4' collide          first-generation per-body kernel (compound bodies, A/B reference)
+//   K5  commit           deferred state commit for compound bodies
+//   K7  reorder          spatial re-ordering of the body rows
+//   gate                 one thread: tail-launches K1b -> K2 -> K3 -> K4<1> when the lists must be rebuilt
 //
-// All kernels are HBM/L2-bound integer + FP32 work: no tensor cores (nothing here is a contraction).
+// All kernels are HBM/L2/latency-bound integer + FP32 work: no tensor cores (nothing here is a contraction).
 #include "rb_device.cuh"
 
 // This file is compiled twice. The normal pass holds every kernel and the host launchers. The second pass
