@@ -1239,7 +1239,10 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
 }
 
 // do_bin: 0 integrate only, 1 integrate + bin (per-tick enumeration), 2 list tick, 3 list tick with a rebuild forced by the host
-__global__ void __launch_bounds__(RB_BLOCK) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
+#ifndef RB_K1_MINBLOCKS
+#define RB_K1_MINBLOCKS 6      // 40 registers: measured 1.5 us faster than the unconstrained 48
+#endif
+__global__ void __launch_bounds__(RB_BLOCK, RB_K1_MINBLOCKS) rb_integrate_bin_kernel(RbParams P, int do_integrate, int do_bin) {
     rb_integrate_bin_body(P, do_integrate, do_bin);
 }
 #ifdef RB_CHAIN_TU
