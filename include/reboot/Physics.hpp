@@ -207,7 +207,7 @@ public:
                 rb_body_init init; StateVector& st = e->_state;
                 init.pos[0] = st._linearPosition.getx(); init.pos[1] = st._linearPosition.gety(); init.pos[2] = st._linearPosition.getz();
                 init.vel[0] = st._linearVelocity.getx(); init.vel[1] = st._linearVelocity.gety(); init.vel[2] = st._linearVelocity.getz();
-                init.flags = (st._active ? RB_ACTIVE : 0u) | (st._gravity ? RB_GRAVITY : 0u);
+                init.flags = (st._active ? (uint32_t)RB_ACTIVE : 0u) | (st._gravity ? (uint32_t)RB_GRAVITY : 0u);
                 ck(_w, rb_add_model(_w, (uint32_t)(obj.size() / 4), obj.data(), e->_worldSpaceTransform.data(), &init, &e->_id));
                 st._owner = this; st._body = e->_id;
                 _bodies.push_back(e);
@@ -294,7 +294,7 @@ inline void StateVector::push_vel() {
 }
 inline void StateVector::push_flags(uint32_t mask) {
     if (!_owner || !_owner->_built) return;
-    uint32_t f = (_active ? RB_ACTIVE : 0u) | (_gravity ? RB_GRAVITY : 0u) | (_contact ? RB_CONTACT : 0u);
+    uint32_t f = (_active ? (uint32_t)RB_ACTIVE : 0u) | (_gravity ? (uint32_t)RB_GRAVITY : 0u) | (_contact ? (uint32_t)RB_CONTACT : 0u);
     Physics::ck(_owner->_w, rb_set_flags(_owner->_w, _body, 1, &f, mask));
 }
 inline void StateVector::push_force() {
