@@ -184,6 +184,11 @@ class Physics {
     std::vector<Entity*> _entities, _bodies, _geoms;
     ModelIntersections _triangleIntersectionList;
     bool _built = false;
+    // Physics::_lock (physics/include/Physics.h:44) + StateVector::_stateLock (math/include/StateVector.h:46) in one: the
+    // clock thread ticks while render / input threads read contacts, sync state and push setters, and an rb_world must
+    // be externally serialised (reboot_physics.h "Threading"). Recursive: a consumer may call back into the facade.
+    std::recursive_mutex _lock;
+    using Guard = std::lock_guard<std::recursive_mutex>;
     static void ck(rb_world* w, int rc) { if (rc) throw std::runtime_error(std::string("reboot_b200: ") + rb_last_error(w)); }
 public:
     // Physics::Physics -- physics/src/Physics.cpp:7-12 (OSP 2000^3, leaf cap 500 -> config defaults)
@@ -221,9 +226,10 @@ public:
     // _updateKinematics subscription plus _physicsProcess.
     void run(MasterClock* clock = nullptr) { if (clock) clock->subscribeKinematicsRate([this](int ms) { tick(ms); }); }
     // one kinematics tick: every Entity::_updateKinematics(ms) then Physics::_physicsProcess(ms)
-    void tick(int milliseconds = 5) { ck(_w, rb_step(_w, milliseconds)); }
+    void tick(int milliseconds = 5) { Guard g(_lock); ck(_w, rb_step(_w, milliseconds)); }
     // refresh every Entity's StateVector / model translations from the device
     void syncState() {
+        Guard g(_lock);
         size_t n = _bodies.size(); if (!n) return;
         std::vector<float> p(n * 4), v(n * 4), m(n * 4), pm(n * 4); std::vector<uint32_t> f(n);
         ck(_w, rb_get_state(_w, p.data(), v.data(), f.data()));
@@ -238,6 +244,7 @@ public:
     // Physics::visualize -- physics/src/Physics.cpp:51-79: hands the triangles in contact per entity to a
     // consumer (the reference's DebugShader) and clears the list.
     void visualize(const std::function<void(Entity*, const std::set<std::pair<Entity*, uint32_t>>&)>& consumer = nullptr) {
+        Guard g(_lock);
         uint64_t n = 0; ck(_w, rb_contact_count(_w, &n));
         std::vector<rb_contact> c(n ? n : 1);
         ck(_w, rb_query_contacts(_w, c.data(), c.size(), &n, 1));
@@ -245,7 +252,8 @@ public:
         if (consumer) for (auto& kv : _triangleIntersectionList) consumer(kv.first, kv.second);
         _triangleIntersectionList.clear();
     }
-    const ModelIntersections& intersections() {   // contacts of the last tick without clearing
+    const ModelIntersections& intersections() {   // contacts of the last tick without clearing (the caller holds no lock: copy if threads are ticking)
+        Guard g(_lock);
         _triangleIntersectionList.clear(); uint64_t n = 0; ck(_w, rb_contact_count(_w, &n));
         std::vector<rb_contact> c(n ? n : 1); ck(_w, rb_query_contacts(_w, c.data(), c.size(), &n, 1));
         for (uint64_t i = 0; i < n; i++) if (c[i].kind == 1) _triangleIntersectionList[_bodies[c[i].body]].insert({_geoms[c[i].other], c[i].other_prim});
@@ -255,6 +263,7 @@ public:
     // non-empty static cells that meet the frustum, front to back. inverseViewProjection is what the reference builds
     // as view.inverse() * projection.inverse() (:129-130).
     std::vector<uint32_t> getVisibleFrustumCulling(const Matrix& inverseViewProjection) {
+        Guard g(_lock);
         rb_stats_t st; ck(_w, rb_get_stats(_w, &st));
         std::vector<uint32_t> cells((size_t)st.tri_cols_x * st.tri_cols_z + 1); uint32_t n = 0;
         ck(_w, rb_frustum_cull_static(_w, inverseViewProjection.data(), cells.data(), (uint32_t)cells.size(), &n));
@@ -284,26 +293,31 @@ inline void buildGeometryData(Model* model, const std::vector<float>& xyz3, cons
 
 inline void StateVector::push_pos() {
     if (!_owner || !_owner->_built) return;
+    std::lock_guard<std::recursive_mutex> g(_owner->_lock);
     float p[4] = {_linearPosition.getx(), _linearPosition.gety(), _linearPosition.getz(), 1.f};
     Physics::ck(_owner->_w, rb_set_state(_owner->_w, _body, 1, p, nullptr));
 }
 inline void StateVector::push_vel() {
     if (!_owner || !_owner->_built) return;
+    std::lock_guard<std::recursive_mutex> g(_owner->_lock);
     float v[4] = {_linearVelocity.getx(), _linearVelocity.gety(), _linearVelocity.getz(), 0.f};
     Physics::ck(_owner->_w, rb_set_state(_owner->_w, _body, 1, nullptr, v));
 }
 inline void StateVector::push_flags(uint32_t mask) {
     if (!_owner || !_owner->_built) return;
+    std::lock_guard<std::recursive_mutex> g(_owner->_lock);
     uint32_t f = (_active ? (uint32_t)RB_ACTIVE : 0u) | (_gravity ? (uint32_t)RB_GRAVITY : 0u) | (_contact ? (uint32_t)RB_CONTACT : 0u);
     Physics::ck(_owner->_w, rb_set_flags(_owner->_w, _body, 1, &f, mask));
 }
 inline void StateVector::push_force() {
     if (!_owner || !_owner->_built) return;
+    std::lock_guard<std::recursive_mutex> g(_owner->_lock);
     float f[4] = {_force.getx(), _force.gety(), _force.getz(), 0.f};
     Physics::ck(_owner->_w, rb_set_force(_owner->_w, _body, 1, f)); Physics::ck(_owner->_w, rb_sync(_owner->_w));
 }
 inline void StateVector::push_torque() {
     if (!_owner || !_owner->_built) return;
+    std::lock_guard<std::recursive_mutex> g(_owner->_lock);
     float t[4] = {_torque.getx(), _torque.gety(), _torque.getz(), 0.f};
     Physics::ck(_owner->_w, rb_set_torque(_owner->_w, _body, 1, t));
 }

@@ -16,7 +16,9 @@
  * entities), body ids for sphere models (Sphere-type entities). Threading follows the reference:
  * one caller thread per world; rb_step only enqueues work on the world's CUDA stream, the
  * query/get calls synchronise (the reference's physics thread produces, its render thread reads
- * under Physics::_lock, Physics.h:44).
+ * under Physics::_lock, Physics.h:44). An rb_world is NOT thread-safe: calls on one world must be
+ * serialised by the caller (reboot::Physics in reboot/Physics.hpp holds the lock the reference holds);
+ * distinct worlds are independent.
  */
 #ifndef REBOOT_PHYSICS_H
 #define REBOOT_PHYSICS_H
@@ -208,6 +210,10 @@ int         rb_step_host_async(rb_world* w, int ms, const float* force4, float* 
 /* The same with packed xyz arrays (3 floats per body each way; masses keep their values): the pipelined
  * round trip is bound by the PCIe copies, so 12 instead of 16 bytes per body is a quarter less time. */
 int         rb_step_host_async3(rb_world* w, int ms, const float* force3, float* pos3, uint64_t* n_contacts_done);
+/* rows the host buffers of rb_step_host* must hold: n_bodies for a single world; for a slab (multi-GPU) world, whose
+ * row count changes as bodies migrate, the most rows it can ever own. Slab worlds hand out ROWS (rb_get_body_ids says
+ * which body each row is) and take no force upload (force4 must be NULL there). */
+uint32_t    rb_host_row_capacity(const rb_world* w);
 
 int         rb_get_stats(rb_world* w, rb_stats_t* out);
 /* cumulative CUDA-event time (ms) of each kernel family since the last reset, when profiling is on:

@@ -81,6 +81,7 @@ SIGNATURES = {
     "rb_step_host": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(C.c_uint64)]),
     "rb_step_host_async": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(C.c_uint64)]),
     "rb_step_host_async3": (C.c_int, [_P, C.c_int, _P, _P, C.POINTER(C.c_uint64)]),
+    "rb_host_row_capacity": (C.c_uint32, [_P]),
     "rb_get_stats": (C.c_int, [_P, C.POINTER(RbStats)]),
     "rb_profile": (C.c_int, [_P, C.c_int]),
     "rb_get_kernel_ms": (C.c_int, [_P, _P, C.POINTER(C.c_uint64)]),

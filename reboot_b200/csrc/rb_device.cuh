@@ -39,7 +39,9 @@ struct __align__(16) RbContactRec {
 // counters[] layout (unsigned long long)
 enum { RB_C_TESTS_SS = 0, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST,
        RB_C_OVERFLOW, RB_C_DROPPED, RB_C_NCONTACT /* per step, reset */, RB_C_NCHANGED /* per step */,
-       RB_C_HALO_SENT, RB_C_MIGRATED, RB_C_COUNT = 16 };
+       RB_C_HALO_SENT, RB_C_MIGRATED,
+       RB_C_IMM_DROPPED /* sticky: immigrants a full slab could not take */, RB_C_HALO_OVF /* sticky: ghost / migrant records that did not fit a halo buffer */,
+       RB_C_COUNT = 16 };
 
 // ---- multi-GPU halo exchange records (rb_dist.cu) ------------------------------------------------
 struct __align__(16) RbHaloHeader { uint32_t n_ghost, n_migr, ghost_overflow, migr_overflow; };

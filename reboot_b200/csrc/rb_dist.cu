@@ -154,7 +154,9 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
         if (t >= n0 + n1) return;
         const RbMigrRec m = t < n0 ? D.in_migr[0][t] : D.in_migr[1][t - n0];
         uint32_t i = atomicAdd(&D.dn[0], 1u);
-        if (i >= ghost_floor) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_OVERFLOW], 1ull); return; }
+        // no room: the body is lost to the simulation (its old owner already removed it). Counted in a STICKY counter the
+        // per-tick clears never touch; the next rb_step / rb_step_group / rb_get_state / rb_get_stats fails with RB_ERR_CAPACITY.
+        if (i >= ghost_floor) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_IMM_DROPPED], 1ull); return; }
         P.pos[i] = m.pos; P.vel[i] = m.vel; P.mt[i] = m.mt; P.pt[i] = m.pt; P.flags[i] = m.flags;
         D.sph_obj_w[i] = m.obj; D.gid[i] = m.gid;
         // same world sphere K1 computed on the old owner (same state, same formula)
@@ -283,6 +285,14 @@ int rb_dist_refresh_counts(rb_world* w) {
         if (d->h_hdr[0].ghost_overflow || d->h_hdr[1].ghost_overflow || d->h_hdr[0].migr_overflow || d->h_hdr[1].migr_overflow)
             return fail(w, RB_ERR_CAPACITY, "halo buffer overflow (ghost cap %u, migrant cap %u)", d->ghost_cap, d->migr_cap);
     }
+    // sticky counters: an overflow of ANY earlier tick (the per-tick headers above only show the last one)
+    unsigned long long st[2] = { 0, 0 };
+    CU(cudaMemcpy(st, w->P.counters + RB_C_IMM_DROPPED, sizeof st, cudaMemcpyDeviceToHost));
+    return rb_dist_sticky_error(w, st[0], st[1]);
+}
+int rb_dist_sticky_error(rb_world* w, unsigned long long imm_dropped, unsigned long long halo_ovf) {
+    if (imm_dropped) return fail(w, RB_ERR_CAPACITY, "%llu immigrant bodies were dropped: the slab world is full (capacity %u rows); bodies have been lost", imm_dropped, w->cap_local);
+    if (halo_ovf) return fail(w, RB_ERR_CAPACITY, "%llu ghost / migrant records did not fit the halo buffers (ghost cap %u): cross-face contacts may have been missed; raise rb_config.halo_ghost_cap", halo_ovf, w->ghost_cap);
     return RB_OK;
 }
 

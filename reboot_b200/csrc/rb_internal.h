@@ -43,6 +43,7 @@ int rb_dist_list_exchange(rb_world* w, int list_mode);
 extern "C" int rb_list_tick_tail(rb_world* w, bool reorder_due);
 void rb_dist_destroy(RbDist* d);
 int rb_dist_refresh_counts(rb_world* w);
+int rb_dist_sticky_error(rb_world* w, unsigned long long imm_dropped, unsigned long long halo_ovf);   // RB_ERR_CAPACITY if a slab world ever overflowed
 extern "C" int rb_reorder_rows_now(rb_world* w);
 extern "C" bool rb_step_will_use_lists(rb_world* w);
 int rb_dist_rows_moved(rb_world* w);   // the per-body arrays were swapped: refresh the device copy of the halo parameters
@@ -99,6 +100,7 @@ struct rb_world {
     bool vl_cdp = false;                     // K1 launches the rebuild chain from the device (library built with -rdc=true)
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
     uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}
+    unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step
     void* d_cull_out = nullptr; void* d_cull_cubes = nullptr; uint32_t* d_cull_cnt = nullptr; uint32_t cull_cap = 0;   // frustum-culling scratch (rb_extras.cu)
     cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)
     cudaStream_t vl_side = nullptr; cudaEvent_t vl_fork = nullptr, vl_join = nullptr;   // the hot bodies' launch runs next to the list kernel
@@ -120,6 +122,7 @@ struct rb_world {
     float4* p_force[RB_PIPE] = {}; float4* p_pos[RB_PIPE] = {};
     unsigned long long* p_cnt = nullptr;     // pinned, RB_PIPE entries
     uint64_t p_calls = 0;
+    uint32_t p_rows = 0;                     // rows each staging buffer of the ring holds
     RbDist* dist = nullptr;
     rb_stats_t dist_stats;
     // ---- slab worlds (rb_dist.cu) ----

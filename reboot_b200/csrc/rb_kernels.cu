@@ -131,19 +131,19 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
                     mr.mt = P.mt[b]; mr.pt = P.pt[b]; mr.obj = o; mr.flags = f; mr.gid = D.gid[b]; mr.pad0 = mr.pad1 = 0;
                     D.out_migr[dir][kk] = mr;
                     D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
-                    if (in_grid) { uint32_t g = atomicAdd(D.self_cnt, 1u); if (g < D.ghost_cap) { RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0; D.self_ghost[g] = q; } }
+                    if (in_grid) { uint32_t g = atomicAdd(D.self_cnt, 1u); if (g < D.ghost_cap) { RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0; D.self_ghost[g] = q; } else atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }
                     in_grid = false;        // leaves this slab: not binned here
-                } else atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u);   // stays owned here one more tick
+                } else { atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }   // stays owned here one more tick
             } else if (in_grid) {
                 float reach = r + margin + P.rm_max + D.mig_band;   // own grown radius + the largest grown radius anywhere (+ how far a neighbour's body may sit on our side)
                 RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0;
                 if (D.has_left && c.x - reach < D.slab_lo) {
                     uint32_t kk = atomicAdd(&D.out_hdr[0]->n_ghost, 1u);
-                    if (kk < D.ghost_cap) D.out_ghost[0][kk] = q; else atomicAdd(&D.out_hdr[0]->ghost_overflow, 1u);
+                    if (kk < D.ghost_cap) D.out_ghost[0][kk] = q; else { atomicAdd(&D.out_hdr[0]->ghost_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }
                 }
                 if (D.has_right && c.x + reach >= D.slab_hi) {
                     uint32_t kk = atomicAdd(&D.out_hdr[1]->n_ghost, 1u);
-                    if (kk < D.ghost_cap) D.out_ghost[1][kk] = q; else atomicAdd(&D.out_hdr[1]->ghost_overflow, 1u);
+                    if (kk < D.ghost_cap) D.out_ghost[1][kk] = q; else { atomicAdd(&D.out_hdr[1]->ghost_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }
                 }
             }
         }

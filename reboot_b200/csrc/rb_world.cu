@@ -69,6 +69,7 @@ void rb_world_destroy(rb_world* w) {
     for (auto& b : w->allocs) cudaFree(b.p);
     if (w->h_counters) cudaFreeHost(w->h_counters);
     if (w->vl_host) cudaFreeHost(w->vl_host);
+    if (w->h_sticky) cudaFreeHost(w->h_sticky);
     cudaFree(w->d_cull_out); cudaFree(w->d_cull_cubes); cudaFree(w->d_cull_cnt);
     if (w->vl_side) { cudaStreamDestroy(w->vl_side); cudaEventDestroy(w->vl_fork); cudaEventDestroy(w->vl_join); }
     if (w->vl_pace[0]) { cudaEventDestroy(w->vl_pace[0]); cudaEventDestroy(w->vl_pace[1]); }
@@ -664,8 +665,15 @@ int rb_step(rb_world* w, int ms) {
         // the device always has 16+ ticks queued (no bubble), the host is never more than 32 ahead.
         const int k = (int)((w->steps >> 4) & 1u);
         if (!w->vl_pace[0]) { CU(cudaEventCreateWithFlags(&w->vl_pace[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_pace[1], cudaEventDisableTiming)); }
+        if (w->d_dn) {      // slab worlds: the sticky overflow counters ride along (a lost body / missed ghost must not go unnoticed)
+            if (!w->h_sticky) { CU(cudaMallocHost((void**)&w->h_sticky, 4 * sizeof(unsigned long long))); memset(w->h_sticky, 0, 4 * sizeof(unsigned long long)); }
+            CU(cudaMemcpyAsync(w->h_sticky + 2 * k, w->P.counters + RB_C_IMM_DROPPED, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+        }
         CU(cudaEventRecord(w->vl_pace[k], w->stream));
-        if (w->vl_pace_armed[k ^ 1]) CU(cudaEventSynchronize(w->vl_pace[k ^ 1]));
+        if (w->vl_pace_armed[k ^ 1]) {
+            CU(cudaEventSynchronize(w->vl_pace[k ^ 1]));
+            if (w->h_sticky) { int e = rb_dist_sticky_error(w, w->h_sticky[2 * (k ^ 1)], w->h_sticky[2 * (k ^ 1) + 1]); if (e) return e; }
+        }
         w->vl_pace_armed[k] = true;
     }
     return RB_OK;
@@ -836,7 +844,8 @@ static int range_ok(rb_world* w, uint32_t first, uint32_t count) {
 int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4) {
     int r = range_ok(w, first, count); if (r) return r;
     w->vl_force = true;
-    if ((pos4 && !finite_all(pos4, (size_t)count * 3)) || (vel4 && !finite_all(vel4, (size_t)count * 3))) { /* w component is padding */ }
+    for (const float* a : { pos4, vel4 })      // NaN / Inf are rejected like at rb_add_model (the w lane is padding)
+        if (a) for (size_t i = 0; i < count; i++) if (!finite_all(a + 4 * i, 3)) return fail(w, RB_ERR_INVALID, "rb_set_state: non-finite value for body %u", first + (uint32_t)i);
     if (pos4) { r = write_rows_f4(w, w->P.pos, first, count, pos4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
     if (vel4) { r = write_rows_f4(w, w->P.vel, first, count, vel4); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
@@ -869,8 +878,15 @@ static int ensure_angular(rb_world* w) {
     w->P.apos = a; w->P.avel = b; w->P.torque = t;
     return ensure_force(w);
 }
+// Slab (multi-GPU) worlds move rows between ranks; force / torque / angular arrays do not travel with them,
+// so the setters refuse instead of leaving a force on a row that now holds another body.
+static int no_slab(rb_world* w, const char* what) {
+    if (w && w->d_dn) return fail(w, RB_ERR_INVALID, "%s is not available on slab (multi-GPU) worlds: migrating bodies do not carry force / torque / angular state", what);
+    return RB_OK;
+}
 int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
     int r = range_ok(w, first, count); if (r) return r;
+    r = no_slab(w, "rb_set_force"); if (r) return r;
     if (!xyz4) return fail(w, RB_ERR_INVALID, "xyz4 is NULL");
     r = ensure_force(w); if (r) return r;
     r = ensure_stage(w, count); if (r) return r;
@@ -880,6 +896,7 @@ int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4)
 }
 int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
     int r = range_ok(w, first, count); if (r) return r;
+    r = no_slab(w, "rb_set_torque"); if (r) return r;
     if (!xyz4) return fail(w, RB_ERR_INVALID, "xyz4 is NULL");
     r = ensure_angular(w); if (r) return r;
     r = ensure_stage(w, count); if (r) return r;
@@ -890,6 +907,7 @@ int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4
 }
 int rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ap4, const float* av4) {
     int r = range_ok(w, first, count); if (r) return r;
+    r = no_slab(w, "rb_set_angular"); if (r) return r;
     r = ensure_angular(w); if (r) return r;
     if (ap4) { r = write_rows_f4(w, w->P.apos, first, count, ap4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
     if (av4) { r = write_rows_f4(w, w->P.avel, first, count, av4); if (r) return r; }
@@ -897,6 +915,10 @@ int rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ap4
     return RB_OK;
 }
 
+uint32_t rb_host_row_capacity(const rb_world* w) {
+    if (!w || !w->built) return 0;
+    return w->d_dn ? w->cap_local - 3u * w->ghost_cap : w->n_owned_host;
+}
 int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts) {
     if (!w || !w->built) return RB_ERR_INVALID;
     int r;
@@ -923,14 +945,18 @@ int rb_step_host_async3(rb_world* w, int ms, const float* force3, float* pos3, u
 static int step_host_async(rb_world* w, int ms, const float* force4, float* pos4, uint64_t* n_contacts_done, int stride) {
     if (!w || !w->built) return RB_ERR_INVALID;
     CU(cudaSetDevice(w->cfg.device));
-    const size_t nb = w->n_owned_host;
+    if (force4) { int e = no_slab(w, "the force upload of rb_step_host_async"); if (e) return e; }
+    // slab worlds gain and lose rows: the staging ring is sized for the most rows the world can ever own
+    // (rb_host_row_capacity), and a call never moves more rows than that
+    if (!w->p_rows) w->p_rows = rb_host_row_capacity(w);
+    const size_t nb = std::min<size_t>(w->n_owned_host, w->p_rows);
     if (!w->s_h2d) {
         CU(cudaStreamCreateWithFlags(&w->s_h2d, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&w->s_d2h, cudaStreamNonBlocking));
         for (int k = 0; k < RB_PIPE; k++) {
             CU(cudaEventCreateWithFlags(&w->pe_h2d[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->pe_force[k], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&w->pe_step[k], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->pe_d2h[k], cudaEventDisableTiming));
-            ALLOC(w->p_force[k], nb); ALLOC(w->p_pos[k], nb);
+            ALLOC(w->p_force[k], w->p_rows); ALLOC(w->p_pos[k], w->p_rows);
         }
         CU(cudaMallocHost((void**)&w->p_cnt, RB_PIPE * sizeof(unsigned long long)));
         for (int k = 0; k < RB_PIPE; k++) w->p_cnt[k] = 0;
@@ -1044,6 +1070,7 @@ int rb_collide_only(rb_world* w, bool resolve) { return enqueue_collide(w, resol
 int rb_dist_step_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 int rb_dist_list_exchange(rb_world* w, int) { return fail(w, RB_ERR_INVALID, "multi-GPU slabs not built"); }
 int rb_dist_refresh_counts(rb_world*) { return RB_OK; }
+int rb_dist_sticky_error(rb_world*, unsigned long long, unsigned long long) { return RB_OK; }
 int rb_dist_rows_moved(rb_world*) { return RB_OK; }
 void rb_dist_destroy(RbDist*) {}
 extern "C" int rb_dist_unique_id(const char*, uint8_t*) { g_create_error = "multi-GPU slabs not built"; return RB_ERR_INVALID; }
