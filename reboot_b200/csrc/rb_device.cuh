@@ -26,6 +26,7 @@
 #define RB_VL_NFAST   5   // per-tick kernel only: bodies whose one-tick margin alone exceeds the skin (saturates at hot_cap)
 #define RB_VL_NREBUILD 2  // rebuild ticks so far
 #define RB_VL_NTICK   3   // list ticks so far
+#define RB_VL_NHOT_LAST 7  // hot bodies of the most recent list tick
 
 // device contact record, 32 B (two 16-B stores)
 struct __align__(16) RbContactRec {
@@ -110,10 +111,17 @@ struct RbParams {
     // straight from the uploaded id-ordered array, the resolve kernels leave the final positions in id order ----
     const float* force_in; uint32_t force_in_stride;   // NULL: forces come from P.force as usual
     float* pos_out; uint32_t pos_out_stride;            // NULL: nobody asked
-    // ---- candidate lists, indexed by body row (single-sphere worlds, slot-major) ----
-    uint4* e_rec;                 // per row: { npart | nc << 8 | slow << 16, first three triangle ids }
-    uint32_t* e_pg; uint32_t* e_pl;   // [RB_SSCAND_MAX][ns] partner global id / local row
-    uint32_t* e_cand;             // [RB_CAND_MAX - 3][ns] the triangle ids beyond the third, ascending
+    // ---- candidate lists, indexed by body row (single-sphere worlds) ----
+    uint32_t* e_hdr;              // per row: partners (bits 0-7) | triangles (8-15) | offset of its first triangle in the block's tile (16-31)
+    uint32_t* e_pg; uint32_t* e_pl;   // [RB_SSCAND_MAX][ns] partner global id / local row (slot-major)
+    // Triangle tiles: the rows of one block of the list-step kernel (256 consecutive rows) keep their candidate triangles
+    // -- the 48-B vertex records themselves, in row order, each row's ascending by global id -- in ONE contiguous region of
+    // the pool, followed by the global triangle ids. The kernel stages the region in shared memory with a single bulk
+    // copy (TMA, cp.async.bulk) instead of gathering 48 B per test through the cache hierarchy.
+    uint4* tile_pool;             // 16-B units; a region of n entries is 3 n units of vertices + ceil(n / 4) units of ids
+    uint2* blk_tile;              // per block: { first unit of its region, entries }
+    uint32_t* tile_cursor;        // next free unit (reset when a rebuild starts)
+    uint32_t tile_pool_units;     // capacity of the pool
     // ---- persistent lists ("Verlet lists"): the lists above are built for spheres grown by vl_skin and
     // reused until some body has used its skin up; the sort and the enumeration only run on those ticks ----
     uint32_t* vl;                 // device words, see RB_VL_*
@@ -125,9 +133,21 @@ struct RbParams {
     // "hot" bodies have used their skin up (fast movers): they enumerate for themselves every tick (triangles
     // from the static grid, cold partners from the sort of the last rebuild, which is off by less than the
     // skin) and are published in a coarse (x,z) cell table so that cold bodies and other hot bodies find them
-    uint32_t* hot_head;           // [hcn * hcn] chain heads (index + 1, 0 = empty), then the hot counter word
-    uint32_t* hot_row; uint32_t* hot_next; uint32_t hot_cap;
+    unsigned long long* hot_head; // [hcn * hcn] chain heads: tick << 32 | index + 1. An entry of an earlier tick is an empty cell, so
+                                  // the table is never cleared (the tick number is its version)
+    uint32_t* hot_row; uint32_t* hot_next; uint32_t hot_cap;      // hot_cap = every row: the table cannot overflow
+    uint32_t hot_soft;            // the number of hot bodies at which a rebuild pays (heuristics only)
     uint32_t hcn; float hc_inv_w;
+    uint32_t tick;                // version of this tick's hot-table entries (never 0)
+    uint32_t* nhot;               // this tick's hot-body counter
+    unsigned long long* ncontact; // this tick's contact counter (appended records)
+    uint32_t* tb_next;            // single worlds: the 4 words {contacts lo, hi, hot bodies, -} of the NEXT tick, zeroed by K1 (no clear launch)
+    uint32_t soft;                // single-GPU worlds: the device never asks for a rebuild -- a body that enters the grid steps without a
+                                  // list, one that leaves is marked in its world sphere (w < 0), the hot table holds every row -- and
+                                  // the host schedules rebuilds from the hot counts it sees
+    uint32_t lazy_mt;             // list ticks of worlds with W.t = 0 and centred spheres: the model translation is 0 + p, never loaded or stored
+    uint32_t mt_in_valid;         // ... K1: the mt array is valid on entry (first list tick after other activity), else derive it
+    uint32_t obj_zero;            // every sphere is centred on its body (sph_obj.xyz = +0): the radius rides in pos.w, sph_obj is never read
     // ---- deferred commit (compound-body path) ----
     uint32_t* ch_body; float4* ch_pos; float4* ch_vel; float4* ch_mt; float4* ch_pt; uint32_t* ch_flags;
     // ---- slab ownership (multi-GPU) ----
@@ -260,4 +280,25 @@ __host__ __device__ __forceinline__ uint32_t rb_col(float x, float half, float i
     if (!(t > 0.0f)) return 0;
     if (t >= (float)n) return n - 1;
     return (uint32_t)t;
+}
+
+// ---- hot-body cell table (persistent lists). Entries carry the tick they were written in: an entry of an earlier tick is an
+// empty cell, so nothing is cleared between ticks. ----
+__device__ __forceinline__ uint32_t hot_cell_head(const RbParams& P, uint32_t cell) {
+    const unsigned long long e = P.hot_head[cell];
+    return (uint32_t)(e >> 32) == P.tick ? (uint32_t)e : 0u;
+}
+// link entry h (already holding its row) into the cell of centre (x, z)
+__device__ __forceinline__ void hot_link(const RbParams& P, uint32_t h, float x, float z) {
+    const uint32_t cell = rb_col(z, P.half, P.hc_inv_w, P.hcn) * P.hcn + rb_col(x, P.half, P.hc_inv_w, P.hcn);
+    const unsigned long long old = atomicExch(&P.hot_head[cell], ((unsigned long long)P.tick << 32) | (unsigned long long)(h + 1u));
+    P.hot_next[h] = (uint32_t)(old >> 32) == P.tick ? (uint32_t)old : 0u;
+}
+// a body that steps without its list this tick: its entry in the table, RB_NONE if the table is full (only possible when hot_cap < rows)
+__device__ __forceinline__ uint32_t hot_push(const RbParams& P, uint32_t row, float x, float z) {
+    const uint32_t h = (*(volatile uint32_t*)P.nhot >= P.hot_cap) ? P.hot_cap : atomicAdd(P.nhot, 1u);
+    if (h >= P.hot_cap) return RB_NONE;
+    P.hot_row[h] = row;
+    hot_link(P, h, x, z);
+    return h;
 }

@@ -182,14 +182,14 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
     const uint32_t gi = atomicAdd(&D.dn[1], 1u);
     uint32_t i = D.cap_local - 1u - gi;
     P.ws[i] = q.ws;
+    P.pos[i] = make_float4(q.ws.x, q.ws.y, q.ws.z, q.r);      // single-sphere bodies carry their exact world radius in pos.w (the list step reads a partner's there)
     D.sph_obj_w[i] = make_float4(0.f, 0.f, 0.f, q.r);
     D.gid[i] = q.gid;
     P.flags[i] = RB_F_ACTIVE;
     if (list_tick) {
-        const uint32_t h = P.hot_cap + gi;
-        const uint32_t cell = rb_col(q.ws.z, P.half, P.hc_inv_w, P.hcn) * P.hcn + rb_col(q.ws.x, P.half, P.hc_inv_w, P.hcn);
+        const uint32_t h = P.hot_cap + gi;          // behind the own hot bodies' entries
         P.hot_row[h] = i;
-        P.hot_next[h] = atomicExch(&P.hot_head[cell], h + 1u);
+        hot_link(P, h, q.ws.x, q.ws.z);
         P.key[i] = RB_NONE;
         return;
     }
@@ -329,10 +329,14 @@ static int dist_phase_a(rb_world* w, int do_integrate, int list_mode) {
     P.dp = d->d_dp[p];
     // clears as kernels (a memset may land on a copy engine and queue behind a host transfer)
     if (list_mode != 2) { rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++; }      // (list ticks leave the histogram clean themselves)
-    if (list_mode) {   // hot cell table + hot counter + rebuild flag | the tick block, and below the per-step counters
-        rb_launch_clear(P.hot_head, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), w->d_dn + 1, 11, w->stream); w->launches++;
+    if (list_mode) {   // contact + hot counters and the rebuild flag (5 adjacent words, see rb_build) | the tick block of the halo step
+        rb_list_tick_params(w);
+        rb_launch_clear(w->d_tb + 4 * (RB_TB_BLOCKS - 1), 20, w->d_dn + 1, 11, w->stream); w->launches++;
+    } else {
+        int r = rb_plain_tick_params(w); if (r) return r;
+        rb_launch_clear(nullptr, 0, w->d_dn + 1, 11, w->stream); w->launches++;            // n_ghost, self ghosts, emigrants, both out headers
         rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
-    } else { rb_launch_clear(nullptr, 0, w->d_dn + 1, 11, w->stream); w->launches++; }    // n_ghost, self ghosts, emigrants, both out headers
+    }
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, list_mode ? list_mode : 1, w->stream); w->launches++;     // integrate + bin + halo pack
     if (w->profile) CU(cudaEventRecord(w->ev[5], w->stream));
@@ -476,10 +480,11 @@ static int group_collide(rb_world** ws, int n, int ms, int do_integrate, int res
         w->group_list_mode = 0;
         if (do_integrate && resolve && rb_step_will_use_lists(w)) {
             const bool reorder_due = w->reorder_every > 0 && (w->steps + 1) % (uint64_t)w->reorder_every == 0;
-            w->group_list_mode = (w->vl_force || reorder_due) ? 3 : 2;
+            w->group_list_mode = rb_list_tick_begin(w, reorder_due) ? 3 : 2;
         }
         if (w->vl_on && !w->group_list_mode) CU(cudaMemsetAsync(w->P.vl + RB_VL_NFAST, 0, 4, w->stream));     // K1 counts the fast movers while the lists sit a phase out
         int r = dist_phase_a(w, do_integrate, w->group_list_mode); if (r) return r;
+        if (w->group_list_mode) rb_list_tick_k1_enqueued(w);
     }
     for (int i = 0; i < n; i++) { rb_world* w = ws[i]; CU(cudaSetDevice(w->cfg.device)); CU(cudaStreamSynchronize(w->stream)); }
     // (the records and headers already sit in the neighbours' in buffers: K1 and the signal kernel stored them there)

@@ -22,16 +22,18 @@ void rb_launch_clear(void* a, size_t bytes_a, uint32_t* b, uint32_t words_b, cud
 void rb_launch_vl_bin(const RbParams& P, cudaStream_t st);
 void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate);
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows);
+uint32_t rb_list_tile_bytes();
+void rb_launch_mt_refresh(const float4* pos, const float4* wt, float4* mt, uint32_t n, cudaStream_t st);
 bool rb_have_device_launch();
 void rb_launch_vl_gate(const RbParams& P, cudaStream_t st);
 void rb_launch_apply_force(const uint32_t* flags, const float4* in, float4* out, const uint32_t* inv, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
 void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t* inv, uint32_t first, uint32_t count, uint32_t mask, cudaStream_t st);
-void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st);
+void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, int w_one, cudaStream_t st);
 void rb_launch_apply_force3(const uint32_t* flags, const float* in3, float4* out, const uint32_t* inv, uint32_t count, cudaStream_t st);
 void rb_launch_rows_to_ids_f3(const float4* rows, const uint32_t* gid, float* out3, uint32_t n, cudaStream_t st);
 void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st);
-void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st);
+void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, int keep_w, cudaStream_t st);
 void rb_launch_reorder(const RbParams& P, const void* R, cudaStream_t st);
 void rb_launch_owned_flags(const RbParams& P, uint32_t* out, uint32_t n, cudaStream_t st);
 void rb_launch_model_matrices(const float4* w3, const uint32_t* gid, const float4* mt, const float4* pt, float4* cur, float4* prev, uint32_t n, int prev_is_default, cudaStream_t st);
@@ -48,6 +50,12 @@ extern "C" int rb_reorder_rows_now(rb_world* w);
 extern "C" bool rb_step_will_use_lists(rb_world* w);
 int rb_dist_rows_moved(rb_world* w);   // the per-body arrays were swapped: refresh the device copy of the halo parameters
 extern "C" int enqueue_broadphase_tail(rb_world* w);
+extern "C" void rb_list_tick_params(rb_world* w);      // per-tick parameters of a persistent-list tick (before K1 is launched)
+extern "C" int rb_plain_tick_params(rb_world* w);      // ... of every other path (per-tick enumeration, stand-alone phases): explicit model translations
+extern "C" bool rb_list_tick_begin(rb_world* w, bool reorder_due);   // a list tick starts: true if the host makes it a rebuild tick
+extern "C" void rb_list_tick_k1_enqueued(rb_world* w);               // ... its K1 is in the stream
+extern "C" int rb_ensure_mt(rb_world* w);              // materialise the model translations list ticks keep implicit
+#define RB_TB_BLOCKS 8                      // ring of per-tick counter blocks {contacts lo, hi, hot bodies, -}: a tick's block survives the next 6 ticks
 
 extern thread_local std::string g_create_error;
 
@@ -99,7 +107,18 @@ struct rb_world {
     bool vl_gate_ok = true;                  // recent rebuild rate is low enough for the device-launched chain (else the host enqueues it)
     bool vl_cdp = false;                     // K1 launches the rebuild chain from the device (library built with -rdc=true)
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
-    uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks}
+    uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks, fast movers, hot bodies, tick of that count, ...}
+    uint32_t* d_tb = nullptr;                // RB_TB_BLOCKS counter blocks, the list words (P.vl) right behind them
+    unsigned long long* ncontact_dev = nullptr;   // where the contact count of the last step / detect lives
+    uint32_t tick_seq = 0;                   // list ticks enqueued so far (version of the hot table entries)
+    bool slim = false;                       // single-sphere bodies, W.t = 0, centred spheres: list ticks keep the model translations implicit
+    bool mt_stale = false;                   // ... and the mt array has not been refreshed since
+    uint32_t vl_period = 16, vl_since = 0;   // single worlds: the host schedules the list rebuilds (every vl_period list ticks, adapted to the hot counts it sees)
+    uint32_t vl_seen_tick = 0;               // last device report (tick number) the schedule has digested
+    uint32_t vl_rebuild_ring[8] = {}; uint32_t vl_rebuild_n = 0;   // list tick numbers of the last rebuilds enqueued (reports are matched with theirs)
+    uint32_t vl_hot_floor = 0;               // hot bodies on a rebuild tick itself: rows that can have no list
+    uint32_t vl_judged_at = 0;               // list tick at which the lists-pay-off decision was last taken
+    bool vl_tick_rebuilds = false;           // this list tick rebuilds at the host's request
     unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step
     void* d_cull_out = nullptr; void* d_cull_cubes = nullptr; uint32_t* d_cull_cnt = nullptr; uint32_t cull_cap = 0;   // frustum-culling scratch (rb_extras.cu)
     cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)

@@ -50,11 +50,20 @@ __device__ __forceinline__ void vl_request_rebuild(const RbParams& P, uint32_t w
 __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const int do_integrate, const int do_bin) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_owned = rb_n_owned(P);
+    if (b == 0 && P.tb_next) {      // the per-tick words of the NEXT tick (nobody touches them during this one)
+        P.tb_next[0] = 0u; P.tb_next[1] = 0u; P.tb_next[2] = 0u; P.tb_next[3] = 0u;
+        if (do_bin >= 2) P.vl[RB_VL_REBUILD] = do_bin == 3 ? 1u : 0u;      // soft worlds: only the host asks for rebuilds
+    }
     if (b >= (P.dn ? n_owned : P.nb)) return;
     float4 p4 = P.pos[b], v4 = P.vel[b];
     uint32_t f = P.flags[b];
     f3 p = xyz(p4), v = xyz(v4);
     const float dt = P.dt;
+    // list ticks of worlds whose model translation is always 0 + p (W.t = 0): the mt array is neither read nor written
+    const bool lazy = P.lazy_mt && do_bin >= 2 && do_integrate;
+    f3 m;
+    if (lazy && !P.mt_in_valid) m = mk3(0.f + p.x, 0.f + p.y, 0.f + p.z);      // Entity::_mvp as the previous tick left it
+    else m = xyz(P.mt[b]);
     if (do_integrate) {
         float4 F = make_float4(0.f, 0.f, 0.f, 1.0f);
         if (P.force && b < n_owned) {
@@ -91,28 +100,29 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
         }
         // Entity::_updateKinematics runs for inactive entities too: prevMVP = mvp; mvp = T(p) * W
         if (b < n_owned) {
-            float4 m_old = P.mt[b];
-            P.pt[b] = m_old;
+            P.pt[b] = make_float4(m.x, m.y, m.z, 0.f);
             f3 w = P.wt ? xyz(P.wt[b]) : mk3(0.f, 0.f, 0.f);
-            P.mt[b] = make_float4(w.x + p.x, w.y + p.y, w.z + p.z, 0.f);
+            m = mk3(w.x + p.x, w.y + p.y, w.z + p.z);
+            if (!lazy) P.mt[b] = make_float4(m.x, m.y, m.z, 0.f);
         }
     }
     if (!do_bin && !P.dn) return;
-    f3 m = xyz(P.mt[b]);
     float speed = mag3(v);
     uint32_t s0 = P.single ? b : P.body_start[b];
     uint32_t s1 = P.single ? b + 1 : P.body_start[b + 1];
     for (uint32_t s = s0; s < s1; ++s) {
-        float4 o = P.sph_obj[s];
+        // single-sphere bodies carry their world radius in pos.w; centred spheres (obj_zero) never read sph_obj
+        float4 o = (P.single && P.obj_zero) ? make_float4(0.f, 0.f, 0.f, p4.w) : P.sph_obj[s];
         f3 c = mk3(o.x + m.x, o.y + m.y, o.z + m.z);
         float r = o.w;
         // candidate margin: how far this body may be displaced inside one step (pruning only)
         float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * dt + 0.01f * r, 1e-3f));
-        P.ws[s] = make_float4(c.x, c.y, c.z, r + margin);
         uint32_t k = RB_NONE;
         // Q3/Q7: only active bodies are (re)inserted in the broadphase, and only while they touch
         // the OSP root cube (physics/src/OSP.cpp:182-239)
         bool in_grid = (f & RB_F_ACTIVE) && sphere_in_world(c, r, P.half);
+        // a sphere outside the broadphase carries w < 0: a list that still names it as a partner skips it
+        P.ws[s] = make_float4(c.x, c.y, c.z, in_grid ? r + margin : -1.0f);
         if (P.dp && do_bin && (f & RB_F_ACTIVE)) {
             // K6a fused here: slab worlds hand migrants and ghosts to the halo buffers while the sphere is
             // still in registers (single-sphere bodies: s == b)
@@ -128,9 +138,10 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
                 uint32_t kk = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
                 if (kk < D.migr_cap) {
                     RbMigrRec mr; mr.pos = make_float4(p.x, p.y, p.z, p4.w); mr.vel = make_float4(v.x, v.y, v.z, v4.w);
-                    mr.mt = P.mt[b]; mr.pt = P.pt[b]; mr.obj = o; mr.flags = f; mr.gid = D.gid[b]; mr.pad0 = mr.pad1 = 0;
+                    mr.mt = make_float4(m.x, m.y, m.z, 0.f); mr.pt = P.pt[b]; mr.obj = o; mr.flags = f; mr.gid = D.gid[b]; mr.pad0 = mr.pad1 = 0;
                     D.out_migr[dir][kk] = mr;
                     D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
+                    if (do_bin >= 2) vl_request_rebuild(P, 1u);      // rows move (swap-remove): every list is stale, in the grid or not
                     if (in_grid) { uint32_t g = atomicAdd(D.self_cnt, 1u); if (g < D.ghost_cap) { RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0; D.self_ghost[g] = q; } else atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }
                     in_grid = false;        // leaves this slab: not binned here
                 } else { atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }   // stays owned here one more tick
@@ -158,7 +169,7 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             // keep reporting how many bodies outrun the skin within one tick, so that it knows when to come back
             if (do_bin == 1 && P.vl && !(8.0f * speed * dt + 0.01f * r <= P.vl_skin)) {        // a list would not last it ~6 ticks
                 volatile uint32_t* nf = P.vl + RB_VL_NFAST;
-                if (*nf < P.hot_cap) atomicAdd(&P.vl[RB_VL_NFAST], 1u);
+                if (*nf < P.hot_soft) atomicAdd(&P.vl[RB_VL_NFAST], 1u);
             }
         }
         if (do_bin >= 2) {
@@ -168,23 +179,25 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             const float4 wb = P.ws_build[s];
             const float ddx = c.x - wb.x, ddy = c.y - wb.y, ddz = c.z - wb.z;
             const float moved = sqrtf((ddx * ddx + ddy * ddy) + ddz * ddz);
+            bool hot = false;
             if (do_bin == 3) { /* the host asked for a rebuild: nothing to classify */ }
-            else if ((k_prev == RB_NONE) != (k == RB_NONE)) vl_request_rebuild(P, 1u);
-            else if (k != RB_NONE && (!(moved + margin <= P.vl_skin) || wb.w < 0.f)) {      // w < 0: more partners than a list holds
-                // hot: steps without its list this tick. Too many of them and rebuilding is cheaper
-                // (once the table is full nobody queues up on the counter any more).
-                uint32_t* nhot = P.hot_head + P.hcn * P.hcn;
-                const uint32_t h = (*(volatile uint32_t*)nhot >= P.hot_cap) ? P.hot_cap : atomicAdd(nhot, 1u);
-                if (h < P.hot_cap) {
-                    const uint32_t cell = rb_col(c.z, P.half, P.hc_inv_w, P.hcn) * P.hcn + rb_col(c.x, P.half, P.hc_inv_w, P.hcn);
-                    P.hot_row[h] = s;
-                    P.hot_next[h] = atomicExch(&P.hot_head[cell], h + 1u);
-                } else vl_request_rebuild(P, 2u);
+            else if ((k_prev == RB_NONE) != (k == RB_NONE)) {
+                if (!P.soft) vl_request_rebuild(P, 1u);
+                else if (k != RB_NONE) { hot = true; P.ws_build[s].w = -1.0f; }     // entered the grid: no list until the next rebuild
+                // (left the grid: its world sphere says so, w < 0)
+            }
+            else if (k != RB_NONE && (!(moved + margin <= P.vl_skin) || wb.w < 0.f)) hot = true;      // w < 0: this row has no usable list
+            if (hot) {
+                // hot: steps without its list this tick (its own small launch, rb_collide_single_kernel<3>)
+                // (slab worlds: once more bodies are hot than a rebuild costs, the device asks for one; single worlds leave that to the host)
+                const uint32_t h = hot_push(P, s, c.x, c.z);
+                if (h == RB_NONE || (!P.soft && h >= P.hot_soft)) vl_request_rebuild(P, 2u);
                 k |= RB_HOT_BIT;
             }
-            if (s == 0 && do_bin == 3) { P.vl[RB_VL_REBUILD] = 1u; P.vl[RB_VL_WHY] |= 4u; }
-        }
-        P.key[s] = k;
+            if (s == 0 && do_bin == 3 && !P.tb_next) { P.vl[RB_VL_REBUILD] = 1u; P.vl[RB_VL_WHY] |= 4u; }
+            if (s == 0 && do_bin == 3 && P.tb_next) P.vl[RB_VL_WHY] |= 4u;
+            if (k != k_prev) P.key[s] = k;
+        } else P.key[s] = k;
     }
 }
 
@@ -373,6 +386,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_clear_kernel(uint4* __restrict__ 
 __global__ void __launch_bounds__(RB_BLOCK) rb_vl_bin_kernel(RbParams P) {
     if (!P.vl[RB_VL_REBUILD]) return;
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0 && P.tile_cursor) *P.tile_cursor = 0u;      // the enumeration at the end of this chain refills the triangle tiles
     if (s >= (P.dn ? P.dn[0] : P.ns)) return;       // slab worlds: owned rows only (ghosts never enter the sort of a list tick)
     P.ws_build[s] = P.ws[s];
     uint32_t k = P.key[s];
@@ -425,7 +439,7 @@ __device__ __forceinline__ void record_hit(const RbParams& P, HitBuf& H, uint32_
         uint32_t i = H.n;
         H.a[i] = a; H.b[i] = b; H.depth[i] = depth; H.nx[i] = n.x; H.ny[i] = n.y; H.nz[i] = n.z; H.r[i] = r;
     } else {   // rare: more contacts than the local buffer holds -> direct append
-        unsigned long long slot = atomicAdd(&P.counters[RB_C_NCONTACT], 1ull);
+        unsigned long long slot = atomicAdd(P.ncontact, 1ull);
         store_contact(P, slot, a, b, depth, n.x, n.y, n.z, r);
         if (slot >= P.contact_cap) atomicAdd(&P.counters[RB_C_DROPPED], 1ull);
     }
@@ -522,7 +536,7 @@ __device__ __forceinline__ void collide_epilogue(const RbParams& P, HitBuf& H, T
     uint32_t wtotal = __shfl_sync(0xffffffffu, incl, 31);
     if (wtotal) {
         unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&P.counters[RB_C_NCONTACT], (unsigned long long)wtotal);
+        if (lane == 0) base = atomicAdd(P.ncontact, (unsigned long long)wtotal);
         base = __shfl_sync(0xffffffffu, base, 0);
         unsigned long long slot = base + (incl - nloc);
         uint32_t dropped = 0;
@@ -574,22 +588,22 @@ __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 
     }
 }
 
-// the same over the coarse table of hot bodies (persistent lists, reuse ticks)
+// the same over the coarse table of hot bodies and ghosts (persistent lists)
 __device__ __forceinline__ void scan_hot_partners(const RbParams& P, uint32_t A, f3 fc, float frm, uint32_t lo,
-                                                  uint32_t& best, uint32_t& best_local, uint32_t& eligible, bool ghosts_only) {
+                                                  uint32_t& best, uint32_t& best_local, uint32_t& eligible) {
     const float reach = frm + P.rm_max;
     const uint32_t hx0 = rb_col(fc.x - reach, P.half, P.hc_inv_w, P.hcn), hx1 = rb_col(fc.x + reach, P.half, P.hc_inv_w, P.hcn);
     const uint32_t hz0 = rb_col(fc.z - reach, P.half, P.hc_inv_w, P.hcn), hz1 = rb_col(fc.z + reach, P.half, P.hc_inv_w, P.hcn);
     for (uint32_t hz = hz0; hz <= hz1; ++hz)
         for (uint32_t hx = hx0; hx <= hx1; ++hx)
-            for (uint32_t h = P.hot_head[hz * P.hcn + hx]; h; h = P.hot_next[h - 1u]) {
+            for (uint32_t h = hot_cell_head(P, hz * P.hcn + hx); h; h = P.hot_next[h - 1u]) {
                 const uint32_t Bl = P.hot_row[h - 1u];
-                if (Bl == A || (ghosts_only && h - 1u < P.hot_cap)) continue;
+                if (Bl == A) continue;
                 const float4 o = P.ws[Bl];
                 float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
-                if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
+                if (o.w < 0.f || (dx * dx + dy * dy) + dz * dz > rr * rr) continue;
                 const uint32_t B = rb_gid(P, Bl);
-                if (B < lo) continue;
+                if (B < lo || B == best) continue;
                 eligible++;
                 if (B < best) { best = B; best_local = Bl; }
             }
@@ -701,7 +715,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
             if (disp > fa0.w - P.sph_obj[s0].w) T.overflow++;
             if (SINGLE) {
                 if (S.changed) {
-                    P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+                    P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, P.sph_obj[s0].w);      // single-sphere bodies keep their world radius in pos.w
                     P.vel[A] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
                     P.mt[A] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
                     P.pt[A] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
@@ -736,14 +750,12 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
 // ------------------------------------------------------------------------------------------
 #define RB_CAND_MAX 12
 #define RB_SSCAND_MAX 4
+#define RB_TILE_CAP 768      // triangles one block's tile holds (39 KB of shared memory in the list-step kernel)
 #ifndef RB_COLLIDE_MINBLOCKS
 #define RB_COLLIDE_MINBLOCKS 3
 #endif
 #ifndef RB_COLLIDE_MINBLOCKS_ENUM
 #define RB_COLLIDE_MINBLOCKS_ENUM 4
-#endif
-#ifndef RB_COLLIDE_MINBLOCKS_LISTS
-#define RB_COLLIDE_MINBLOCKS_LISTS 4      // stepping from lists is lighter: 64 registers, 4 blocks per SM measured faster (3 for the fused kernel)
 #endif
 
 template <bool RESOLVE>
@@ -752,6 +764,7 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
     const bool lo_is_a = gA < gB;
     if (!RESOLVE && !lo_is_a) return;
     float4 wb = P.ws[Bl];                       // partner at its frozen pose
+    if (wb.w < 0.f) return;                     // it has left the broadphase since the list was built (Q3 / Q7)
     float rb = P.sph_obj[Bl].w;
     f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
     f3 cb = xyz(wb);
@@ -771,40 +784,36 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
     }
 }
 
-// MODE 0: everything in one launch (per-tick enumeration). MODE 1: enumerate only (P1 + P3, plus the exact-predicate
-// pruning of persistent lists), results parked in global lists indexed by body row. MODE 2: test / resolve only
-// (P2, P4, P5), one thread per row, from those lists. MODE 3: the hot bodies of a list-reuse tick, one thread each,
-// enumerating for themselves like MODE 0 but against the sort of the last rebuild + the hot-body table.
-// All modes run the same tests in the same canonical order: results are bit-identical.
+// MODE 0: everything in one launch (per-tick enumeration), one thread per sorted sphere.
+// MODE 1: list rebuild -- enumerate only (P1 + P3 + the exact-predicate pruning), one thread per body ROW: partners and the
+//         row's slice of its block's triangle tile are parked for rb_list_step_kernel; rows that cannot have a list (more
+//         partners than a list holds, spheres wider than the fast walk, a block whose tile would overflow) are marked and
+//         handed to MODE 3 from this tick on.
+// MODE 3: the hot bodies of a list tick (no usable list: fast movers, new in the grid, marked rows), one thread each,
+//         enumerating for themselves like MODE 0 but against the sort of the last rebuild + the hot-body table.
+// All modes run the same tests in the same canonical order as rb_list_step_kernel: results are bit-identical.
 template <bool RESOLVE, int MODE>
-__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : (MODE == 2) ? RB_COLLIDE_MINBLOCKS_LISTS : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(const RbParams P) {
+__device__ __forceinline__ void collide_single_rows(const RbParams& P, const uint32_t tid) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
     HitBuf H; H.n = 0;
-    if (MODE == 1 && P.vl && !P.vl[RB_VL_REBUILD]) return;       // persistent lists still valid: nothing to enumerate
-    if (MODE == 3 && P.vl[RB_VL_REBUILD]) return;                // rebuild tick: everybody steps from the fresh lists
+    if (MODE == 1 && !P.vl[RB_VL_REBUILD]) return;       // persistent lists still valid: nothing to enumerate
     bool valid;
-    uint32_t A = 0, keyA = RB_NONE;
+    uint32_t A = 0;
     float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     bool had_contact = false;
-    if (MODE == 2) {
-        // one thread per body ROW: the lists are indexed by row and may be older than this tick's poses,
-        // so the frozen sphere comes from K1's world-sphere array, not from a sort
+    if (MODE == 1) {
+        // one thread per body ROW (the rows of a block share a triangle tile); the own sphere is grown by the skin like
+        // the entries of the sort it is matched against
         A = tid;
-        uint32_t fl = 0;
-        if (tid < rb_n_owned(P)) { keyA = P.key[tid]; rec = P.e_rec[tid]; f0 = P.ws[tid]; fl = P.flags[tid]; }    // all in flight together
-        valid = keyA != RB_NONE;
-        had_contact = valid && (fl & RB_F_CONTACT) != 0;
-        // hot bodies (they have used their skin up) step in their own launch (MODE 3) on reuse ticks
-        if (P.vl && !P.vl[RB_VL_REBUILD] && (keyA & RB_HOT_BIT)) valid = false;
+        valid = tid < rb_n_owned(P) && P.key[tid] != RB_NONE;
+        if (valid) { f0 = P.ws[tid]; f0.w += P.vl_skin; }
     } else if (MODE == 3) {
-        // one thread per hot body of this tick (K1's table): it enumerates for itself -- partners from the sort of
-        // the last rebuild, whose entries are off by less than the skin they were grown by, plus the other hot
-        // bodies, triangles from the static grid -- and then steps exactly like the fused kernel
-        const uint32_t nh = min(P.hot_head[P.hcn * P.hcn], P.hot_cap);
+        // one thread per hot body of this tick: it enumerates for itself -- partners from the sort of the last rebuild,
+        // whose entries are off by less than the skin they were grown by, plus the other hot bodies (and, in slab worlds,
+        // the neighbours' ghosts), triangles from the static grid -- and then steps exactly like the fused kernel
+        const uint32_t nh = min(*P.nhot, P.hot_cap);
         valid = tid < nh;
         if (valid) { A = P.hot_row[tid]; f0 = P.ws[A]; had_contact = (P.flags[A] & RB_F_CONTACT) != 0; }
     } else {
@@ -820,28 +829,26 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     // body state is loaded lazily: a body with no partner and no staged triangle needs none of it
     // (a body that was in contact last tick will almost surely need it: start the gathers now)
     if (MODE != 1 && valid && had_contact) {
-        rb_prefetch(P.pos + A); rb_prefetch(P.vel + A); rb_prefetch(P.mt + A); rb_prefetch(P.sph_obj + A);
+        rb_prefetch(P.pos + A); rb_prefetch(P.vel + A); rb_prefetch(P.sph_obj + A);
     }
+    const bool lazy = MODE == 3 && P.lazy_mt;      // list ticks of W.t = 0 worlds: model translation = 0 + p, never loaded or stored
     BodyState S; S.changed = false; S.flags = 0;
     S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
     float4 oa = make_float4(0.f, 0.f, 0.f, 0.f);
     const uint32_t gA = valid ? rb_gid(P, A) : 0u;
     const f3 fc = xyz(f0);
     const float frm = f0.w;
-    // reuse tick of the persistent lists (warp-uniform): hot bodies are in nobody's list, everybody looks them up
-    const bool reuse = MODE == 3 || (MODE == 2 && P.vl && !P.vl[RB_VL_REBUILD]);
-    const bool enu = MODE != 2 && valid;      // lanes that enumerate in this launch
 
     // ---------------- P1: partner scan ----------------
     uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
 #pragma unroll
     for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
     uint32_t npart = 0;
-    if (MODE != 2) {
+    {
         // every lane walks its (up to 3) z-rows entry by entry; the loop is warp-uniform so the lanes
         // stay in lock step (independent thread scheduling would otherwise let sub-groups run ahead)
         uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0, ni = 0, ne = 0;
-        if (enu) {
+        if (valid) {
             float reach = frm + P.rm_max;
             cx0 = rb_col(fc.x - reach, -P.s_x0, P.s_inv_w, P.scx); cx1 = rb_col(fc.x + reach, -P.s_x0, P.s_inv_w, P.scx);
             cz = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz); cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
@@ -887,19 +894,9 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
             __syncwarp();
         }
     }
-    const uint32_t hdr = rec.x;
-    if (MODE == 2 && valid) {                  // partners from the list
-        npart = hdr & 0xffu;
-        if (npart) {
-#pragma unroll
-            for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < min(npart, (uint32_t)RB_SSCAND_MAX)) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
-        }
-    }
-    // slab worlds: the neighbours' ghosts are in nobody's list either (their rows change every tick); they sit in
-    // the same cell table behind the own hot bodies (entries >= hot_cap) and are looked up on EVERY list tick
-    const bool ghosts_only = (MODE == 2 || MODE == 3) && !reuse;
-    if ((MODE == 2 || MODE == 3) && (reuse || P.dn)) {
-        // hot bodies are nobody's list: everybody looks them up in the coarse cell table (<= 2 x 2 cells)
+    if (MODE == 3) {
+        // hot bodies (and, in slab worlds, the neighbours' ghosts) are in nobody's list and may have left the place the
+        // old sort has them at: everybody looks them up in the coarse cell table (<= 2 x 2 cells)
         uint32_t hcell[4] = { 0, 0, 0, 0 }, hn = 0;
         if (valid) {
             const float reach = frm + P.rm_max;
@@ -911,17 +908,16 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         }
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
-            uint32_t h = (q < hn) ? __ldg(P.hot_head + hcell[q]) : 0u;
+            uint32_t h = (q < hn) ? hot_cell_head(P, hcell[q]) : 0u;
             while (true) {
                 if (!__any_sync(0xffffffffu, h != 0u)) break;
                 if (h) {
                     const uint32_t Bl = P.hot_row[h - 1u];
-                    const bool skip = ghosts_only && h - 1u < P.hot_cap;     // rebuild tick: own hot bodies are in the fresh lists
                     h = P.hot_next[h - 1u];
-                    if (Bl != A && !skip) {
+                    if (Bl != A) {
                         const float4 o = P.ws[Bl];
                         float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
-                        if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
+                        if (o.w >= 0.f && !((dx * dx + dy * dy) + dz * dz > rr * rr)) {
                             uint32_t g = rb_gid(P, Bl), bl = Bl;
                             bool dup = false;
 #pragma unroll
@@ -945,11 +941,11 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     // canonical order; a triangle registered in two columns shows up twice).
     uint32_t nc = 0;
     bool st_slow = false;
-    if (MODE != 2) {
+    {
         uint32_t cur[4], end[4];
 #pragma unroll
         for (uint32_t k = 0; k < 4; ++k) cur[k] = end[k] = 0;
-        if (enu && P.nt) {
+        if (valid && P.nt) {
             uint32_t cx0 = rb_col(fc.x - frm, P.half, P.t_inv_w, P.tcx), cx1 = rb_col(fc.x + frm, P.half, P.t_inv_w, P.tcx);
             uint32_t cz0 = rb_col(fc.z - frm, P.half, P.t_inv_w, P.tcz), cz1 = rb_col(fc.z + frm, P.half, P.t_inv_w, P.tcz);
             uint32_t nx = cx1 - cx0 + 1, ncol = nx * (cz1 - cz0 + 1);
@@ -1017,7 +1013,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         nc = nu;
         __syncwarp();
     }
-    if (MODE == 1 && P.vl && !P.vl[RB_VL_STORM]) {     // (not while every tick rebuilds: those lists die young, pruning them is wasted work)
+    if (MODE == 1) {     // (always: a block's tile is sized for pruned lists -- unpruned ones overflow it, the block's rows lose their lists, and that asks for the next rebuild)
         // Persistent lists keep only the triangles the sphere can actually reach while its list lives: the
         // exact predicate, run once at the build pose with the radius grown by the skin (a body steps from
         // its list only while displacement + margin <= skin, and the distance to a triangle is 1-Lipschitz
@@ -1056,35 +1052,58 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         T.tests_st += nc;
         nc = nu;
     }
-    if (MODE == 1) {        // park the lists by body row (slot-major; rows follow the sort order closely) and stop
-        if (valid) {
-            // one 16-B record per row: header + the first three triangles (most bodies have no more); the rest
-            // and the partners go to slot-major arrays
-            uint4 r4;
-            r4.x = min(npart, 255u) | (nc << 8) | (st_slow ? 0x10000u : 0u);
-            r4.y = nc > 0 ? s_cand[0][threadIdx.x] : 0u; r4.z = nc > 1 ? s_cand[1][threadIdx.x] : 0u; r4.w = nc > 2 ? s_cand[2][threadIdx.x] : 0u;
-            P.e_rec[A] = r4;
-#pragma unroll
-            for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + A] = pg[k]; P.e_pl[(size_t)k * P.ns + A] = pl[k]; }
-            for (uint32_t j = 3; j < nc; ++j) P.e_cand[(size_t)(j - 3) * P.ns + A] = s_cand[j][threadIdx.x];
-            if (P.vl && npart > RB_SSCAND_MAX) P.ws_build[A].w = -1.0f;     // crowded: no list can hold its partners, it enumerates every tick (hot)
+    if (MODE == 1) {
+        // Park the lists. Partners: slot-major arrays by row. Triangles: the rows of this block pack theirs, in row order,
+        // into one contiguous region of the tile pool -- vertex records first, global ids behind them -- which the list-step
+        // kernel stages with a single bulk copy. A row that cannot have a list steps as a hot body from now on.
+        __shared__ uint32_t s_total, s_base, s_over;
+        bool no_list = valid && (npart > RB_SSCAND_MAX || st_slow);
+        const uint32_t mine = (valid && !no_list) ? nc : 0u;
+        const uint32_t off = block_excl_scan(mine, &s_total);
+        if (threadIdx.x == 0) {
+            const uint32_t total = s_total;
+            uint32_t over = total > RB_TILE_CAP ? 1u : 0u, base = 0u;
+            if (!over && total) {
+                const uint32_t units = 3u * total + ((total + 3u) >> 2);
+                base = atomicAdd(P.tile_cursor, units);
+                if (base + units > P.tile_pool_units) over = 1u;       // pool exhausted (sized for 3 triangles per row on average)
+            }
+            s_base = base; s_over = over;
+            P.blk_tile[blockIdx.x] = make_uint2(base, over ? 0u : total);
         }
+        __syncthreads();
+        if (valid) {
+            no_list = no_list || s_over != 0u;
+            uint32_t hdr = 0u;
+            if (!no_list) {
+                hdr = npart | (nc << 8) | (off << 16);
+                uint4* reg = P.tile_pool + s_base;
+                uint32_t* ids = reinterpret_cast<uint32_t*>(reg + 3ull * s_total);
+                for (uint32_t j = 0; j < nc; ++j) {
+                    const uint32_t t = s_cand[j][threadIdx.x];
+                    const uint4* tp = reinterpret_cast<const uint4*>(P.tri + 3ull * t);
+                    uint4* dst = reg + 3ull * (off + j);
+                    dst[0] = __ldg(tp); dst[1] = __ldg(tp + 1); dst[2] = __ldg(tp + 2);
+                    ids[off + j] = t;
+                }
+#pragma unroll
+                for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + A] = pg[k]; P.e_pl[(size_t)k * P.ns + A] = pl[k]; }
+            } else {
+                // no list for this row: hot from this tick on (its own launch enumerates for it every tick)
+                P.ws_build[A].w = -1.0f;
+                const uint32_t kA = P.key[A];
+                if (!(kA & RB_HOT_BIT)) { P.key[A] = kA | RB_HOT_BIT; hot_push(P, A, fc.x, fc.z); }      // (K1 may have pushed it already: slab worlds rebuild on ticks that classify)
+            }
+            P.e_hdr[A] = hdr;
+        } else if (tid < rb_n_owned(P)) P.e_hdr[A] = 0u;      // not in the broadphase: no list (should it enter the grid it steps as a hot body)
         collide_epilogue(P, H, T, lane);
         return;
     }
-    if (MODE == 2 && valid) {
-        nc = (hdr >> 8) & 0xffu; st_slow = (hdr & 0x10000u) != 0;
-        // the exact tests gather these 48-B triangles a little later: start the loads now
-        if (nc > 0) { s_cand[0][threadIdx.x] = rec.y; rb_prefetch(P.tri + 3ull * rec.y); rb_prefetch(P.tri + 3ull * rec.y + 2); }
-        if (nc > 1) { s_cand[1][threadIdx.x] = rec.z; rb_prefetch(P.tri + 3ull * rec.z); rb_prefetch(P.tri + 3ull * rec.z + 2); }
-        if (nc > 2) { s_cand[2][threadIdx.x] = rec.w; rb_prefetch(P.tri + 3ull * rec.w); rb_prefetch(P.tri + 3ull * rec.w + 2); }
-        for (uint32_t j = 3; j < nc; ++j) s_cand[j][threadIdx.x] = P.e_cand[(size_t)(j - 3) * P.ns + A];
-    }
-    if (MODE == 2) __syncwarp();
     // ---------------- lazy state load ----------------
     const bool need = valid && (npart || nc || st_slow);
     if (need) {
-        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]);
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]);
+        if (lazy) S.mt = mk3(0.f + S.p.x, 0.f + S.p.y, 0.f + S.p.z); else S.mt = xyz(P.mt[A]);
         if (npart) S.pt = xyz(P.pt[A]);      // only a sphere-sphere hit reads the previous pose (snap-back); every other path overwrites it first
         if (P.wt) S.wt = xyz(P.wt[A]);
         S.flags = P.flags[A];
@@ -1105,7 +1124,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         while (true) {
             uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
             scan_partners<true>(P, A, fc, frm, lo, best, best_local, eligible, T);
-            if (reuse || P.dn) scan_hot_partners(P, A, fc, frm, lo, best, best_local, eligible, ghosts_only);
+            if (MODE == 3) scan_hot_partners(P, A, fc, frm, lo, best, best_local, eligible);
             if (best == RB_NONE) break;
             ss_pair_single<RESOLVE>(P, S, H, T, A, gA, oa, best_local, best);
             lo = best + 1;
@@ -1199,9 +1218,10 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
             float disp = mag3(sub3(S.mt, mt_frozen));
             if (disp > frm - oa.w) T.overflow++;
             if (S.changed) {
-                P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+                // (single-sphere bodies keep their world radius in pos.w)
+                P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, oa.w);
                 P.vel[A] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
-                P.mt[A] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+                if (!lazy) P.mt[A] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
                 P.pt[A] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
             }
             if (S.flags != flags_in) P.flags[A] = S.flags;
@@ -1209,22 +1229,337 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
             atomicAnd(&P.flags[A], ~RB_F_CONTACT);       // touched nothing: lose the contact flag, no state gather
         }
     }
-    if ((MODE == 2 || MODE == 3) && P.pos_out) {
+    if (MODE == 3 && P.pos_out && valid) {
         // the host asked for this tick's positions in id order: every row is written exactly once, by the launch that
-        // owns it this tick (hot rows by MODE 3 on reuse ticks, everything else by MODE 2)
-        const bool mine = MODE == 3 ? valid : (tid < rb_n_owned(P) && !(P.vl && !P.vl[RB_VL_REBUILD] && keyA != RB_NONE && (keyA & RB_HOT_BIT)));
-        if (mine) {
-            f3 pf = S.p;
-            if (!need) pf = xyz(P.pos[A]);
-            float* po = P.pos_out + (size_t)P.pos_out_stride * rb_gid(P, A);
-            po[0] = pf.x; po[1] = pf.y; po[2] = pf.z;
-            if (P.pos_out_stride == 4) po[3] = 1.0f;
-        }
+        // owns it this tick (hot rows here, everything else by the list-step kernel)
+        f3 pf = S.p;
+        if (!need) pf = xyz(P.pos[A]);
+        float* po = P.pos_out + (size_t)P.pos_out_stride * rb_gid(P, A);
+        po[0] = pf.x; po[1] = pf.y; po[2] = pf.z;
+        if (P.pos_out_stride == 4) po[3] = 1.0f;
     }
     collide_epilogue(P, H, T, lane);
     if (MODE == 0 && P.vl && P.vl_host && tid == 0) P.vl_host[2] = P.vl[RB_VL_NFAST];     // lists switched off: K1's count of fast movers
-    if (MODE == 2 && P.vl && tid == 0) {        // end of a persistent-list tick: book-keeping
-        const uint32_t f = P.vl[RB_VL_REBUILD];      // (cleared by the next tick's memset: other blocks of this launch still read it)
+}
+template <bool RESOLVE, int MODE>
+__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(const RbParams P) {
+    if (MODE == 3) {
+        // the grid is sized from the hot count the host saw last (several ticks old): stride over the table, whatever its size.
+        // Everything a pass shares lives per warp (staging columns, hit masks), so passes need no block barrier in between.
+        const uint32_t nh = min(*P.nhot, P.hot_cap);
+        for (uint32_t first = blockIdx.x * blockDim.x; first < nh; first += gridDim.x * blockDim.x)
+            collide_single_rows<RESOLVE, MODE>(P, first + threadIdx.x);
+    } else collide_single_rows<RESOLVE, MODE>(P, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4L: the list step -- one thread per body ROW, every tick of the persistent-list regime.
+// Everything a row needs is addressed by its row number: state (pos | radius, vel), the list header, up to four
+// partner rows, and its slice of the block's triangle tile, which one elected thread stages in shared memory with a
+// single TMA bulk copy (cp.async.bulk + mbarrier) while the block is still busy with the sphere-sphere phase. The
+// exact tests then read shared memory: no per-test 48-B gather, no dependent load behind the list.
+// Same canonical order and the same FP32 expression trees as rb_collide_single_kernel: bit-identical results.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// append n contact records of the calling lanes with one atomic (any converged subset of a warp may call this)
+__device__ __forceinline__ void append_contact(const RbParams& P, uint32_t a, uint32_t b, float depth, f3 n, float r) {
+    const uint32_t active = __activemask();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t leader = __ffs(active) - 1, rank = __popc(active & ((1u << lane) - 1u));
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(P.ncontact, (unsigned long long)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    const unsigned long long slot = base + rank;
+    if (slot < P.contact_cap) store_contact(P, slot, a, b, depth, n.x, n.y, n.z, r);
+    else atomicAdd(&P.counters[RB_C_DROPPED], 1ull);
+}
+
+#ifndef RB_LIST_MINBLOCKS
+#define RB_LIST_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kernel(const RbParams P) {
+    extern __shared__ __align__(16) uint4 s_tile[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint32_t s_mask[RB_BLOCK];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    // ---- the block's triangle tile: one bulk copy, in flight while the partners are dealt with ----
+    const uint2 bt = P.blk_tile[blockIdx.x];
+    const uint32_t tile_n = bt.y;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        if (tile_n) {
+            const uint32_t bytes = (3u * tile_n + ((tile_n + 3u) >> 2)) * 16u;
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(s_tile, P.tile_pool + bt.x, bytes, &s_bar);
+        }
+    }
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    const uint32_t n_owned = rb_n_owned(P);
+    const uint32_t A = tid;
+    uint32_t keyA = RB_NONE, hdr = 0, fl = 0;
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = p4;
+    if (tid < n_owned) { keyA = P.key[tid]; hdr = P.e_hdr[tid]; fl = P.flags[tid]; p4 = P.pos[tid]; v4 = P.vel[tid]; }     // all in flight together
+    // rows outside the broadphase have nothing to do; hot rows step in their own launch (rb_collide_single_kernel<3>)
+    const bool valid = keyA != RB_NONE && !(keyA & RB_HOT_BIT);
+    const bool had_contact = valid && (fl & RB_F_CONTACT) != 0;
+    BodyState S; S.changed = false; S.flags = fl;
+    S.p = xyz(p4); S.v = xyz(v4); S.pt = S.wt = mk3(0.f, 0.f, 0.f);
+    float4 oa = make_float4(0.f, 0.f, 0.f, p4.w);            // centred sphere: the world radius rides in pos.w
+    if (valid) {
+        if (!P.obj_zero) oa = P.sph_obj[A];
+        if (P.wt) S.wt = xyz(P.wt[A]);
+    }
+    if (P.lazy_mt) S.mt = mk3(0.f + S.p.x, 0.f + S.p.y, 0.f + S.p.z);      // Entity::_mvp after K1: translation(p) * W with W.t = 0
+    else S.mt = valid ? xyz(P.mt[A]) : mk3(0.f, 0.f, 0.f);
+    const uint32_t gA = valid ? rb_gid(P, A) : 0u;
+    // the frozen sphere K1 published for this row (same expressions, same bits): centre and grown radius
+    const f3 fc = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+    const float frm = oa.w + fminf(P.margin_cap, fmaxf(2.0f * mag3(S.v) * P.dt + 0.01f * oa.w, 1e-3f));
+    const f3 mt_frozen = S.mt;
+
+    // ---------------- partners: from the list, plus whoever is in the hot-body table ----------------
+    uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
+#pragma unroll
+    for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+    uint32_t npart = valid ? (hdr & 0xffu) : 0u;
+    const uint32_t nc = valid ? ((hdr >> 8) & 0xffu) : 0u;
+    const uint32_t toff = hdr >> 16;
+#pragma unroll
+    for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < npart) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
+    {
+        // hot bodies (and, in slab worlds, the neighbours' ghosts) are in nobody's list: everybody looks them up in the
+        // coarse cell table (<= 2 x 2 cells). Entries of earlier ticks read as empty cells.
+        uint32_t hcell[4] = { 0, 0, 0, 0 }, hn = 0;
+        if (valid) {
+            const float reach = frm + P.rm_max;
+            const uint32_t hx0 = rb_col(fc.x - reach, P.half, P.hc_inv_w, P.hcn), hx1 = rb_col(fc.x + reach, P.half, P.hc_inv_w, P.hcn);
+            const uint32_t hz0 = rb_col(fc.z - reach, P.half, P.hc_inv_w, P.hcn), hz1 = rb_col(fc.z + reach, P.half, P.hc_inv_w, P.hcn);
+            hcell[0] = hz0 * P.hcn + hx0; hn = 1;
+            if (hx1 != hx0) hcell[hn++] = hz0 * P.hcn + hx1;
+            if (hz1 != hz0) { hcell[hn++] = hz1 * P.hcn + hx0; if (hx1 != hx0) hcell[hn++] = hz1 * P.hcn + hx1; }
+        }
+        uint32_t hh[4];
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) hh[q] = (q < hn) ? hot_cell_head(P, hcell[q]) : 0u;      // the (<= 4) heads, all requested up front
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+            uint32_t h = hh[q];
+            while (true) {
+                if (!__any_sync(0xffffffffu, h != 0u)) break;
+                if (h) {
+                    const uint32_t Bl = P.hot_row[h - 1u];
+                    h = P.hot_next[h - 1u];
+                    if (Bl != A) {
+                        const float4 o = P.ws[Bl];
+                        float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+                        if (o.w >= 0.f && !((dx * dx + dy * dy) + dz * dz > rr * rr)) {
+                            uint32_t g = rb_gid(P, Bl), bl = Bl;
+                            bool dup = false;
+#pragma unroll
+                            for (int k = 0; k < RB_SSCAND_MAX; ++k) dup |= (pg[k] == g);
+                            if (!dup) {
+                                T.cand_ss++; npart++;
+#pragma unroll
+                                for (int k = 0; k < RB_SSCAND_MAX; ++k)
+                                    if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = bl; g = tg; bl = tl; }
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    // ---------------- sphere-sphere in ascending partner id ----------------
+    // GeometryMath::sphereSphereDetection (math/src/GeometryMath.cpp:211-230): hit iff (rA + rB) - sqrt(d2) >= 0, i.e.
+    // sqrt_rn(d2) <= radii. A pair with d2 > radii^2 * (1 + 2^-20) cannot pass (sqrt is monotone, the bound is > 3 ulp of
+    // radii away), so it is rejected without the square root; everything closer runs the reference expressions.
+    bool pt_loaded = false;
+#pragma unroll
+    for (int k = 0; k < RB_SSCAND_MAX; ++k) {
+        if (!__any_sync(0xffffffffu, pg[k] != RB_NONE)) break;
+        if (pg[k] != RB_NONE) {
+            const uint32_t Bl = pl[k], gB = pg[k];
+            const bool lo_is_a = gA < gB;
+            const float4 wb = P.ws[Bl];                        // partner at its frozen pose
+            if (wb.w >= 0.f) {                                 // (w < 0: it has left the broadphase since the list was built, Q3 / Q7)
+                const float rb = P.pos[Bl].w;                  // its exact radius (pos.w never changes)
+                const f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+                const f3 cb = xyz(wb);
+                const f3 cn = lo_is_a ? sub3(ca, cb) : sub3(cb, ca);          // lower id plays sphereA / modelA
+                const float radii = lo_is_a ? (oa.w + rb) : (rb + oa.w);
+                const float d2 = (cn.x * cn.x + cn.y * cn.y) + cn.z * cn.z;
+                if (lo_is_a) T.tests_ss++;
+                if (!(d2 > (radii * radii) * 1.000001f)) {
+                    const float dist = sqrtf(d2);
+                    if (radii - dist >= 0) {
+                        const f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
+                        if (lo_is_a) { T.hits_ss++; append_contact(P, gA, gB, radii - dist, n1, oa.w); }
+                        f3 n = n1;
+                        if (!lo_is_a) { n = neg3(n); n = normalize3(n); }
+                        const float sp = mag3(S.v);
+                        S.v = mul3(mul3(n, sp), P.ss_damp);
+                        if (!pt_loaded && !S.changed) S.pt = xyz(P.pt[A]);      // the previous pose K1 left (only a snap-back reads it)
+                        pt_loaded = true;
+                        body_set_position(S, S.pt);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (npart > RB_SSCAND_MAX) {            // hot neighbours pushed the count past what is staged: continue above the last staged id by rescanning
+        HitBuf H; H.n = 0;
+        if (!pt_loaded && !S.changed) { S.pt = xyz(P.pt[A]); pt_loaded = true; }
+        uint32_t lo = pg[RB_SSCAND_MAX - 1] + 1;
+        const float4 oa_s = make_float4(oa.x, oa.y, oa.z, oa.w);
+        while (true) {
+            uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
+            scan_partners<true>(P, A, fc, frm, lo, best, best_local, eligible, T);
+            scan_hot_partners(P, A, fc, frm, lo, best, best_local, eligible);
+            if (best == RB_NONE) break;
+            ss_pair_single<true>(P, S, H, T, A, gA, oa_s, best_local, best);
+            lo = best + 1;
+            if (eligible <= 1) break;
+        }
+        for (uint32_t i = 0; i < min(H.n, (uint32_t)RB_MAXLOCAL); ++i) append_contact(P, H.a[i], H.b[i], H.depth[i], mk3(H.nx[i], H.ny[i], H.nz[i]), H.r[i]);
+    }
+
+    // ---------------- sphere-triangle: pooled exact tests out of the staged tile ----------------
+    __syncthreads();                        // the barrier word is initialised (thread 0) before anybody polls it
+    if (tile_n) mbar_wait(&s_bar, 0);
+    const uint32_t* tile_ids = reinterpret_cast<const uint32_t*>(s_tile + 3u * tile_n);
+    bool hit_any = false;
+    {
+        // Speculative, load-balanced rounds (see rb_collide_single_kernel P4): every round pools the remaining tests of the
+        // warp and deals them out 32 at a time; each owner then takes its FIRST hit in canonical order, resolves it, and
+        // re-enters the next round with the triangles behind that hit.
+        uint32_t j0 = 0;
+        while (true) {
+            const uint32_t rem = j0 < nc ? nc - j0 : 0;
+            if (!__any_sync(0xffffffffu, rem != 0)) break;
+            const uint32_t incl = warp_incl_scan(rem, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
+            s_mask[threadIdx.x] = 0;
+            __syncwarp();
+            const uint32_t wbase = threadIdx.x & ~31u;
+            const uint32_t first_ent = toff + j0;                                // this lane's first remaining tile entry
+            for (uint32_t base = 0; base < total; base += 32) {
+                const uint32_t item = base + lane;
+                uint32_t lo = 0;                                   // owner = number of lanes whose inclusive count is <= item
+#pragma unroll
+                for (int st = 16; st >= 1; st >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, incl, (lo + st - 1) & 31); if (v <= item) lo += st; }
+                const uint32_t owner = lo & 31;
+                const uint32_t o_excl = __shfl_sync(0xffffffffu, incl - rem, owner), o_ent = __shfl_sync(0xffffffffu, first_ent, owner);
+                const float ox = __shfl_sync(0xffffffffu, c.x, owner), oy = __shfl_sync(0xffffffffu, c.y, owner), oz = __shfl_sync(0xffffffffu, c.z, owner);
+                const float orad = __shfl_sync(0xffffffffu, oa.w, owner);
+                if (item < total) {
+                    const uint32_t k = item - o_excl;
+                    const uint4* tp = s_tile + 3u * (o_ent + k);
+                    const uint4 a4 = tp[0], b4 = tp[1], c4 = tp[2];
+                    if (sphere_triangle_detect(mk3(ox, oy, oz), orad,
+                                               mk3(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z)),
+                                               mk3(__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z)),
+                                               mk3(__uint_as_float(c4.x), __uint_as_float(c4.y), __uint_as_float(c4.z))))
+                        atomicOr(&s_mask[wbase + owner], 1u << k);
+                }
+                __syncwarp();
+            }
+            __syncwarp();
+            const uint32_t m = s_mask[threadIdx.x];
+            if (rem) {
+                // sequential accounting: the tests up to and including the first hit are the ones the one-at-a-time order runs
+                const uint32_t first = m ? (uint32_t)__ffs(m) - 1 : rem;
+                T.tests_st += m ? first + 1 : rem;
+                if (m) {
+                    const uint32_t ent = first_ent + first;
+                    const uint4* tp = s_tile + 3u * ent;
+                    const uint4 a4 = tp[0], b4 = tp[1], c4 = tp[2];
+                    const f3 TA = mk3(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z));
+                    const f3 TB = mk3(__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z));
+                    const f3 TC = mk3(__uint_as_float(c4.x), __uint_as_float(c4.y), __uint_as_float(c4.z));
+                    hit_any = true;
+                    T.hits_st++;
+                    const f3 q = closest_point(c, TA, TB, TC);
+                    const f3 ov = sub3(c, q);
+                    const float dist = mag3(ov);
+                    const f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
+                    append_contact(P, gA, RB_TRI_BIT | tile_ids[ent], oa.w - dist, o, oa.w);
+                    // GeometryMath::sphereTriangleResolution (math/src/GeometryMath.cpp:489-522); the triangle normal
+                    // normalize((C-A)x(B-A)) is static: pre-computed at build (w lanes)
+                    const f3 normal = mk3(__uint_as_float(a4.w), __uint_as_float(b4.w), __uint_as_float(c4.w));
+                    const f3 delta = sub3(add3(mul3(o, oa.w * P.pushout), q), c);
+                    const float ncomp = dot3(S.v, normal);
+                    const f3 rv = sub3(S.v, mul3(normal, ncomp));
+                    body_set_position(S, add3(S.p, delta));
+                    S.v = rv;
+                    S.flags |= RB_F_CONTACT;
+                    j0 += first + 1;
+                } else j0 = nc;
+            }
+            __syncwarp();
+        }
+    }
+    // ---------------- flags, write-back ----------------
+    if (valid) {
+        if ((fl & RB_F_CONTACT) && !hit_any) S.flags &= ~RB_F_CONTACT;     // Physics.cpp:201-207
+        if (S.changed) {
+            const float disp = mag3(sub3(S.mt, mt_frozen));
+            if (disp > frm - oa.w) T.overflow++;
+            P.pos[A] = make_float4(S.p.x, S.p.y, S.p.z, p4.w);
+            P.vel[A] = make_float4(S.v.x, S.v.y, S.v.z, v4.w);
+            if (!P.lazy_mt) P.mt[A] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+            P.pt[A] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+        }
+        if (S.flags != fl) P.flags[A] = S.flags;
+    }
+    (void)had_contact;
+    if (P.pos_out && tid < n_owned && !(keyA != RB_NONE && (keyA & RB_HOT_BIT))) {
+        // the host asked for this tick's positions in id order: every row is written exactly once, by the launch that
+        // owns it this tick (hot rows by rb_collide_single_kernel<3>, everything else here)
+        float* po = P.pos_out + (size_t)P.pos_out_stride * rb_gid(P, A);
+        po[0] = S.p.x; po[1] = S.p.y; po[2] = S.p.z;
+        if (P.pos_out_stride == 4) po[3] = 1.0f;
+    }
+    {   // cumulative counters: warp reduce, one atomic per warp and non-zero counter on a striped copy
+        uint32_t vals[7] = { T.tests_ss, T.tests_st, T.cand_ss, T.cand_st, T.hits_ss, T.hits_st, T.overflow };
+        const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
+        const uint32_t stripe = ((blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5)) & (RB_STRIPES - 1);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            if (!__any_sync(0xffffffffu, vals[k] != 0u)) continue;
+            const uint32_t sum = __reduce_add_sync(0xffffffffu, vals[k]);
+            if (lane == 0) atomicAdd(&P.stripes[stripe * RB_C_COUNT + map[k]], (unsigned long long)sum);
+        }
+    }
+    if (tid == 0) {        // end of a persistent-list tick: book-keeping (the hot counter is final: K1 and the enumeration are done)
+        const uint32_t f = P.vl[RB_VL_REBUILD];
         if (f) {
             const uint32_t why = P.vl[RB_VL_WHY];
             P.vl[RB_VL_WHY_LAST] = why; P.vl[RB_VL_WHY] = 0u;
@@ -1234,7 +1569,8 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
         P.vl[RB_VL_STORM] = f;                       // the next rebuild, if it comes right away, skips the list pruning
         const uint32_t nr = P.vl[RB_VL_NREBUILD] + (f ? 1u : 0u), nt = P.vl[RB_VL_NTICK] + 1u;
         P.vl[RB_VL_NREBUILD] = nr; P.vl[RB_VL_NTICK] = nt;
-        if (P.vl_host) { P.vl_host[0] = nr; P.vl_host[1] = nt; }
+        P.vl[RB_VL_NHOT_LAST] = *P.nhot;
+        if (P.vl_host) { P.vl_host[0] = nr; P.vl_host[1] = nt; P.vl_host[3] = *P.nhot; P.vl_host[4] = nt; }
     }
 }
 
@@ -1295,9 +1631,13 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_fill_f4_kernel(float4* p, uint32_
     if (i < n) p[i] = v;
 }
 // rows -> id order (readback) and id order -> rows (setters)
-__global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_f4_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ gid, float4* __restrict__ out, uint32_t n) {
+// w_one: the w lane reads 1 (positions of single-sphere bodies keep their world radius there; the interface says 1)
+__global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_f4_kernel(const float4* __restrict__ rows, const uint32_t* __restrict__ gid, float4* __restrict__ out, uint32_t n, int w_one) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[gid[i]] = rows[i];
+    if (i >= n) return;
+    float4 v = rows[i];
+    if (w_one) v.w = 1.0f;
+    out[gid ? gid[i] : i] = v;
 }
 // packed xyz variants of the host round trip (12 B per body each way instead of 16: the round trip is PCIe-bound)
 __global__ void __launch_bounds__(RB_BLOCK) rb_apply_force3_kernel(const uint32_t* __restrict__ flags, const float* __restrict__ in3,
@@ -1321,9 +1661,22 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_rows_to_ids_u32_kernel(const uint
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[gid[i]] = rows[i];
 }
-__global__ void __launch_bounds__(RB_BLOCK) rb_ids_to_rows_f4_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ inv, float4* __restrict__ rows, uint32_t first, uint32_t count) {
+// keep_w: the w lane of the destination survives (single-sphere bodies keep their world radius in pos.w)
+__global__ void __launch_bounds__(RB_BLOCK) rb_ids_to_rows_f4_kernel(const float4* __restrict__ in, const uint32_t* __restrict__ inv, float4* __restrict__ rows, uint32_t first, uint32_t count, int keep_w) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) rows[inv[first + i]] = in[i];
+    if (i >= count) return;
+    const uint32_t row = inv ? inv[first + i] : first + i;
+    float4 v = in[i];
+    if (keep_w) v.w = rows[row].w;
+    rows[row] = v;
+}
+// Entity::_mvp's translation for worlds that keep it implicit on list ticks (W.t = 0): after any complete tick it is
+// 0 + p -- K1 leaves translation(p) * W, a resolution leaves p = mt = the same sum (rb_collide_single_kernel P5)
+__global__ void __launch_bounds__(RB_BLOCK) rb_mt_refresh_kernel(const float4* __restrict__ pos, float4* __restrict__ mt, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pos[i];
+    mt[i] = make_float4(0.f + p.x, 0.f + p.y, 0.f + p.z, 0.f);
 }
 
 // K8: model-matrix export. total = translation(p) * W keeps W's 3x3 and carries the translation the step
@@ -1451,15 +1804,16 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 }
 // The hot bodies' launch is small and latency-bound (a few warps walking dependent loads): it runs on a side
 // stream next to the big list kernel. Both only write the bodies they own and read frozen data of the others.
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate) {
+uint32_t rb_list_tile_bytes() { return (3u * RB_TILE_CAP + RB_TILE_CAP / 4u) * 16u; }
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows) {
     if (!P.nb) return 0;
     const uint32_t g = cdiv(P.ns, RB_BLOCK);
     if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
     cudaEventRecord(fork, st);
     cudaStreamWaitEvent(side, fork, 0);
-    rb_collide_single_kernel<true, 3><<<cdiv(P.hot_cap, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies (reuse ticks)
+    rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies: one thread per entry of the table
     cudaEventRecord(join, side);
-    rb_collide_single_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P);                              // everybody else, from the lists
+    rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);                         // everybody else, from the lists
     cudaStreamWaitEvent(st, join, 0);
     return 3;
 }
@@ -1470,13 +1824,9 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
         if (variant == 1) {     // first-generation kernel, kept for A/B checks (RB_COLLIDE_V1=1)
             if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
             else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
-        } else if (variant == 2 || !P.e_rec) {     // fused phases in one launch
+        } else {                                   // fused phases in one launch
             if (resolve) rb_collide_single_kernel<true, 0><<<g, RB_BLOCK, 0, st>>>(P);
             else rb_collide_single_kernel<false, 0><<<g, RB_BLOCK, 0, st>>>(P);
-        } else {                                   // enumerate at high occupancy, then test / resolve
-            if (resolve) { rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P); rb_collide_single_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P); }
-            else { rb_collide_single_kernel<false, 1><<<g, RB_BLOCK, 0, st>>>(P); rb_collide_single_kernel<false, 2><<<g, RB_BLOCK, 0, st>>>(P); }
-            return 2;
         }
         return 1;
     }
@@ -1498,8 +1848,8 @@ void rb_launch_set_flags(uint32_t* flags, const uint32_t* values, const uint32_t
 void rb_launch_fill_f4(float4* p, uint32_t n, float4 v, cudaStream_t st) {
     if (n) rb_fill_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(p, n, v);
 }
-void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, cudaStream_t st) {
-    if (n) rb_rows_to_ids_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n);
+void rb_launch_rows_to_ids_f4(const float4* rows, const uint32_t* gid, float4* out, uint32_t n, int w_one, cudaStream_t st) {
+    if (n) rb_rows_to_ids_f4_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n, w_one);
 }
 void rb_launch_apply_force3(const uint32_t* flags, const float* in3, float4* out, const uint32_t* inv, uint32_t count, cudaStream_t st) {
     if (count) rb_apply_force3_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(flags, in3, out, inv, count);
@@ -1510,8 +1860,11 @@ void rb_launch_rows_to_ids_f3(const float4* rows, const uint32_t* gid, float* ou
 void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32_t* out, uint32_t n, cudaStream_t st) {
     if (n) rb_rows_to_ids_u32_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(rows, gid, out, n);
 }
-void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, cudaStream_t st) {
-    if (count) rb_ids_to_rows_f4_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(in, inv, rows, first, count);
+void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, int keep_w, cudaStream_t st) {
+    if (count) rb_ids_to_rows_f4_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(in, inv, rows, first, count, keep_w);
+}
+void rb_launch_mt_refresh(const float4* pos, const float4*, float4* mt, uint32_t n, cudaStream_t st) {
+    if (n) rb_mt_refresh_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(pos, mt, n);
 }
 void rb_launch_model_matrices(const float4* w3, const uint32_t* gid, const float4* mt, const float4* pt, float4* cur, float4* prev, uint32_t n, int prev_is_default, cudaStream_t st) {
     if (n) rb_model_matrix_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(w3, gid, mt, pt, cur, prev, n, prev_is_default);

@@ -259,10 +259,11 @@ static int ensure_io(rb_world* w) {
     ALLOC(w->d_io4, w->P.nb); ALLOC(w->d_io_u, w->P.nb);
     return RB_OK;
 }
-static int read_rows_f4(rb_world* w, const float4* rows, float* host, size_t n) {
-    if (!w->d_inv) { CU(cudaMemcpyAsync(host, rows, n * 16, cudaMemcpyDeviceToHost, w->stream)); return RB_OK; }
+// w_one: the w lane reads 1 (single-sphere bodies keep their world radius in pos.w; the interface says positions carry w = 1)
+static int read_rows_f4(rb_world* w, const float4* rows, float* host, size_t n, int w_one = 0) {
+    if (!w->d_inv && !w_one) { CU(cudaMemcpyAsync(host, rows, n * 16, cudaMemcpyDeviceToHost, w->stream)); return RB_OK; }
     int r = ensure_io(w); if (r) return r;
-    rb_launch_rows_to_ids_f4(rows, w->P.gid, w->d_io4, (uint32_t)n, w->stream); w->launches++;
+    rb_launch_rows_to_ids_f4(rows, w->d_inv ? w->P.gid : nullptr, w->d_io4, (uint32_t)n, w_one, w->stream); w->launches++;
     CU(cudaMemcpyAsync(host, w->d_io4, n * 16, cudaMemcpyDeviceToHost, w->stream));
     return RB_OK;
 }
@@ -273,11 +274,40 @@ static int read_rows_u32(rb_world* w, const uint32_t* rows, uint32_t* host, size
     CU(cudaMemcpyAsync(host, w->d_io_u, n * 4, cudaMemcpyDeviceToHost, w->stream));
     return RB_OK;
 }
-static int write_rows_f4(rb_world* w, float4* rows, uint32_t first, uint32_t count, const float* host) {
-    if (!w->d_inv) { CU(cudaMemcpyAsync(rows + first, host, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream)); return RB_OK; }
+// keep_w: the w lane of the rows survives (single-sphere bodies keep their world radius in pos.w)
+static int write_rows_f4(rb_world* w, float4* rows, uint32_t first, uint32_t count, const float* host, int keep_w = 0) {
+    if (!w->d_inv && !keep_w) { CU(cudaMemcpyAsync(rows + first, host, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream)); return RB_OK; }
     int r = ensure_stage(w, count); if (r) return r;
     CU(cudaMemcpyAsync(w->d_stage, host, (size_t)count * 16, cudaMemcpyHostToDevice, w->stream));
-    rb_launch_ids_to_rows_f4(w->d_stage, w->d_inv, rows, first, count, w->stream); w->launches++;
+    rb_launch_ids_to_rows_f4(w->d_stage, w->d_inv, rows, first, count, keep_w, w->stream); w->launches++;
+    return RB_OK;
+}
+
+// List ticks of slim worlds keep Entity::_mvp's translation implicit (0 + p); everybody else wants the array
+int rb_ensure_mt(rb_world* w) {
+    if (!w->mt_stale) return RB_OK;
+    const uint32_t n = w->d_dn ? w->cap_local : w->P.nb;
+    rb_launch_mt_refresh(w->P.pos, nullptr, w->P.mt, n, w->stream); w->launches++;
+    CU(cudaGetLastError());
+    w->mt_stale = false;
+    return RB_OK;
+}
+void rb_list_tick_params(rb_world* w) {
+    RbParams& P = w->P;
+    P.tick = ++w->tick_seq; if (!P.tick) P.tick = ++w->tick_seq;
+    // single worlds rotate through the ring of counter blocks and K1 zeroes the next one; slab worlds use the last block,
+    // which their per-tick clear launch zeroes together with the rebuild flag right behind it
+    const uint32_t blk = P.soft ? w->tick_seq % RB_TB_BLOCKS : RB_TB_BLOCKS - 1;
+    P.ncontact = (unsigned long long*)(w->d_tb + 4 * blk); P.nhot = w->d_tb + 4 * blk + 2;
+    P.tb_next = P.soft ? w->d_tb + 4 * ((blk + 1) % RB_TB_BLOCKS) : nullptr;
+    w->ncontact_dev = P.ncontact;
+    P.lazy_mt = w->slim ? 1u : 0u; P.mt_in_valid = w->mt_stale ? 0u : 1u;
+}
+int rb_plain_tick_params(rb_world* w) {
+    RbParams& P = w->P;
+    int r = rb_ensure_mt(w); if (r) return r;
+    P.ncontact = P.counters + RB_C_NCONTACT; w->ncontact_dev = P.ncontact;
+    P.tb_next = nullptr; P.lazy_mt = 0u; P.mt_in_valid = 1u;
     return RB_OK;
 }
 
@@ -292,7 +322,8 @@ static int reorder_rows(rb_world* w, bool intick) {
     const size_t nb = P.nb;
     // intick: between the sort and the enumeration of a list-rebuild tick -- K1's per-row outputs (world spheres,
     // build poses, keys) travel too and the sorted ids are rewritten, so the lists are built for the new rows
-    float4** cur[RB_REORDER_MAX] = { &P.pos, &P.vel, &P.mt, &P.pt, const_cast<float4**>(&P.sph_obj), const_cast<float4**>(&P.wt), &P.force, &P.torque, &P.apos, &P.avel,
+    // (a stale mt array -- list ticks of slim worlds keep it implicit -- does not travel: rb_ensure_mt rewrites all of it)
+    float4** cur[RB_REORDER_MAX] = { &P.pos, &P.vel, w->mt_stale ? nullptr : &P.mt, &P.pt, const_cast<float4**>(&P.sph_obj), const_cast<float4**>(&P.wt), &P.force, &P.torque, &P.apos, &P.avel,
                                      intick ? &P.ws : nullptr, intick ? &P.ws_build : nullptr };
     if (!w->d_gid_alt) {
         if (!slab) { ALLOC(w->d_inv, nb); ALLOC(w->d_gid, nb); }
@@ -378,6 +409,15 @@ int rb_build(rb_world* w) {
             rmax = std::max(rmax, std::fabs((float)r));
         }
     }
+    // centred spheres (object centre +0 after W): the world radius rides in pos.w and sph_obj is never read on the hot path
+    bool obj_zero = P.single != 0;
+    for (size_t i = 0; i < (size_t)ns * 4 && obj_zero; i += 4) {
+        uint32_t bx, by, bz; memcpy(&bx, &sph[i], 4); memcpy(&by, &sph[i + 1], 4); memcpy(&bz, &sph[i + 2], 4);
+        obj_zero = (bx | by | bz) == 0u;
+    }
+    P.obj_zero = obj_zero ? 1u : 0u;
+    w->slim = P.single && obj_zero && !w->any_wt;
+    P.soft = slab ? 0u : 1u;
     if (slab && w->cfg.rm_max_hint > rmax) rmax = w->cfg.rm_max_hint;   // every rank must use the same reach
     if (!(w->cfg.margin_cap > 0.f)) w->cfg.margin_cap = std::max(0.5f * rmax, 1e-3f);   // auto: half the largest radius
     P.margin_cap = w->cfg.margin_cap;
@@ -441,7 +481,7 @@ int rb_build(rb_world* w) {
     std::vector<float> p4((size_t)std::max<uint32_t>(nb, 1) * 4, 0.f), v4 = p4, wt4 = p4;
     for (uint32_t b = 0; b < nb; b++) {
         for (int k = 0; k < 3; k++) { p4[(size_t)b * 4 + k] = w->h_pos[(size_t)b * 3 + k]; v4[(size_t)b * 4 + k] = w->h_vel[(size_t)b * 3 + k]; wt4[(size_t)b * 4 + k] = w->h_W[(size_t)b * 12 + 9 + k]; }
-        p4[(size_t)b * 4 + 3] = 1.f;
+        p4[(size_t)b * 4 + 3] = P.single ? sph[(size_t)b * 4 + 3] : 1.f;      // single-sphere bodies: world radius (GeometryMath.cpp:83-87) in pos.w
     }
     CU(cudaMemcpyAsync(d_pos, p4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_vel, v4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
@@ -464,8 +504,8 @@ int rb_build(rb_world* w) {
         float4* wb;
         ALLOC(wb, nsa); CU(cudaMemsetAsync(wb, 0, (size_t)nsa * 16, w->stream));
         CU(cudaMemsetAsync(d_key, 0xff, (size_t)nsa * 4, w->stream));                 // "not in the grid" until the first K1
-        CU(cudaHostAlloc((void**)&w->vl_host, 4 * sizeof(uint32_t), cudaHostAllocMapped));
-        w->vl_host[0] = w->vl_host[1] = w->vl_host[2] = w->vl_host[3] = 0;
+        CU(cudaHostAlloc((void**)&w->vl_host, 8 * sizeof(uint32_t), cudaHostAllocMapped));
+        for (int k = 0; k < 8; k++) w->vl_host[k] = 0;
         uint32_t* dv = nullptr; CU(cudaHostGetDevicePointer((void**)&dv, w->vl_host, 0));
         P.ws_build = wb; P.vl_host = dv;
         CU(cudaStreamCreateWithFlags(&w->vl_side, cudaStreamNonBlocking));
@@ -474,21 +514,29 @@ int rb_build(rb_world* w) {
         const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 256.0f);
         P.hcn = (uint32_t)std::max(1L, (long)std::floor(2.0 * P.half / lc));
         P.hc_inv_w = (float)P.hcn / (2.0f * P.half);
-        P.hot_cap = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(1024u, ns / 128u);
-        // one blob: cell heads | hot counter | list words. The per-tick memset clears the heads, the counter and the
-        // first list word (the rebuild flag) in one go; the words behind it persist.
-        uint32_t *hh, *hr, *hn;
+        // every row has a slot (the table cannot overflow); hot_soft is the count at which rebuilding the lists pays
+        P.hot_cap = (uint32_t)nsa;
+        P.hot_soft = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(1024u, ns / 128u);
+        unsigned long long* hh; uint32_t *hr, *hn;
         const size_t ncell = (size_t)P.hcn * P.hcn;
-        ALLOC(hh, ncell + 1 + RB_VL_WORDS); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
-        CU(cudaMemsetAsync(hh, 0, (ncell + 1 + RB_VL_WORDS) * sizeof(uint32_t), w->stream));
-        P.hot_head = hh; P.hot_row = hr; P.hot_next = hn; P.vl = hh + ncell + 1;
+        ALLOC(hh, ncell); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
+        CU(cudaMemsetAsync(hh, 0, ncell * sizeof(unsigned long long), w->stream));      // tick 0 never runs: every cell starts empty, and stays versioned
+        P.hot_head = hh; P.hot_row = hr; P.hot_next = hn;
+        // ring of per-tick counter blocks {contacts lo, hi, hot bodies, -} and, right behind it, the list words (rebuild flag first)
+        ALLOC(w->d_tb, 4 * RB_TB_BLOCKS + RB_VL_WORDS);
+        CU(cudaMemsetAsync(w->d_tb, 0, (4 * RB_TB_BLOCKS + RB_VL_WORDS) * sizeof(uint32_t), w->stream));
+        P.vl = w->d_tb + 4 * RB_TB_BLOCKS;
         P.scan_status = w->d_scan_status; P.scan_ticket = w->d_scan_ticket; P.ncols = w->ncols;      // for the device-launched rebuild chain
         static_assert(RB_VL_REBUILD == 0, "the rebuild flag must be the first list word");
-    }
-    if (P.single && P.ns) {     // enumerate -> resolve hand-over lists
-        uint4* eh; uint32_t *eg, *el, *ec;
-        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4); ALLOC(ec, (size_t)P.ns * 9);
-        P.e_rec = eh; P.e_pg = eg; P.e_pl = el; P.e_cand = ec;
+        // candidate lists: header + partners per row, triangles in per-block tiles (sized for 3 per row on average; a block
+        // that does not fit steps without lists)
+        uint32_t *eh, *eg, *el, *tc; uint4* tp; uint2* bt;
+        const size_t nblk = ((size_t)P.ns + 255) / 256;
+        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4);
+        P.tile_pool_units = (uint32_t)std::min<size_t>(0xF0000000ull, (size_t)P.ns * 10 + 4096);
+        ALLOC(tp, P.tile_pool_units); ALLOC(bt, nblk); ALLOC(tc, 4);
+        CU(cudaMemsetAsync(eh, 0, (size_t)P.ns * 4, w->stream)); CU(cudaMemsetAsync(bt, 0, nblk * sizeof(uint2), w->stream)); CU(cudaMemsetAsync(tc, 0, 16, w->stream));
+        P.e_hdr = eh; P.e_pg = eg; P.e_pl = el; P.tile_pool = tp; P.blk_tile = bt; P.tile_cursor = tc;
     }
     {   // static 3x3 of every _worldSpaceTransform, kept only when some body is not identity (model-matrix export)
         bool any = false;
@@ -506,9 +554,10 @@ int rb_build(rb_world* w) {
     P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(slab ? cap : ns) * 4 + 1024;
     RbContactRec* d_c; ALLOC(d_c, (size_t)P.contact_cap); P.contacts = d_c;
     unsigned long long* d_cnt; ALLOC(d_cnt, RB_C_COUNT * (RB_STRIPES + 1)); P.counters = d_cnt; P.stripes = d_cnt + RB_C_COUNT;
+    P.ncontact = d_cnt + RB_C_NCONTACT; w->ncontact_dev = P.ncontact; P.mt_in_valid = 1u;
     CU(cudaMemsetAsync(d_cnt, 0, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long), w->stream));
-    CU(cudaMallocHost((void**)&w->h_counters, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long)));
-    memset(w->h_counters, 0, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long));
+    CU(cudaMallocHost((void**)&w->h_counters, (RB_C_COUNT * (RB_STRIPES + 1) + 1) * sizeof(unsigned long long)));
+    memset(w->h_counters, 0, (RB_C_COUNT * (RB_STRIPES + 1) + 1) * sizeof(unsigned long long));
     for (auto& e : w->ev) CU(cudaEventCreate(&e));
     CU(cudaStreamSynchronize(w->stream));
     int r = build_triangle_grid(w);
@@ -546,6 +595,7 @@ int enqueue_broadphase_tail(rb_world* w) {
 static int enqueue_broadphase(rb_world* w, int do_integrate) {
     RbParams& P = w->P;
     if (w->dist) return rb_dist_step_exchange(w, do_integrate);
+    { int r = rb_plain_tick_params(w); if (r) return r; }
     rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++;      // histogram + scan ticket / status
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, 1, w->stream); w->launches++;
@@ -569,20 +619,32 @@ static int enqueue_collide(rb_world* w, bool resolve) {
     return RB_OK;
 }
 
-// One tick with persistent candidate lists. K1 integrates, checks whether every sphere is still inside the
-// skin its list was built with, and raises the device-side rebuild flag if not; bin -> scan -> scatter ->
-// enumerate follow as launches that return at once while the flag is down (the host never has to look), and
-// the test / resolve kernel runs every tick from the lists. Results are the ones of the per-tick enumeration:
-// the lists are supersets of it and every decision is taken by the same exact tests in the same order.
-// second half of a list tick: the conditional rebuild chain and the resolve launches (slab worlds get here after their
-// halo exchange; K1 ran before it)
+// One tick with persistent candidate lists. K1 integrates and checks, per body, whether the sphere is still inside the
+// skin its list was built with; a body that is not steps without its list this tick (rb_collide_single_kernel<3>, a small
+// launch next to the list kernel). The lists are rebuilt (bin -> scan -> scatter -> enumerate)
+//   * single worlds ("soft"): when the HOST says so -- every vl_period list ticks, a period it adapts to the hot-body counts
+//     the device reports through mapped memory -- so a reuse tick is three launches (K1, hot bodies, list step) and
+//     nothing on the device ever waits for a decision;
+//   * slab worlds: when the device raises the rebuild flag (a row moved between ranks, too many hot bodies) or the host
+//     forces it; the chain kernels follow as launches that return at once while the flag is down, or are tail-launched by
+//     a one-thread gate kernel (library built with device-side launches).
+// Results are the ones of the per-tick enumeration: the lists are supersets of it and every decision is taken by the same
+// exact tests in the same order.
+// (second half of a list tick: slab worlds get here after their halo exchange; K1 ran before it)
+static uint32_t list_hot_rows(rb_world* w) {
+    // grid of the hot bodies' launch: it strides over the table, so any size is correct; sized from the last count seen
+    const uint32_t seen = w->vl_host ? w->vl_host[3] : 0u;
+    const uint32_t want = std::max<uint32_t>(4096u, 2u * seen);
+    return std::min<uint32_t>(want, std::max<uint32_t>(w->P.ns, 1u));
+}
 int rb_list_tick_tail(rb_world* w, bool reorder_due) {
-    const bool tail_forced = w->vl_force || reorder_due;
     RbParams& P = w->P;
-    // built with device-side launches: a one-thread gate kernel tail-launches bin -> scan -> scatter -> enumerate when the
-    // rebuild flag is up (rb_kernels.cu), so the host only enqueues the chain itself on the ticks it forces
-    const bool chain = !w->vl_cdp || tail_forced || !w->vl_gate_ok;
-    if (!chain) rb_launch_vl_gate(P, w->stream);
+    const bool rebuild_now = w->vl_tick_rebuilds;           // the host forced (or, single worlds, scheduled) a rebuild this tick
+    // slab worlds built with device-side launches: a one-thread gate kernel tail-launches bin -> scan -> scatter -> enumerate
+    // when the rebuild flag is up (rb_kernels.cu), so the host only enqueues the chain itself on the ticks it forces
+    const bool chain = P.soft ? rebuild_now : (!w->vl_cdp || rebuild_now || !w->vl_gate_ok);
+    const bool gate = !P.soft && !chain;
+    if (gate) rb_launch_vl_gate(P, w->stream);
     if (chain) rb_launch_vl_bin(P, w->stream);
     if (w->profile) CU(cudaEventRecord(w->ev[1], w->stream));
     if (chain) rb_launch_vl_scan(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
@@ -590,7 +652,7 @@ int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     if (chain) rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (reorder_due) { int r = reorder_rows(w, true); if (r) return r; }     // rows into sort order before the lists are built for them
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
-    w->launches += (chain ? 4 : 2) + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join, chain);
+    w->launches += (chain ? 3 : 0) + (gate ? 1 : 0) + 1 /* K1 */ + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join, chain, list_hot_rows(w));
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
@@ -604,40 +666,87 @@ int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     w->vl_force = false;
     return RB_OK;
 }
+// single worlds: digest the device's latest report {hot bodies, list tick it was counted in} and adapt the rebuild period.
+// The report is up to ~32 ticks old (the host runs ahead), so it is matched with the rebuild that was current at ITS tick.
+static void list_schedule_digest(rb_world* w) {
+    const uint32_t t1 = w->vl_host[4], h = w->vl_host[3], t2 = w->vl_host[4];
+    if (t1 != t2 || t1 == w->vl_seen_tick) return;
+    w->vl_seen_tick = t1;
+    uint32_t r_at = 0; bool found = false;
+    for (int k = 0; k < 8; k++) { const uint32_t r = w->vl_rebuild_ring[k]; if (r && r <= t1 && (!found || r > r_at)) { r_at = r; found = true; } }
+    if (!found) return;
+    const uint32_t age = t1 - r_at;                     // list ticks since that rebuild (0: the rebuild tick itself)
+    if (age == 0) { w->vl_hot_floor = h; return; }      // rows that can have no list at all (crowded, oversized): a rebuild does not cure them
+    const uint32_t floor_h = std::min(w->vl_hot_floor, h);
+    const uint32_t grown = h - floor_h;
+    // hot bodies accumulate roughly linearly with the age of the lists: the period at which they would reach hot_soft
+    uint32_t est = grown ? (uint32_t)std::min<uint64_t>(64u, (uint64_t)age * w->P.hot_soft / grown) : 64u;
+    if (grown <= w->P.hot_soft && est < age) est = age;  // it got this far below the limit
+    est = std::max<uint32_t>(est, 1u);
+    w->vl_period = std::max<uint32_t>(1u, (3u * w->vl_period + est + 2u) / 4u);
+}
+// A list tick starts: does the host make it a rebuild tick? (forced by other activity since the last list tick, a row
+// re-ordering, or -- single worlds -- the schedule)
+bool rb_list_tick_begin(rb_world* w, bool reorder_due) {
+    bool force = w->vl_force || reorder_due;
+    if (w->P.soft && !force) { list_schedule_digest(w); if (w->vl_since + 1 >= w->vl_period) force = true; }
+    w->vl_tick_rebuilds = force;
+    return force;
+}
+// ... and its K1 has been enqueued
+void rb_list_tick_k1_enqueued(rb_world* w) {
+    if (w->slim) w->mt_stale = true;                     // from here on Entity::_mvp's translation is implicit (0 + p)
+    if (w->vl_tick_rebuilds) { w->vl_since = 0; w->vl_rebuild_ring[w->vl_rebuild_n++ & 7u] = w->tick_seq; }
+    else w->vl_since++;
+}
 static int enqueue_list_tick(rb_world* w, bool reorder_due) {
     RbParams& P = w->P;
-    const bool force = w->vl_force || reorder_due;
+    const bool force = rb_list_tick_begin(w, reorder_due);
     if (w->dist) { int r = rb_dist_list_exchange(w, force ? 3 : 2); if (r) return r; }      // K1 (+ pack), exchange, remove + unpack
     else {
-        if (force) { rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++; }   // other paths may have left counts behind
-        // hot cell table + hot counter + rebuild flag, and the per-step contact / changed counters, in one launch
-        rb_launch_clear(P.hot_head, ((size_t)P.hcn * P.hcn + 2) * sizeof(uint32_t), (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
+        if (w->vl_force) { rb_launch_clear(P.col_count, w->hist_clear_bytes, nullptr, 0, w->stream); w->launches++; }   // other paths may have left counts behind (list ticks leave the histogram clean)
+        rb_list_tick_params(w);
+        if (!P.soft) { rb_launch_clear(w->d_tb + 4 * (RB_TB_BLOCKS - 1), 20, nullptr, 0, w->stream); w->launches++; }
         if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
         rb_launch_integrate_bin(P, 1, force ? 3 : 2, w->stream);
     }
+    rb_list_tick_k1_enqueued(w);
     return rb_list_tick_tail(w, reorder_due);
 }
 
 // Will the next rb_step run from the persistent lists? (decided once per step)
-// The device reports {rebuild ticks, list ticks} through mapped host memory; the host only looks at it (never
-// waits for it) to notice phases in which nearly every tick rebuilds, and sits those out on the per-tick
-// kernel. Both paths give the same results, so the switch is invisible.
+// The device reports {rebuild ticks, list ticks, hot bodies} through mapped host memory; the host only looks at it (never
+// waits for it) to notice phases in which nearly every tick would rebuild (free fall: every body outruns its skin
+// within a tick or two), and sits those out on the per-tick kernel. Both paths give the same results, so the switch is
+// invisible.
 bool rb_step_will_use_lists(rb_world* w) {
     if (!w->vl_on) return false;
     if (w->vl_decided_for == w->steps + 1) return w->vl_active;
     w->vl_decided_for = w->steps + 1;
     if (w->vl_active) {
-        const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
-        if (nt - w->vl_seen_t >= 16u) {
-            const bool mostly_rebuilding = 2u * (nr - w->vl_seen_r) > (nt - w->vl_seen_t);
-            w->vl_gate_ok = 8u * (nr - w->vl_seen_r) <= (nt - w->vl_seen_t);     // device-launched rebuilds pay off while rebuilds are rare
-            w->vl_seen_r = nr; w->vl_seen_t = nt;
+        bool mostly_rebuilding = false, judged = false;
+        if (w->P.soft) {
+            // the schedule has converged on rebuilding (nearly) every tick
+            if (w->tick_seq - w->vl_judged_at >= 16u) { judged = true; w->vl_judged_at = w->tick_seq; mostly_rebuilding = w->vl_period < 3u; }
+        } else {
+            const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
+            if (nt - w->vl_seen_t >= 16u) {
+                judged = true;
+                mostly_rebuilding = 2u * (nr - w->vl_seen_r) > (nt - w->vl_seen_t);
+                w->vl_gate_ok = 8u * (nr - w->vl_seen_r) <= (nt - w->vl_seen_t);     // device-launched rebuilds pay off while rebuilds are rare
+                w->vl_seen_r = nr; w->vl_seen_t = nt;
+            }
+        }
+        if (judged) {
             if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
             else w->vl_backoff = 32;
         }
     } else if (w->steps >= w->vl_resume_at) {
         // come back once few enough bodies outrun the skin (the per-tick kernel keeps counting them)
-        if (w->vl_host[2] < w->P.hot_cap / 2u) { w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1]; }
+        if (w->vl_host[2] < w->P.hot_soft / 2u) {
+            w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1];
+            w->vl_period = 8; w->vl_judged_at = w->tick_seq;
+        }
         else w->vl_resume_at = w->steps + 16;
     }
     return w->vl_active;
@@ -683,6 +792,7 @@ int rb_integrate(rb_world* w, int ms) {
     w->vl_force = true;
     CU(cudaSetDevice(w->cfg.device));
     w->P.dt = (float)ms / 1000.0f;
+    { int r = rb_plain_tick_params(w); if (r) return r; }
     rb_launch_integrate_bin(w->P, 1, 0, w->stream); w->launches++;
     w->pose_updates++;
     CU(cudaGetLastError());
@@ -711,7 +821,10 @@ int rb_sync(rb_world* w) {
 
 static int fetch_counters(rb_world* w) {
     CU(cudaMemcpyAsync(w->h_counters, w->P.counters, RB_C_COUNT * (RB_STRIPES + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    if (w->ncontact_dev && w->ncontact_dev != w->P.counters + RB_C_NCONTACT)      // list ticks count their contacts in the tick's own counter block
+        CU(cudaMemcpyAsync(w->h_counters + RB_C_COUNT * (RB_STRIPES + 1), w->ncontact_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
+    if (w->ncontact_dev && w->ncontact_dev != w->P.counters + RB_C_NCONTACT) w->h_counters[RB_C_NCONTACT] = w->h_counters[RB_C_COUNT * (RB_STRIPES + 1)];
     for (int k = 0; k <= RB_C_OVERFLOW; k++) {          // cumulative test / hit counters live in the stripes
         unsigned long long sum = w->h_counters[k];      // base copy (halo capacity overflow is counted there)
         for (int st = 0; st < RB_STRIPES; st++) sum += w->h_counters[(size_t)(st + 1) * RB_C_COUNT + k];
@@ -772,7 +885,7 @@ int rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags) {
     if (!w || !w->built) return RB_ERR_INVALID;
     if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
     size_t nb = w->n_owned_host;
-    if (pos4) { int r = read_rows_f4(w, w->P.pos, pos4, nb); if (r) return r; }
+    if (pos4) { int r = read_rows_f4(w, w->P.pos, pos4, nb, w->P.single ? 1 : 0); if (r) return r; }
     if (vel4) { int r = read_rows_f4(w, w->P.vel, vel4, nb); if (r) return r; }
     if (flags) { int r = read_rows_u32(w, w->P.flags, flags, nb); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
@@ -781,6 +894,7 @@ int rb_get_state(rb_world* w, float* pos4, float* vel4, uint32_t* flags) {
 int rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4) {
     if (!w || !w->built) return RB_ERR_INVALID;
     if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
+    { int r = rb_ensure_mt(w); if (r) return r; }
     size_t nb = w->n_owned_host;
     if (model_t4) { int r = read_rows_f4(w, w->P.mt, model_t4, nb); if (r) return r; }
     if (prev_t4) { int r = read_rows_f4(w, w->P.pt, prev_t4, nb); if (r) return r; }
@@ -793,6 +907,7 @@ int rb_export_model_matrices(rb_world* w, const float** cur_dev, const float** p
     CU(cudaSetDevice(w->cfg.device));
     const size_t nb = w->n_owned_host;
     if (!w->d_mm_cur) { ALLOC(w->d_mm_cur, std::max<size_t>(nb, 1) * 4); ALLOC(w->d_mm_prev, std::max<size_t>(nb, 1) * 4); }
+    { int r = rb_ensure_mt(w); if (r) return r; }
     rb_launch_model_matrices(w->d_w3, w->d_inv ? w->P.gid : nullptr, w->P.mt, w->P.pt, w->d_mm_cur, w->d_mm_prev, (uint32_t)nb, w->pose_updates == 0 ? 1 : 0, w->stream); w->launches++;
     CU(cudaGetLastError());
     if (cur_dev) *cur_dev = (const float*)w->d_mm_cur;
@@ -820,6 +935,7 @@ int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     if (!w || !w->built || !xyzr4) return RB_ERR_INVALID;
     w->vl_force = true;
     // recompute from the current model translations (no integration, no binning side effects on state)
+    { int r = rb_plain_tick_params(w); if (r) return r; }
     CU(cudaMemsetAsync(w->P.col_count, 0, w->hist_clear_bytes, w->stream));
     rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
     size_t ns = w->d_dn ? w->n_owned_host : w->P.ns;
@@ -846,7 +962,8 @@ int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4,
     w->vl_force = true;
     for (const float* a : { pos4, vel4 })      // NaN / Inf are rejected like at rb_add_model (the w lane is padding)
         if (a) for (size_t i = 0; i < count; i++) if (!finite_all(a + 4 * i, 3)) return fail(w, RB_ERR_INVALID, "rb_set_state: non-finite value for body %u", first + (uint32_t)i);
-    if (pos4) { r = write_rows_f4(w, w->P.pos, first, count, pos4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
+    r = rb_ensure_mt(w); if (r) return r;       // Entity::_mvp keeps the pose of the last kinematics update, not the edited one
+    if (pos4) { r = write_rows_f4(w, w->P.pos, first, count, pos4, w->P.single ? 1 : 0); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
     if (vel4) { r = write_rows_f4(w, w->P.vel, first, count, vel4); if (r) return r; }
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
@@ -924,8 +1041,8 @@ int rb_step_host(rb_world* w, int ms, const float* force4, float* pos4, uint64_t
     int r;
     if (force4) { r = rb_set_force(w, 0, w->n_owned_host, force4); if (r) return r; }
     r = rb_step(w, ms); if (r) return r;
-    if (pos4) { r = read_rows_f4(w, w->P.pos, pos4, w->n_owned_host); if (r) return r; }
-    CU(cudaMemcpyAsync(w->h_counters + RB_C_NCONTACT, w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
+    if (pos4) { r = read_rows_f4(w, w->P.pos, pos4, w->n_owned_host, w->P.single ? 1 : 0); if (r) return r; }
+    CU(cudaMemcpyAsync(w->h_counters + RB_C_NCONTACT, w->ncontact_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaStreamSynchronize(w->stream));
     w->contacts_last = w->h_counters[RB_C_NCONTACT];
     if (n_contacts) *n_contacts = w->contacts_last;
@@ -991,13 +1108,13 @@ static int step_host_async(rb_world* w, int ms, const float* force4, float* pos4
     if (!fused_io && w->p_calls >= RB_PIPE) CU(cudaStreamWaitEvent(w->stream, w->pe_d2h[b], 0));         // output staging b was read RB_PIPE calls ago
     if (pos4 && !fused_io) {
         if (stride == 3) { rb_launch_rows_to_ids_f3(w->P.pos, w->d_inv ? w->P.gid : nullptr, (float*)w->p_pos[b], (uint32_t)nb, w->stream); w->launches++; }
-        else if (w->d_inv) { rb_launch_rows_to_ids_f4(w->P.pos, w->P.gid, w->p_pos[b], (uint32_t)nb, w->stream); w->launches++; }
+        else if (w->d_inv || w->P.single) { rb_launch_rows_to_ids_f4(w->P.pos, w->d_inv ? w->P.gid : nullptr, w->p_pos[b], (uint32_t)nb, w->P.single ? 1 : 0, w->stream); w->launches++; }
         else CU(cudaMemcpyAsync(w->p_pos[b], w->P.pos, nb * 16, cudaMemcpyDeviceToDevice, w->stream));
     }
     CU(cudaEventRecord(w->pe_step[b], w->stream));
     CU(cudaStreamWaitEvent(w->s_d2h, w->pe_step[b], 0));
     if (pos4) CU(cudaMemcpyAsync(pos4, w->p_pos[b], nb * 4 * stride, cudaMemcpyDeviceToHost, w->s_d2h));
-    CU(cudaMemcpyAsync(&w->p_cnt[b], w->P.counters + RB_C_NCONTACT, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->s_d2h));
+    CU(cudaMemcpyAsync(&w->p_cnt[b], w->ncontact_dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->s_d2h));
     CU(cudaEventRecord(w->pe_d2h[b], w->s_d2h));
     // results of the call made RB_PIPE - 1 calls ago
     if (w->p_calls >= RB_PIPE - 1) {
@@ -1036,10 +1153,10 @@ int rb_get_stats(rb_world* w, rb_stats_t* out) {
     }
     if (w->built && w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }
     if (w->built && w->vl_on) {
-        uint32_t v[RB_VL_WORDS], nh = 0;
+        uint32_t v[RB_VL_WORDS];
         CU(cudaMemcpyAsync(v, w->P.vl, sizeof v, cudaMemcpyDeviceToHost, w->stream));
-        CU(cudaMemcpyAsync(&nh, w->P.hot_head + (size_t)w->P.hcn * w->P.hcn, 4, cudaMemcpyDeviceToHost, w->stream));
         CU(cudaStreamSynchronize(w->stream));
+        const uint32_t nh = v[RB_VL_NHOT_LAST];
         out->list_rebuilds = v[RB_VL_NREBUILD]; out->list_ticks = v[RB_VL_NTICK]; out->list_skin = w->P.vl_skin;
         out->list_hot_last = nh; out->list_rebuild_reason = v[RB_VL_WHY_LAST];
         for (int b = 0; b < 4; b++) out->list_rebuilds_by_reason[b] = v[RB_VL_NWHY + b];
