@@ -484,7 +484,7 @@ def run_ours(args):
             "free_fall": {"ms_per_step": ff_ms, "steps_per_s": N * 1000.0 / ff_ms, "contact_tests_per_step": ff_tests},
             "audit": {"contacts_dropped": final["contacts_dropped"], "margin_overflow": final["margin_overflow"],
                       "halo_sent_last": final["halo_sent_last"], "halo_recv_last": final["halo_recv_last"], "device_bytes": final["device_bytes"],
-                      "list_ticks": final["list_ticks"], "list_rebuilds": final["list_rebuilds"], "list_hot_last": final["list_hot_last"], "list_skin": final["list_skin"],
+                      "list_ticks": final["list_ticks"], "list_rebuilds": final["list_rebuilds"], "timed_list_rebuilds": st1["list_rebuilds"] - st0["list_rebuilds"], "list_hot_last": final["list_hot_last"], "list_skin": final["list_skin"],
                       "list_rebuilds_by_reason": dict(zip(("grid_or_emigrant", "hot_table_full", "host", "immigrant"), final["list_rebuilds_by_reason"]))},
         }
         if c5 is not None:

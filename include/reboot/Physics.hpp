@@ -133,6 +133,15 @@ public:
 
 class Physics;
 
+// MVP (math/include/MVP.h): only the model matrix is on the physics path
+class MVP {
+    Matrix _model;
+public:
+    Matrix getModelMatrix() const { return _model; }
+    float* getModelBuffer() { return _model.getFlatBuffer(); }
+    void setModel(Matrix m) { _model = m; }
+};
+
 // Host-side mirror of one body's StateVector. Setters before Physics::addEntities define the initial
 // state; afterwards they are forwarded to the device (same gating as StateVector.cpp:147-167 for
 // setForce/setTorque, applied on the device). Getters return the last Physics::syncState() snapshot.
@@ -161,6 +170,7 @@ class Entity {
     friend class Physics;
     Model* _model; Matrix _worldSpaceTransform; StateVector _state;
     Vector4 _modelTranslation, _prevModelTranslation;
+    MVP _mvp, _prevMVP;     // model matrices at the last syncState()
     uint32_t _id = 0;       // geom id (Triangle type) or body id (Sphere type) once added
 public:
     explicit Entity(Model* model, Matrix worldSpaceTransform = Matrix()) : _model(model), _worldSpaceTransform(worldSpaceTransform) {}
@@ -172,6 +182,15 @@ public:
     Vector4 getModelTranslation() const { return _modelTranslation; }
     Vector4 getPrevModelTranslation() const { return _prevModelTranslation; }
     void setVelocity(Vector4 v) { _state.setLinearVelocity(v); }
+    // Entity::setPosition -- model/include/Entity.h:50, model/src/Entity.cpp:373-391: total = translation(p) * W; the linear
+    // position becomes total's translation (Q1), _prevMVP takes the current model matrix, _mvp becomes total. On the device
+    // once the entity has been added (the mirrors here follow at the next syncState()); before that it only sets the
+    // initial position.
+    inline void setPosition(Vector4 position);
+    // Entity::getMVP / getPrevMVP -- model/include/Entity.h:66-68: the model matrices translation(p) * W as of the last
+    // Physics::syncState()
+    MVP* getMVP() { return &_mvp; }
+    MVP* getPrevMVP() { return &_prevMVP; }
 };
 
 // (geometry entity, triangle index) pairs per sphere entity: the reference's
@@ -179,7 +198,7 @@ public:
 using ModelIntersections = std::map<Entity*, std::set<std::pair<Entity*, uint32_t>>>;
 
 class Physics {
-    friend class StateVector;
+    friend class StateVector; friend class Entity;
     rb_world* _w = nullptr;
     std::vector<Entity*> _entities, _bodies, _geoms;
     ModelIntersections _triangleIntersectionList;
@@ -221,6 +240,26 @@ public:
         ck(_w, rb_build(_w));
         _built = true;
     }
+    // Physics::addEntity -- physics/include/Physics.h:49, physics/src/Physics.cpp:47-49: one more entity after addEntities.
+    // A Sphere-type entity takes part from the next tick on (rb_add_model after rb_build: the world is re-laid out, O(world)).
+    // A Triangle-type entity is kept in the list but never collides: the reference only ever builds triangles into the tree in
+    // addEntities -- same here.
+    void addEntity(Entity* e) {
+        Guard g(_lock);
+        if (!_built) throw std::runtime_error("reboot_b200: Physics::addEntity before addEntities");
+        _entities.push_back(e);
+        if (e->getModel()->getGeometryType() == GeometryType::Triangle) return;
+        std::vector<float> obj;
+        for (const Sphere& s : *e->getGeometry()->getSpheres()) { Vector4 p = s.getObjectPosition(); obj.push_back(p.getx()); obj.push_back(p.gety()); obj.push_back(p.getz()); obj.push_back(s.getObjectRadius()); }
+        rb_body_init init; StateVector& st = e->_state;
+        init.pos[0] = st._linearPosition.getx(); init.pos[1] = st._linearPosition.gety(); init.pos[2] = st._linearPosition.getz();
+        init.vel[0] = st._linearVelocity.getx(); init.vel[1] = st._linearVelocity.gety(); init.vel[2] = st._linearVelocity.getz();
+        init.flags = (st._active ? (uint32_t)RB_ACTIVE : 0u) | (st._gravity ? (uint32_t)RB_GRAVITY : 0u);
+        ck(_w, rb_sync(_w));
+        ck(_w, rb_add_model(_w, (uint32_t)(obj.size() / 4), obj.data(), e->_worldSpaceTransform.data(), &init, &e->_id));
+        st._owner = this; st._body = e->_id;
+        _bodies.push_back(e);
+    }
     // Physics::run -- physics/src/Physics.cpp:18-24: subscribe the step to the 5 ms kinematics tick of a
     // MasterClock (NULL: the caller drives tick() itself). One subscription replaces every Entity's
     // _updateKinematics subscription plus _physicsProcess.
@@ -231,14 +270,16 @@ public:
     void syncState() {
         Guard g(_lock);
         size_t n = _bodies.size(); if (!n) return;
-        std::vector<float> p(n * 4), v(n * 4), m(n * 4), pm(n * 4); std::vector<uint32_t> f(n);
+        std::vector<float> p(n * 4), v(n * 4), m(n * 4), pm(n * 4), mm(n * 16), pmm(n * 16); std::vector<uint32_t> f(n);
         ck(_w, rb_get_state(_w, p.data(), v.data(), f.data()));
         ck(_w, rb_get_model_translations(_w, m.data(), pm.data()));
+        ck(_w, rb_get_model_matrices(_w, mm.data(), pmm.data()));
         for (size_t i = 0; i < n; i++) {
             Entity* e = _bodies[i]; StateVector& s = e->_state;
             s._linearPosition = Vector4(p[4 * i], p[4 * i + 1], p[4 * i + 2]); s._linearVelocity = Vector4(v[4 * i], v[4 * i + 1], v[4 * i + 2]);
             s._active = f[i] & RB_ACTIVE; s._gravity = f[i] & RB_GRAVITY; s._contact = f[i] & RB_CONTACT;
             e->_modelTranslation = Vector4(m[4 * i], m[4 * i + 1], m[4 * i + 2]); e->_prevModelTranslation = Vector4(pm[4 * i], pm[4 * i + 1], pm[4 * i + 2]);
+            for (int k = 0; k < 16; k++) { e->_mvp.getModelBuffer()[k] = mm[16 * i + k]; e->_prevMVP.getModelBuffer()[k] = pmm[16 * i + k]; }
         }
     }
     // Physics::visualize -- physics/src/Physics.cpp:51-79: hands the triangles in contact per entity to a
@@ -291,6 +332,13 @@ inline void buildGeometryData(Model* model, const std::vector<float>& xyz3, cons
     }
 }
 
+inline void Entity::setPosition(Vector4 position) {
+    Physics* owner = _state._owner;
+    if (!owner || !owner->_built) { _state._linearPosition = position; return; }
+    std::lock_guard<std::recursive_mutex> g(owner->_lock);
+    const float p[3] = {position.getx(), position.gety(), position.getz()};
+    Physics::ck(owner->_w, rb_entity_set_position(owner->_w, _state._body, p));
+}
 inline void StateVector::push_pos() {
     if (!_owner || !_owner->_built) return;
     std::lock_guard<std::recursive_mutex> g(_owner->_lock);

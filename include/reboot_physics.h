@@ -125,7 +125,13 @@ int         rb_add_static_geometry(rb_world* w, uint32_t ntri, const float* xyz9
 
 /* add-model: a Sphere-type entity. Geometry::addSphere (physics/src/Geometry.cpp:15-17) for each
  * object-space sphere (x,y,z,r) + Entity ctor (model/src/Entity.cpp:24,45): world_xform16 is the
- * row-major _worldSpaceTransform (NULL = identity; last row must be 0 0 0 1). */
+ * row-major _worldSpaceTransform (NULL = identity; last row must be 0 0 0 1).
+ * After rb_build this is Physics::addEntity (physics/include/Physics.h:49, physics/src/Physics.cpp:47-49): the body
+ * takes the next id and joins the simulation with the next tick, like an entity the reference appends to its list
+ * (physics/src/OSP.cpp:182-210 inserts it at the next update). Every device structure is laid out at build time, so a
+ * post-build add re-lays the world out -- O(world) per call; add batches with rb_add_models. Ids, state (bit for bit),
+ * forces and contacts flags of the existing bodies are kept; pending rb_step_host_async results are not (rb_sync first).
+ * Single-GPU worlds only. Triangles cannot be added after the build (the reference never inserts them either, Q9). */
 int         rb_add_model(rb_world* w, uint32_t nspheres, const float* obj_center_radius4,
                          const float* world_xform16, const rb_body_init* init, uint32_t* body_id);
 
@@ -184,6 +190,11 @@ int         rb_get_world_spheres(rb_world* w, float* xyzr4);
  * starting at `first`; pos4/vel4 are count*4 floats, either may be NULL. Like the reference these
  * do not touch the model matrices until the next step. */
 int         rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4, const float* vel4);
+/* Entity::setPosition (model/include/Entity.h:50, model/src/Entity.cpp:373-391) for one body, e.g. a teleport by game
+ * logic: total = translation(pos) * W; the linear position becomes total's translation (W.t + pos: with a translated W the
+ * offset is added again, like the reference), _prevMVP takes the current model matrix and _mvp becomes total. The spheres
+ * follow at the next tick. Asynchronous on the world's stream. Not available on slab (multi-GPU) worlds. */
+int         rb_entity_set_position(rb_world* w, uint32_t body, const float* pos3);
 /* StateVector::setActive / setGravity / setContact (StateVector.cpp:117-120, 169-177): for each of
  * `count` bodies starting at `first`, flags = (flags & ~mask) | (values[i] & mask). */
 int         rb_set_flags(rb_world* w, uint32_t first, uint32_t count, const uint32_t* values, uint32_t mask);

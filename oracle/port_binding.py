@@ -58,6 +58,7 @@ def lib():
         L.orc_get_angular.argtypes = [C.c_void_p, _f32p, _f32p]
         L.orc_set_state.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_flags.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_entity_set_position.argtypes = [C.c_void_p, C.c_int, _f32p]
         L.orc_set_force.argtypes = [C.c_void_p, C.c_int, _f32p]
         L.orc_set_torque.argtypes = [C.c_void_p, C.c_int, _f32p]
         L.orc_get_world_spheres.argtypes = [C.c_void_p, C.c_int, _f32p]
@@ -117,6 +118,20 @@ class OrcWorld:
 
     def build(self, octree=True):
         self.L.orc_build(self.h, 1 if octree else 0)
+
+    def add_body_late(self, obj_spheres, pos, vel=(0, 0, 0), active=1, gravity=1, scale=1.0) -> int:
+        """Physics::addEntity (physics/src/Physics.cpp:47-49): appended to the entity list after the build; it is
+        integrated and collides from the next tick on. Only meaningful without the octree (canonical all-pairs order)."""
+        sp = np.ascontiguousarray(obj_spheres, dtype=np.float32).reshape(-1, 4)
+        W = scale_matrix(scale)
+        self.L.orc_add_body(self.h, sp.shape[0], sp, W.ctypes.data_as(C.c_void_p), np.ascontiguousarray(pos, dtype=np.float32),
+                            np.ascontiguousarray(vel, dtype=np.float32), int(active), int(gravity))
+        self.n_bodies += 1
+        return self.n_bodies - 1
+
+    def entity_set_position(self, body, pos):
+        """Entity::setPosition (model/src/Entity.cpp:373-391)"""
+        self.L.orc_entity_set_position(self.h, int(body), np.ascontiguousarray(pos, dtype=np.float32))
 
     def step(self, ms=5, order=ORDER_REFERENCE):
         self.L.orc_step(self.h, ms, order)

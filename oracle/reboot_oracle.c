@@ -711,6 +711,10 @@ void orc_set_state(orc_world* w, int b, const float* pos3, const float* vel3) {
     if (pos3) e->st.lin_pos = v3_make(pos3[0], pos3[1], pos3[2]);
     if (vel3) e->st.lin_vel = v3_make(vel3[0], vel3[1], vel3[2]);
 }
+/* Entity::setPosition from the host -- Entity.cpp:373-391 */
+void orc_entity_set_position(orc_world* w, int b, const float* pos3) {
+    entity_set_position(&w->ent[w->n_geoms + b], v3_make(pos3[0], pos3[1], pos3[2]));
+}
 void orc_set_flags(orc_world* w, int b, int active, int gravity, int contact) {
     entity_t* e = &w->ent[w->n_geoms + b];
     if (active >= 0) e->st.flags = (e->st.flags & ~F_ACTIVE) | (active ? F_ACTIVE : 0);

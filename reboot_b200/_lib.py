@@ -74,6 +74,7 @@ SIGNATURES = {
     "rb_get_angular": (C.c_int, [_P, _P, _P]),
     "rb_get_world_spheres": (C.c_int, [_P, _P]),
     "rb_set_state": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
+    "rb_entity_set_position": (C.c_int, [_P, C.c_uint32, _P]),
     "rb_set_flags": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint32]),
     "rb_set_force": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),
     "rb_set_torque": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P]),

@@ -27,6 +27,10 @@
 #define RB_VL_NREBUILD 2  // rebuild ticks so far
 #define RB_VL_NTICK   3   // list ticks so far
 #define RB_VL_NHOT_LAST 7  // hot bodies of the most recent list tick
+#define RB_VL_AGE     12  // list ticks since the lists were built (0 on the rebuild tick)
+#define RB_VL_EXPIRY  13  // the age at which more than hot_soft bodies were hot for the first time (0: not yet) -- the lists' useful life
+#define RB_VL_GEN     14  // list generations so far (rebuild ticks of list ticks)
+#define RB_VL_FLOOR   15  // hot bodies on the rebuild tick itself: rows that can have no list (crowded, oversized) -- a rebuild does not cure them
 
 // device contact record, 32 B (two 16-B stores)
 struct __align__(16) RbContactRec {

@@ -24,6 +24,7 @@ void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* st
 void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows);
 uint32_t rb_list_tile_bytes();
+void rb_launch_entity_set_position(float4* pos, float4* mt, float4* pt, const float4* wt, const uint32_t* inv, uint32_t body, const float* xyz, cudaStream_t st);
 void rb_launch_mt_refresh(const float4* pos, const float4* wt, float4* mt, uint32_t n, cudaStream_t st);
 bool rb_have_device_launch();
 void rb_launch_vl_gate(const RbParams& P, cudaStream_t st);
@@ -67,6 +68,7 @@ struct DevBuf { void* p = nullptr; size_t bytes = 0; };
 
 struct rb_world {
     rb_config cfg;
+    rb_config cfg_user;                       // as given to rb_world_create (rb_build fills in the automatic values of cfg)
     std::string err;
     bool built = false;
     cudaStream_t stream = nullptr;
@@ -81,6 +83,7 @@ struct rb_world {
     std::vector<uint32_t> h_flags;
     std::vector<uint32_t> h_sph_body;
     bool any_wt = false;
+    std::vector<uint8_t> h_presummed;         // per body: its spheres are already W3x3 * centre, W[0] * radius (bodies carried over by a post-build add)
     // ---- device ----
     RbParams P;
     std::vector<DevBuf> allocs;
@@ -107,7 +110,7 @@ struct rb_world {
     bool vl_gate_ok = true;                  // recent rebuild rate is low enough for the device-launched chain (else the host enqueues it)
     bool vl_cdp = false;                     // K1 launches the rebuild chain from the device (library built with -rdc=true)
     int vl_hot_cfg = 0;                      // capacity of the hot-body table, 0 = auto (bodies / 128)
-    uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks, fast movers, hot bodies, tick of that count, ...}
+    uint32_t* vl_host = nullptr;             // mapped pinned {rebuilds, ticks, fast movers, hot bodies, tick of the report, expiry age, generation, age, previous generation: ticks served, its expiry}
     uint32_t* d_tb = nullptr;                // RB_TB_BLOCKS counter blocks, the list words (P.vl) right behind them
     unsigned long long* ncontact_dev = nullptr;   // where the contact count of the last step / detect lives
     uint32_t tick_seq = 0;                   // list ticks enqueued so far (version of the hot table entries)
@@ -115,8 +118,8 @@ struct rb_world {
     bool mt_stale = false;                   // ... and the mt array has not been refreshed since
     uint32_t vl_period = 16, vl_since = 0;   // single worlds: the host schedules the list rebuilds (every vl_period list ticks, adapted to the hot counts it sees)
     uint32_t vl_seen_tick = 0;               // last device report (tick number) the schedule has digested
-    uint32_t vl_rebuild_ring[8] = {}; uint32_t vl_rebuild_n = 0;   // list tick numbers of the last rebuilds enqueued (reports are matched with theirs)
-    uint32_t vl_hot_floor = 0;               // hot bodies on a rebuild tick itself: rows that can have no list
+    uint32_t vl_gen_expired = 0xffffffffu;   // the list generation whose expiry the schedule has acted on
+    uint32_t vl_gen_seen = 0xffffffffu;      // the generation of the last report digested
     uint32_t vl_judged_at = 0;               // list tick at which the lists-pay-off decision was last taken
     bool vl_tick_rebuilds = false;           // this list tick rebuilds at the host's request
     unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step

@@ -1300,12 +1300,25 @@ __device__ __forceinline__ void append_contact(const RbParams& P, uint32_t a, ui
 #ifndef RB_LIST_MINBLOCKS
 #define RB_LIST_MINBLOCKS 4
 #endif
+// dynamic shared memory of the list step: the tile (vertex records + ids), then one owner word per tile entry and the work
+// list of the later test rounds
+#define RB_LS_TILE_BYTES ((3u * RB_TILE_CAP + RB_TILE_CAP / 4u) * 16u)
+#define RB_LS_SMEM_BYTES (RB_LS_TILE_BYTES + 2u * RB_TILE_CAP * 2u)
 __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kernel(const RbParams P) {
     extern __shared__ __align__(16) uint4 s_tile[];
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ uint32_t s_mask[RB_BLOCK];
+    __shared__ __align__(16) float4 s_pose[RB_BLOCK];      // current sphere of each row of the block (w < 0: the row does not step here)
+    __shared__ uint32_t s_mask[RB_BLOCK];                  // hits of the round, one bit per entry of the row's list
+    __shared__ uint32_t s_nwork[2];
+    uint16_t* s_own = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_tile) + RB_LS_TILE_BYTES);      // per tile entry: owner thread | index in its list << 8
+    uint16_t* s_work = s_own + RB_TILE_CAP;                // tile entries still to be tested (rounds after the first)
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_owned = rb_n_owned(P);
+    const uint32_t A = tid;
+    uint32_t keyA = RB_NONE, hdr = 0, fl = 0;
+    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = p4;
+    if (tid < n_owned) { keyA = P.key[tid]; hdr = P.e_hdr[tid]; fl = P.flags[tid]; p4 = P.pos[tid]; v4 = P.vel[tid]; }     // all in flight together
     // ---- the block's triangle tile: one bulk copy, in flight while the partners are dealt with ----
     const uint2 bt = P.blk_tile[blockIdx.x];
     const uint32_t tile_n = bt.y;
@@ -1316,13 +1329,10 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
             mbar_expect_tx(&s_bar, bytes);
             bulk_g2s(s_tile, P.tile_pool + bt.x, bytes, &s_bar);
         }
+        s_nwork[0] = 0u; s_nwork[1] = 0u;
     }
+    __syncthreads();        // the barrier word is initialised before anybody polls it (here, where the warps of the block still run together)
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
-    const uint32_t n_owned = rb_n_owned(P);
-    const uint32_t A = tid;
-    uint32_t keyA = RB_NONE, hdr = 0, fl = 0;
-    float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = p4;
-    if (tid < n_owned) { keyA = P.key[tid]; hdr = P.e_hdr[tid]; fl = P.flags[tid]; p4 = P.pos[tid]; v4 = P.vel[tid]; }     // all in flight together
     // rows outside the broadphase have nothing to do; hot rows step in their own launch (rb_collide_single_kernel<3>)
     const bool valid = keyA != RB_NONE && !(keyA & RB_HOT_BIT);
     const bool had_contact = valid && (fl & RB_F_CONTACT) != 0;
@@ -1450,60 +1460,57 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
         for (uint32_t i = 0; i < min(H.n, (uint32_t)RB_MAXLOCAL); ++i) append_contact(P, H.a[i], H.b[i], H.depth[i], mk3(H.nx[i], H.ny[i], H.nz[i]), H.r[i]);
     }
 
-    // ---------------- sphere-triangle: pooled exact tests out of the staged tile ----------------
-    __syncthreads();                        // the barrier word is initialised (thread 0) before anybody polls it
+    // ---------------- sphere-triangle: exact tests out of the staged tile, pooled over the BLOCK ----------------
+    // Speculative rounds (see rb_collide_single_kernel P4): until a sphere is hit its pose does not change, so all of its
+    // remaining triangles can be tested at once. Round 1 tests every entry of the tile, one entry per thread whoever owns
+    // it (the owner's sphere comes from shared memory); each owner then takes its FIRST hit in canonical order, resolves it
+    // and queues the entries behind that hit for the next round -- exactly the sequential test / resolve sequence, with
+    // full warps in every round.
+    const uint32_t nc_list = tid < n_owned ? ((hdr >> 8) & 0xffu) : 0u;      // (a row that is hot this tick still has its slice of the tile)
+    for (uint32_t j = 0; j < nc_list; ++j) s_own[toff + j] = (uint16_t)(threadIdx.x | (j << 8));
+    {
+        const f3 c0 = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
+        s_pose[threadIdx.x] = make_float4(c0.x, c0.y, c0.z, valid ? oa.w : -1.0f);
+    }
+    s_mask[threadIdx.x] = 0u;
     if (tile_n) mbar_wait(&s_bar, 0);
+    __syncthreads();
     const uint32_t* tile_ids = reinterpret_cast<const uint32_t*>(s_tile + 3u * tile_n);
     bool hit_any = false;
     {
-        // Speculative, load-balanced rounds (see rb_collide_single_kernel P4): every round pools the remaining tests of the
-        // warp and deals them out 32 at a time; each owner then takes its FIRST hit in canonical order, resolves it, and
-        // re-enters the next round with the triangles behind that hit.
-        uint32_t j0 = 0;
+        uint32_t j0 = 0, nwork = tile_n, round = 0;
         while (true) {
-            const uint32_t rem = j0 < nc ? nc - j0 : 0;
-            if (!__any_sync(0xffffffffu, rem != 0)) break;
-            const uint32_t incl = warp_incl_scan(rem, lane);
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            const f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
-            s_mask[threadIdx.x] = 0;
-            __syncwarp();
-            const uint32_t wbase = threadIdx.x & ~31u;
-            const uint32_t first_ent = toff + j0;                                // this lane's first remaining tile entry
-            for (uint32_t base = 0; base < total; base += 32) {
-                const uint32_t item = base + lane;
-                uint32_t lo = 0;                                   // owner = number of lanes whose inclusive count is <= item
-#pragma unroll
-                for (int st = 16; st >= 1; st >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, incl, (lo + st - 1) & 31); if (v <= item) lo += st; }
-                const uint32_t owner = lo & 31;
-                const uint32_t o_excl = __shfl_sync(0xffffffffu, incl - rem, owner), o_ent = __shfl_sync(0xffffffffu, first_ent, owner);
-                const float ox = __shfl_sync(0xffffffffu, c.x, owner), oy = __shfl_sync(0xffffffffu, c.y, owner), oz = __shfl_sync(0xffffffffu, c.z, owner);
-                const float orad = __shfl_sync(0xffffffffu, oa.w, owner);
-                if (item < total) {
-                    const uint32_t k = item - o_excl;
-                    const uint4* tp = s_tile + 3u * (o_ent + k);
+            for (uint32_t i = threadIdx.x; i < nwork; i += RB_BLOCK) {
+                const uint32_t e = round ? (uint32_t)s_work[i] : i;
+                const uint32_t ok = s_own[e];
+                const float4 ps = s_pose[ok & 0xffu];
+                if (ps.w >= 0.f) {
+                    const uint4* tp = s_tile + 3u * e;
                     const uint4 a4 = tp[0], b4 = tp[1], c4 = tp[2];
-                    if (sphere_triangle_detect(mk3(ox, oy, oz), orad,
+                    if (sphere_triangle_detect(mk3(ps.x, ps.y, ps.z), ps.w,
                                                mk3(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z)),
                                                mk3(__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z)),
                                                mk3(__uint_as_float(c4.x), __uint_as_float(c4.y), __uint_as_float(c4.z))))
-                        atomicOr(&s_mask[wbase + owner], 1u << k);
+                        atomicOr(&s_mask[ok & 0xffu], 1u << (ok >> 8));
                 }
-                __syncwarp();
             }
-            __syncwarp();
-            const uint32_t m = s_mask[threadIdx.x];
+            __syncthreads();
+            if (threadIdx.x == 0) s_nwork[(round + 1u) & 1u] = 0u;      // the counter of the round after next (its last value has been read by everybody)
+            const uint32_t rem = j0 < nc ? nc - j0 : 0u;
             if (rem) {
+                const uint32_t m = s_mask[threadIdx.x];                 // bit k: entry k of this row's list tested positive (only entries >= j0 were tested)
+                s_mask[threadIdx.x] = 0u;
                 // sequential accounting: the tests up to and including the first hit are the ones the one-at-a-time order runs
-                const uint32_t first = m ? (uint32_t)__ffs(m) - 1 : rem;
-                T.tests_st += m ? first + 1 : rem;
+                const uint32_t first = m ? (uint32_t)__ffs(m) - 1u : nc;
+                T.tests_st += m ? first - j0 + 1u : rem;
                 if (m) {
-                    const uint32_t ent = first_ent + first;
+                    const uint32_t ent = toff + first;
                     const uint4* tp = s_tile + 3u * ent;
                     const uint4 a4 = tp[0], b4 = tp[1], c4 = tp[2];
                     const f3 TA = mk3(__uint_as_float(a4.x), __uint_as_float(a4.y), __uint_as_float(a4.z));
                     const f3 TB = mk3(__uint_as_float(b4.x), __uint_as_float(b4.y), __uint_as_float(b4.z));
                     const f3 TC = mk3(__uint_as_float(c4.x), __uint_as_float(c4.y), __uint_as_float(c4.z));
+                    const f3 c = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
                     hit_any = true;
                     T.hits_st++;
                     const f3 q = closest_point(c, TA, TB, TC);
@@ -1520,10 +1527,19 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
                     body_set_position(S, add3(S.p, delta));
                     S.v = rv;
                     S.flags |= RB_F_CONTACT;
-                    j0 += first + 1;
+                    j0 = first + 1u;
+                    if (j0 < nc) {      // the triangles behind the hit are tested again, at the new pose
+                        const f3 c1 = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+                        s_pose[threadIdx.x] = make_float4(c1.x, c1.y, c1.z, oa.w);
+                        const uint32_t w0 = atomicAdd(&s_nwork[round & 1u], nc - j0);
+                        for (uint32_t k = j0; k < nc; ++k) s_work[w0 + k - j0] = (uint16_t)(toff + k);
+                    }
                 } else j0 = nc;
             }
-            __syncwarp();
+            __syncthreads();
+            nwork = s_nwork[round & 1u];
+            if (!nwork) break;
+            ++round;
         }
     }
     // ---------------- flags, write-back ----------------
@@ -1547,15 +1563,19 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
         po[0] = S.p.x; po[1] = S.p.y; po[2] = S.p.z;
         if (P.pos_out_stride == 4) po[3] = 1.0f;
     }
-    {   // cumulative counters: warp reduce, one atomic per warp and non-zero counter on a striped copy
-        uint32_t vals[7] = { T.tests_ss, T.tests_st, T.cand_ss, T.cand_st, T.hits_ss, T.hits_st, T.overflow };
-        const int map[7] = { RB_C_TESTS_SS, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST, RB_C_OVERFLOW };
+    {   // cumulative counters: two per word (a lane's count stays far below 2^16 / 32), warp reduce, one atomic per warp and
+        // non-zero counter on a striped copy
+        const uint32_t packed[3] = { T.tests_st | (T.hits_st << 16), T.tests_ss | (T.hits_ss << 16), T.cand_ss | (T.overflow << 16) };
+        const int map[3][2] = { { RB_C_TESTS_ST, RB_C_HITS_ST }, { RB_C_TESTS_SS, RB_C_HITS_SS }, { RB_C_CAND_SS, RB_C_OVERFLOW } };
         const uint32_t stripe = ((blockIdx.x * (blockDim.x >> 5)) + (threadIdx.x >> 5)) & (RB_STRIPES - 1);
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            if (!__any_sync(0xffffffffu, vals[k] != 0u)) continue;
-            const uint32_t sum = __reduce_add_sync(0xffffffffu, vals[k]);
-            if (lane == 0) atomicAdd(&P.stripes[stripe * RB_C_COUNT + map[k]], (unsigned long long)sum);
+        for (int k = 0; k < 3; ++k) {
+            if (!__any_sync(0xffffffffu, packed[k] != 0u)) continue;
+            const uint32_t sum = __reduce_add_sync(0xffffffffu, packed[k]);
+            if (lane == 0) {
+                if (sum & 0xffffu) atomicAdd(&P.stripes[stripe * RB_C_COUNT + map[k][0]], (unsigned long long)(sum & 0xffffu));
+                if (sum >> 16) atomicAdd(&P.stripes[stripe * RB_C_COUNT + map[k][1]], (unsigned long long)(sum >> 16));
+            }
         }
     }
     if (tid == 0) {        // end of a persistent-list tick: book-keeping (the hot counter is final: K1 and the enumeration are done)
@@ -1566,11 +1586,26 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
 #pragma unroll
             for (int b = 0; b < 4; ++b) if (why & (1u << b)) P.vl[RB_VL_NWHY + b]++;      // rebuilds by reason (several may apply)
         }
-        P.vl[RB_VL_STORM] = f;                       // the next rebuild, if it comes right away, skips the list pruning
+        P.vl[RB_VL_STORM] = f;
         const uint32_t nr = P.vl[RB_VL_NREBUILD] + (f ? 1u : 0u), nt = P.vl[RB_VL_NTICK] + 1u;
         P.vl[RB_VL_NREBUILD] = nr; P.vl[RB_VL_NTICK] = nt;
-        P.vl[RB_VL_NHOT_LAST] = *P.nhot;
-        if (P.vl_host) { P.vl_host[0] = nr; P.vl_host[1] = nt; P.vl_host[3] = *P.nhot; P.vl_host[4] = nt; }
+        const uint32_t nh = *P.nhot;
+        P.vl[RB_VL_NHOT_LAST] = nh;
+        // the useful life of this generation of lists: the first age at which more bodies step without their list than a
+        // rebuild is worth (the host schedules the rebuilds of single worlds from it)
+        const uint32_t age = f ? 0u : P.vl[RB_VL_AGE] + 1u;
+        uint32_t gen = P.vl[RB_VL_GEN], expiry = P.vl[RB_VL_EXPIRY];
+        if (f) {
+            if (P.vl_host) { P.vl_host[8] = P.vl[RB_VL_AGE]; P.vl_host[9] = expiry; }      // how the previous generation ended: ticks served, expired or not
+            gen++; expiry = 0u; P.vl[RB_VL_FLOOR] = nh;
+        }
+        else if (!expiry && nh > P.vl[RB_VL_FLOOR] + P.hot_soft) expiry = age;
+        P.vl[RB_VL_AGE] = age; P.vl[RB_VL_GEN] = gen; P.vl[RB_VL_EXPIRY] = expiry;
+        if (P.vl_host) {
+            P.vl_host[0] = nr; P.vl_host[1] = nt; P.vl_host[3] = nh;
+            P.vl_host[5] = expiry; P.vl_host[6] = gen; P.vl_host[7] = age;
+            P.vl_host[4] = nt;        // (last: the host takes a report whose tick word it reads unchanged before and after)
+        }
     }
 }
 
@@ -1669,6 +1704,18 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_ids_to_rows_f4_kernel(const float
     float4 v = in[i];
     if (keep_w) v.w = rows[row].w;
     rows[row] = v;
+}
+// Entity::setPosition (model/src/Entity.cpp:373-391) for one body: total = translation(p) * W has the translation W.t + p;
+// linear position := that translation (Q1: W.t is added again), _prevMVP := _mvp, _mvp := total. The spheres follow at the
+// next kinematics update, like _worldSpaceGeometry (their transform is recomputed from the model translation every tick).
+__global__ void rb_entity_set_position_kernel(float4* pos, float4* mt, float4* pt, const float4* wt, const uint32_t* inv, uint32_t body, float x, float y, float z) {
+    if (threadIdx.x || blockIdx.x) return;
+    const uint32_t row = inv ? inv[body] : body;
+    const float4 w = wt ? wt[row] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float tx = w.x + x, ty = w.y + y, tz = w.z + z;
+    pos[row] = make_float4(tx, ty, tz, pos[row].w);
+    pt[row] = mt[row];
+    mt[row] = make_float4(tx, ty, tz, 0.f);
 }
 // Entity::_mvp's translation for worlds that keep it implicit on list ticks (W.t = 0): after any complete tick it is
 // 0 + p -- K1 leaves translation(p) * W, a resolution leaves p = mt = the same sum (rb_collide_single_kernel P5)
@@ -1804,14 +1851,25 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 }
 // The hot bodies' launch is small and latency-bound (a few warps walking dependent loads): it runs on a side
 // stream next to the big list kernel. Both only write the bodies they own and read frozen data of the others.
-uint32_t rb_list_tile_bytes() { return (3u * RB_TILE_CAP + RB_TILE_CAP / 4u) * 16u; }
+uint32_t rb_list_tile_bytes() { return RB_LS_SMEM_BYTES; }
 int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows) {
     if (!P.nb) return 0;
     const uint32_t g = cdiv(P.ns, RB_BLOCK);
     if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
+    static const int side_mode = [] { const char* v = getenv("RB_HOT_SIDE"); return v && *v ? atoi(v) : 1; }();      // (development switch)
+    if (side_mode == 0) {       // everything on one stream: hot bodies first
+        rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
+        rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);
+        return 3;
+    }
+    if (side_mode == 2) {       // one stream, hot bodies last
+        rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);
+        rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
+        return 3;
+    }
     cudaEventRecord(fork, st);
     cudaStreamWaitEvent(side, fork, 0);
-    rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies: one thread per entry of the table
+    rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies: the blocks stride over the table (a block without work returns at once)
     cudaEventRecord(join, side);
     rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);                         // everybody else, from the lists
     cudaStreamWaitEvent(st, join, 0);
@@ -1862,6 +1920,9 @@ void rb_launch_rows_to_ids_u32(const uint32_t* rows, const uint32_t* gid, uint32
 }
 void rb_launch_ids_to_rows_f4(const float4* in, const uint32_t* inv, float4* rows, uint32_t first, uint32_t count, int keep_w, cudaStream_t st) {
     if (count) rb_ids_to_rows_f4_kernel<<<cdiv(count, RB_BLOCK), RB_BLOCK, 0, st>>>(in, inv, rows, first, count, keep_w);
+}
+void rb_launch_entity_set_position(float4* pos, float4* mt, float4* pt, const float4* wt, const uint32_t* inv, uint32_t body, const float* xyz, cudaStream_t st) {
+    rb_entity_set_position_kernel<<<1, 32, 0, st>>>(pos, mt, pt, wt, inv, body, xyz[0], xyz[1], xyz[2]);
 }
 void rb_launch_mt_refresh(const float4* pos, const float4*, float4* mt, uint32_t n, cudaStream_t st) {
     if (n) rb_mt_refresh_kernel<<<cdiv(n, RB_BLOCK), RB_BLOCK, 0, st>>>(pos, mt, n);

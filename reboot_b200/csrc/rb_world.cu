@@ -42,7 +42,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     e = cudaSetDevice(c.device);
     if (e != cudaSuccess) return fail(nullptr, RB_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     rb_world* w = new rb_world();
-    w->cfg = c;
+    w->cfg = c; w->cfg_user = c;
     memset(&w->P, 0, sizeof w->P);
     memset(&w->dist_stats, 0, sizeof w->dist_stats);
     if (c.stream) w->stream = (cudaStream_t)c.stream;
@@ -95,7 +95,7 @@ int rb_add_static_geometry(rb_world* w, uint32_t ntri, const float* xyz9, uint32
     return RB_OK;
 }
 
-static int add_body(rb_world* w, uint32_t nsph, const float* obj4, const float* W12, const float* pos3, const float* vel3, uint32_t flags) {
+static int add_body(rb_world* w, uint32_t nsph, const float* obj4, const float* W12, const float* pos3, const float* vel3, uint32_t flags, bool presummed = false) {
     if (nsph == 0) return fail(w, RB_ERR_INVALID, "a model needs at least one sphere");
     if (!finite_all(obj4, (size_t)nsph * 4) || !finite_all(pos3, 3) || !finite_all(vel3, 3) || !finite_all(W12, 12))
         return fail(w, RB_ERR_INVALID, "non-finite model input");
@@ -108,17 +108,23 @@ static int add_body(rb_world* w, uint32_t nsph, const float* obj4, const float* 
     w->h_pos.insert(w->h_pos.end(), pos3, pos3 + 3);
     w->h_vel.insert(w->h_vel.end(), vel3, vel3 + 3);
     w->h_flags.push_back(flags & (RB_ACTIVE | RB_GRAVITY));
+    w->h_presummed.push_back(presummed ? 1 : 0);
     return RB_OK;
 }
+struct GrowBody { uint32_t nsph; const float* obj4; float W12[12]; const float* pos3; const float* vel3; uint32_t flags; };
+static int world_grow(rb_world* w, const std::vector<GrowBody>& add, uint32_t* first_body_id);
 
 int rb_add_model(rb_world* w, uint32_t nspheres, const float* obj4, const float* X, const rb_body_init* init, uint32_t* body_id) {
     if (!w || !init || !obj4) return w ? fail(w, RB_ERR_INVALID, "NULL argument") : RB_ERR_INVALID;
-    if (w->built) return fail(w, RB_ERR_INVALID, "rb_add_model after rb_build is not supported yet");
     float W12[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0 };
     if (X) {
         if (X[12] != 0.f || X[13] != 0.f || X[14] != 0.f || X[15] != 1.f) return fail(w, RB_ERR_INVALID, "world transform must be affine (last row 0 0 0 1)");
         W12[0] = X[0]; W12[1] = X[1]; W12[2] = X[2]; W12[3] = X[4]; W12[4] = X[5]; W12[5] = X[6]; W12[6] = X[8]; W12[7] = X[9]; W12[8] = X[10];
         W12[9] = X[3]; W12[10] = X[7]; W12[11] = X[11];
+    }
+    if (w->built) {      // Physics::addEntity (physics/src/Physics.cpp:47-49): the entity joins the next tick
+        GrowBody g; g.nsph = nspheres; g.obj4 = obj4; memcpy(g.W12, W12, sizeof W12); g.pos3 = init->pos; g.vel3 = init->vel; g.flags = init->flags;
+        return world_grow(w, std::vector<GrowBody>(1, g), body_id);
     }
     int r = add_body(w, nspheres, obj4, W12, init->pos, init->vel, init->flags);
     if (r) return r;
@@ -129,7 +135,18 @@ int rb_add_model(rb_world* w, uint32_t nspheres, const float* obj4, const float*
 int rb_add_models(rb_world* w, uint32_t n, const uint32_t* sphere_start, const float* obj4, const float* world_scale,
                   const float* pos3, const float* vel3, const uint32_t* flags, uint32_t* first_body_id) {
     if (!w || !sphere_start || !obj4 || !pos3 || !vel3 || !flags) return w ? fail(w, RB_ERR_INVALID, "NULL argument") : RB_ERR_INVALID;
-    if (w->built) return fail(w, RB_ERR_INVALID, "rb_add_models after rb_build is not supported yet");
+    if (w->built) {      // a batch of Physics::addEntity calls: the world is re-laid out once
+        std::vector<GrowBody> add(n);
+        for (uint32_t i = 0; i < n; i++) {
+            if (sphere_start[i + 1] < sphere_start[i]) return fail(w, RB_ERR_INVALID, "sphere_start must be non-decreasing");
+            const float sc = world_scale ? world_scale[i] : 1.0f;
+            GrowBody& g = add[i];
+            g.nsph = sphere_start[i + 1] - sphere_start[i]; g.obj4 = obj4 + (size_t)sphere_start[i] * 4;
+            const float W12[12] = { sc, 0, 0, 0, sc, 0, 0, 0, sc, 0, 0, 0 }; memcpy(g.W12, W12, sizeof W12);
+            g.pos3 = pos3 + 3 * (size_t)i; g.vel3 = vel3 + 3 * (size_t)i; g.flags = flags[i];
+        }
+        return world_grow(w, add, first_body_id);
+    }
     uint32_t first = (uint32_t)w->h_flags.size();
     w->h_obj.reserve(w->h_obj.size() + (size_t)sphere_start[n] * 4);
     for (uint32_t i = 0; i < n; i++) {
@@ -401,6 +418,11 @@ int rb_build(rb_world* w) {
         const float* W = &w->h_W[(size_t)b * 12];
         for (uint32_t s = w->h_body_start[b]; s < w->h_body_start[b + 1]; s++) {
             const float* o = &w->h_obj[(size_t)s * 4];
+            if (w->h_presummed[b]) {      // carried over from the world this one replaces (world_grow): already transformed, bit for bit
+                for (int k = 0; k < 4; k++) sph[(size_t)s * 4 + k] = o[k];
+                rmax = std::max(rmax, std::fabs(o[3]));
+                continue;
+            }
             volatile float x = W[0] * o[0] + W[1] * o[1] + W[2] * o[2];   // ((a + b) + c), no contraction on the host build
             volatile float y = W[3] * o[0] + W[4] * o[1] + W[5] * o[2];
             volatile float z = W[6] * o[0] + W[7] * o[1] + W[8] * o[2];
@@ -504,11 +526,23 @@ int rb_build(rb_world* w) {
         float4* wb;
         ALLOC(wb, nsa); CU(cudaMemsetAsync(wb, 0, (size_t)nsa * 16, w->stream));
         CU(cudaMemsetAsync(d_key, 0xff, (size_t)nsa * 4, w->stream));                 // "not in the grid" until the first K1
-        CU(cudaHostAlloc((void**)&w->vl_host, 8 * sizeof(uint32_t), cudaHostAllocMapped));
-        for (int k = 0; k < 8; k++) w->vl_host[k] = 0;
+        CU(cudaHostAlloc((void**)&w->vl_host, 16 * sizeof(uint32_t), cudaHostAllocMapped));
+        for (int k = 0; k < 16; k++) w->vl_host[k] = 0;
+        if (!slab) {
+            // single worlds start on the per-tick kernel and switch to the lists once the device reports that few bodies would
+            // outrun their skin (a scene that starts at rest gets there within a couple of ticks; one that starts in free fall
+            // -- where every tick would rebuild -- never pays for lists it cannot use)
+            const char* v = getenv("RB_VL_START_ACTIVE");      // (development switch)
+            if (!(v && *v == '1')) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = 1; }
+        }
         uint32_t* dv = nullptr; CU(cudaHostGetDevicePointer((void**)&dv, w->vl_host, 0));
         P.ws_build = wb; P.vl_host = dv;
-        CU(cudaStreamCreateWithFlags(&w->vl_side, cudaStreamNonBlocking));
+        {   // the hot bodies' launch is a handful of latency-bound blocks next to a kernel that fills the GPU: highest priority, so
+            // that they get their SM slots at once
+            int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            const char* v = getenv("RB_SIDE_PRIO");      // (development switch)
+            CU(cudaStreamCreateWithPriority(&w->vl_side, cudaStreamNonBlocking, (v && *v == '0') ? lo : hi));
+        }
         CU(cudaEventCreateWithFlags(&w->vl_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_join, cudaEventDisableTiming));
         // coarse cell table of the hot bodies: cells wide enough that any reach box touches at most 2 x 2 of them
         const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 256.0f);
@@ -577,7 +611,7 @@ int rb_build(rb_world* w) {
     }
     // host staging is no longer needed
     std::vector<float>().swap(w->h_tri); std::vector<float>().swap(w->h_obj); std::vector<float>().swap(w->h_W);
-    std::vector<float>().swap(w->h_pos); std::vector<float>().swap(w->h_vel);
+    std::vector<float>().swap(w->h_pos); std::vector<float>().swap(w->h_vel); std::vector<uint8_t>().swap(w->h_presummed);
     return RB_OK;
 }
 
@@ -632,10 +666,10 @@ static int enqueue_collide(rb_world* w, bool resolve) {
 // exact tests in the same order.
 // (second half of a list tick: slab worlds get here after their halo exchange; K1 ran before it)
 static uint32_t list_hot_rows(rb_world* w) {
-    // grid of the hot bodies' launch: it strides over the table, so any size is correct; sized from the last count seen
-    const uint32_t seen = w->vl_host ? w->vl_host[3] : 0u;
-    const uint32_t want = std::max<uint32_t>(4096u, 2u * seen);
-    return std::min<uint32_t>(want, std::max<uint32_t>(w->P.ns, 1u));
+    // grid of the hot bodies' launch: its blocks stride over the table, so any size is correct. Enough blocks to fill the GPU
+    // whatever the count turns out to be (the host's view of it is many ticks old); a block without work returns at once
+    static const uint32_t blocks = [] { const char* v = getenv("RB_HOT_BLOCKS"); return v && *v ? (uint32_t)atoi(v) : 148u * 3u; }();      // (development switch)
+    return std::min<uint32_t>(std::max<uint32_t>(w->P.ns, 1u), blocks * 256u);
 }
 int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     RbParams& P = w->P;
@@ -666,24 +700,26 @@ int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     w->vl_force = false;
     return RB_OK;
 }
-// single worlds: digest the device's latest report {hot bodies, list tick it was counted in} and adapt the rebuild period.
-// The report is up to ~32 ticks old (the host runs ahead), so it is matched with the rebuild that was current at ITS tick.
+// single worlds: digest the device's latest report {tick, generation of lists, their age, the age at which more than hot_soft
+// bodies were hot} and set the rebuild period from it. The report is up to ~32 ticks old (the host runs ahead).
+//   * a generation that expired at age a: rebuild every a list ticks (the tick that would have been the expensive one rebuilds);
+//     a = 1 says lists do not pay at all right now (free fall: everybody outruns the skin at once) -- rb_step_will_use_lists
+//     sits such phases out on the per-tick kernel
+//   * a generation that was rebuilt before it expired: the period was shorter than it had to be, lengthen it
 static void list_schedule_digest(rb_world* w) {
-    const uint32_t t1 = w->vl_host[4], h = w->vl_host[3], t2 = w->vl_host[4];
+    const uint32_t t1 = w->vl_host[4], expiry = w->vl_host[5], gen = w->vl_host[6], prev_life = w->vl_host[8], prev_expiry = w->vl_host[9], t2 = w->vl_host[4];
     if (t1 != t2 || t1 == w->vl_seen_tick) return;
     w->vl_seen_tick = t1;
-    uint32_t r_at = 0; bool found = false;
-    for (int k = 0; k < 8; k++) { const uint32_t r = w->vl_rebuild_ring[k]; if (r && r <= t1 && (!found || r > r_at)) { r_at = r; found = true; } }
-    if (!found) return;
-    const uint32_t age = t1 - r_at;                     // list ticks since that rebuild (0: the rebuild tick itself)
-    if (age == 0) { w->vl_hot_floor = h; return; }      // rows that can have no list at all (crowded, oversized): a rebuild does not cure them
-    const uint32_t floor_h = std::min(w->vl_hot_floor, h);
-    const uint32_t grown = h - floor_h;
-    // hot bodies accumulate roughly linearly with the age of the lists: the period at which they would reach hot_soft
-    uint32_t est = grown ? (uint32_t)std::min<uint64_t>(64u, (uint64_t)age * w->P.hot_soft / grown) : 64u;
-    if (grown <= w->P.hot_soft && est < age) est = age;  // it got this far below the limit
-    est = std::max<uint32_t>(est, 1u);
-    w->vl_period = std::max<uint32_t>(1u, (3u * w->vl_period + est + 2u) / 4u);
+    static const uint32_t max_period = [] { const char* v = getenv("RB_VL_MAXPERIOD"); return v && *v ? (uint32_t)atoi(v) : 64u; }();      // (development switch)
+    struct Clamp { rb_world* w; uint32_t m; ~Clamp() { if (w->vl_period > m) w->vl_period = m; } } clamp{ w, max_period };
+    if (expiry && gen != w->vl_gen_expired) { w->vl_gen_expired = gen; w->vl_period = std::max<uint32_t>(1u, std::min<uint32_t>(expiry, 64u)); }
+    if (gen != w->vl_gen_seen) {
+        // a new generation: if the one before served (nearly) the whole period without expiring, the period can grow
+        // (one cut short by a forced rebuild -- a row re-ordering, a host edit -- says nothing)
+        if (w->vl_gen_seen != 0xffffffffu && !prev_expiry && !expiry && 4u * (prev_life + 1u) >= 3u * w->vl_period)
+            w->vl_period = std::min<uint32_t>(64u, w->vl_period + std::max<uint32_t>(1u, w->vl_period / 4u));
+        w->vl_gen_seen = gen;
+    }
 }
 // A list tick starts: does the host make it a rebuild tick? (forced by other activity since the last list tick, a row
 // re-ordering, or -- single worlds -- the schedule)
@@ -696,7 +732,7 @@ bool rb_list_tick_begin(rb_world* w, bool reorder_due) {
 // ... and its K1 has been enqueued
 void rb_list_tick_k1_enqueued(rb_world* w) {
     if (w->slim) w->mt_stale = true;                     // from here on Entity::_mvp's translation is implicit (0 + p)
-    if (w->vl_tick_rebuilds) { w->vl_since = 0; w->vl_rebuild_ring[w->vl_rebuild_n++ & 7u] = w->tick_seq; }
+    if (w->vl_tick_rebuilds) w->vl_since = 0;
     else w->vl_since++;
 }
 static int enqueue_list_tick(rb_world* w, bool reorder_due) {
@@ -727,7 +763,8 @@ bool rb_step_will_use_lists(rb_world* w) {
         bool mostly_rebuilding = false, judged = false;
         if (w->P.soft) {
             // the schedule has converged on rebuilding (nearly) every tick
-            if (w->tick_seq - w->vl_judged_at >= 16u) { judged = true; w->vl_judged_at = w->tick_seq; mostly_rebuilding = w->vl_period < 3u; }
+            // (a period of 1 is the schedule's verdict "more hot bodies after one tick than a rebuild is worth": act on it at once)
+            if (w->vl_period < 2u || w->tick_seq - w->vl_judged_at >= 16u) { judged = true; w->vl_judged_at = w->tick_seq; mostly_rebuilding = w->vl_period < 3u; }
         } else {
             const uint32_t nr = w->vl_host[0], nt = w->vl_host[1];
             if (nt - w->vl_seen_t >= 16u) {
@@ -747,7 +784,7 @@ bool rb_step_will_use_lists(rb_world* w) {
             w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1];
             w->vl_period = 8; w->vl_judged_at = w->tick_seq;
         }
-        else w->vl_resume_at = w->steps + 16;
+        else w->vl_resume_at = w->steps + (w->vl_host[2] == 0xffffffffu ? 2 : 16);      // (no report yet: look again soon)
     }
     return w->vl_active;
 }
@@ -968,6 +1005,25 @@ int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4,
     CU(cudaStreamSynchronize(w->stream));
     return RB_OK;
 }
+// Slab (multi-GPU) worlds move rows between ranks; force / torque / angular arrays do not travel with them (DESIGN.md §6),
+// so the setters refuse instead of leaving a force on a row that now holds another body.
+static int no_slab(rb_world* w, const char* what) {
+    if (w && w->d_dn) return fail(w, RB_ERR_INVALID, "%s is not available on slab (multi-GPU) worlds: migrating bodies do not carry force / torque / angular state", what);
+    return RB_OK;
+}
+// Entity::setPosition (model/src/Entity.cpp:373-391) from the host, e.g. a teleport by game logic: unlike rb_set_state it
+// moves the model matrices along (and reproduces Q1: the stored position is W.t + p)
+int rb_entity_set_position(rb_world* w, uint32_t body, const float* pos3) {
+    int r = range_ok(w, body, 1); if (r) return r;
+    r = no_slab(w, "rb_entity_set_position"); if (r) return r;
+    if (!pos3 || !finite_all(pos3, 3)) return fail(w, RB_ERR_INVALID, "rb_entity_set_position: position is NULL or not finite");
+    CU(cudaSetDevice(w->cfg.device));
+    w->vl_force = true;
+    r = rb_ensure_mt(w); if (r) return r;
+    rb_launch_entity_set_position(w->P.pos, w->P.mt, w->P.pt, w->P.wt, w->d_inv, body, pos3, w->stream); w->launches++;
+    CU(cudaGetLastError());
+    return RB_OK;
+}
 int rb_set_flags(rb_world* w, uint32_t first, uint32_t count, const uint32_t* values, uint32_t mask) {
     int r = range_ok(w, first, count); if (r) return r;
     w->vl_force = true;
@@ -994,12 +1050,6 @@ static int ensure_angular(rb_world* w) {
     CU(cudaMemsetAsync(t, 0, (size_t)w->P.nb * 16, w->stream));
     w->P.apos = a; w->P.avel = b; w->P.torque = t;
     return ensure_force(w);
-}
-// Slab (multi-GPU) worlds move rows between ranks; force / torque / angular arrays do not travel with them (DESIGN.md §6),
-// so the setters refuse instead of leaving a force on a row that now holds another body.
-static int no_slab(rb_world* w, const char* what) {
-    if (w && w->d_dn) return fail(w, RB_ERR_INVALID, "%s is not available on slab (multi-GPU) worlds: migrating bodies do not carry force / torque / angular state", what);
-    return RB_OK;
 }
 int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
     int r = range_ok(w, first, count); if (r) return r;
@@ -1177,6 +1227,101 @@ int rb_get_kernel_ms(rb_world* w, float* out5, uint64_t* launches) {
     return RB_OK;
 }
 uint64_t rb_launch_count(const rb_world* w) { return w ? w->launches : 0; }
+
+// ---- Physics::addEntity after the build (physics/src/Physics.cpp:47-49) ---------------------------
+// The reference appends the entity to its list; from the next tick on it is integrated and re-inserted into the tree like
+// everybody else (physics/src/OSP.cpp:182-210). Here every device structure is sized and laid out at rb_build (grids by the
+// largest radius, lists, tiles, row order), so an add re-lays the world out: the complete state comes back from the device
+// -- static triangles, transformed spheres, W, poses, velocities, flags, both model translations, forces, torques, angular
+// state -- a fresh world is built from it plus the new bodies, the dynamic state is restored bit for bit, and the handle
+// takes over the new internals. Cost O(world) per call (rb_add_models adds a batch in one go); ids of existing bodies and
+// geometries are unchanged, the new bodies get the next ids. Triangles stay refused after the build.
+static int world_grow(rb_world* w, const std::vector<GrowBody>& add, uint32_t* first_body_id) {
+    if (w->d_dn) return fail(w, RB_ERR_INVALID, "adding bodies after rb_build is not available on slab (multi-GPU) worlds");
+    for (const GrowBody& g : add) {
+        if (g.nsph == 0) return fail(w, RB_ERR_INVALID, "a model needs at least one sphere");
+        if (!finite_all(g.obj4, (size_t)g.nsph * 4) || !finite_all(g.pos3, 3) || !finite_all(g.vel3, 3) || !finite_all(g.W12, 12)) return fail(w, RB_ERR_INVALID, "non-finite model input");
+    }
+    CU(cudaSetDevice(w->cfg.device));
+    CU(cudaStreamSynchronize(w->stream));
+    RbParams& P = w->P;
+    const uint32_t nb = w->n_owned_host, ns = w->h_body_start.back(), nt = P.nt;
+    // ---- the world as it stands, in id order ----
+    std::vector<float> tri4((size_t)std::max<uint32_t>(nt, 1) * 12), sph((size_t)std::max<uint32_t>(ns, 1) * 4), wt((size_t)std::max<uint32_t>(nb, 1) * 4, 0.f), w3;
+    std::vector<float> pos((size_t)std::max<uint32_t>(nb, 1) * 4), vel(pos.size()), mt(pos.size()), pt(pos.size()), force, torque, apos, avel;
+    std::vector<uint32_t> flags(std::max<uint32_t>(nb, 1));
+    if (nt) CU(cudaMemcpyAsync(tri4.data(), P.tri, (size_t)nt * 48, cudaMemcpyDeviceToHost, w->stream));
+    int r;
+    if (P.single) { r = read_rows_f4(w, P.sph_obj, sph.data(), nb); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
+    else if (ns) CU(cudaMemcpyAsync(sph.data(), P.sph_obj, (size_t)ns * 16, cudaMemcpyDeviceToHost, w->stream));
+    if (P.wt) { r = read_rows_f4(w, P.wt, wt.data(), nb); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
+    if (w->d_w3) { w3.resize((size_t)nb * 12); CU(cudaMemcpyAsync(w3.data(), w->d_w3, (size_t)nb * 48, cudaMemcpyDeviceToHost, w->stream)); }
+    r = rb_ensure_mt(w); if (r) return r;
+    struct { const float4* rows; std::vector<float>* out; } arrays[] = { { P.pos, &pos }, { P.vel, &vel }, { P.mt, &mt }, { P.pt, &pt },
+                                                                         { P.force, &force }, { P.torque, &torque }, { P.apos, &apos }, { P.avel, &avel } };
+    for (auto& a : arrays) {
+        if (!a.rows) continue;
+        a.out->resize((size_t)std::max<uint32_t>(nb, 1) * 4);
+        r = read_rows_f4(w, a.rows, a.out->data(), nb); if (r) return r;
+        CU(cudaStreamSynchronize(w->stream));      // (the id-ordered staging buffer is reused by the next array)
+    }
+    r = read_rows_u32(w, P.flags, flags.data(), nb); if (r) return r;
+    CU(cudaStreamSynchronize(w->stream));
+    // ---- the same world plus the new bodies, laid out afresh ----
+    rb_config c = w->cfg_user;
+    c.stream = w->own_stream ? nullptr : (void*)w->stream;
+    rb_world* f = nullptr;
+    r = rb_world_create(&c, &f);
+    if (r) return fail(w, r, "re-layout for a post-build add failed: %s", g_create_error.c_str());
+    auto bail = [&](int code) { w->err = f->err; rb_world_destroy(f); return code; };
+    for (size_t g = 0; g + 1 < w->h_geom_start.size(); g++) {
+        const uint32_t t0 = w->h_geom_start[g], t1 = w->h_geom_start[g + 1];
+        std::vector<float> xyz9((size_t)(t1 - t0) * 9);
+        for (uint32_t t = t0; t < t1; t++) for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) xyz9[(size_t)(t - t0) * 9 + v * 3 + k] = tri4[(size_t)t * 12 + v * 4 + k];
+        r = rb_add_static_geometry(f, t1 - t0, xyz9.data(), nullptr); if (r) return bail(r);
+    }
+    for (uint32_t b = 0; b < nb; b++) {
+        float W12[12] = { 1, 0, 0, 0, 1, 0, 0, 0, 1, wt[(size_t)b * 4], wt[(size_t)b * 4 + 1], wt[(size_t)b * 4 + 2] };
+        if (!w3.empty()) for (int rr = 0; rr < 3; rr++) for (int cc = 0; cc < 3; cc++) W12[rr * 3 + cc] = w3[(size_t)b * 12 + rr * 4 + cc];
+        const uint32_t s0 = w->h_body_start[b], s1 = w->h_body_start[b + 1];
+        // (add_body's finiteness check is for user input; a body that has blown up to Inf / NaN keeps stepping like in the reference)
+        f->h_obj.insert(f->h_obj.end(), sph.begin() + (size_t)s0 * 4, sph.begin() + (size_t)s1 * 4);
+        for (uint32_t i = s0; i < s1; i++) f->h_sph_body.push_back(b);
+        f->h_body_start.push_back(s1);
+        f->h_W.insert(f->h_W.end(), W12, W12 + 12);
+        if (W12[9] != 0.f || W12[10] != 0.f || W12[11] != 0.f) f->any_wt = true;
+        f->h_pos.insert(f->h_pos.end(), &pos[(size_t)b * 4], &pos[(size_t)b * 4] + 3);
+        f->h_vel.insert(f->h_vel.end(), &vel[(size_t)b * 4], &vel[(size_t)b * 4] + 3);
+        f->h_flags.push_back(flags[b] & (RB_ACTIVE | RB_GRAVITY));
+        f->h_presummed.push_back(1);
+    }
+    for (const GrowBody& g : add) { r = add_body(f, g.nsph, g.obj4, g.W12, g.pos3, g.vel3, g.flags); if (r) return bail(r); }
+    r = rb_build(f); if (r) return bail(r);
+    // ---- the dynamic state of the bodies that were there, bit for bit (new bodies start like at a first build) ----
+    if (nb) {
+        RbParams& Q = f->P;
+        r = write_rows_f4(f, Q.pos, 0, nb, pos.data(), Q.single ? 1 : 0); if (r) return bail(r);
+        CU(cudaStreamSynchronize(f->stream));
+        struct { float4* rows; const std::vector<float>* in; } back[] = { { Q.vel, &vel }, { Q.mt, &mt }, { Q.pt, &pt } };
+        for (auto& a : back) { r = write_rows_f4(f, a.rows, 0, nb, a.in->data()); if (r) return bail(r); CU(cudaStreamSynchronize(f->stream)); }
+        if (!force.empty()) { r = ensure_force(f); if (r) return bail(r); r = write_rows_f4(f, Q.force, 0, nb, force.data()); if (r) return bail(r); CU(cudaStreamSynchronize(f->stream)); }
+        if (!avel.empty()) {
+            r = ensure_angular(f); if (r) return bail(r);
+            struct { float4* rows; const std::vector<float>* in; } ang[] = { { Q.torque, &torque }, { Q.apos, &apos }, { Q.avel, &avel } };
+            for (auto& a : ang) { r = write_rows_f4(f, a.rows, 0, nb, a.in->data()); if (r) return bail(r); CU(cudaStreamSynchronize(f->stream)); }
+        }
+        r = ensure_stage_u(f, nb); if (r) return bail(r);
+        CU(cudaMemcpyAsync(f->d_stage_u, flags.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, f->stream));
+        rb_launch_set_flags(Q.flags, f->d_stage_u, f->d_inv, 0, nb, RB_ACTIVE | RB_GRAVITY | RB_CONTACT, f->stream); f->launches++;
+        CU(cudaStreamSynchronize(f->stream));
+    }
+    f->steps = w->steps; f->pose_updates = w->pose_updates; f->launches += w->launches; f->profile = w->profile;
+    f->vl_force = true;
+    if (first_body_id) *first_body_id = nb;
+    std::swap(*w, *f);          // the caller's handle now owns the new world ...
+    rb_world_destroy(f);        // ... and the old device state goes
+    return RB_OK;
+}
 
 } // extern "C"
 

@@ -219,6 +219,11 @@ class World:
         count = (p if p is not None else v).shape[0]
         self._ck(self.L.rb_set_state(self.h, first, count, ptr(p), ptr(v)))
 
+    def entity_set_position(self, body: int, pos):
+        """Entity::setPosition (model/src/Entity.cpp:373-391): position, _prevMVP and _mvp move together."""
+        p = np.ascontiguousarray(pos, dtype=np.float32).reshape(3)
+        self._ck(self.L.rb_entity_set_position(self.h, int(body), ptr(p)))
+
     def set_flags(self, first, values, mask):
         v = np.ascontiguousarray(values, dtype=np.uint32).reshape(-1)
         self._ck(self.L.rb_set_flags(self.h, first, v.shape[0], ptr(v), mask))
