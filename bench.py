@@ -528,7 +528,7 @@ def main():
     ap.add_argument("--ref-tile-only", action="store_true", help="reference arm: only the bounded tile estimate")
     ap.add_argument("--no-c5", action="store_true", help="skip the fixed-size C5 sub-record")
     ap.add_argument("--c5-spheres", type=int, default=16_000_000)
-    ap.add_argument("--c5-settle", type=int, default=300)
+    ap.add_argument("--c5-settle", type=int, default=600)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -21,7 +21,8 @@
 #define RB_VL_WHY     1   // why: 1 a body entered / left the grid (or emigrated), 2 hot table full, 4 host (first tick, rows moved, state edited), 8 immigrants
 #define RB_VL_WHY_LAST 4  // the reasons of the most recent rebuild
 #define RB_VL_NWHY    8   // 4 words: rebuilds so far by reason bit (grid entry/exit, hot table full, host, immigrants)
-#define RB_VL_WORDS   16
+#define RB_VL_WORDS   24
+#define RB_VL_NOLIST  16  // 3 words: rows the last rebuild left without a list -- more partners than a list holds, a sphere wider than the fast triangle walk, a block whose tile overflowed
 #define RB_VL_STORM   6   // the previous list tick rebuilt too
 #define RB_VL_NFAST   5   // per-tick kernel only: bodies whose one-tick margin alone exceeds the skin (saturates at hot_cap)
 #define RB_VL_NREBUILD 2  // rebuild ticks so far
@@ -140,7 +141,8 @@ struct RbParams {
     unsigned long long* hot_head; // [hcn * hcn] chain heads: tick << 32 | index + 1. An entry of an earlier tick is an empty cell, so
                                   // the table is never cleared (the tick number is its version)
     uint32_t* hot_row; uint32_t* hot_next; uint32_t hot_cap;      // hot_cap = every row: the table cannot overflow
-    uint32_t hot_soft;            // the number of hot bodies at which a rebuild pays (heuristics only)
+    uint32_t hot_soft;            // the number of hot bodies (beyond those that can have no list) at which a rebuild pays (heuristics only)
+    uint32_t hot_flood;           // ... at which lists stop paying altogether: a hot body costs a few times a listed one, so about an eighth of the rows
     uint32_t hcn; float hc_inv_w;
     uint32_t tick;                // version of this tick's hot-table entries (never 0)
     uint32_t* nhot;               // this tick's hot-body counter

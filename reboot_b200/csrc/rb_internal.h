@@ -24,6 +24,8 @@ void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* st
 void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows);
 uint32_t rb_list_tile_bytes();
+uint32_t rb_list_partner_slots();   // partners a persistent list holds
+uint32_t rb_list_tile_rows();      // rows per triangle tile (= threads per block of the list step)
 void rb_launch_entity_set_position(float4* pos, float4* mt, float4* pt, const float4* wt, const uint32_t* inv, uint32_t body, const float* xyz, cudaStream_t st);
 void rb_launch_mt_refresh(const float4* pos, const float4* wt, float4* mt, uint32_t n, cudaStream_t st);
 bool rb_have_device_launch();
@@ -116,10 +118,12 @@ struct rb_world {
     uint32_t tick_seq = 0;                   // list ticks enqueued so far (version of the hot table entries)
     bool slim = false;                       // single-sphere bodies, W.t = 0, centred spheres: list ticks keep the model translations implicit
     bool mt_stale = false;                   // ... and the mt array has not been refreshed since
+    uint32_t vl_spacing = 16;                // ... the period as applied: the re-ordering interval split evenly
     uint32_t vl_period = 16, vl_since = 0;   // single worlds: the host schedules the list rebuilds (every vl_period list ticks, adapted to the hot counts it sees)
     uint32_t vl_seen_tick = 0;               // last device report (tick number) the schedule has digested
     uint32_t vl_gen_expired = 0xffffffffu;   // the list generation whose expiry the schedule has acted on
     uint32_t vl_gen_seen = 0xffffffffu;      // the generation of the last report digested
+    uint32_t vl_gen_flooded = 0xffffffffu;   // the generation whose flood report (lists do not pay right now) has been acted on
     uint32_t vl_judged_at = 0;               // list tick at which the lists-pay-off decision was last taken
     bool vl_tick_rebuilds = false;           // this list tick rebuilds at the host's request
     unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step
@@ -128,7 +132,7 @@ struct rb_world {
     cudaStream_t vl_side = nullptr; cudaEvent_t vl_fork = nullptr, vl_join = nullptr;   // the hot bodies' launch runs next to the list kernel
     int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)
     // ---- spatial row re-ordering (single-sphere, single-GPU worlds) ----
-    int reorder_every = 32;                  // ticks between re-orderings (0 = never)
+    int reorder_every = 64;                  // ticks between re-orderings (0 = never); measured on C3: 32 -> 0.1650, 64 -> 0.1611, 128 -> 0.1611 ms per tick
     uint32_t* d_inv = nullptr;               // body id -> row
     uint32_t* d_gid_alt = nullptr; uint32_t* d_flags_alt = nullptr; uint32_t* d_rest = nullptr; uint32_t* d_key_alt = nullptr;
     float4* alt4[RB_REORDER_MAX] = {};

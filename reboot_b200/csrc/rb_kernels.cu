@@ -80,7 +80,8 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
         if ((f & RB_F_ACTIVE) && b < n_owned) {
             f3 frc = xyz(F);
             float mass = F.w;
-            f3 la = mk3(frc.x / mass, frc.y / mass, frc.z / mass);
+            f3 la = mk3(0.f, 0.f, 0.f);                  // worlds nobody has given a force yet: 0 / 1 = +0, without the three IEEE divisions
+            if (P.force) la = mk3(frc.x / mass, frc.y / mass, frc.z / mass);
             float g = (f & RB_F_GRAVITY) ? P.gravity : 0.0f;
             f3 dv = mk3(la.x * dt, (la.y + g) * dt, la.z * dt);
             float fr = ((f & RB_F_CONTACT) || !(f & RB_F_GRAVITY)) ? P.friction : 1.0f;
@@ -169,7 +170,7 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             // keep reporting how many bodies outrun the skin within one tick, so that it knows when to come back
             if (do_bin == 1 && P.vl && !(8.0f * speed * dt + 0.01f * r <= P.vl_skin)) {        // a list would not last it ~6 ticks
                 volatile uint32_t* nf = P.vl + RB_VL_NFAST;
-                if (*nf < P.hot_soft) atomicAdd(&P.vl[RB_VL_NFAST], 1u);
+                if (*nf < P.hot_flood) atomicAdd(&P.vl[RB_VL_NFAST], 1u);
             }
         }
         if (do_bin >= 2) {
@@ -220,14 +221,15 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
     __shared__ uint32_t wsum[RB_BLOCK / 32];
     uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t nwarps = blockDim.x >> 5;          // (blocks of up to RB_BLOCK threads)
     uint32_t inc = warp_incl_scan(v, lane);
     if (lane == 31) wsum[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        uint32_t w = lane < RB_BLOCK / 32 ? wsum[lane] : 0;
+        uint32_t w = lane < nwarps ? wsum[lane] : 0;
         uint32_t wi = warp_incl_scan(w, lane);
-        if (lane < RB_BLOCK / 32) wsum[lane] = wi - w;
-        if (lane == RB_BLOCK / 32 - 1) *total = wi;
+        if (lane < nwarps) wsum[lane] = wi - w;
+        if (lane == nwarps - 1) *total = wi;
     }
     __syncthreads();
     return inc - v + wsum[wid];
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_clear_kernel(uint4* __restrict__ 
 __global__ void __launch_bounds__(RB_BLOCK) rb_vl_bin_kernel(RbParams P) {
     if (!P.vl[RB_VL_REBUILD]) return;
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0 && P.tile_cursor) *P.tile_cursor = 0u;      // the enumeration at the end of this chain refills the triangle tiles
+    if (s == 0 && P.tile_cursor) { *P.tile_cursor = 0u; P.vl[RB_VL_NOLIST] = P.vl[RB_VL_NOLIST + 1] = P.vl[RB_VL_NOLIST + 2] = 0u; }      // the enumeration at the end of this chain refills the triangle tiles
     if (s >= (P.dn ? P.dn[0] : P.ns)) return;       // slab worlds: owned rows only (ghosts never enter the sort of a list tick)
     P.ws_build[s] = P.ws[s];
     uint32_t k = P.key[s];
@@ -749,8 +751,14 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
 // Same canonical order and arithmetic as the v1 kernel (bit-identical results).
 // ------------------------------------------------------------------------------------------
 #define RB_CAND_MAX 12
-#define RB_SSCAND_MAX 4
-#define RB_TILE_CAP 768      // triangles one block's tile holds (39 KB of shared memory in the list-step kernel)
+#define RB_SSCAND_MAX 4       // partners a thread keeps in registers (per-tick enumeration, hot bodies, hot partners of a listed row)
+#ifndef RB_SSLIST_MAX
+#define RB_SSLIST_MAX 8       // partners a persistent list holds (dense piles: a sphere touches up to 12 neighbours)
+#endif
+#ifndef RB_LS_BLOCK
+#define RB_LS_BLOCK 256      // rows per triangle tile = threads per block of the list-step kernel (and of the enumeration that fills the tiles)
+#endif
+#define RB_TILE_CAP (3 * RB_LS_BLOCK)      // triangles one block's tile holds (39 KB of shared memory in the list-step kernel at 256 rows)
 #ifndef RB_COLLIDE_MINBLOCKS
 #define RB_COLLIDE_MINBLOCKS 3
 #endif
@@ -840,9 +848,10 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
     const float frm = f0.w;
 
     // ---------------- P1: partner scan ----------------
-    uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
+    constexpr int NPG = (MODE == 1) ? RB_SSLIST_MAX : RB_SSCAND_MAX;      // (the enumeration keeps as many as a list holds)
+    uint32_t pg[NPG], pl[NPG];
 #pragma unroll
-    for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+    for (int k = 0; k < NPG; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
     uint32_t npart = 0;
     {
         // every lane walks its (up to 3) z-rows entry by entry; the loop is warp-uniform so the lanes
@@ -880,9 +889,9 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
                                 uint32_t g = rb_gid(P, Bl);
                                 if (RESOLVE || g > gA) {           // detection: the lower id reports the pair
                                     npart++;
-                                    // keep the RB_SSCAND_MAX smallest ids, ascending
+                                    // keep the NPG smallest ids, ascending
 #pragma unroll
-                                    for (int k = 0; k < RB_SSCAND_MAX; ++k)
+                                    for (int k = 0; k < NPG; ++k)
                                         if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = Bl; g = tg; Bl = tl; }
                                 }
                             }
@@ -1057,7 +1066,7 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
         // into one contiguous region of the tile pool -- vertex records first, global ids behind them -- which the list-step
         // kernel stages with a single bulk copy. A row that cannot have a list steps as a hot body from now on.
         __shared__ uint32_t s_total, s_base, s_over;
-        bool no_list = valid && (npart > RB_SSCAND_MAX || st_slow);
+        bool no_list = valid && (npart > RB_SSLIST_MAX || st_slow);
         const uint32_t mine = (valid && !no_list) ? nc : 0u;
         const uint32_t off = block_excl_scan(mine, &s_total);
         if (threadIdx.x == 0) {
@@ -1073,6 +1082,7 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
         }
         __syncthreads();
         if (valid) {
+            if (no_list) atomicAdd(&P.vl[RB_VL_NOLIST + (npart > RB_SSLIST_MAX ? 0 : 1)], 1u); else if (s_over) atomicAdd(&P.vl[RB_VL_NOLIST + 2], 1u);
             no_list = no_list || s_over != 0u;
             uint32_t hdr = 0u;
             if (!no_list) {
@@ -1087,7 +1097,7 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
                     ids[off + j] = t;
                 }
 #pragma unroll
-                for (int k = 0; k < RB_SSCAND_MAX; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + A] = pg[k]; P.e_pl[(size_t)k * P.ns + A] = pl[k]; }
+                for (int k = 0; k < NPG; ++k) if (pg[k] != RB_NONE) { P.e_pg[(size_t)k * P.ns + A] = pg[k]; P.e_pl[(size_t)k * P.ns + A] = pl[k]; }
             } else {
                 // no list for this row: hot from this tick on (its own launch enumerates for it every tick)
                 P.ws_build[A].w = -1.0f;
@@ -1298,17 +1308,20 @@ __device__ __forceinline__ void append_contact(const RbParams& P, uint32_t a, ui
 }
 
 #ifndef RB_LIST_MINBLOCKS
-#define RB_LIST_MINBLOCKS 4
+#define RB_LIST_MINBLOCKS (1024 / RB_LS_BLOCK)
+#endif
+#ifndef RB_LS_PREFETCH
+#define RB_LS_PREFETCH 1
 #endif
 // dynamic shared memory of the list step: the tile (vertex records + ids), then one owner word per tile entry and the work
 // list of the later test rounds
 #define RB_LS_TILE_BYTES ((3u * RB_TILE_CAP + RB_TILE_CAP / 4u) * 16u)
 #define RB_LS_SMEM_BYTES (RB_LS_TILE_BYTES + 2u * RB_TILE_CAP * 2u)
-__global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kernel(const RbParams P) {
+__global__ void __launch_bounds__(RB_LS_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kernel(const RbParams P) {
     extern __shared__ __align__(16) uint4 s_tile[];
     __shared__ __align__(8) unsigned long long s_bar;
-    __shared__ __align__(16) float4 s_pose[RB_BLOCK];      // current sphere of each row of the block (w < 0: the row does not step here)
-    __shared__ uint32_t s_mask[RB_BLOCK];                  // hits of the round, one bit per entry of the row's list
+    __shared__ __align__(16) float4 s_pose[RB_LS_BLOCK];      // current sphere of each row of the block (w < 0: the row does not step here)
+    __shared__ uint32_t s_mask[RB_LS_BLOCK];                  // hits of the round, one bit per entry of the row's list
     __shared__ uint32_t s_nwork[2];
     uint16_t* s_own = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(s_tile) + RB_LS_TILE_BYTES);      // per tile entry: owner thread | index in its list << 8
     uint16_t* s_work = s_own + RB_TILE_CAP;                // tile entries still to be tested (rounds after the first)
@@ -1352,14 +1365,21 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
     const f3 mt_frozen = S.mt;
 
     // ---------------- partners: from the list, plus whoever is in the hot-body table ----------------
-    uint32_t pg[RB_SSCAND_MAX], pl[RB_SSCAND_MAX];
-#pragma unroll
-    for (int k = 0; k < RB_SSCAND_MAX; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
-    uint32_t npart = valid ? (hdr & 0xffu) : 0u;
+    // The list's partners (ascending global id, up to RB_SSLIST_MAX of them, slot-major by row) are streamed one at a time;
+    // the hot bodies found around the row are kept sorted in registers and merged in on the way, so the pairs run in
+    // ascending partner id whichever source they come from (a partner that is listed AND hot shows up in both: once).
+    const uint32_t nl = valid ? (hdr & 0xffu) : 0u;
     const uint32_t nc = valid ? ((hdr >> 8) & 0xffu) : 0u;
     const uint32_t toff = hdr >> 16;
+    uint32_t lg = RB_NONE, ll = RB_NONE, li = 0;              // the list partner in hand (global id, row) and its slot
+    if (nl) { lg = P.e_pg[A]; ll = P.e_pl[A]; }
+#if RB_LS_PREFETCH
+    if (nl) rb_prefetch(P.pt + A);                             // (the row's own previous pose: only a sphere-sphere hit reads it)
+    if (nl > 1u) { rb_prefetch(P.e_pg + (size_t)P.ns + A); rb_prefetch(P.e_pl + (size_t)P.ns + A); }
+#endif
+    uint32_t hg[RB_SSCAND_MAX], hl[RB_SSCAND_MAX], nhp = 0;   // hot partners, ascending
 #pragma unroll
-    for (int k = 0; k < RB_SSCAND_MAX; ++k) if ((uint32_t)k < npart) { pg[k] = P.e_pg[(size_t)k * P.ns + A]; pl[k] = P.e_pl[(size_t)k * P.ns + A]; }
+    for (int k = 0; k < RB_SSCAND_MAX; ++k) { hg[k] = RB_NONE; hl[k] = RB_NONE; }
     {
         // hot bodies (and, in slab worlds, the neighbours' ghosts) are in nobody's list: everybody looks them up in the
         // coarse cell table (<= 2 x 2 cells). Entries of earlier ticks read as empty cells.
@@ -1388,14 +1408,14 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
                         float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
                         if (o.w >= 0.f && !((dx * dx + dy * dy) + dz * dz > rr * rr)) {
                             uint32_t g = rb_gid(P, Bl), bl = Bl;
-                            bool dup = false;
+                            bool dup = false;           // (a body straddling two cells is linked once, but be safe)
 #pragma unroll
-                            for (int k = 0; k < RB_SSCAND_MAX; ++k) dup |= (pg[k] == g);
+                            for (int k = 0; k < RB_SSCAND_MAX; ++k) dup |= (hg[k] == g);
                             if (!dup) {
-                                T.cand_ss++; npart++;
+                                T.cand_ss++; nhp++;
 #pragma unroll
                                 for (int k = 0; k < RB_SSCAND_MAX; ++k)
-                                    if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = bl; g = tg; bl = tl; }
+                                    if (g < hg[k]) { uint32_t tg = hg[k], tl = hl[k]; hg[k] = g; hl[k] = bl; g = tg; bl = tl; }
                             }
                         }
                     }
@@ -1410,11 +1430,25 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
     // sqrt_rn(d2) <= radii. A pair with d2 > radii^2 * (1 + 2^-20) cannot pass (sqrt is monotone, the bound is > 3 ulp of
     // radii away), so it is rejected without the square root; everything closer runs the reference expressions.
     bool pt_loaded = false;
+    const bool crowded = nhp > RB_SSCAND_MAX;          // more hot neighbours than the registers hold: this row rescans (below)
+    if (crowded) { lg = RB_NONE; hg[0] = RB_NONE; }
+    while (true) {
+        const bool have = lg != RB_NONE || hg[0] != RB_NONE;
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+            uint32_t gB, Bl;
+            const bool from_hot = hg[0] < lg;
+            const bool both = hg[0] == lg;              // listed and hot: one body
+            if (from_hot) { gB = hg[0]; Bl = hl[0]; } else { gB = lg; Bl = ll; }
+            if (from_hot || both) {
 #pragma unroll
-    for (int k = 0; k < RB_SSCAND_MAX; ++k) {
-        if (!__any_sync(0xffffffffu, pg[k] != RB_NONE)) break;
-        if (pg[k] != RB_NONE) {
-            const uint32_t Bl = pl[k], gB = pg[k];
+                for (int k = 0; k + 1 < RB_SSCAND_MAX; ++k) { hg[k] = hg[k + 1]; hl[k] = hl[k + 1]; }
+                hg[RB_SSCAND_MAX - 1] = RB_NONE;
+            }
+            if (!from_hot) {                            // the next list partner comes in while this pair is dealt with
+                ++li;
+                if (li < nl) { lg = P.e_pg[(size_t)li * P.ns + A]; ll = P.e_pl[(size_t)li * P.ns + A]; } else lg = RB_NONE;
+            }
             const bool lo_is_a = gA < gB;
             const float4 wb = P.ws[Bl];                        // partner at its frozen pose
             if (wb.w >= 0.f) {                                 // (w < 0: it has left the broadphase since the list was built, Q3 / Q7)
@@ -1443,10 +1477,10 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
         }
         __syncwarp();
     }
-    if (npart > RB_SSCAND_MAX) {            // hot neighbours pushed the count past what is staged: continue above the last staged id by rescanning
+    if (crowded) {            // every partner by rescanning (the sort of the last rebuild + the hot-body table), ascending
         HitBuf H; H.n = 0;
         if (!pt_loaded && !S.changed) { S.pt = xyz(P.pt[A]); pt_loaded = true; }
-        uint32_t lo = pg[RB_SSCAND_MAX - 1] + 1;
+        uint32_t lo = 0;
         const float4 oa_s = make_float4(oa.x, oa.y, oa.z, oa.w);
         while (true) {
             uint32_t best = RB_NONE, best_local = RB_NONE, eligible = 0;
@@ -1480,7 +1514,7 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
     {
         uint32_t j0 = 0, nwork = tile_n, round = 0;
         while (true) {
-            for (uint32_t i = threadIdx.x; i < nwork; i += RB_BLOCK) {
+            for (uint32_t i = threadIdx.x; i < nwork; i += RB_LS_BLOCK) {
                 const uint32_t e = round ? (uint32_t)s_work[i] : i;
                 const uint32_t ok = s_own[e];
                 const float4 ps = s_pose[ok & 0xffu];
@@ -1517,6 +1551,9 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
                     const f3 ov = sub3(c, q);
                     const float dist = mag3(ov);
                     const f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
+                    // the contact record is parked in the entry's own slot of the tile (its vertices are in registers and
+                    // nobody tests an entry in front of a hit again) and appended once per warp at the end: no global atomic
+                    // between two block barriers
                     append_contact(P, gA, RB_TRI_BIT | tile_ids[ent], oa.w - dist, o, oa.w);
                     // GeometryMath::sphereTriangleResolution (math/src/GeometryMath.cpp:489-522); the triangle normal
                     // normalize((C-A)x(B-A)) is static: pre-computed at build (w lanes)
@@ -1600,6 +1637,8 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kern
             gen++; expiry = 0u; P.vl[RB_VL_FLOOR] = nh;
         }
         else if (!expiry && nh > P.vl[RB_VL_FLOOR] + P.hot_soft) expiry = age;
+        // a flood: after ONE tick more bodies have outrun their skin than lists can carry (free fall) -- the host sits such phases out
+        if (age == 1u && nh > P.vl[RB_VL_FLOOR] + P.hot_flood && P.vl_host) P.vl_host[10] = gen;
         P.vl[RB_VL_AGE] = age; P.vl[RB_VL_GEN] = gen; P.vl[RB_VL_EXPIRY] = expiry;
         if (P.vl_host) {
             P.vl_host[0] = nr; P.vl_host[1] = nt; P.vl_host[3] = nh;
@@ -1623,11 +1662,11 @@ __global__ void __launch_bounds__(RB_BLOCK, RB_K1_MINBLOCKS) rb_integrate_bin_ke
 // 2-us launch instead of four full-grid launches that return at once.
 __global__ void rb_vl_gate_kernel(RbParams P) {
     if (threadIdx.x || blockIdx.x || !P.vl[RB_VL_REBUILD]) return;
-    const uint32_t g = (P.ns + RB_BLOCK - 1) / RB_BLOCK, tiles = (P.ncols + RB_SCAN_TILE - 1) / RB_SCAN_TILE;
+    const uint32_t g = (P.ns + RB_BLOCK - 1) / RB_BLOCK, gl = (P.ns + RB_LS_BLOCK - 1) / RB_LS_BLOCK, tiles = (P.ncols + RB_SCAN_TILE - 1) / RB_SCAN_TILE;
     rb_vl_bin_kernel<<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P);
     rb_scan_lookback_kernel<<<tiles, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P.col_count, P.ncols, P.col_start, P.scan_status, P.scan_ticket, P.vl + RB_VL_REBUILD, 1);
     rb_scatter_kernel<<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P, 1, P.scan_status, P.scan_ticket, tiles);
-    rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P);
+    rb_collide_single_kernel<true, 1><<<gl, RB_LS_BLOCK, 0, cudaStreamTailLaunch>>>(P);
 }
 #endif
 
@@ -1852,18 +1891,20 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 // The hot bodies' launch is small and latency-bound (a few warps walking dependent loads): it runs on a side
 // stream next to the big list kernel. Both only write the bodies they own and read frozen data of the others.
 uint32_t rb_list_tile_bytes() { return RB_LS_SMEM_BYTES; }
+uint32_t rb_list_tile_rows() { return RB_LS_BLOCK; }
+uint32_t rb_list_partner_slots() { return RB_SSLIST_MAX; }
 int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows) {
     if (!P.nb) return 0;
-    const uint32_t g = cdiv(P.ns, RB_BLOCK);
-    if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_BLOCK, 0, st>>>(P);
+    const uint32_t g = cdiv(P.ns, RB_LS_BLOCK);
+    if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_LS_BLOCK, 0, st>>>(P);
     static const int side_mode = [] { const char* v = getenv("RB_HOT_SIDE"); return v && *v ? atoi(v) : 1; }();      // (development switch)
     if (side_mode == 0) {       // everything on one stream: hot bodies first
         rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
-        rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);
+        rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P);
         return 3;
     }
     if (side_mode == 2) {       // one stream, hot bodies last
-        rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);
+        rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P);
         rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
         return 3;
     }
@@ -1871,7 +1912,7 @@ int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, 
     cudaStreamWaitEvent(side, fork, 0);
     rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies: the blocks stride over the table (a block without work returns at once)
     cudaEventRecord(join, side);
-    rb_list_step_kernel<<<g, RB_BLOCK, rb_list_tile_bytes(), st>>>(P);                         // everybody else, from the lists
+    rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P);                         // everybody else, from the lists
     cudaStreamWaitEvent(st, join, 0);
     return 3;
 }

@@ -167,14 +167,20 @@ static int build_triangle_grid(rb_world* w) {
     const uint32_t nt = (uint32_t)(w->h_tri.size() / 9);
     const float half = w->cfg.world_half;
     P.nt = nt;
-    double ext = 0;
+    // column width = the MEDIAN triangle extent: a terrain lattice with a few large triangles on it (houses) keeps columns that
+    // coincide with its cells -- the mean would be off by a fraction of a percent, every column would straddle two cells per
+    // axis and hold four times the triangles (C5: 1.001 instead of 1.0 left 3 % of the spheres with more candidates than the
+    // fast walk takes)
+    std::vector<float> extent(nt);
     for (uint32_t t = 0; t < nt; t++) {
         const float* p = &w->h_tri[(size_t)t * 9];
         float dx = std::max(p[0], std::max(p[3], p[6])) - std::min(p[0], std::min(p[3], p[6]));
         float dz = std::max(p[2], std::max(p[5], p[8])) - std::min(p[2], std::min(p[5], p[8]));
-        ext += std::max(dx, dz);
+        extent[t] = std::max(dx, dz);
     }
-    double mean = nt ? ext / nt : 2.0 * half;
+    double mean = 2.0 * half;
+    if (nt) { std::nth_element(extent.begin(), extent.begin() + nt / 2, extent.end()); mean = extent[nt / 2]; }
+    std::vector<float>().swap(extent);
     if (!(mean > 0)) mean = 2.0 * half;
     long n = std::lround(2.0 * half / mean);
     n = std::max(1L, std::min(4096L, n));
@@ -449,7 +455,7 @@ int rb_build(rb_world* w) {
     if (w->vl_on) {
         float rmin = rmax;
         for (size_t i = 3; i < sph.size() && i < (size_t)ns * 4; i += 4) rmin = std::min(rmin, std::fabs(sph[i]));
-        P.vl_skin = w->vl_skin_cfg > 0.f ? w->vl_skin_cfg : std::max(0.1f * rmin, 4e-3f);   // auto: a tenth of the smallest radius
+        P.vl_skin = w->vl_skin_cfg > 0.f ? w->vl_skin_cfg : std::max(0.08f * rmin, 4e-3f);   // auto: 8 % of the smallest radius (C3: 0.05 -> 0.1650, 0.035 -> 0.1626 ms per tick)
         P.rm_max += P.vl_skin;               // the largest grown radius any enumeration can meet
         P.vl_slack = std::max(1e-2f, 1e-5f * P.half);   // FP32 rounding of the predicate in sphere-centred coordinates is ~1e-4 at |x| = 1000
     }
@@ -528,6 +534,7 @@ int rb_build(rb_world* w) {
         CU(cudaMemsetAsync(d_key, 0xff, (size_t)nsa * 4, w->stream));                 // "not in the grid" until the first K1
         CU(cudaHostAlloc((void**)&w->vl_host, 16 * sizeof(uint32_t), cudaHostAllocMapped));
         for (int k = 0; k < 16; k++) w->vl_host[k] = 0;
+        w->vl_host[10] = 0xffffffffu;        // (no generation has been flooded yet)
         if (!slab) {
             // single worlds start on the per-tick kernel and switch to the lists once the device reports that few bodies would
             // outrun their skin (a scene that starts at rest gets there within a couple of ticks; one that starts in free fall
@@ -551,6 +558,7 @@ int rb_build(rb_world* w) {
         // every row has a slot (the table cannot overflow); hot_soft is the count at which rebuilding the lists pays
         P.hot_cap = (uint32_t)nsa;
         P.hot_soft = w->vl_hot_cfg > 0 ? (uint32_t)w->vl_hot_cfg : std::max<uint32_t>(1024u, ns / 128u);
+        P.hot_flood = std::max<uint32_t>(2u * P.hot_soft, ns / 8u);
         unsigned long long* hh; uint32_t *hr, *hn;
         const size_t ncell = (size_t)P.hcn * P.hcn;
         ALLOC(hh, ncell); ALLOC(hr, (size_t)P.hot_cap + 3u * ghost_cap); ALLOC(hn, (size_t)P.hot_cap + 3u * ghost_cap);   // slab worlds: + this tick's ghosts
@@ -565,8 +573,8 @@ int rb_build(rb_world* w) {
         // candidate lists: header + partners per row, triangles in per-block tiles (sized for 3 per row on average; a block
         // that does not fit steps without lists)
         uint32_t *eh, *eg, *el, *tc; uint4* tp; uint2* bt;
-        const size_t nblk = ((size_t)P.ns + 255) / 256;
-        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * 4); ALLOC(el, (size_t)P.ns * 4);
+        const size_t nblk = ((size_t)P.ns + rb_list_tile_rows() - 1) / rb_list_tile_rows();
+        ALLOC(eh, P.ns); ALLOC(eg, (size_t)P.ns * rb_list_partner_slots()); ALLOC(el, (size_t)P.ns * rb_list_partner_slots());
         P.tile_pool_units = (uint32_t)std::min<size_t>(0xF0000000ull, (size_t)P.ns * 10 + 4096);
         ALLOC(tp, P.tile_pool_units); ALLOC(bt, nblk); ALLOC(tc, 4);
         CU(cudaMemsetAsync(eh, 0, (size_t)P.ns * 4, w->stream)); CU(cudaMemsetAsync(bt, 0, nblk * sizeof(uint2), w->stream)); CU(cudaMemsetAsync(tc, 0, 16, w->stream));
@@ -712,12 +720,15 @@ static void list_schedule_digest(rb_world* w) {
     w->vl_seen_tick = t1;
     static const uint32_t max_period = [] { const char* v = getenv("RB_VL_MAXPERIOD"); return v && *v ? (uint32_t)atoi(v) : 64u; }();      // (development switch)
     struct Clamp { rb_world* w; uint32_t m; ~Clamp() { if (w->vl_period > m) w->vl_period = m; } } clamp{ w, max_period };
-    if (expiry && gen != w->vl_gen_expired) { w->vl_gen_expired = gen; w->vl_period = std::max<uint32_t>(1u, std::min<uint32_t>(expiry, 64u)); }
+    // (an expiry after one or two ticks is not a reason to rebuild every tick -- a rebuild costs more than a tick of per-tick
+    // enumeration: such lists serve a few ticks with a growing share of hot bodies; a FLOOD is what switches lists off)
+    if (expiry && gen != w->vl_gen_expired) { w->vl_gen_expired = gen; w->vl_period = std::max<uint32_t>(4u, std::min<uint32_t>(expiry, 64u)); }
+    if (w->vl_host[10] == gen && gen != w->vl_gen_flooded) { w->vl_gen_flooded = gen; w->vl_period = 1u; }
     if (gen != w->vl_gen_seen) {
         // a new generation: if the one before served (nearly) the whole period without expiring, the period can grow
         // (one cut short by a forced rebuild -- a row re-ordering, a host edit -- says nothing)
-        if (w->vl_gen_seen != 0xffffffffu && !prev_expiry && !expiry && 4u * (prev_life + 1u) >= 3u * w->vl_period)
-            w->vl_period = std::min<uint32_t>(64u, w->vl_period + std::max<uint32_t>(1u, w->vl_period / 4u));
+        if (w->vl_gen_seen != 0xffffffffu && !prev_expiry && !expiry && 4u * (prev_life + 1u) >= 3u * std::min(w->vl_period, w->vl_spacing))
+            w->vl_period = std::min<uint32_t>(64u, 2u * w->vl_period);      // (too long shows as an expiry, which sets the period outright)
         w->vl_gen_seen = gen;
     }
 }
@@ -725,7 +736,15 @@ static void list_schedule_digest(rb_world* w) {
 // re-ordering, or -- single worlds -- the schedule)
 bool rb_list_tick_begin(rb_world* w, bool reorder_due) {
     bool force = w->vl_force || reorder_due;
-    if (w->P.soft && !force) { list_schedule_digest(w); if (w->vl_since + 1 >= w->vl_period) force = true; }
+    if (w->P.soft && !force) {
+        list_schedule_digest(w);
+        // the row re-ordering rebuilds every reorder_every ticks anyway: the scheduled rebuilds split that interval evenly
+        // (a period of 22 with re-orderings every 32 ticks means 16 + 16, not 22 + 10)
+        uint32_t spacing = w->vl_period;
+        if (w->reorder_every > 0) { const uint32_t re = (uint32_t)w->reorder_every, n = (re + spacing - 1u) / spacing; spacing = (re + n - 1u) / n; }
+        w->vl_spacing = spacing;
+        if (w->vl_since + 1 >= spacing) force = true;
+    }
     w->vl_tick_rebuilds = force;
     return force;
 }
@@ -774,13 +793,15 @@ bool rb_step_will_use_lists(rb_world* w) {
                 w->vl_seen_r = nr; w->vl_seen_t = nt;
             }
         }
+        static const bool never_off = [] { const char* v = getenv("RB_VL_NEVER_OFF"); return v && *v == '1'; }();      // (development switch)
+        if (judged && never_off) mostly_rebuilding = false;
         if (judged) {
             if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
             else w->vl_backoff = 32;
         }
     } else if (w->steps >= w->vl_resume_at) {
         // come back once few enough bodies outrun the skin (the per-tick kernel keeps counting them)
-        if (w->vl_host[2] < w->P.hot_soft / 2u) {
+        if (w->vl_host[2] < w->P.hot_flood / 2u) {
             w->vl_active = true; w->vl_force = true; w->vl_seen_r = w->vl_host[0]; w->vl_seen_t = w->vl_host[1];
             w->vl_period = 8; w->vl_judged_at = w->tick_seq;
         }
@@ -1207,6 +1228,9 @@ int rb_get_stats(rb_world* w, rb_stats_t* out) {
         CU(cudaMemcpyAsync(v, w->P.vl, sizeof v, cudaMemcpyDeviceToHost, w->stream));
         CU(cudaStreamSynchronize(w->stream));
         const uint32_t nh = v[RB_VL_NHOT_LAST];
+        { static const bool dbg = [] { const char* e = getenv("RB_DEBUG_LISTS"); return e && *e == '1'; }();      // (development switch)
+          if (dbg) fprintf(stderr, "[lists] period %u spacing %u floor %u hot %u no-list rows of the last rebuild: crowded %u, wide %u, tile overflow %u\n",
+                           w->vl_period, w->vl_spacing, v[RB_VL_FLOOR], nh, v[RB_VL_NOLIST], v[RB_VL_NOLIST + 1], v[RB_VL_NOLIST + 2]); }
         out->list_rebuilds = v[RB_VL_NREBUILD]; out->list_ticks = v[RB_VL_NTICK]; out->list_skin = w->P.vl_skin;
         out->list_hot_last = nh; out->list_rebuild_reason = v[RB_VL_WHY_LAST];
         for (int b = 0; b < 4; b++) out->list_rebuilds_by_reason[b] = v[RB_VL_NWHY + b];
