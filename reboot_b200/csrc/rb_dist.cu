@@ -119,7 +119,9 @@ __device__ __forceinline__ void halo_wait(const uint32_t* arrive0, const uint32_
 // K6a (pack ghosts and migrants) is fused into rb_integrate_bin_kernel (rb_kernels.cu).
 
 // ---- K6b: swap-remove the emigrants (few per tick; one thread keeps it simple and ordered) --------
-__global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t* arrive0, const uint32_t* arrive1, uint32_t step, uint32_t* timeout_flag) {
+// list_tick: K1 has linked the hot rows into the cell table by ROW (their entry index rides in P.rank): a row that is moved into
+// a hole takes its entry along, an emigrant's entry is invalidated
+__global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t* arrive0, const uint32_t* arrive1, uint32_t step, uint32_t* timeout_flag, int list_tick) {
     if (threadIdx.x || blockIdx.x) return;
     if (arrive0 || arrive1) halo_wait(arrive0, arrive1, step, timeout_flag);     // fused-transport ticks: the neighbours' records must have landed
     uint32_t m = *D.emig_cnt;
@@ -129,6 +131,11 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
     float4* sph = D.sph_obj_w;
     for (uint32_t i = 0; i < m; ++i) {
         uint32_t h = D.emig[i], last = n - 1;
+        if (list_tick) {
+            const uint32_t kh = P.key[h], kl = P.key[last];
+            if (kh != RB_NONE && (kh & RB_HOT_BIT)) P.hot_row[P.rank[h]] = RB_NONE;
+            if (h != last && kl != RB_NONE && (kl & RB_HOT_BIT)) P.hot_row[P.rank[last]] = h;
+        }
         if (h != last) {
             P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
             sph[h] = sph[last]; D.gid[h] = D.gid[last]; P.ws[h] = P.ws[last]; P.key[h] = P.key[last]; P.rank[h] = P.rank[last];
@@ -355,7 +362,7 @@ static int dist_phase_b(rb_world* w, int list_mode) {
     const bool remote = d->mode == RB_X_P2P || d->mode == RB_X_LOCAL;
     const int p = remote ? (int)(d->halo_step & 1) : 0;
     const bool wait = d->mode == RB_X_P2P;
-    rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->Dp[p], wait && d->peer_blob[0] ? d->arrive(0) : nullptr, wait && d->peer_blob[1] ? d->arrive(1) : nullptr, d->halo_step, d->timeout_flag());
+    rb_halo_remove_kernel<<<1, 32, 0, w->stream>>>(P, d->Dp[p], wait && d->peer_blob[0] ? d->arrive(0) : nullptr, wait && d->peer_blob[1] ? d->arrive(1) : nullptr, d->halo_step, d->timeout_flag(), list_mode ? 1 : 0);
     const uint32_t imm_blocks = cdiv(2 * d->migr_cap, RB_BLOCK);
     rb_halo_unpack_kernel<<<imm_blocks + cdiv(3 * d->ghost_cap, RB_BLOCK), RB_BLOCK, 0, w->stream>>>(P, d->Dp[p], imm_blocks, list_mode ? 1 : 0);
     w->launches += 2;

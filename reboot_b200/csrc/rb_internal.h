@@ -126,6 +126,7 @@ struct rb_world {
     uint32_t vl_gen_flooded = 0xffffffffu;   // the generation whose flood report (lists do not pay right now) has been acted on
     uint32_t vl_judged_at = 0;               // list tick at which the lists-pay-off decision was last taken
     bool vl_tick_rebuilds = false;           // this list tick rebuilds at the host's request
+    bool vl_never_off = false;               // RB_VL_NEVER_OFF=1 (tests): never sit a rebuild-heavy phase out on the per-tick kernel
     unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step
     void* d_cull_out = nullptr; void* d_cull_cubes = nullptr; uint32_t* d_cull_cnt = nullptr; uint32_t cull_cap = 0;   // frustum-culling scratch (rb_extras.cu)
     cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)

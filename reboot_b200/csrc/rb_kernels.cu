@@ -193,6 +193,7 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
                 // (slab worlds: once more bodies are hot than a rebuild costs, the device asks for one; single worlds leave that to the host)
                 const uint32_t h = hot_push(P, s, c.x, c.z);
                 if (h == RB_NONE || (!P.soft && h >= P.hot_soft)) vl_request_rebuild(P, 2u);
+                if (P.dn && h != RB_NONE) P.rank[s] = h;      // slab worlds: a swap-remove that moves this row later in the tick repoints its entry (rb_halo_remove_kernel)
                 k |= RB_HOT_BIT;
             }
             if (s == 0 && do_bin == 3 && !P.tb_next) { P.vl[RB_VL_REBUILD] = 1u; P.vl[RB_VL_WHY] |= 4u; }
@@ -600,7 +601,7 @@ __device__ __forceinline__ void scan_hot_partners(const RbParams& P, uint32_t A,
         for (uint32_t hx = hx0; hx <= hx1; ++hx)
             for (uint32_t h = hot_cell_head(P, hz * P.hcn + hx); h; h = P.hot_next[h - 1u]) {
                 const uint32_t Bl = P.hot_row[h - 1u];
-                if (Bl == A) continue;
+                if (Bl == A || Bl == RB_NONE) continue;
                 const float4 o = P.ws[Bl];
                 float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
                 if (o.w < 0.f || (dx * dx + dy * dy) + dz * dz > rr * rr) continue;
@@ -823,7 +824,8 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
         // the neighbours' ghosts), triangles from the static grid -- and then steps exactly like the fused kernel
         const uint32_t nh = min(*P.nhot, P.hot_cap);
         valid = tid < nh;
-        if (valid) { A = P.hot_row[tid]; f0 = P.ws[A]; had_contact = (P.flags[A] & RB_F_CONTACT) != 0; }
+        if (valid) { A = P.hot_row[tid]; valid = A != RB_NONE; }      // (an entry whose row emigrated after K1 linked it)
+        if (valid) { f0 = P.ws[A]; had_contact = (P.flags[A] & RB_F_CONTACT) != 0; }
     } else {
         const uint32_t n_sorted = P.col_start[P.scx * P.scz];
         valid = tid < n_sorted;
@@ -923,7 +925,7 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
                 if (h) {
                     const uint32_t Bl = P.hot_row[h - 1u];
                     h = P.hot_next[h - 1u];
-                    if (Bl != A) {
+                    if (Bl != A && Bl != RB_NONE) {
                         const float4 o = P.ws[Bl];
                         float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
                         if (o.w >= 0.f && !((dx * dx + dy * dy) + dz * dz > rr * rr)) {
@@ -1403,7 +1405,7 @@ __global__ void __launch_bounds__(RB_LS_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_k
                 if (h) {
                     const uint32_t Bl = P.hot_row[h - 1u];
                     h = P.hot_next[h - 1u];
-                    if (Bl != A) {
+                    if (Bl != A && Bl != RB_NONE) {
                         const float4 o = P.ws[Bl];
                         float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
                         if (o.w >= 0.f && !((dx * dx + dy * dy) + dz * dz > rr * rr)) {

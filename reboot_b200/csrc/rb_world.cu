@@ -53,6 +53,7 @@ int rb_world_create(const rb_config* cfg, rb_world** out) {
     { const char* v = getenv("RB_COLLIDE_VARIANT"); if (v && *v) w->collide_variant = atoi(v); }
     { const char* v = getenv("RB_VERLET"); w->vl_on = !(v && *v == '0'); }          // persistent candidate lists (default on where they apply)
     { const char* v = getenv("RB_VERLET_SKIN"); if (v && *v) w->vl_skin_cfg = (float)atof(v); }
+    { const char* v = getenv("RB_VL_NEVER_OFF"); w->vl_never_off = v && *v == '1'; }      // tests: stay on the lists however often they rebuild
     { const char* v = getenv("RB_VERLET_HOT"); if (v && *v) w->vl_hot_cfg = atoi(v); }
     { const char* v = getenv("RB_VERLET_CDP"); w->vl_cdp = rb_have_device_launch() && !(v && *v == '0'); }
     { const char* v = getenv("RB_SCAN_V1"); if (v && *v == '1') w->scan_variant = 1; }
@@ -793,8 +794,7 @@ bool rb_step_will_use_lists(rb_world* w) {
                 w->vl_seen_r = nr; w->vl_seen_t = nt;
             }
         }
-        static const bool never_off = [] { const char* v = getenv("RB_VL_NEVER_OFF"); return v && *v == '1'; }();      // (development switch)
-        if (judged && never_off) mostly_rebuilding = false;
+        if (judged && w->vl_never_off) mostly_rebuilding = false;
         if (judged) {
             if (mostly_rebuilding) { w->vl_active = false; w->vl_host[2] = 0xffffffffu; w->vl_resume_at = w->steps + w->vl_backoff; w->vl_backoff = std::min<uint32_t>(w->vl_backoff * 2u, 256u); }
             else w->vl_backoff = 32;

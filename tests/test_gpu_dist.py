@@ -124,3 +124,33 @@ def test_mismatched_halo_layouts_are_refused(mods):
     # and the helper picks one layout for uneven partitions (the bug this guards against: per-rank auto values)
     L = ws[0].L
     assert L.rb_halo_ghost_cap_auto(500_000, 0.5, 0.0, 1000.0) != L.rb_halo_ghost_cap_auto(505_000, 0.5, 0.0, 1000.0)
+
+
+@pytest.mark.parametrize("nslabs", [2, 4])
+def test_slab_lists_with_migration_every_few_ticks(mods, nslabs, monkeypatch):
+    """Slab worlds kept on the persistent lists (RB_VL_NEVER_OFF=1) through a violent phase: bodies cross the faces every
+    few ticks, so list ticks remove emigrants (swap-remove: the last row moves into the hole AFTER K1 linked the hot rows
+    into the cell table by row), append immigrants and rebuild on the device's request. No host read in between -- the
+    host's own decisions run on stale reports, like in a long bench run. Regression: a moved hot row missed its tick."""
+    World, dist, scenes = mods
+    sc = _crossing_scene(scenes)
+    sc.body_vel[:, 0] *= np.float32(1.5)
+    monkeypatch.setenv("RB_VL_NEVER_OFF", "1")
+    single = World(sc)
+    group = dist.SlabGroup(sc, nslabs)
+    monkeypatch.delenv("RB_VL_NEVER_OFF")
+    for k in range(140):
+        single.step(5)
+        group.step(5)
+    a = single.state(); b = group.state(sc.n_bodies)
+    assert (b["owner"] >= 0).all(), "a body was lost in migration"
+    for key in ("pos", "vel", "model_t", "prev_t"):
+        assert np.array_equal(bits(a[key]), bits(b[key])), key
+    assert np.array_equal(a["flags"], b["flags"])
+    sa, sb = single.contact_sets(), group.contact_sets()
+    assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1])
+    st = [w.stats() for w in group.worlds]
+    busy = [s for s in st if s["n_bodies"] > 100]
+    assert busy and all(s["list_ticks"] >= 139 for s in busy), [(s["n_bodies"], s["list_ticks"]) for s in st]
+    assert sum(s["list_rebuilds_by_reason"][0] + s["list_rebuilds_by_reason"][3] for s in st) > 10, "migrations must have forced rebuilds"
+    single.close(); group.close()
