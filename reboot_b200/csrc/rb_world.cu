@@ -553,7 +553,8 @@ int rb_build(rb_world* w) {
         }
         CU(cudaEventCreateWithFlags(&w->vl_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_join, cudaEventDisableTiming));
         // coarse cell table of the hot bodies: cells wide enough that any reach box touches at most 2 x 2 of them
-        const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 256.0f);
+        // (as fine as that allows, up to 2048^2 cells: the chains every row walks stay short even when most bodies are hot)
+        const float lc = std::max(4.0f * P.rm_max, 2.0f * P.half / 2048.0f);
         P.hcn = (uint32_t)std::max(1L, (long)std::floor(2.0 * P.half / lc));
         P.hc_inv_w = (float)P.hcn / (2.0f * P.half);
         // every row has a slot (the table cannot overflow); hot_soft is the count at which rebuilding the lists pays
@@ -826,11 +827,11 @@ int rb_step(rb_world* w, int ms) {
     }
     w->steps++; w->pose_updates++;
     if (reorder_due && !(w->vl_on && w->vl_active)) { r = reorder_rows(w); if (r) return r; }      // (list ticks re-order inside the tick)
-    if (w->vl_on && (w->steps & 15u) == 0) {
+    if (w->vl_on && (w->steps & 7u) == 0) {
         // bounded run-ahead: the use-lists decision above feeds on what the device reports, so a host that enqueues
-        // hundreds of ticks ahead would decide blind. Every 16 ticks wait for the tick enqueued 16 ticks earlier:
-        // the device always has 16+ ticks queued (no bubble), the host is never more than 32 ahead.
-        const int k = (int)((w->steps >> 4) & 1u);
+        // hundreds of ticks ahead would decide blind. Every 8 ticks wait for the tick enqueued 8 ticks earlier:
+        // the device always has 8+ ticks queued (no bubble), the host is never more than 16 ahead.
+        const int k = (int)((w->steps >> 3) & 1u);
         if (!w->vl_pace[0]) { CU(cudaEventCreateWithFlags(&w->vl_pace[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_pace[1], cudaEventDisableTiming)); }
         if (w->d_dn) {      // slab worlds: the sticky overflow counters ride along (a lost body / missed ghost must not go unnoticed)
             if (!w->h_sticky) { CU(cudaMallocHost((void**)&w->h_sticky, 4 * sizeof(unsigned long long))); memset(w->h_sticky, 0, 4 * sizeof(unsigned long long)); }
