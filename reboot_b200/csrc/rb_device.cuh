@@ -127,6 +127,10 @@ struct RbParams {
     uint2* blk_tile;              // per block: { first unit of its region, entries }
     uint32_t* tile_cursor;        // next free unit (reset when a rebuild starts)
     uint32_t tile_pool_units;     // capacity of the pool
+    // slab worlds: the list step of a tick runs in two launches, the blocks none of whose rows can reach a neighbour's sphere
+    // BEFORE the halo step waits for the neighbours (their records arrive meanwhile), everybody else after it
+    uint32_t* blk_bnd;            // per block: the tick in which K1 last saw one of its rows within reach of a slab face (or leaving)
+    uint32_t* blk_done;           // per block: the tick in which the early launch stepped it
     // ---- persistent lists ("Verlet lists"): the lists above are built for spheres grown by vl_skin and
     // reused until some body has used its skin up; the sort and the enumeration only run on those ticks ----
     uint32_t* vl;                 // device words, see RB_VL_*
@@ -162,6 +166,10 @@ struct RbParams {
                                   // local bodies [0, dn[0]) are owned, [dn[0], dn[0]+dn[1]) are ghosts
     const uint32_t* gid;          // global body id per local body (NULL: id == local index)
     float s_x0;                   // x origin of the sphere column grid (-half for whole-world grids)
+    // the sphere grid's column key is cv * g_nu + cu: u is the axis whose neighbouring columns are contiguous in the sort, v the
+    // outer one. Single worlds: (u, v) = (x, z). Slab worlds: (u, v) = (z, x), so that the row order (which follows the sort)
+    // runs along x and the rows near the slab faces are the first and the last blocks
+    uint32_t g_swap, g_nu, g_nv; float g_off_u, g_off_v;
     const RbDistParams* dp;       // device copy of the halo parameters (slab worlds with neighbours), else NULL
 };
 
@@ -179,6 +187,8 @@ __device__ __forceinline__ void rb_prefetch(const void* p) {
 #endif
 }
 __device__ __forceinline__ uint32_t rb_gid(const RbParams& P, uint32_t local) { return P.gid ? P.gid[local] : local; }
+__device__ __forceinline__ float rb_gu(const RbParams& P, float x, float z) { return P.g_swap ? z : x; }
+__device__ __forceinline__ float rb_gv(const RbParams& P, float x, float z) { return P.g_swap ? x : z; }
 
 // K7 arguments: every per-body array pair (current rows -> re-ordered rows)
 #define RB_REORDER_MAX 12
@@ -288,6 +298,10 @@ __host__ __device__ __forceinline__ uint32_t rb_col(float x, float half, float i
     return (uint32_t)t;
 }
 
+// sphere-grid column of a point
+__device__ __forceinline__ uint32_t rb_sphere_col(const RbParams& P, float x, float z) {
+    return rb_col(rb_gv(P, x, z), P.g_off_v, P.s_inv_w, P.g_nv) * P.g_nu + rb_col(rb_gu(P, x, z), P.g_off_u, P.s_inv_w, P.g_nu);
+}
 // ---- hot-body cell table (persistent lists). Entries carry the tick they were written in: an entry of an earlier tick is an
 // empty cell, so nothing is cleared between ticks. ----
 __device__ __forceinline__ uint32_t hot_cell_head(const RbParams& P, uint32_t cell) {

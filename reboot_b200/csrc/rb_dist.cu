@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
         P.ws[i] = make_float4(c.x, c.y, c.z, m.obj.w + margin);
         uint32_t k = RB_NONE;
         if ((m.flags & RB_F_ACTIVE) && sphere_in_world(c, m.obj.w, P.half)) {
-            k = rb_col(c.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
+            k = rb_sphere_col(P, c.x, c.z);
             if (!list_tick) P.rank[i] = atomicAdd(&P.col_count[k], 1u);
         }
         P.key[i] = k;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
         P.key[i] = RB_NONE;
         return;
     }
-    uint32_t k = rb_col(q.ws.z, P.half, P.s_inv_w, P.scz) * P.scx + rb_col(q.ws.x, -P.s_x0, P.s_inv_w, P.scx);
+    uint32_t k = rb_sphere_col(P, q.ws.x, q.ws.z);
     P.key[i] = k;
     P.rank[i] = atomicAdd(&P.col_count[k], 1u);
 }
@@ -354,6 +354,10 @@ static int dist_phase_a(rb_world* w, int do_integrate, int list_mode) {
         if (d->peer_blob[k]) { ph[k] = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p).hdr(); pa[k] = RbDist::arrive_at(d->peer_blob[k], d->buf_bytes, 1 - k); }
     }
     rb_halo_signal_kernel<<<1, 32, 0, w->stream>>>(d->Dp[p].out_hdr[0], d->Dp[p].out_hdr[1], ph[0], ph[1], pa[0], pa[1], d->halo_step); w->launches++;
+    // list ticks the host does not turn into rebuilds: the blocks no ghost can reach step now, while the neighbours' records
+    // are still on their way (phase B waits for them)
+    w->halo_split = false;
+    if (list_mode == 2 && P.blk_bnd) { rb_launch_list_step_early(P, w->stream, w->vl_side, w->vl_fork, w->vl_join, rb_list_hot_rows(w)); w->launches += 2; w->halo_split = true; }
     return RB_OK;
 }
 // phase B: unpack + scan + scatter (everything after the exchange)

@@ -22,7 +22,9 @@ void rb_launch_clear(void* a, size_t bytes_a, uint32_t* b, uint32_t words_b, cud
 void rb_launch_vl_bin(const RbParams& P, cudaStream_t st);
 void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows);
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows, int phase);
+void rb_launch_list_step_early(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, uint32_t hot_rows);
+extern "C" uint32_t rb_list_hot_rows(rb_world* w);
 uint32_t rb_list_tile_bytes();
 uint32_t rb_list_partner_slots();   // partners a persistent list holds
 uint32_t rb_list_tile_rows();      // rows per triangle tile (= threads per block of the list step)
@@ -126,6 +128,7 @@ struct rb_world {
     uint32_t vl_gen_flooded = 0xffffffffu;   // the generation whose flood report (lists do not pay right now) has been acted on
     uint32_t vl_judged_at = 0;               // list tick at which the lists-pay-off decision was last taken
     bool vl_tick_rebuilds = false;           // this list tick rebuilds at the host's request
+    bool halo_split = false;                 // slab worlds: this list tick launched the early part of the list step before the halo wait
     bool vl_never_off = false;               // RB_VL_NEVER_OFF=1 (tests): never sit a rebuild-heavy phase out on the per-tick kernel
     unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step
     void* d_cull_out = nullptr; void* d_cull_cubes = nullptr; uint32_t* d_cull_cnt = nullptr; uint32_t cull_cap = 0;   // frustum-culling scratch (rb_extras.cu)

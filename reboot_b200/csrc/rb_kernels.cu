@@ -29,6 +29,9 @@
 namespace RB_KNS {
 
 #define RB_BLOCK 256
+#ifndef RB_LS_BLOCK
+#define RB_LS_BLOCK 256      // rows per triangle tile = threads per block of the list-step kernel (and of the enumeration that fills the tiles)
+#endif
 #define RB_MAXLOCAL 6   // contacts a thread buffers before the warp-aggregated append
 
 // ------------------------------------------------------------------------------------------
@@ -136,6 +139,7 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             // schedules anyway (do_bin == 3) or until it is further out than the band. Ownership never shows in results.
             if (dir >= 0 && do_bin == 2 && (dir == 0 ? D.slab_lo - c.x : c.x - D.slab_hi) <= D.mig_band) dir = -1;
             if (dir >= 0) {
+                if (P.blk_bnd && do_bin >= 2) P.blk_bnd[b / RB_LS_BLOCK] = P.tick;
                 uint32_t kk = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
                 if (kk < D.migr_cap) {
                     RbMigrRec mr; mr.pos = make_float4(p.x, p.y, p.z, p4.w); mr.vel = make_float4(v.x, v.y, v.z, v4.w);
@@ -149,6 +153,8 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             } else if (in_grid) {
                 float reach = r + margin + P.rm_max + D.mig_band;   // own grown radius + the largest grown radius anywhere (+ how far a neighbour's body may sit on our side)
                 RbGhostRec q; q.ws = make_float4(c.x, c.y, c.z, r + margin); q.r = r; q.gid = D.gid[b]; q.pad0 = q.pad1 = 0;
+                // (a row that is somebody's ghost is exactly a row a ghost can reach: its block waits for the halo)
+                if (P.blk_bnd && do_bin >= 2 && ((D.has_left && c.x - reach < D.slab_lo) || (D.has_right && c.x + reach >= D.slab_hi))) P.blk_bnd[b / RB_LS_BLOCK] = P.tick;
                 if (D.has_left && c.x - reach < D.slab_lo) {
                     uint32_t kk = atomicAdd(&D.out_hdr[0]->n_ghost, 1u);
                     if (kk < D.ghost_cap) D.out_ghost[0][kk] = q; else { atomicAdd(&D.out_hdr[0]->ghost_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }
@@ -161,9 +167,7 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
         }
         if (in_grid) {
             if (do_bin) {
-                uint32_t cx = rb_col(c.x, -P.s_x0, P.s_inv_w, P.scx);
-                uint32_t cz = rb_col(c.z, P.half, P.s_inv_w, P.scz);
-                k = cz * P.scx + cx;
+                k = rb_sphere_col(P, c.x, c.z);
                 if (do_bin == 1) P.rank[s] = atomicAdd(&P.col_count[k], 1u);
             } else k = 0;
             // lists switched off for now (the host sits out a phase of constant rebuilding on the per-tick kernel):
@@ -572,11 +576,12 @@ template <bool SINGLE>
 __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 fc, float frm, uint32_t lo,
                                               uint32_t& best, uint32_t& best_local, uint32_t& eligible, Tally& T) {
     float reach = frm + P.rm_max;
-    uint32_t cx0 = rb_col(fc.x - reach, -P.s_x0, P.s_inv_w, P.scx), cx1 = rb_col(fc.x + reach, -P.s_x0, P.s_inv_w, P.scx);
-    uint32_t cz0 = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz), cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
+    const float fu = rb_gu(P, fc.x, fc.z), fv = rb_gv(P, fc.x, fc.z);
+    uint32_t cx0 = rb_col(fu - reach, P.g_off_u, P.s_inv_w, P.g_nu), cx1 = rb_col(fu + reach, P.g_off_u, P.s_inv_w, P.g_nu);
+    uint32_t cz0 = rb_col(fv - reach, P.g_off_v, P.s_inv_w, P.g_nv), cz1 = rb_col(fv + reach, P.g_off_v, P.s_inv_w, P.g_nv);
     for (uint32_t cz = cz0; cz <= cz1; ++cz) {
-        uint32_t row = cz * P.scx;
-        uint32_t i = P.col_start[row + cx0], e = P.col_start[row + cx1 + 1];   // x-adjacent columns are contiguous
+        uint32_t row = cz * P.g_nu;
+        uint32_t i = P.col_start[row + cx0], e = P.col_start[row + cx1 + 1];   // u-adjacent columns are contiguous
         for (; i < e; ++i) {
             float4 o = P.sorted[i];
             float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
@@ -758,9 +763,6 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
 #ifndef RB_SSLIST_MAX
 #define RB_SSLIST_MAX 8       // partners a persistent list holds (dense piles: a sphere touches up to 12 neighbours)
 #endif
-#ifndef RB_LS_BLOCK
-#define RB_LS_BLOCK 256      // rows per triangle tile = threads per block of the list-step kernel (and of the enumeration that fills the tiles)
-#endif
 #define RB_TILE_CAP (3 * RB_LS_BLOCK)      // triangles one block's tile holds (39 KB of shared memory in the list-step kernel at 256 rows)
 #ifndef RB_COLLIDE_MINBLOCKS
 #define RB_COLLIDE_MINBLOCKS 3
@@ -804,7 +806,7 @@ __device__ __forceinline__ void ss_pair_single(const RbParams& P, BodyState& S, 
 //         enumerating for themselves like MODE 0 but against the sort of the last rebuild + the hot-body table.
 // All modes run the same tests in the same canonical order as rb_list_step_kernel: results are bit-identical.
 template <bool RESOLVE, int MODE>
-__device__ __forceinline__ void collide_single_rows(const RbParams& P, const uint32_t tid) {
+__device__ __forceinline__ void collide_single_rows(const RbParams& P, const uint32_t tid, const int phase) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t lane = threadIdx.x & 31;
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
@@ -827,6 +829,10 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
         const uint32_t nh = min(*P.nhot, P.hot_cap);
         valid = tid < nh;
         if (valid) { A = P.hot_row[tid]; valid = A != RB_NONE; }      // (an entry whose row emigrated after K1 linked it)
+        // slab worlds split the tick around the halo exchange like the list step: early, the hot rows of the blocks no ghost can
+        // reach; late, the rows of every block the early launches did not step
+        if (valid && phase == 1) valid = P.blk_bnd[A / RB_LS_BLOCK] != P.tick;
+        if (valid && phase == 2) valid = P.blk_done[A / RB_LS_BLOCK] != P.tick;
         if (valid) { f0 = P.ws[A]; had_contact = (P.flags[A] & RB_F_CONTACT) != 0; }
     } else {
         const uint32_t n_sorted = P.col_start[P.scx * P.scz];
@@ -863,15 +869,16 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
         uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0, ni = 0, ne = 0;
         if (valid) {
             float reach = frm + P.rm_max;
-            cx0 = rb_col(fc.x - reach, -P.s_x0, P.s_inv_w, P.scx); cx1 = rb_col(fc.x + reach, -P.s_x0, P.s_inv_w, P.scx);
-            cz = rb_col(fc.z - reach, P.half, P.s_inv_w, P.scz); cz1 = rb_col(fc.z + reach, P.half, P.s_inv_w, P.scz);
-            i = P.col_start[cz * P.scx + cx0]; e = P.col_start[cz * P.scx + cx1 + 1];
-            if (cz < cz1) { ni = P.col_start[(cz + 1) * P.scx + cx0]; ne = P.col_start[(cz + 1) * P.scx + cx1 + 1]; }   // next row, in flight early
+            const float fu = rb_gu(P, fc.x, fc.z), fv = rb_gv(P, fc.x, fc.z);      // (u: the axis whose columns are contiguous in the sort)
+            cx0 = rb_col(fu - reach, P.g_off_u, P.s_inv_w, P.g_nu); cx1 = rb_col(fu + reach, P.g_off_u, P.s_inv_w, P.g_nu);
+            cz = rb_col(fv - reach, P.g_off_v, P.s_inv_w, P.g_nv); cz1 = rb_col(fv + reach, P.g_off_v, P.s_inv_w, P.g_nv);
+            i = P.col_start[cz * P.g_nu + cx0]; e = P.col_start[cz * P.g_nu + cx1 + 1];
+            if (cz < cz1) { ni = P.col_start[(cz + 1) * P.g_nu + cx0]; ne = P.col_start[(cz + 1) * P.g_nu + cx1 + 1]; }   // next row, in flight early
         }
         while (true) {
             while (i >= e && cz < cz1) {
                 ++cz; i = ni; e = ne;
-                if (cz < cz1) { ni = P.col_start[(cz + 1) * P.scx + cx0]; ne = P.col_start[(cz + 1) * P.scx + cx1 + 1]; }
+                if (cz < cz1) { ni = P.col_start[(cz + 1) * P.g_nu + cx0]; ne = P.col_start[(cz + 1) * P.g_nu + cx1 + 1]; }
             }
             const bool work = i < e;
             if (!__any_sync(0xffffffffu, work)) break;
@@ -1256,14 +1263,15 @@ __device__ __forceinline__ void collide_single_rows(const RbParams& P, const uin
     if (MODE == 0 && P.vl && P.vl_host && tid == 0) P.vl_host[2] = P.vl[RB_VL_NFAST];     // lists switched off: K1's count of fast movers
 }
 template <bool RESOLVE, int MODE>
-__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(const RbParams P) {
+__global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_ENUM : RB_COLLIDE_MINBLOCKS) rb_collide_single_kernel(const RbParams P, const int phase) {
     if (MODE == 3) {
+        if (phase == 1 && P.vl[RB_VL_REBUILD]) return;      // K1 has asked for a rebuild (rows are about to move): everything steps after the exchange
         // the grid is sized from the hot count the host saw last (several ticks old): stride over the table, whatever its size.
         // Everything a pass shares lives per warp (staging columns, hit masks), so passes need no block barrier in between.
         const uint32_t nh = min(*P.nhot, P.hot_cap);
         for (uint32_t first = blockIdx.x * blockDim.x; first < nh; first += gridDim.x * blockDim.x)
-            collide_single_rows<RESOLVE, MODE>(P, first + threadIdx.x);
-    } else collide_single_rows<RESOLVE, MODE>(P, blockIdx.x * blockDim.x + threadIdx.x);
+            collide_single_rows<RESOLVE, MODE>(P, first + threadIdx.x, phase);
+    } else collide_single_rows<RESOLVE, MODE>(P, blockIdx.x * blockDim.x + threadIdx.x, 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1321,7 +1329,13 @@ __device__ __forceinline__ void append_contact(const RbParams& P, uint32_t a, ui
 // list of the later test rounds
 #define RB_LS_TILE_BYTES ((3u * RB_TILE_CAP + RB_TILE_CAP / 4u) * 16u)
 #define RB_LS_SMEM_BYTES (RB_LS_TILE_BYTES + 2u * RB_TILE_CAP * 2u)
-__global__ void __launch_bounds__(RB_LS_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kernel(const RbParams P) {
+// phase 0: every row (single worlds). Slab worlds split the step around the halo exchange: phase 1 = the blocks no ghost can
+// reach, launched before the wait for the neighbours (skipped altogether when K1 has asked for a rebuild: rows are about to
+// move); phase 2 = all the other blocks, after the ghosts have been linked in, plus the end-of-tick book-keeping.
+__device__ __forceinline__ void list_tick_bookkeeping(const RbParams& P);
+__global__ void __launch_bounds__(RB_LS_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_kernel(const RbParams P, const int phase) {
+    if (phase == 1) { if (P.vl[RB_VL_REBUILD] || P.blk_bnd[blockIdx.x] == P.tick) return; }
+    else if (phase == 2 && P.blk_done[blockIdx.x] == P.tick) { if (blockIdx.x == 0 && threadIdx.x == 0) list_tick_bookkeeping(P); return; }
     extern __shared__ __align__(16) uint4 s_tile[];
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ __align__(16) float4 s_pose[RB_LS_BLOCK];      // current sphere of each row of the block (w < 0: the row does not step here)
@@ -1619,7 +1633,11 @@ __global__ void __launch_bounds__(RB_LS_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_k
             }
         }
     }
-    if (tid == 0) {        // end of a persistent-list tick: book-keeping (the hot counter is final: K1 and the enumeration are done)
+    if (phase == 1) { if (threadIdx.x == 0) P.blk_done[blockIdx.x] = P.tick; }
+    else if (tid == 0) list_tick_bookkeeping(P);
+}
+// end of a persistent-list tick (one thread): the hot counter is final -- K1 and the enumeration are done
+__device__ __forceinline__ void list_tick_bookkeeping(const RbParams& P) {        // end of a persistent-list tick: book-keeping (the hot counter is final: K1 and the enumeration are done)
         const uint32_t f = P.vl[RB_VL_REBUILD];
         if (f) {
             const uint32_t why = P.vl[RB_VL_WHY];
@@ -1649,7 +1667,6 @@ __global__ void __launch_bounds__(RB_LS_BLOCK, RB_LIST_MINBLOCKS) rb_list_step_k
             P.vl_host[5] = expiry; P.vl_host[6] = gen; P.vl_host[7] = age;
             P.vl_host[4] = nt;        // (last: the host takes a report whose tick word it reads unchanged before and after)
         }
-    }
 }
 
 // do_bin: 0 integrate only, 1 integrate + bin (per-tick enumeration), 2 list tick, 3 list tick with a rebuild forced by the host
@@ -1670,7 +1687,7 @@ __global__ void rb_vl_gate_kernel(RbParams P) {
     rb_vl_bin_kernel<<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P);
     rb_scan_lookback_kernel<<<tiles, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P.col_count, P.ncols, P.col_start, P.scan_status, P.scan_ticket, P.vl + RB_VL_REBUILD, 1);
     rb_scatter_kernel<<<g, RB_BLOCK, 0, cudaStreamTailLaunch>>>(P, 1, P.scan_status, P.scan_ticket, tiles);
-    rb_collide_single_kernel<true, 1><<<gl, RB_LS_BLOCK, 0, cudaStreamTailLaunch>>>(P);
+    rb_collide_single_kernel<true, 1><<<gl, RB_LS_BLOCK, 0, cudaStreamTailLaunch>>>(P, 0);
 }
 #endif
 
@@ -1897,28 +1914,38 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 uint32_t rb_list_tile_bytes() { return RB_LS_SMEM_BYTES; }
 uint32_t rb_list_tile_rows() { return RB_LS_BLOCK; }
 uint32_t rb_list_partner_slots() { return RB_SSLIST_MAX; }
-int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows) {
+int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows, int phase) {
     if (!P.nb) return 0;
     const uint32_t g = cdiv(P.ns, RB_LS_BLOCK);
-    if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_LS_BLOCK, 0, st>>>(P);
+    if (with_enumerate) rb_collide_single_kernel<true, 1><<<g, RB_LS_BLOCK, 0, st>>>(P, 0);
     static const int side_mode = [] { const char* v = getenv("RB_HOT_SIDE"); return v && *v ? atoi(v) : 1; }();      // (development switch)
     if (side_mode == 0) {       // everything on one stream: hot bodies first
-        rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
-        rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P);
+        rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, phase);
+        rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P, phase);
         return 3;
     }
     if (side_mode == 2) {       // one stream, hot bodies last
-        rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P);
-        rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P);
+        rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P, phase);
+        rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, phase);
         return 3;
     }
     cudaEventRecord(fork, st);
     cudaStreamWaitEvent(side, fork, 0);
-    rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P);     // hot bodies: the blocks stride over the table (a block without work returns at once)
+    rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P, phase);     // hot bodies: the blocks stride over the table (a block without work returns at once)
     cudaEventRecord(join, side);
-    rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P);                         // everybody else, from the lists
+    rb_list_step_kernel<<<g, RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P, phase);                         // everybody else, from the lists
     cudaStreamWaitEvent(st, join, 0);
     return 3;
+}
+// slab worlds: the early part of the list step (blocks no ghost can reach), before the halo wait
+void rb_launch_list_step_early(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, uint32_t hot_rows) {
+    if (!P.nb) return;
+    cudaEventRecord(fork, st);
+    cudaStreamWaitEvent(side, fork, 0);
+    rb_collide_single_kernel<true, 3><<<cdiv(hot_rows, RB_BLOCK), RB_BLOCK, 0, side>>>(P, 1);
+    cudaEventRecord(join, side);
+    rb_list_step_kernel<<<cdiv(P.ns, RB_LS_BLOCK), RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P, 1);
+    cudaStreamWaitEvent(st, join, 0);
 }
 int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st) {
     if (!P.nb) return 0;
@@ -1928,8 +1955,8 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
             if (resolve) rb_collide_kernel<true, true><<<g, RB_BLOCK, 0, st>>>(P);
             else rb_collide_kernel<true, false><<<g, RB_BLOCK, 0, st>>>(P);
         } else {                                   // fused phases in one launch
-            if (resolve) rb_collide_single_kernel<true, 0><<<g, RB_BLOCK, 0, st>>>(P);
-            else rb_collide_single_kernel<false, 0><<<g, RB_BLOCK, 0, st>>>(P);
+            if (resolve) rb_collide_single_kernel<true, 0><<<g, RB_BLOCK, 0, st>>>(P, 0);
+            else rb_collide_single_kernel<false, 0><<<g, RB_BLOCK, 0, st>>>(P, 0);
         }
         return 1;
     }

@@ -480,6 +480,9 @@ int rb_build(rb_world* w) {
             P.scx = (uint32_t)std::max(1L, std::min((long)n, (long)std::ceil((hi - P.s_x0) / cw)));
         }
         w->ncols = P.scx * P.scz;
+        P.g_swap = slab ? 1u : 0u;
+        P.g_nu = slab ? P.scz : P.scx; P.g_nv = slab ? P.scx : P.scz;
+        P.g_off_u = slab ? P.half : -P.s_x0; P.g_off_v = slab ? -P.s_x0 : P.half;
     }
     // ---- device state ----
     float4 *d_pos, *d_vel, *d_mt, *d_pt, *d_sph, *d_ws, *d_sorted; uint32_t *d_flags, *d_key, *d_rank, *d_cc, *d_cs, *d_sid;
@@ -581,6 +584,18 @@ int rb_build(rb_world* w) {
         ALLOC(tp, P.tile_pool_units); ALLOC(bt, nblk); ALLOC(tc, 4);
         CU(cudaMemsetAsync(eh, 0, (size_t)P.ns * 4, w->stream)); CU(cudaMemsetAsync(bt, 0, nblk * sizeof(uint2), w->stream)); CU(cudaMemsetAsync(tc, 0, 16, w->stream));
         P.e_hdr = eh; P.e_pg = eg; P.e_pl = el; P.tile_pool = tp; P.blk_tile = bt; P.tile_cursor = tc;
+        if (slab) {
+            // RB_HALO_SPLIT=1: the list step (and the hot bodies' launch) split around the halo exchange -- the blocks no ghost can
+            // reach step before the wait for the neighbours. Measured at N=2 (C3 weak): the wait disappears (halo stage 25 -> 3 us)
+            // but the late hot-body launch, a handful of latency-bound warps that used to hide behind the full list step, is now
+            // exposed (35 us): 0.227 against 0.201 ms per tick. Off by default. (tick numbers as versions: never cleared)
+            const char* v = getenv("RB_HALO_SPLIT");
+            if (v && *v == '1') {
+                uint32_t *bb, *bd; ALLOC(bb, nblk); ALLOC(bd, nblk);
+                CU(cudaMemsetAsync(bb, 0, nblk * 4, w->stream)); CU(cudaMemsetAsync(bd, 0, nblk * 4, w->stream));
+                P.blk_bnd = bb; P.blk_done = bd;
+            }
+        }
     }
     {   // static 3x3 of every _worldSpaceTransform, kept only when some body is not identity (model-matrix export)
         bool any = false;
@@ -675,6 +690,8 @@ static int enqueue_collide(rb_world* w, bool resolve) {
 // Results are the ones of the per-tick enumeration: the lists are supersets of it and every decision is taken by the same
 // exact tests in the same order.
 // (second half of a list tick: slab worlds get here after their halo exchange; K1 ran before it)
+static uint32_t list_hot_rows(rb_world* w);
+uint32_t rb_list_hot_rows(rb_world* w) { return list_hot_rows(w); }
 static uint32_t list_hot_rows(rb_world* w) {
     // grid of the hot bodies' launch: its blocks stride over the table, so any size is correct. Enough blocks to fill the GPU
     // whatever the count turns out to be (the host's view of it is many ticks old); a block without work returns at once
@@ -696,7 +713,8 @@ int rb_list_tick_tail(rb_world* w, bool reorder_due) {
     if (chain) rb_launch_vl_scatter(P, w->ncols, w->d_scan_status, w->d_scan_ticket, w->stream);
     if (reorder_due) { int r = reorder_rows(w, true); if (r) return r; }     // rows into sort order before the lists are built for them
     if (w->profile) CU(cudaEventRecord(w->ev[3], w->stream));
-    w->launches += (chain ? 3 : 0) + (gate ? 1 : 0) + 1 /* K1 */ + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join, chain, list_hot_rows(w));
+    w->launches += (chain ? 3 : 0) + (gate ? 1 : 0) + 1 /* K1 */ + rb_launch_vl_collide(P, w->stream, w->vl_side, w->vl_fork, w->vl_join, chain, list_hot_rows(w), w->halo_split ? 2 : 0);
+    w->halo_split = false;
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
