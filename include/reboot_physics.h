@@ -270,6 +270,12 @@ int         rb_frustum_cull_cubes(rb_world* w, const float planes24[24], uint32_
 int         rb_frustum_cull_static(rb_world* w, const float inv_view_proj[16], uint32_t* cells, uint32_t cap, uint32_t* n_visible);
 int         rb_get_static_cells(rb_world* w, float* boxes6, uint32_t* ntri);
 
+/* GeometryMath::triangleCubeDetection (math/src/GeometryMath.cpp:233-411), the predicate OSP::generateGeometryOSP hands
+ * triangles down its tree with (physics/src/OSP.cpp:242-332), evaluated on the device for n (triangle, cube) pairs:
+ * tri9 = n * (A, B, C), cube6 = n * (centre xyz, length, height, width) as in the reference's Cube; out[i] = 1 on overlap.
+ * rb_build uses the same device function to register each static triangle in the grid columns its surface crosses. */
+int         rb_triangle_cube_test(rb_world* w, uint32_t n, const float* tri9, const float* cube6, uint32_t* out);
+
 /* Collider ingest: FbxLoader::_buildGeometryData (model/src/FbxLoader.cpp:1109-1216) for a neutral indexed mesh
  * (xyz3 vertices, idx). trs9 = node translation, rotation in degrees (x, y, z), scale: the node transform is
  * translation * rotX * rotY * rotZ * scale (:1114-1131). Pure host functions, bit-identical to the reference's

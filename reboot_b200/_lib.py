@@ -95,6 +95,7 @@ SIGNATURES = {
     "rb_frustum_cull_cubes": (C.c_int, [_P, _P, C.c_uint32, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "rb_frustum_cull_static": (C.c_int, [_P, _P, _P, C.c_uint32, C.POINTER(C.c_uint32)]),
     "rb_get_static_cells": (C.c_int, [_P, _P, _P]),
+    "rb_triangle_cube_test": (C.c_int, [_P, C.c_uint32, _P, _P, _P]),
     "rb_ingest_trs_matrix": (C.c_int, [_P, _P]),
     "rb_ingest_mesh_triangles": (C.c_int, [C.c_uint32, _P, C.c_uint32, _P, _P, _P]),
     "rb_ingest_mesh_sphere": (C.c_int, [C.c_uint32, _P, C.c_uint32, _P, _P, _P]),

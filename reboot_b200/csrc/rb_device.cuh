@@ -246,6 +246,43 @@ __device__ __forceinline__ bool sphere_triangle_detect(f3 P, float r, f3 ta, f3 
     return true;
 }
 
+// GeometryMath::triangleCubeDetection (math/src/GeometryMath.cpp:233-411): Akenine-Moeller's triangle / AABB separating-axis
+// test in box-centred coordinates -- nine cross-product axes, the three box axes, the triangle plane. The reference pairs
+// height / 2 with x, width / 2 with y and length / 2 with z (:238-240); strict comparisons (touching = overlap), the plane
+// test closed on the far side (:405-409). ctr + (length, height, width) is the reference's Cube.
+__host__ __device__ __forceinline__ float rb_fmax2(float a, float b) { return a > b ? a : b; }      // GeometryMath.cpp:556-559
+__host__ __device__ __forceinline__ float rb_fmin2(float a, float b) { return a < b ? a : b; }      // :561-564
+__device__ __forceinline__ bool tri_cube_axis_separates(f3 v0, f3 v1, f3 v2, f3 axis, float e0, float e1, float e2) {
+    const float p0 = dot3(v0, axis), p1 = dot3(v1, axis), p2 = dot3(v2, axis);
+    // r = e0 |u0 . a| + e1 |u1 . a| + e2 |u2 . a| with the unit axes spelled out like the reference's dot products
+    const float r = e0 * fabsf((1.0f * axis.x + 0.0f * axis.y) + 0.0f * axis.z) + e1 * fabsf((0.0f * axis.x + 1.0f * axis.y) + 0.0f * axis.z) + e2 * fabsf((0.0f * axis.x + 0.0f * axis.y) + 1.0f * axis.z);
+    return (rb_fmax2(p2, rb_fmax2(p0, p1)) < -r) || (rb_fmin2(p2, rb_fmin2(p0, p1)) > r);
+}
+__device__ __forceinline__ bool triangle_cube_detect(f3 ta, f3 tb, f3 tc, f3 ctr, float length, float height, float width) {
+    const float e0 = height / 2.0f, e1 = width / 2.0f, e2 = length / 2.0f;
+    const f3 v0 = sub3(ta, ctr), v1 = sub3(tb, ctr), v2 = sub3(tc, ctr);
+    const f3 f0 = sub3(v1, v0), f1 = sub3(v2, v1), f2 = sub3(v0, v2);
+    const f3 u[3] = { mk3(1.f, 0.f, 0.f), mk3(0.f, 1.f, 0.f), mk3(0.f, 0.f, 1.f) };
+    const f3 f[3] = { f0, f1, f2 };
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (tri_cube_axis_separates(v0, v1, v2, cross3(u[i], f[j]), e0, e1, e2)) return false;
+    if ((rb_fmax2(v0.x, rb_fmax2(v1.x, v2.x)) < -e0) || (rb_fmin2(v0.x, rb_fmin2(v1.x, v2.x)) > e0)) return false;
+    if ((rb_fmax2(v0.y, rb_fmax2(v1.y, v2.y)) < -e1) || (rb_fmin2(v0.y, rb_fmin2(v1.y, v2.y)) > e1)) return false;
+    if ((rb_fmax2(v0.z, rb_fmax2(v1.z, v2.z)) < -e2) || (rb_fmin2(v0.z, rb_fmin2(v1.z, v2.z)) > e2)) return false;
+    const f3 normal = cross3(f0, f1);
+    const float d = -dot3(normal, v0);
+    f3 vmin, vmax;
+    if (normal.x > 0.0f) { vmin.x = -e0; vmax.x = e0; } else { vmin.x = e0; vmax.x = -e0; }
+    if (normal.y > 0.0f) { vmin.y = -e1; vmax.y = e1; } else { vmin.y = e1; vmax.y = -e1; }
+    if (normal.z > 0.0f) { vmin.z = -e2; vmax.z = e2; } else { vmin.z = e2; vmax.z = -e2; }
+    if (dot3(normal, vmin) + d > 0.0f) return false;
+    if (dot3(normal, vmax) + d >= 0.0f) return true;
+    return false;
+}
+
 // GeometryMath::_closestPoint (math/src/GeometryMath.cpp:566-628), Ericson pp.141-142.
 __device__ __forceinline__ f3 closest_point(f3 P, f3 A, f3 B, f3 C) {
     f3 ab = sub3(B, A), ac = sub3(C, A), ap = sub3(P, A);

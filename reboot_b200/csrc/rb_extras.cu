@@ -233,6 +233,138 @@ int rb_get_static_cells(rb_world* w, float* boxes6, uint32_t* ntri) {
     return RB_OK;
 }
 
+// ---- static triangle column grid, built on the device (replaces the per-leaf triangle sets of OSP::generateGeometryOSP,
+// physics/src/OSP.cpp:25-60, 242-332; built once: triangles never move) -------------------------------------------------
+// A triangle is registered in the columns of its box's column range (half-open at the upper boundary with a 2.5e-4
+// tolerance, < the smallest candidate margin of 1e-3, so an aligned lattice registers one column per cell); when that range
+// spans several columns, only in those its surface actually crosses: the reference's own triangle / box predicate
+// (GeometryMath::triangleCubeDetection, the test OSP uses to hand triangles down its tree) against the column prism grown by
+// a slack far above the predicate's rounding. A sphere that touches the triangle touches it at a point of some column its
+// box overlaps, and the triangle crosses that column: nothing is lost.
+struct RbTriGrid { uint32_t n; float half, inv_w, cw, slack; };
+__device__ __forceinline__ void tgrid_range(const RbTriGrid& G, float lo, float hi, uint32_t& c0, uint32_t& c1) {
+    c0 = rb_col(lo, G.half, G.inv_w, G.n);
+    c1 = rb_col(hi, G.half, G.inv_w, G.n);
+    const uint32_t c1t = rb_col(hi - 2.5e-4f, G.half, G.inv_w, G.n);
+    if (c1 > c0 && c1t < c1) c1 = c1t;
+}
+__device__ __forceinline__ bool tgrid_crosses(const RbTriGrid& G, f3 a, f3 b, f3 c, uint32_t x, uint32_t z, bool multi) {
+    if (!multi) return true;
+    const f3 ctr = mk3(-G.half + ((float)x + 0.5f) * G.cw, 0.0f, -G.half + ((float)z + 0.5f) * G.cw);
+    // Cube(length, height, width): height pairs with x, width with y, length with z (GeometryMath.cpp:238-240)
+    return triangle_cube_detect(a, b, c, ctr, G.cw + 2.0f * G.slack, G.cw + 2.0f * G.slack, 16.0f * G.half);
+}
+// pass 1: device triangle records (vertices + the static normal of GeometryMath::sphereTriangleResolution, :499-503:
+// normalize((C - A) x (B - A)) in the reference's rounding order, w lanes) and the per-column counts
+// pass 2 (fill != NULL): the entries -- triangle id + its box -- at start[col] + arrival rank
+__global__ void __launch_bounds__(RB_BLOCK) rb_tgrid_scatter_kernel(RbTriGrid G, const float* __restrict__ xyz9, uint32_t nt, float4* __restrict__ tri,
+                                                                   uint32_t* __restrict__ count, const uint32_t* __restrict__ start,
+                                                                   uint32_t* __restrict__ list, float4* __restrict__ ent) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    const float* p = xyz9 + 9ull * t;
+    const f3 a = mk3(p[0], p[1], p[2]), b = mk3(p[3], p[4], p[5]), c = mk3(p[6], p[7], p[8]);
+    if (tri) {
+        const f3 nrm = normalize3(cross3(sub3(c, a), sub3(b, a)));
+        tri[3ull * t] = make_float4(a.x, a.y, a.z, nrm.x); tri[3ull * t + 1] = make_float4(b.x, b.y, b.z, nrm.y); tri[3ull * t + 2] = make_float4(c.x, c.y, c.z, nrm.z);
+    }
+    const float bx0 = fminf(a.x, fminf(b.x, c.x)), bx1 = fmaxf(a.x, fmaxf(b.x, c.x));
+    const float by0 = fminf(a.y, fminf(b.y, c.y)), by1 = fmaxf(a.y, fmaxf(b.y, c.y));
+    const float bz0 = fminf(a.z, fminf(b.z, c.z)), bz1 = fmaxf(a.z, fmaxf(b.z, c.z));
+    uint32_t x0, x1, z0, z1; tgrid_range(G, bx0, bx1, x0, x1); tgrid_range(G, bz0, bz1, z0, z1);
+    const bool multi = x1 > x0 || z1 > z0;
+    for (uint32_t z = z0; z <= z1; ++z)
+        for (uint32_t x = x0; x <= x1; ++x) {
+            if (!tgrid_crosses(G, a, b, c, x, z, multi)) continue;
+            const size_t col = (size_t)z * G.n + x;
+            const uint32_t r = atomicAdd(&count[col], 1u);
+            if (list) {
+                const uint32_t k = start[col] + r;
+                list[k] = t;
+                ent[2ull * k] = make_float4(bx0, bx1, bz0, bz1);
+                ent[2ull * k + 1] = make_float4(by0, by1, __uint_as_float(t), 0.f);
+            }
+        }
+}
+// pass 3: one thread per column -- its entries into ascending triangle id (the canonical order of the narrowphase walks) and
+// the y range of what it holds
+__global__ void __launch_bounds__(RB_BLOCK) rb_tgrid_finish_kernel(uint32_t ncol, const uint32_t* __restrict__ start, uint32_t* __restrict__ list,
+                                                                  float4* __restrict__ ent, float2* __restrict__ yr) {
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncol) return;
+    const uint32_t s = start[col], e = start[col + 1];
+    float lo = INFINITY, hi = -INFINITY;
+    for (uint32_t i = s + 1; i < e; ++i) {      // insertion sort: columns hold a handful of entries, arrival order is nearly sorted
+        const uint32_t t = list[i]; const float4 e0 = ent[2ull * i], e1 = ent[2ull * i + 1];
+        uint32_t j = i;
+        while (j > s && list[j - 1] > t) { list[j] = list[j - 1]; ent[2ull * j] = ent[2ull * (j - 1)]; ent[2ull * j + 1] = ent[2ull * (j - 1) + 1]; --j; }
+        list[j] = t; ent[2ull * j] = e0; ent[2ull * j + 1] = e1;
+    }
+    for (uint32_t i = s; i < e; ++i) { const float4 e1 = ent[2ull * i + 1]; lo = fminf(lo, e1.x); hi = fmaxf(hi, e1.y); }
+    yr[col] = make_float2(lo, hi);
+}
+// host driver (called by rb_build): n columns per axis, triangles in w->h_tri
+int rb_build_triangle_grid_device(rb_world* w, uint32_t n) {
+    RbParams& P = w->P;
+    const uint32_t nt = P.nt;
+    const float half = w->cfg.world_half;
+    const size_t ncol = (size_t)n * n;
+    RbTriGrid G; G.n = n; G.half = half; G.inv_w = P.t_inv_w; G.cw = 2.0f * half / (float)n; G.slack = std::max(1e-3f * G.cw, 5e-4f);
+    float* d_xyz = nullptr; uint32_t *d_count = nullptr, *d_tiles = nullptr;
+    float4* d_tri; uint32_t* d_start; float2* d_yr;
+    ALLOC(d_tri, (size_t)std::max<uint32_t>(nt, 1) * 3); ALLOC(d_start, ncol + 1); ALLOC(d_yr, ncol);
+    CU(cudaMalloc(&d_xyz, std::max<size_t>((size_t)nt * 9, 1) * sizeof(float)));
+    CU(cudaMalloc(&d_count, (ncol + 1) * sizeof(uint32_t)));
+    CU(cudaMalloc(&d_tiles, (rb_scan_tiles((uint32_t)ncol) + 1) * sizeof(uint32_t)));
+    auto cleanup = [&] { cudaFree(d_xyz); cudaFree(d_count); cudaFree(d_tiles); };
+    cudaError_t e = cudaMemcpyAsync(d_xyz, w->h_tri.data(), (size_t)nt * 9 * sizeof(float), cudaMemcpyHostToDevice, w->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_count, 0, (ncol + 1) * sizeof(uint32_t), w->stream);
+    const uint32_t gt = (nt + RB_BLOCK - 1) / RB_BLOCK;
+    if (e == cudaSuccess && nt) rb_tgrid_scatter_kernel<<<gt, RB_BLOCK, 0, w->stream>>>(G, d_xyz, nt, d_tri, d_count, nullptr, nullptr, nullptr);
+    if (e == cudaSuccess) { rb_launch_scan(d_count, (uint32_t)ncol, d_start, d_tiles, w->stream); w->launches += 4; }
+    uint32_t total = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_start + ncol, 4, cudaMemcpyDeviceToHost, w->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(w, RB_ERR_CUDA, "static grid build: %s", cudaGetErrorString(e)); }
+    uint32_t* d_list; float4* d_ent;
+    { int r = dev_alloc(w, &d_list, std::max<size_t>(total, 1)); if (r) { cleanup(); return r; } }
+    { int r = dev_alloc(w, &d_ent, std::max<size_t>(total, 1) * 2); if (r) { cleanup(); return r; } }
+    e = cudaMemsetAsync(d_count, 0, (ncol + 1) * sizeof(uint32_t), w->stream);
+    if (e == cudaSuccess && nt) rb_tgrid_scatter_kernel<<<gt, RB_BLOCK, 0, w->stream>>>(G, d_xyz, nt, nullptr, d_count, d_start, d_list, d_ent);
+    if (e == cudaSuccess) rb_tgrid_finish_kernel<<<(uint32_t)((ncol + RB_BLOCK - 1) / RB_BLOCK), RB_BLOCK, 0, w->stream>>>((uint32_t)ncol, d_start, d_list, d_ent, d_yr);
+    w->launches += 2;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    cleanup();
+    if (e != cudaSuccess) return fail(w, RB_ERR_CUDA, "static grid build: %s", cudaGetErrorString(e));
+    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list; P.tcol_yr = d_yr; P.tcol_ent = d_ent;
+    return RB_OK;
+}
+
+// GeometryMath::triangleCubeDetection for n (triangle, cube) pairs on the device: tri9 = n * (A, B, C), cube6 = n * (centre xyz,
+// length, height, width); out[i] = 1 when they overlap
+__global__ void __launch_bounds__(RB_BLOCK) rb_triangle_cube_kernel(uint32_t n, const float* __restrict__ tri9, const float* __restrict__ cube6, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = tri9 + 9ull * i; const float* q = cube6 + 6ull * i;
+    out[i] = triangle_cube_detect(mk3(t[0], t[1], t[2]), mk3(t[3], t[4], t[5]), mk3(t[6], t[7], t[8]), mk3(q[0], q[1], q[2]), q[3], q[4], q[5]) ? 1u : 0u;
+}
+extern "C" int rb_triangle_cube_test(rb_world* w, uint32_t n, const float* tri9, const float* cube6, uint32_t* out) {
+    if (!w || (n && (!tri9 || !cube6 || !out))) return w ? fail(w, RB_ERR_INVALID, "NULL argument") : RB_ERR_INVALID;
+    if (!n) return RB_OK;
+    CU(cudaSetDevice(w->cfg.device));
+    float *d_t = nullptr, *d_c = nullptr; uint32_t* d_o = nullptr;
+    CU(cudaMalloc(&d_t, (size_t)n * 36)); CU(cudaMalloc(&d_c, (size_t)n * 24)); CU(cudaMalloc(&d_o, (size_t)n * 4));
+    cudaError_t e = cudaMemcpyAsync(d_t, tri9, (size_t)n * 36, cudaMemcpyHostToDevice, w->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, cube6, (size_t)n * 24, cudaMemcpyHostToDevice, w->stream);
+    if (e == cudaSuccess) { rb_triangle_cube_kernel<<<(n + RB_BLOCK - 1) / RB_BLOCK, RB_BLOCK, 0, w->stream>>>(n, d_t, d_c, d_o); w->launches++; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, w->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+    cudaFree(d_t); cudaFree(d_c); cudaFree(d_o);
+    if (e != cudaSuccess) return fail(w, RB_ERR_CUDA, "rb_triangle_cube_test: %s", cudaGetErrorString(e));
+    return RB_OK;
+}
+
 // ---- collider ingest ------------------------------------------------------------------------------
 // node transform = translation * rotX * rotY * rotZ * scale, trs9 = (tx,ty,tz, rx,ry,rz in degrees, sx,sy,sz)
 int rb_ingest_trs_matrix(const float trs9[9], float out16[16]) {

@@ -25,6 +25,7 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows, int phase);
 void rb_launch_list_step_early(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, uint32_t hot_rows);
 extern "C" uint32_t rb_list_hot_rows(rb_world* w);
+extern "C" int rb_build_triangle_grid_device(rb_world* w, uint32_t n);      // rb_extras.cu: static triangle column grid (n columns per axis) from w->h_tri
 uint32_t rb_list_tile_bytes();
 uint32_t rb_list_partner_slots();   // partners a persistent list holds
 uint32_t rb_list_tile_rows();      // rows per triangle tile (= threads per block of the list step)

@@ -187,81 +187,8 @@ static int build_triangle_grid(rb_world* w) {
     n = std::max(1L, std::min(4096L, n));
     P.tcx = P.tcz = (uint32_t)n;
     P.t_inv_w = (float)n / (2.0f * half);
-    const size_t ncol = (size_t)n * n;
-    std::vector<uint32_t> start(ncol + 1, 0);
-    auto range = [&](const float* p, int axis, uint32_t& c0, uint32_t& c1) {
-        float lo = std::min(p[axis], std::min(p[3 + axis], p[6 + axis]));
-        float hi = std::max(p[axis], std::max(p[3 + axis], p[6 + axis]));
-        c0 = rb_col(lo, half, P.t_inv_w, (uint32_t)n);
-        c1 = rb_col(hi, half, P.t_inv_w, (uint32_t)n);
-        // a triangle that only touches the upper column at its boundary line is reachable from the
-        // lower one by every sphere whose margin-grown box touches it (margins are > 0)
-        // (tolerance 2.5e-4 world units < the smallest candidate margin of 1e-3, so lattices whose cell
-        // size is not exactly representable still register one column per cell)
-        float t = (hi - 2.5e-4f + half) * P.t_inv_w;
-        uint32_t c1t = rb_col(hi - 2.5e-4f, half, P.t_inv_w, (uint32_t)n);
-        if (c1 > c0 && c1t < c1) c1 = c1t;
-        (void)t;
-    };
-    for (uint32_t t = 0; t < nt; t++) {
-        const float* p = &w->h_tri[(size_t)t * 9];
-        uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
-        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) start[(size_t)z * n + x + 1]++;
-    }
-    for (size_t i = 0; i < ncol; i++) start[i + 1] += start[i];
-    std::vector<uint32_t> list(std::max<size_t>(start[ncol], 1));
-    std::vector<uint32_t> fill(start.begin(), start.end() - 1);
-    std::vector<float> ent(list.size() * 8, 0.f);
-    for (uint32_t t = 0; t < nt; t++) {   // ascending t => every column list is ascending
-        const float* p = &w->h_tri[(size_t)t * 9];
-        uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
-        float bx0 = std::min(p[0], std::min(p[3], p[6])), bx1 = std::max(p[0], std::max(p[3], p[6]));
-        float by0 = std::min(p[1], std::min(p[4], p[7])), by1 = std::max(p[1], std::max(p[4], p[7]));
-        float bz0 = std::min(p[2], std::min(p[5], p[8])), bz1 = std::max(p[2], std::max(p[5], p[8]));
-        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) {
-            uint32_t k = fill[(size_t)z * n + x]++;
-            list[k] = t;
-            float* e = &ent[(size_t)k * 8];
-            e[0] = bx0; e[1] = bx1; e[2] = bz0; e[3] = bz1; e[4] = by0; e[5] = by1; memcpy(&e[6], &t, 4); e[7] = 0.f;
-        }
-    }
-    std::vector<float> yr(ncol * 2);
-    for (size_t i = 0; i < ncol; i++) { yr[2 * i] = INFINITY; yr[2 * i + 1] = -INFINITY; }
-    for (uint32_t t = 0; t < nt; t++) {
-        const float* p = &w->h_tri[(size_t)t * 9];
-        float lo = std::min(p[1], std::min(p[4], p[7])), hi = std::max(p[1], std::max(p[4], p[7]));
-        uint32_t x0, x1, z0, z1; range(p, 0, x0, x1); range(p, 2, z0, z1);
-        for (uint32_t z = z0; z <= z1; z++) for (uint32_t x = x0; x <= x1; x++) { size_t c = (size_t)z * n + x; yr[2 * c] = std::min(yr[2 * c], lo); yr[2 * c + 1] = std::max(yr[2 * c + 1], hi); }
-    }
-    std::vector<float> tri4((size_t)std::max<uint32_t>(nt, 1) * 12, 0.f);
-    for (uint32_t t = 0; t < nt; t++) {
-        for (int v = 0; v < 3; v++) for (int k = 0; k < 3; k++) tri4[(size_t)t * 12 + v * 4 + k] = w->h_tri[(size_t)t * 9 + v * 3 + k];
-        // static triangle normal of GeometryMath::sphereTriangleResolution (GeometryMath.cpp:499-503):
-        // normalize((C - A) x (B - A)) in the reference's FP32 rounding order, stored in the w lanes
-        const float* p = &w->h_tri[(size_t)t * 9];
-        volatile float ux = p[6] - p[0], uy = p[7] - p[1], uz = p[8] - p[2];     // C - A
-        volatile float vx = p[3] - p[0], vy = p[4] - p[1], vz = p[5] - p[2];     // B - A
-        volatile float m1 = uy * vz, m2 = uz * vy, m3 = uz * vx, m4 = ux * vz, m5 = ux * vy, m6 = uy * vx;
-        volatile float nx = m1 - m2, ny = m3 - m4, nz = m5 - m6;
-        volatile float s1 = nx * nx, s2 = ny * ny, s3 = nz * nz;
-        volatile float s12 = s1 + s2; volatile float ss = s12 + s3;
-        volatile float mag = sqrtf(ss);
-        tri4[(size_t)t * 12 + 3] = nx / mag; tri4[(size_t)t * 12 + 7] = ny / mag; tri4[(size_t)t * 12 + 11] = nz / mag;
-    }
-    float4* d_tri; uint32_t* d_start; uint32_t* d_list; float2* d_yr; float4* d_ent;
-    ALLOC(d_ent, std::max<size_t>(list.size(), 1) * 2);
-    CU(cudaMemcpyAsync(d_ent, ent.data(), ent.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
-    ALLOC(d_yr, ncol);
-    CU(cudaMemcpyAsync(d_yr, yr.data(), yr.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
-    ALLOC(d_tri, (size_t)std::max<uint32_t>(nt, 1) * 3);
-    ALLOC(d_start, ncol + 1);
-    ALLOC(d_list, list.size());
-    CU(cudaMemcpyAsync(d_tri, tri4.data(), tri4.size() * sizeof(float), cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(d_start, start.data(), start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(d_list, list.data(), list.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    CU(cudaStreamSynchronize(w->stream));
-    P.tri = d_tri; P.tcol_start = d_start; P.tcol_tri = d_list; P.tcol_yr = d_yr; P.tcol_ent = d_ent;
-    return RB_OK;
+    // registration, the device triangle records and the per-column y ranges: on the device (rb_extras.cu)
+    return rb_build_triangle_grid_device(w, (uint32_t)n);
 }
 
 static int ensure_stage(rb_world* w, size_t elems) {

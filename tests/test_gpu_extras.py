@@ -121,3 +121,33 @@ def test_world_built_through_ingest_equals_world_built_from_oracle_primitives(mo
         assert np.array_equal(bits(a[key]), bits(b[key])), key
     assert np.array_equal(wa.contacts(), wb.contacts()) and wa.stats()["hits_st"] > 1000
     wa.close(); wb.close()
+
+
+def test_triangle_cube_predicate_on_the_device_matches_reference_fixture(golden):
+    """GeometryMath::triangleCubeDetection as the device evaluates it (rb_triangle_cube_test; the same device function
+    registers static triangles in the grid columns at rb_build) against the fixture generated from the reference's own
+    compiled predicate, plus random pairs against the oracle restatement."""
+    import ctypes as C
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from reboot_b200 import World
+    from reboot_b200._lib import ptr
+    from oracle import port_binding as pb
+    m = golden["micro"]
+    w = World()
+    tri = np.ascontiguousarray(m["tc_tri"], np.float32).reshape(-1, 9); cube = np.ascontiguousarray(m["tc_cube"], np.float32).reshape(-1, 6)
+    out = np.zeros(tri.shape[0], np.uint32)
+    assert w.L.rb_triangle_cube_test(w.h, tri.shape[0], ptr(tri), ptr(cube), ptr(out)) == 0
+    assert np.array_equal(out.astype(np.int32), np.asarray(m["tc_hit"]).astype(np.int32)) and 0 < out.sum() < len(out)
+    rng = np.random.default_rng(12)
+    n = 200000
+    tri = rng.uniform(-3, 3, (n, 9)).astype(np.float32)
+    cube = np.concatenate([rng.uniform(-2, 2, (n, 3)), rng.uniform(0.05, 4, (n, 3))], axis=1).astype(np.float32)
+    tri[: n // 4] *= np.float32(0.2)                      # small triangles: inside, outside and grazing boxes
+    tri[n // 4: n // 2, 1::3] = tri[n // 4: n // 2, 1:2]   # axis-aligned planes (y constant): the degenerate cross-product axes
+    out = np.zeros(n, np.uint32)
+    assert w.L.rb_triangle_cube_test(w.h, n, ptr(tri), ptr(cube), ptr(out)) == 0
+    ref = pb.pred_triangle_cube(tri, cube)
+    assert np.array_equal(out.astype(np.int32), np.asarray(ref).astype(np.int32)) and 0.05 < out.mean() < 0.95
+    w.close()
