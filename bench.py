@@ -47,7 +47,7 @@ C3_G = 1000
 
 def measured_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (or None)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         return float(json.load(open(p))["traffic_bytes_per_launch"])
     except Exception:

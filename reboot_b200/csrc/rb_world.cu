@@ -907,12 +907,15 @@ int rb_get_model_translations(rb_world* w, float* model_t4, float* prev_t4) {
 }
 int rb_export_model_matrices(rb_world* w, const float** cur_dev, const float** prev_dev) {
     if (!w || !w->built) return RB_ERR_INVALID;
-    if (w->d_dn) return fail(w, RB_ERR_INVALID, "model-matrix export is not available on slab worlds yet");
     CU(cudaSetDevice(w->cfg.device));
+    // slab (multi-GPU) worlds: the rows this rank owns right now, in the order of rb_get_state / rb_get_body_ids (bodies with a
+    // scaled or rotated W keep their 3x3 in build order, which migration does not carry: identity W only)
+    if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; if (w->d_w3) return fail(w, RB_ERR_INVALID, "model-matrix export on slab worlds needs W = identity"); }
     const size_t nb = w->n_owned_host;
-    if (!w->d_mm_cur) { ALLOC(w->d_mm_cur, std::max<size_t>(nb, 1) * 4); ALLOC(w->d_mm_prev, std::max<size_t>(nb, 1) * 4); }
+    const size_t cap = w->d_dn ? w->cap_local : nb;
+    if (!w->d_mm_cur) { ALLOC(w->d_mm_cur, std::max<size_t>(cap, 1) * 4); ALLOC(w->d_mm_prev, std::max<size_t>(cap, 1) * 4); }
     { int r = rb_ensure_mt(w); if (r) return r; }
-    rb_launch_model_matrices(w->d_w3, w->d_inv ? w->P.gid : nullptr, w->P.mt, w->P.pt, w->d_mm_cur, w->d_mm_prev, (uint32_t)nb, w->pose_updates == 0 ? 1 : 0, w->stream); w->launches++;
+    rb_launch_model_matrices(w->d_w3, (w->d_inv && !w->d_dn) ? w->P.gid : nullptr, w->P.mt, w->P.pt, w->d_mm_cur, w->d_mm_prev, (uint32_t)nb, w->pose_updates == 0 ? 1 : 0, w->stream); w->launches++;
     CU(cudaGetLastError());
     if (cur_dev) *cur_dev = (const float*)w->d_mm_cur;
     if (prev_dev) *prev_dev = (const float*)w->d_mm_prev;
@@ -941,7 +944,8 @@ int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     // recompute from the current model translations (no integration, no binning side effects on state)
     { int r = rb_plain_tick_params(w); if (r) return r; }
     CU(cudaMemsetAsync(w->P.col_count, 0, w->hist_clear_bytes, w->stream));
-    rb_launch_integrate_bin(w->P, 0, 1, w->stream); w->launches++;
+    { RbParams Q = w->P; Q.dp = nullptr;      // (slab worlds: no halo records, no signal -- this is not a tick)
+      rb_launch_integrate_bin(Q, 0, 1, w->stream); w->launches++; }
     size_t ns = w->d_dn ? w->n_owned_host : w->P.ns;
     std::vector<float> tmp(ns * 4), obj(ns * 4);
     if (w->P.single) {

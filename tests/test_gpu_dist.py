@@ -154,3 +154,23 @@ def test_slab_lists_with_migration_every_few_ticks(mods, nslabs, monkeypatch):
     assert busy and all(s["list_ticks"] >= 139 for s in busy), [(s["n_bodies"], s["list_ticks"]) for s in st]
     assert sum(s["list_rebuilds_by_reason"][0] + s["list_rebuilds_by_reason"][3] for s in st) > 10, "migrations must have forced rebuilds"
     single.close(); group.close()
+
+
+def test_slab_worlds_export_model_matrices(mods):
+    """Entity::getMVP / getPrevMVP model matrices from slab worlds (rows a rank owns, aligned with its body ids) equal the
+    single world's, body by body, after bodies have migrated."""
+    World, dist, scenes = mods
+    sc = _crossing_scene(scenes)
+    single = World(sc)
+    group = dist.SlabGroup(sc, 2)
+    for k in range(90):
+        single.step(5); group.step(5)
+    cur, prev = single.model_matrices()
+    seen = np.zeros(sc.n_bodies, np.int32)
+    for w in group.worlds:
+        ids = w.body_ids()
+        c, p = w.model_matrices()
+        assert np.array_equal(bits(c), bits(cur[ids])) and np.array_equal(bits(p), bits(prev[ids]))
+        seen[ids] += 1
+    assert (seen == 1).all()
+    single.close(); group.close()
