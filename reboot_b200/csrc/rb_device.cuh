@@ -171,7 +171,19 @@ struct RbParams {
     // runs along x and the rows near the slab faces are the first and the last blocks
     uint32_t g_swap, g_nu, g_nv; float g_off_u, g_off_v;
     const RbDistParams* dp;       // device copy of the halo parameters (slab worlds with neighbours), else NULL
+    // ---- compound bodies (multi-sphere entities, physics/src/Geometry.cpp:27-31) ----
+    uint32_t grp_lg;              // log2 of the lanes one body gets in rb_collide_group_kernel (2..5, from the largest sphere count)
+    uint32_t kstride;             // slab worlds: the spheres of body row b sit at rows [b * kstride, b * kstride + body_cnt[b]) (0: CSR through body_start)
+    const uint32_t* body_cnt;     // kstride worlds: spheres per body row
+    const uint32_t* sgid0;        // kstride worlds: global id of the body's first sphere (contacts name global sphere ids)
 };
+
+// body -> spheres (CSR in single worlds, fixed stride in slab worlds where rows come and go)
+__device__ __forceinline__ uint32_t rb_body_s0(const RbParams& P, uint32_t b) { return P.kstride ? b * P.kstride : P.body_start[b]; }
+__device__ __forceinline__ uint32_t rb_body_ns(const RbParams& P, uint32_t b) { return P.kstride ? P.body_cnt[b] : P.body_start[b + 1] - P.body_start[b]; }
+__device__ __forceinline__ uint32_t rb_sph_owner(const RbParams& P, uint32_t s) { return P.kstride ? s / P.kstride : P.sph_body[s]; }
+// the id a contact record names sphere i of body row b by
+__device__ __forceinline__ uint32_t rb_sph_gid(const RbParams& P, uint32_t b, uint32_t s0, uint32_t i) { return (P.sgid0 ? P.sgid0[b] : s0) + i; }
 
 __device__ __forceinline__ uint32_t rb_n_owned(const RbParams& P) { return P.dn ? P.dn[0] : P.n_owned; }
 __device__ __forceinline__ uint32_t rb_n_local(const RbParams& P) { return P.dn ? P.dn[0] + P.dn[1] : P.ns; }

@@ -1274,6 +1274,435 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
     } else collide_single_rows<RESOLVE, MODE>(P, blockIdx.x * blockDim.x + threadIdx.x, 0);
 }
 
+
+#ifndef RB_CHAIN_TU
+// ------------------------------------------------------------------------------------------
+// K4G: compound bodies (multi-sphere entities: Physics.cpp:102-138 loops spheresA x spheresB, Geometry.cpp:27-31 moves
+// every sphere of an entity by the same model matrix). Each body gets a group of L = 2^lg lanes (L >= its sphere count
+// whenever that is <= 32), lane j owns spheres j, j + L, ...: the enumeration -- the partner scan of the sphere grid and the
+// walk of the triangle columns, both pointer chasing -- runs per SPHERE, like the single-sphere kernel, while the body's
+// state is replicated over the lanes of its group and every resolution is computed by all of them (same operands, same
+// result), so nothing has to be sent around. The sequential test / resolve order of the canonical step is kept by
+// speculation: until something hits, the pose does not change, so the lanes test everything that is left at once, the FIRST
+// hit in canonical order is resolved, what came before it is final and what comes after it is tested again.
+// Same canonical order and arithmetic as rb_collide_kernel<false, .> (bit-identical results; RB_COLLIDE_V1=1 runs that one).
+// ------------------------------------------------------------------------------------------
+#define RB_GRP_PART 4
+
+// reductions over the aligned group of L lanes a body owns; every lane of the WARP takes part (xor partners below L stay inside the group)
+__device__ __forceinline__ uint32_t group_min(uint32_t v, const uint32_t L) {
+    for (uint32_t d = 1; d < L; d <<= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, d));
+    return v;
+}
+__device__ __forceinline__ uint32_t group_sum(uint32_t v, const uint32_t L) {
+    for (uint32_t d = 1; d < L; d <<= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// one pass over the sphere grid around frozen sphere (fc, frm): the RB_GRP_PART smallest partner BODY ids >= lo, ascending and
+// unique; `over` = some id did not fit. Warp-uniform (every lane of the warp calls it; `work` says who has a sphere).
+template <bool RESOLVE>
+__device__ __forceinline__ void group_scan_sphere(const RbParams& P, const bool work_in, const uint32_t A, const uint32_t gA, const f3 fc, const float frm,
+                                                  const uint32_t lo, uint32_t (&pg)[RB_GRP_PART], uint32_t (&pl)[RB_GRP_PART], bool& over, Tally& T) {
+    uint32_t cz = 1, cz1 = 0, cx0 = 0, cx1 = 0, i = 0, e = 0;
+    if (work_in) {
+        const float reach = frm + P.rm_max;
+        const float fu = rb_gu(P, fc.x, fc.z), fv = rb_gv(P, fc.x, fc.z);
+        cx0 = rb_col(fu - reach, P.g_off_u, P.s_inv_w, P.g_nu); cx1 = rb_col(fu + reach, P.g_off_u, P.s_inv_w, P.g_nu);
+        cz = rb_col(fv - reach, P.g_off_v, P.s_inv_w, P.g_nv); cz1 = rb_col(fv + reach, P.g_off_v, P.s_inv_w, P.g_nv);
+        i = P.col_start[cz * P.g_nu + cx0]; e = P.col_start[cz * P.g_nu + cx1 + 1];
+    }
+    while (true) {
+        while (i >= e && cz < cz1) { ++cz; i = P.col_start[cz * P.g_nu + cx0]; e = P.col_start[cz * P.g_nu + cx1 + 1]; }
+        const bool work = i < e;
+        if (!__any_sync(0xffffffffu, work)) break;
+        if (work) {
+            const uint32_t nb4 = min(e - i, 4u);
+            float4 ov[4];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) ov[u] = P.sorted[min(i + u, e - 1)];
+#pragma unroll
+            for (uint32_t u = 0; u < 4; ++u) {
+                if (u < nb4) {
+                    const float4 o = ov[u];
+                    float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
+                    if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) {
+                        uint32_t Bl = rb_sph_owner(P, P.sorted_id[i + u] & ~RB_TRI_BIT);
+                        if (Bl != A) {
+                            T.cand_ss++;
+                            uint32_t g = rb_gid(P, Bl);
+                            if (g >= lo && (RESOLVE || g > gA)) {          // detection: the lower id reports the pair
+                                bool dup = false;
+#pragma unroll
+                                for (int k = 0; k < RB_GRP_PART; ++k) dup |= (pg[k] == g);
+                                if (!dup) {
+#pragma unroll
+                                    for (int k = 0; k < RB_GRP_PART; ++k)
+                                        if (g < pg[k]) { uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = Bl; g = tg; Bl = tl; }
+                                    if (g != RB_NONE) over = true;         // pushed off the end (or never fitted)
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            i += nb4;
+        }
+        __syncwarp();
+    }
+}
+
+// P3 of the single-sphere kernel for one sphere per lane: walk of the <= 4 triangle columns the grown frozen box touches, box
+// prune on the column entries, survivors staged in this thread's shared-memory column, sorted + de-duplicated. Warp-uniform.
+__device__ __forceinline__ void group_stage_triangles(const RbParams& P, const bool work_in, const f3 fc, const float frm,
+                                                      uint32_t (*s_cand)[RB_BLOCK], uint32_t& nc, bool& st_slow, Tally& T) {
+    nc = 0; st_slow = false;
+    uint32_t cur[4], end[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) cur[k] = end[k] = 0;
+    if (work_in && P.nt) {
+        uint32_t cx0 = rb_col(fc.x - frm, P.half, P.t_inv_w, P.tcx), cx1 = rb_col(fc.x + frm, P.half, P.t_inv_w, P.tcx);
+        uint32_t cz0 = rb_col(fc.z - frm, P.half, P.t_inv_w, P.tcz), cz1 = rb_col(fc.z + frm, P.half, P.t_inv_w, P.tcz);
+        uint32_t nx = cx1 - cx0 + 1, ncol = nx * (cz1 - cz0 + 1);
+        if (ncol > 4) st_slow = true;
+        else {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                if (k < ncol) {
+                    uint32_t col = (cz0 + k / nx) * P.tcx + cx0 + k % nx;
+                    float2 yr = __ldg(P.tcol_yr + col);
+                    if (!(yr.x > fc.y + frm || yr.y < fc.y - frm)) { cur[k] = __ldg(P.tcol_start + col); end[k] = __ldg(P.tcol_start + col + 1); }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+        while (true) {
+            const bool work = cur[k] < end[k];
+            if (!__any_sync(0xffffffffu, work)) break;
+            if (work) {
+                const uint32_t n2 = min(end[k] - cur[k], 2u);
+                const float4* ep = P.tcol_ent + 2ull * cur[k];
+                float4 ea0 = __ldg(ep), ea1 = __ldg(ep + 1);
+                float4 eb0 = ea0, eb1 = ea1;
+                if (n2 == 2) { eb0 = __ldg(ep + 2); eb1 = __ldg(ep + 3); }
+#pragma unroll
+                for (uint32_t u = 0; u < 2; ++u) {
+                    if (u < n2) {
+                        const float4 e0 = u ? eb0 : ea0, e1 = u ? eb1 : ea1;
+                        T.cand_st++;
+                        bool keep = !(e0.x > fc.x + frm || e0.y < fc.x - frm) && !(e0.z > fc.z + frm || e0.w < fc.z - frm) &&
+                                    !(e1.x > fc.y + frm || e1.y < fc.y - frm);
+                        if (keep) {
+                            if (nc == RB_CAND_MAX) st_slow = true;
+                            else {
+                                const uint32_t tcand = __float_as_uint(e1.z);
+                                s_cand[nc++][threadIdx.x] = tcand;
+                                rb_prefetch(P.tri + 3ull * tcand); rb_prefetch(P.tri + 3ull * tcand + 2);
+                            }
+                        }
+                    }
+                }
+                cur[k] = st_slow ? end[k] : cur[k] + n2;
+            }
+            __syncwarp();
+        }
+    }
+    if (st_slow) nc = 0;
+    for (uint32_t i = 1; i < nc; ++i) {
+        uint32_t v = s_cand[i][threadIdx.x];
+        int j = (int)i - 1;
+        while (j >= 0 && s_cand[j][threadIdx.x] > v) { s_cand[j + 1][threadIdx.x] = s_cand[j][threadIdx.x]; --j; }
+        s_cand[j + 1][threadIdx.x] = v;
+    }
+    uint32_t nu = 0;
+    for (uint32_t i = 0; i < nc; ++i) {
+        uint32_t v = s_cand[i][threadIdx.x];
+        if (nu == 0 || s_cand[nu - 1][threadIdx.x] != v) s_cand[nu++][threadIdx.x] = v;
+    }
+    nc = nu;
+    __syncwarp();
+}
+
+// state of a body from one lane of its group to all of them
+__device__ __forceinline__ void group_bcast_state(BodyState& S, const uint32_t gmask, const uint32_t src) {
+    S.p.x = __shfl_sync(gmask, S.p.x, src); S.p.y = __shfl_sync(gmask, S.p.y, src); S.p.z = __shfl_sync(gmask, S.p.z, src);
+    S.v.x = __shfl_sync(gmask, S.v.x, src); S.v.y = __shfl_sync(gmask, S.v.y, src); S.v.z = __shfl_sync(gmask, S.v.z, src);
+    S.mt.x = __shfl_sync(gmask, S.mt.x, src); S.mt.y = __shfl_sync(gmask, S.mt.y, src); S.mt.z = __shfl_sync(gmask, S.mt.z, src);
+    S.pt.x = __shfl_sync(gmask, S.pt.x, src); S.pt.y = __shfl_sync(gmask, S.pt.y, src); S.pt.z = __shfl_sync(gmask, S.pt.z, src);
+    S.flags = __shfl_sync(gmask, S.flags, src);
+    S.changed = __shfl_sync(gmask, (int)S.changed, src) != 0;
+}
+
+template <bool RESOLVE>
+__global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbParams P) {
+    __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
+    const uint32_t lg = P.grp_lg, L = 1u << lg;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (L - 1), gbase = lane & ~(L - 1);
+    const bool leader = sub == 0;
+    const uint32_t A = tid >> lg;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    bool valid = A < rb_n_owned(P);                 // (uniform over the group)
+    uint32_t s0 = 0, nsph = 0, flags_in = 0;
+    if (valid) { flags_in = P.flags[A]; valid = (flags_in & RB_F_ACTIVE) != 0; }
+    BodyState S; S.changed = false; S.flags = flags_in;
+    S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
+    uint32_t gA = 0;
+    if (valid) {
+        s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A);
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        if (P.wt) S.wt = xyz(P.wt[A]);
+        gA = rb_gid(P, A);
+    }
+    const f3 mt_frozen = S.mt;
+    const uint32_t nchunk_w = __reduce_max_sync(0xffffffffu, (nsph + L - 1) >> lg);      // chunks of L spheres, warp-wide maximum
+
+    // ---------------- sphere-sphere: partner bodies in ascending id ----------------
+    {
+        uint32_t pg[RB_GRP_PART], pl[RB_GRP_PART];
+#pragma unroll
+        for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+        bool over = false, need = valid;
+        uint32_t lo = 0;
+        // spheres of A inside the broadphase (the lower body id counts the tests: one per pair of such spheres)
+        uint32_t nA_in = 0;
+        for (uint32_t c = 0; c < nchunk_w; ++c) {
+            const uint32_t i = (c << lg) + sub;
+            const bool in = valid && i < nsph && P.key[s0 + i] != RB_NONE;
+            nA_in += group_sum(in ? 1u : 0u, L);
+        }
+        while (true) {
+            if (__any_sync(0xffffffffu, need)) {
+                // (re)fill this lane's list: the smallest partner ids >= lo over the spheres it owns
+                if (need) {
+#pragma unroll
+                    for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+                    over = false;
+                }
+                for (uint32_t c = 0; c < nchunk_w; ++c) {
+                    const uint32_t i = (c << lg) + sub;
+                    bool w = need && i < nsph && P.key[s0 + i] != RB_NONE;
+                    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (w) fa = P.ws[s0 + i];
+                    group_scan_sphere<RESOLVE>(P, w, A, gA, xyz(fa), fa.w, lo, pg, pl, over, T);
+                }
+                need = false;
+            }
+            uint32_t mine = RB_NONE, mine_l = RB_NONE;
+            if (valid) {
+#pragma unroll
+                for (int k = RB_GRP_PART - 1; k >= 0; --k) if (pg[k] != RB_NONE && pg[k] >= lo) { mine = pg[k]; mine_l = pl[k]; }
+            }
+            const uint32_t best = group_min(valid ? mine : RB_NONE, L);
+            const bool more = valid && best != RB_NONE;
+            if (!__any_sync(0xffffffffu, more)) break;
+            // the pair (A, B = next partner): every loop below is warp-uniform (the groups of a warp stay in lock step)
+            const uint32_t src = group_min((more && mine == best) ? lane : RB_NONE, L);
+            const uint32_t B = __shfl_sync(0xffffffffu, mine_l, more ? src : lane);
+            const bool lo_is_a = gA < best;
+            const bool act = more && (RESOLVE || lo_is_a);
+            uint32_t t0 = 0, nb_sph = 0, n_in = 1, npairs = 0;
+            f3 bmt = mk3(0.f, 0.f, 0.f), bpt = bmt, bwt = bmt;
+            bool b_toggled = false;
+            if (act) {
+                t0 = rb_body_s0(P, B); nb_sph = rb_body_ns(P, B);
+                bmt = xyz(P.mt[B]); bpt = xyz(P.pt[B]);
+                if (P.wt) bwt = xyz(P.wt[B]);
+                n_in = lo_is_a ? nb_sph : nsph; npairs = nsph * nb_sph;
+                if (lo_is_a && leader) {
+                    uint32_t nB_in = 0;
+                    for (uint32_t i = 0; i < nb_sph; ++i) nB_in += P.key[t0 + i] != RB_NONE;
+                    T.tests_ss += nA_in * nB_in;
+                }
+            }
+            uint32_t q_start = 0;
+            while (true) {
+                // every lane: its share of the pairs that are left, in canonical order, at the current poses
+                uint32_t myq = RB_NONE;
+                if (act) {
+                    for (uint32_t q = q_start + sub; q < npairs; q += L) {
+                        const uint32_t io = q / n_in, ii = q - io * n_in;
+                        const uint32_t ia = lo_is_a ? io : ii, ib = lo_is_a ? ii : io;
+                        const uint32_t sa = s0 + ia, sb = t0 + ib;
+                        if (P.key[sa] == RB_NONE || P.key[sb] == RB_NONE) continue;
+                        const float4 oa = P.sph_obj[sa], ob = P.sph_obj[sb];
+                        const f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+                        f3 cb;
+                        if (!b_toggled) cb = xyz(P.ws[sb]); else cb = mk3(ob.x + bmt.x, ob.y + bmt.y, ob.z + bmt.z);
+                        const f3 cn = lo_is_a ? sub3(ca, cb) : sub3(cb, ca);
+                        const float dist = mag3(cn);
+                        const float radii = lo_is_a ? (oa.w + ob.w) : (ob.w + oa.w);
+                        if (!(radii - dist >= 0)) continue;
+                        if (RESOLVE) { myq = q; break; }
+                        // detection only: nothing moves, every hit is final
+                        T.hits_ss++;
+                        record_hit(P, H, rb_sph_gid(P, A, s0, ia), rb_sph_gid(P, B, t0, ib), radii - dist, mk3(cn.x / dist, cn.y / dist, cn.z / dist), oa.w);
+                    }
+                }
+                if (!RESOLVE) break;
+                const uint32_t qs = group_min(myq, L);
+                if (!__any_sync(0xffffffffu, qs != RB_NONE)) break;
+                if (qs != RB_NONE) {
+                    // the first hit in canonical order, resolved by every lane of the group alike
+                    const uint32_t io = qs / n_in, ii = qs - io * n_in;
+                    const uint32_t ia = lo_is_a ? io : ii, ib = lo_is_a ? ii : io;
+                    const uint32_t sa = s0 + ia, sb = t0 + ib;
+                    const float4 oa = P.sph_obj[sa], ob = P.sph_obj[sb];
+                    const f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+                    f3 cb;
+                    if (!b_toggled) cb = xyz(P.ws[sb]); else cb = mk3(ob.x + bmt.x, ob.y + bmt.y, ob.z + bmt.z);
+                    const f3 cn = lo_is_a ? sub3(ca, cb) : sub3(cb, ca);
+                    const float dist = mag3(cn);
+                    const float radii = lo_is_a ? (oa.w + ob.w) : (ob.w + oa.w);
+                    const f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
+                    if (lo_is_a && leader) { T.hits_ss++; record_hit(P, H, rb_sph_gid(P, A, s0, ia), rb_sph_gid(P, B, t0, ib), radii - dist, n1, oa.w); }
+                    f3 n = n1;
+                    if (!lo_is_a) { n = neg3(n); n = normalize3(n); }      // "Opposite reaction", normalised again
+                    const float sp = mag3(S.v);
+                    S.v = mul3(mul3(n, sp), P.ss_damp);
+                    body_set_position(S, S.pt);                             // snap back to the previous pose
+                    const f3 t = mk3(bwt.x + bpt.x, bwt.y + bpt.y, bwt.z + bpt.z);      // the partner does the same on its side
+                    bpt = bmt; bmt = t; b_toggled = true;
+                    q_start = qs + 1;
+                }
+                __syncwarp();
+            }
+            if (more) {
+                lo = best + 1;
+                need = over && pg[RB_GRP_PART - 1] < lo;      // this lane's list is used up and there was more
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---------------- sphere-triangle: own spheres ascending, triangles in ascending id ----------------
+    bool last_hit = false;
+    for (uint32_t c = 0; c < nchunk_w; ++c) {
+        const uint32_t i = (c << lg) + sub;
+        const bool in_body = valid && i < nsph;
+        const uint32_t sa = s0 + i;
+        const bool sv = in_body && P.key[sa] != RB_NONE;
+        float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), oa = fa;
+        if (sv) { fa = P.ws[sa]; oa = P.sph_obj[sa]; }
+        uint32_t nc; bool st_slow;
+        group_stage_triangles(P, sv, xyz(fa), fa.w, s_cand, nc, st_slow, T);
+        const bool chunk_live = valid && (c << lg) < nsph;          // (uniform over the group)
+        const bool slow = group_min(st_slow ? 0u : 1u, L) == 0u && chunk_live;
+        bool my_hit = false;
+        if (slow) {
+            // a sphere wider than the fast walk (or with more candidates than a column of the staging area holds): the
+            // leader takes this chunk's spheres one after the other through the generic walk and hands the state back
+            if (leader) {
+                const uint32_t i1 = min(nsph, (c + 1) << lg);
+                for (uint32_t k = c << lg; k < i1; ++k) {
+                    bool hk = false;
+                    if (P.key[s0 + k] != RB_NONE) {
+                        const float4 fk = P.ws[s0 + k], ok = P.sph_obj[s0 + k];
+                        sphere_vs_triangles<RESOLVE>(P, S, H, T, rb_sph_gid(P, A, s0, k), xyz(ok), ok.w, xyz(fk), fk.w, hk);
+                    }
+                    if (k == nsph - 1) last_hit = hk;
+                }
+            }
+        }
+        __syncwarp();
+        if (__any_sync(0xffffffffu, slow)) {
+            BodyState S2 = S; bool lh = last_hit;
+            group_bcast_state(S2, 0xffffffffu, gbase);
+            lh = __shfl_sync(0xffffffffu, (int)lh, gbase) != 0;
+            if (slow) { S = S2; last_hit = lh; }
+        }
+        // Speculative rounds, warp-uniform (the groups of a warp stay in lock step): every lane tests what its sphere has left
+        // at the current pose; per group, the lowest sphere with a hit takes its first one, every lane of the group resolves it
+        // alike, the spheres in front of it are final and the ones behind it start over at the new pose.
+        {
+            const bool live = chunk_live && !slow;
+            uint32_t j0 = 0;
+            bool done = !(live && sv && nc);
+            while (true) {
+                uint32_t m = 0, my_t = 0;
+                if (!done) {
+                    const f3 cc = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
+                    for (uint32_t j = j0; j < nc; ++j) {
+                        const uint32_t t = s_cand[j][threadIdx.x];
+                        const float4* tp = P.tri + 3ull * t;
+                        const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                        if (sphere_triangle_detect(cc, oa.w, xyz(a4), xyz(b4), xyz(c4))) {
+                            m |= 1u << (j - j0);
+                            if (RESOLVE) { my_t = t; break; }
+                            const f3 q = closest_point(cc, xyz(a4), xyz(b4), xyz(c4));
+                            const f3 ov = sub3(cc, q);
+                            const float dist = mag3(ov);
+                            T.hits_st++; my_hit = true;
+                            record_hit(P, H, rb_sph_gid(P, A, s0, i), RB_TRI_BIT | t, oa.w - dist, mk3(ov.x / dist, ov.y / dist, ov.z / dist), oa.w);
+                        }
+                    }
+                }
+                const uint32_t hits_all = __ballot_sync(0xffffffffu, m != 0);
+                if (!RESOLVE || !hits_all) { if (!done) T.tests_st += nc - j0; break; }
+                const uint32_t wmin = group_min(m ? lane : RB_NONE, L);
+                const bool hits = wmin != RB_NONE;
+                const uint32_t wl = hits ? wmin : lane;                           // the lowest sphere with a hit: first in canonical order
+                const uint32_t first = m ? (uint32_t)__ffs(m) - 1u : 0u;
+                if (!done && (!hits || lane < wl)) { T.tests_st += nc - j0; done = true; }     // nothing hit in front of it: final
+                const uint32_t t = __shfl_sync(0xffffffffu, my_t, wl);
+                const float wox = __shfl_sync(0xffffffffu, oa.x, wl), woy = __shfl_sync(0xffffffffu, oa.y, wl), woz = __shfl_sync(0xffffffffu, oa.z, wl), wr = __shfl_sync(0xffffffffu, oa.w, wl);
+                if (hits) {
+                    // resolved by every lane of the group alike (process_triangle above, same expressions)
+                    const float4* tp = P.tri + 3ull * t;
+                    const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                    const f3 TA = xyz(a4), TB = xyz(b4), TC = xyz(c4);
+                    const f3 cw = mk3(wox + S.mt.x, woy + S.mt.y, woz + S.mt.z);
+                    const f3 q = closest_point(cw, TA, TB, TC);
+                    const f3 ov = sub3(cw, q);
+                    const float dist = mag3(ov);
+                    const f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
+                    if (lane == wl) {
+                        T.tests_st += first + 1; T.hits_st++; my_hit = true;
+                        record_hit(P, H, rb_sph_gid(P, A, s0, i), RB_TRI_BIT | t, wr - dist, o, wr);
+                        j0 += first + 1;
+                        done = j0 >= nc;
+                    }
+                    const f3 normal = mk3(a4.w, b4.w, c4.w);
+                    const f3 delta = sub3(add3(mul3(o, wr * P.pushout), q), cw);
+                    const float ncomp = dot3(S.v, normal);
+                    const f3 rv = sub3(S.v, mul3(normal, ncomp));
+                    body_set_position(S, add3(S.p, delta));
+                    S.v = rv;
+                    S.flags |= RB_F_CONTACT;
+                }
+                __syncwarp();
+            }
+            // did the body's LAST sphere find a triangle (Physics.cpp:201-207)?
+            const uint32_t lsrc = gbase + ((nsph - 1) & (L - 1));
+            const bool lh = __shfl_sync(0xffffffffu, (int)my_hit, valid ? lsrc : lane) != 0;
+            if (live && ((nsph - 1) >> lg) == c) last_hit = lh;
+        }
+        __syncwarp();
+    }
+
+    if (RESOLVE && valid && leader) {
+        if ((flags_in & RB_F_CONTACT) && !last_hit) S.flags &= ~RB_F_CONTACT;
+        // margin audit: the candidate sets were built for displacements up to the smallest margin
+        const float disp = mag3(sub3(S.mt, mt_frozen));
+        if (nsph && disp > P.ws[s0].w - P.sph_obj[s0].w) T.overflow++;
+        if (S.changed || S.flags != flags_in) {
+            // partners read our frozen pose concurrently: commit after the kernel (K5)
+            const uint32_t k = (uint32_t)atomicAdd(&P.counters[RB_C_NCHANGED], 1ull);
+            P.ch_body[k] = A;
+            P.ch_pos[k] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+            P.ch_vel[k] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
+            P.ch_mt[k] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+            P.ch_pt[k] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+            P.ch_flags[k] = S.flags;
+        }
+    }
+    collide_epilogue(P, H, T, lane);
+}
+#endif // !RB_CHAIN_TU
+
 // ------------------------------------------------------------------------------------------
 // K4L: the list step -- one thread per body ROW, every tick of the persistent-list regime.
 // Everything a row needs is addressed by its row number: state (pos | radius, vel), the list header, up to four
@@ -1961,7 +2390,17 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
         return 1;
     }
     uint32_t g = cdiv(P.nb, RB_BLOCK);
-    if (resolve) {
+    if (variant != 1) {         // a group of lanes per body (K4G)
+        const uint32_t gg = cdiv(P.nb << P.grp_lg, RB_BLOCK);
+        if (resolve) {
+            rb_collide_group_kernel<true><<<gg, RB_BLOCK, 0, st>>>(P);
+            rb_commit_kernel<<<g, RB_BLOCK, 0, st>>>(P);
+            return 2;
+        }
+        rb_collide_group_kernel<false><<<gg, RB_BLOCK, 0, st>>>(P);
+        return 1;
+    }
+    if (resolve) {              // first-generation kernel, one thread per body (RB_COLLIDE_V1=1)
         rb_collide_kernel<false, true><<<g, RB_BLOCK, 0, st>>>(P);
         rb_commit_kernel<<<g, RB_BLOCK, 0, st>>>(P);
         return 2;

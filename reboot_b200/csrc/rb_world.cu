@@ -455,6 +455,10 @@ int rb_build(rb_world* w) {
         CU(cudaMemcpyAsync(d_sb, w->h_sph_body.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, w->stream));
         CU(cudaMemcpyAsync(d_bs, w->h_body_start.data(), ((size_t)nb + 1) * 4, cudaMemcpyHostToDevice, w->stream));
         P.sph_body = d_sb; P.body_start = d_bs;
+        // lanes per body in the group kernel: the next power of two above the largest sphere count, 4 .. 32
+        uint32_t kmax = 1; for (uint32_t b = 0; b < nb; b++) kmax = std::max(kmax, w->h_body_start[b + 1] - w->h_body_start[b]);
+        P.grp_lg = 2; while ((1u << P.grp_lg) < kmax && P.grp_lg < 5) P.grp_lg++;
+        { const char* v = getenv("RB_GROUP_LG"); if (v && *v) P.grp_lg = (uint32_t)std::min(5, std::max(1, atoi(v))); }      // (development switch)
         uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
         ALLOC(cb, nb); ALLOC(c1, nb); ALLOC(c2, nb); ALLOC(c3, nb); ALLOC(c4, nb); ALLOC(cf, nb);
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
