@@ -66,6 +66,10 @@ typedef struct rb_config {
                               * store into, so it must be the SAME on every rank: pass the maximum over the ranks of
                               * rb_halo_ghost_cap_auto(). 0 = this rank's own auto value (fine when all ranks hold
                               * equally many bodies; connecting ranks with different layouts is refused). */
+    /* multi-GPU worlds of compound bodies (entities with several collision spheres, physics/src/Geometry.cpp:27-31): rows
+     * migrate between ranks, so every body keeps its spheres at a fixed stride -- the SAME on every rank */
+    uint32_t sphere_stride;  /* largest sphere count of any body over ALL ranks (0 = this rank's own; 1 = single-sphere worlds) */
+    float    body_reach_hint;/* largest max_i(|centre_i.x| + r_i) of any body over ALL ranks, world units after W (0 = this rank's own) */
 } rb_config;
 
 /* initial state of a body: StateVector setters, math/include/StateVector.h:48-60 */

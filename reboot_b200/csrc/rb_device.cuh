@@ -62,6 +62,11 @@ struct RbDistParams {
     uint32_t ghost_cap, migr_cap, cap_local;
     float slab_lo, slab_hi; int has_left, has_right;
     float mig_band;               // list ticks: a body up to this far beyond a face stays with its owner until the next scheduled rebuild
+    // compound bodies (P.kstride): records are byte strings of a per-world size -- a ghost body is {mt | gid, pt | spheres,
+    // spheres x {obj, ws}}, a migrant {pos, vel, mt, pt, {flags, gid, spheres, -}, spheres x obj} -- and a body reaches as far
+    // from its model translation as its farthest sphere: ext_max is the largest such reach (grown by the margin cap) anywhere
+    uint32_t ghost_stride, migr_stride;
+    float ext_max;
     uint32_t* dn;                                   // {n_owned, n_ghost}
     uint32_t* gid; float4* sph_obj_w; unsigned long long* counters;
 };
@@ -172,18 +177,16 @@ struct RbParams {
     uint32_t g_swap, g_nu, g_nv; float g_off_u, g_off_v;
     const RbDistParams* dp;       // device copy of the halo parameters (slab worlds with neighbours), else NULL
     // ---- compound bodies (multi-sphere entities, physics/src/Geometry.cpp:27-31) ----
+    uint32_t grp_on;              // compound bodies step through rb_collide_group_kernel (RB_COMPOUND_GROUP=1) instead of the per-body kernel
     uint32_t grp_lg;              // log2 of the lanes one body gets in rb_collide_group_kernel (2..5, from the largest sphere count)
     uint32_t kstride;             // slab worlds: the spheres of body row b sit at rows [b * kstride, b * kstride + body_cnt[b]) (0: CSR through body_start)
-    const uint32_t* body_cnt;     // kstride worlds: spheres per body row
-    const uint32_t* sgid0;        // kstride worlds: global id of the body's first sphere (contacts name global sphere ids)
+    uint32_t* body_cnt;           // kstride worlds: spheres per body row
 };
 
 // body -> spheres (CSR in single worlds, fixed stride in slab worlds where rows come and go)
 __device__ __forceinline__ uint32_t rb_body_s0(const RbParams& P, uint32_t b) { return P.kstride ? b * P.kstride : P.body_start[b]; }
 __device__ __forceinline__ uint32_t rb_body_ns(const RbParams& P, uint32_t b) { return P.kstride ? P.body_cnt[b] : P.body_start[b + 1] - P.body_start[b]; }
 __device__ __forceinline__ uint32_t rb_sph_owner(const RbParams& P, uint32_t s) { return P.kstride ? s / P.kstride : P.sph_body[s]; }
-// the id a contact record names sphere i of body row b by
-__device__ __forceinline__ uint32_t rb_sph_gid(const RbParams& P, uint32_t b, uint32_t s0, uint32_t i) { return (P.sgid0 ? P.sgid0[b] : s0) + i; }
 
 __device__ __forceinline__ uint32_t rb_n_owned(const RbParams& P) { return P.dn ? P.dn[0] : P.n_owned; }
 __device__ __forceinline__ uint32_t rb_n_local(const RbParams& P) { return P.dn ? P.dn[0] + P.dn[1] : P.ns; }
@@ -199,6 +202,9 @@ __device__ __forceinline__ void rb_prefetch(const void* p) {
 #endif
 }
 __device__ __forceinline__ uint32_t rb_gid(const RbParams& P, uint32_t local) { return P.gid ? P.gid[local] : local; }
+// the id a contact record names sphere i of body row b by: its sphere id in a single world, global body id * stride + i in a slab
+// world (rb_query_contacts takes it apart again)
+__device__ __forceinline__ uint32_t rb_sph_gid(const RbParams& P, uint32_t b, uint32_t s0, uint32_t i) { return (P.kstride ? rb_gid(P, b) * P.kstride : s0) + i; }
 __device__ __forceinline__ float rb_gu(const RbParams& P, float x, float z) { return P.g_swap ? z : x; }
 __device__ __forceinline__ float rb_gv(const RbParams& P, float x, float z) { return P.g_swap ? x : z; }
 

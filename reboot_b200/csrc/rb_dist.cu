@@ -21,7 +21,7 @@ struct RbHaloBuf {
     uint8_t* base = nullptr; size_t bytes = 0;
     RbHaloHeader* hdr() const { return (RbHaloHeader*)base; }
     RbGhostRec* ghosts() const { return (RbGhostRec*)(base + sizeof(RbHaloHeader)); }
-    RbMigrRec* migr(uint32_t ghost_cap) const { return (RbMigrRec*)(base + sizeof(RbHaloHeader) + (size_t)ghost_cap * sizeof(RbGhostRec)); }
+    RbMigrRec* migr(uint32_t ghost_cap, uint32_t ghost_stride = sizeof(RbGhostRec)) const { return (RbMigrRec*)(base + sizeof(RbHaloHeader) + (size_t)ghost_cap * ghost_stride); }
 };
 
 // ---- NCCL through dlopen (no link-time dependency; the host says which libnccl to use) -----------
@@ -81,6 +81,7 @@ struct RbDist {
     bool params_valid = false;
     RbDistParams* d_dp[2] = { nullptr, nullptr };    // device copies, one per parity
     uint32_t ghost_cap = 0, migr_cap = 0;
+    uint32_t ghost_stride = sizeof(RbGhostRec), migr_stride = sizeof(RbMigrRec);      // bytes per record (compound bodies: per-world sizes)
     uint32_t halo_step = 0;
     uint32_t* h_dn = nullptr;                        // pinned
     RbHaloHeader* h_hdr = nullptr;                   // pinned, 4 headers (out L/R, in L/R)
@@ -136,7 +137,15 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
             if (kh != RB_NONE && (kh & RB_HOT_BIT)) P.hot_row[P.rank[h]] = RB_NONE;
             if (h != last && kl != RB_NONE && (kl & RB_HOT_BIT)) P.hot_row[P.rank[last]] = h;
         }
-        if (h != last) {
+        if (h != last && P.kstride) {
+            // compound bodies: the K sphere rows travel with the body row
+            P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
+            D.gid[h] = D.gid[last]; P.body_cnt[h] = P.body_cnt[last];
+            for (uint32_t j = 0; j < P.kstride; ++j) {
+                const uint32_t a = h * P.kstride + j, b = last * P.kstride + j;
+                sph[a] = sph[b]; P.ws[a] = P.ws[b]; P.key[a] = P.key[b]; P.rank[a] = P.rank[b];
+            }
+        } else if (h != last) {
             P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
             sph[h] = sph[last]; D.gid[h] = D.gid[last]; P.ws[h] = P.ws[last]; P.key[h] = P.key[last]; P.rank[h] = P.rank[last];
         }
@@ -154,6 +163,61 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
 // bodies (entry hot_cap + ghost index), where every owned body looks them up.
 __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, RbDistParams D, uint32_t imm_blocks, int list_tick) {
     const uint32_t ghost_floor = D.cap_local - 3u * D.ghost_cap;      // rows [ghost_floor, cap) are reserved for ghosts
+    if (P.kstride) {
+        // compound bodies: one thread per record, the body's spheres go to rows [row * K, row * K + spheres)
+        const uint32_t K = P.kstride;
+        if (blockIdx.x < imm_blocks) {
+            const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+            const uint32_t n0 = min(D.in_hdr[0]->n_migr, D.migr_cap), n1 = min(D.in_hdr[1]->n_migr, D.migr_cap);
+            if (t >= n0 + n1) return;
+            const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(t < n0 ? D.in_migr[0] : D.in_migr[1]) + (size_t)(t < n0 ? t : t - n0) * D.migr_stride);
+            const uint32_t i = atomicAdd(&D.dn[0], 1u);
+            if (i >= ghost_floor) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_IMM_DROPPED], 1ull); return; }      // (sticky: see the single-sphere branch)
+            const float4 pos = r[0], vel = r[1], mt = r[2], pt = r[3], h = r[4];
+            const uint32_t flags = __float_as_uint(h.x), gid = __float_as_uint(h.y), cnt = __float_as_uint(h.z);
+            P.pos[i] = pos; P.vel[i] = vel; P.mt[i] = mt; P.pt[i] = pt; P.flags[i] = flags; D.gid[i] = gid; P.body_cnt[i] = cnt;
+            const float speed = mag3(xyz(vel));
+            for (uint32_t j = 0; j < K; ++j) {
+                const uint32_t s = i * K + j;
+                uint32_t k = RB_NONE;
+                if (j < cnt) {
+                    // the world sphere K1 computed on the old owner (same state, same formula)
+                    const float4 o = r[5 + j];
+                    D.sph_obj_w[s] = o;
+                    const f3 c = mk3(o.x + mt.x, o.y + mt.y, o.z + mt.z);
+                    const float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * P.dt + 0.01f * o.w, 1e-3f));
+                    const bool in = (flags & RB_F_ACTIVE) && sphere_in_world(c, o.w, P.half);
+                    P.ws[s] = make_float4(c.x, c.y, c.z, in ? o.w + margin : -1.0f);
+                    if (in) { k = rb_sphere_col(P, c.x, c.z); P.rank[s] = atomicAdd(&P.col_count[k], 1u); }
+                }
+                P.key[s] = k;
+            }
+            return;
+        }
+        const uint32_t t = (blockIdx.x - imm_blocks) * blockDim.x + threadIdx.x;
+        const uint32_t n0 = min(D.in_hdr[0]->n_ghost, D.ghost_cap), n1 = min(D.in_hdr[1]->n_ghost, D.ghost_cap), n2 = min(*D.self_cnt, D.ghost_cap);
+        if (t >= n0 + n1 + n2) return;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(t < n0 ? D.in_ghost[0] : (t < n0 + n1 ? D.in_ghost[1] : D.self_ghost));
+        const float4* r = reinterpret_cast<const float4*>(base + (size_t)(t < n0 ? t : (t < n0 + n1 ? t - n0 : t - n0 - n1)) * D.ghost_stride);
+        const uint32_t gi = atomicAdd(&D.dn[1], 1u);
+        const uint32_t i = D.cap_local - 1u - gi;
+        const float4 h0 = r[0], h1 = r[1];
+        const uint32_t cnt = __float_as_uint(h1.w);
+        P.mt[i] = make_float4(h0.x, h0.y, h0.z, 0.f); P.pt[i] = make_float4(h1.x, h1.y, h1.z, 0.f);
+        P.pos[i] = make_float4(h0.x, h0.y, h0.z, 1.f);
+        D.gid[i] = __float_as_uint(h0.w); P.body_cnt[i] = cnt; P.flags[i] = RB_F_ACTIVE;
+        for (uint32_t j = 0; j < K; ++j) {
+            const uint32_t s = i * K + j;
+            uint32_t k = RB_NONE;
+            if (j < cnt) {
+                const float4 w = r[3 + 2 * j];
+                D.sph_obj_w[s] = r[2 + 2 * j]; P.ws[s] = w;
+                if (w.w >= 0.f) { k = rb_sphere_col(P, w.x, w.z); P.rank[s] = atomicAdd(&P.col_count[k], 1u); }
+            }
+            P.key[s] = k;
+        }
+        return;
+    }
     if (blockIdx.x < imm_blocks) {
         uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
         uint32_t n0 = min(D.in_hdr[0]->n_migr, D.migr_cap);
@@ -214,7 +278,8 @@ static int dist_alloc(rb_world* w) {
     RbDist* d = new RbDist();
     d->ghost_cap = w->ghost_cap;
     d->migr_cap = std::max<uint32_t>(1024u, w->ghost_cap / 8);
-    size_t bytes = sizeof(RbHaloHeader) + (size_t)d->ghost_cap * sizeof(RbGhostRec) + (size_t)d->migr_cap * sizeof(RbMigrRec);
+    if (w->P.kstride) { d->ghost_stride = 32u + 32u * w->P.kstride; d->migr_stride = 80u + 16u * w->P.kstride; }
+    size_t bytes = sizeof(RbHaloHeader) + (size_t)d->ghost_cap * d->ghost_stride + (size_t)d->migr_cap * d->migr_stride;
     bytes = (bytes + 255) / 256 * 256;
     d->buf_bytes = bytes;
     for (int k = 0; k < 2; k++) {
@@ -226,22 +291,23 @@ static int dist_alloc(rb_world* w) {
     ALLOC(d->blob, d->blob_bytes);
     CU(cudaMemsetAsync(d->blob, 0, d->blob_bytes, w->stream));
     // per-tick counters sit behind {n_owned, n_ghost} so ONE memset clears them: [2] self ghosts, [3] emigrants, [4..7] / [8..11] out headers
-    RbGhostRec* sg; uint32_t *em; ALLOC(sg, d->ghost_cap); ALLOC(em, d->migr_cap * 2 + 16);
+    RbGhostRec* sg; uint32_t *em; { uint8_t* sgb; ALLOC(sgb, (size_t)d->ghost_cap * d->ghost_stride); sg = (RbGhostRec*)sgb; } ALLOC(em, d->migr_cap * 2 + 16);
     uint32_t* cnts = w->d_dn + 2;
     CU(cudaMallocHost((void**)&d->h_dn, 4 * sizeof(uint32_t)));
     CU(cudaMallocHost((void**)&d->h_hdr, 4 * sizeof(RbHaloHeader)));
     RbDistParams& D = d->D;
     memset(&D, 0, sizeof D);
     for (int k = 0; k < 2; k++) {
-        D.out_hdr[k] = (RbHaloHeader*)(w->d_dn + 4 + 4 * k); D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap);
+        D.out_hdr[k] = (RbHaloHeader*)(w->d_dn + 4 + 4 * k); D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap, d->ghost_stride);
         RbHaloBuf ib = d->in_buf(k, 0);
-        D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
+        D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap, d->ghost_stride);
     }
     D.self_ghost = sg; D.self_cnt = cnts; D.emig = em; D.emig_cnt = cnts + 1;
     D.ghost_cap = d->ghost_cap; D.migr_cap = d->migr_cap; D.cap_local = w->cap_local;
     D.slab_lo = w->cfg.slab_lo; D.slab_hi = w->cfg.slab_hi;
     D.has_left = w->cfg.rank > 0; D.has_right = w->cfg.rank < w->cfg.nranks - 1;
     D.mig_band = w->vl_on ? w->P.margin_cap : 0.0f;
+    D.ghost_stride = d->ghost_stride; D.migr_stride = d->migr_stride; D.ext_max = w->ext_max;
     D.dn = w->d_dn; D.gid = w->d_gid; D.sph_obj_w = const_cast<float4*>(w->P.sph_obj); D.counters = w->P.counters;
     ALLOC(d->d_dp[0], 1); ALLOC(d->d_dp[1], 1);
     CU(cudaMemcpyAsync(d->d_dp[0], &D, sizeof D, cudaMemcpyHostToDevice, w->stream));
@@ -315,10 +381,10 @@ static int dist_upload_params(rb_world* w) {
             if (remote && d->mode == RB_X_LOCAL && d->peer[k] && !d->peer_blob[k]) d->peer_blob[k] = d->peer[k]->dist->blob;
             if (remote && d->peer_blob[k]) {
                 RbHaloBuf pb = RbDist::buf_at(d->peer_blob[k], d->buf_bytes, 1 - k, p);      // my left neighbour receives on ITS right side
-                D.out_ghost[k] = pb.ghosts(); D.out_migr[k] = pb.migr(d->ghost_cap);
-            } else { D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap); }
+                D.out_ghost[k] = pb.ghosts(); D.out_migr[k] = pb.migr(d->ghost_cap, d->ghost_stride);
+            } else { D.out_ghost[k] = d->out[k].ghosts(); D.out_migr[k] = d->out[k].migr(d->ghost_cap, d->ghost_stride); }
             RbHaloBuf ib = d->in_buf(k, remote ? p : 0);
-            D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap);
+            D.in_hdr[k] = ib.hdr(); D.in_ghost[k] = ib.ghosts(); D.in_migr[k] = ib.migr(d->ghost_cap, d->ghost_stride);
         }
         d->Dp[p] = D;
         CU(cudaMemcpyAsync(d->d_dp[p], &d->Dp[p], sizeof D, cudaMemcpyHostToDevice, w->stream));

@@ -159,6 +159,7 @@ struct rb_world {
     // ---- slab worlds (rb_dist.cu) ----
     uint32_t cap_local = 0;                  // capacity of the per-body / per-sphere arrays
     uint32_t ghost_cap = 0;                  // ghosts per face the halo buffers hold
+    float ext_max = 0.f;                     // compound slab worlds: the farthest any body reaches from its model translation along x (+ margin cap)
     uint32_t* d_dn = nullptr;                // device {n_owned, n_ghost}
     uint32_t* d_gid = nullptr;
     std::vector<uint32_t> h_gid;             // ids given before rb_build

@@ -50,6 +50,79 @@ __device__ __forceinline__ void vl_request_rebuild(const RbParams& P, uint32_t w
     if (!(v[RB_VL_WHY] & why)) atomicOr(&P.vl[RB_VL_WHY], why);
 }
 
+
+// ---- compound bodies in slab (multi-GPU) worlds: body row b keeps its spheres at rows [b * K, b * K + spheres) ----
+// halo records of a compound body (byte strings of a per-world size, see RbDistParams)
+__device__ __forceinline__ void write_ghost_body(uint8_t* dst, const RbParams& P, uint32_t b, uint32_t s0, uint32_t cnt, f3 m, uint32_t gid) {
+    float4* d = reinterpret_cast<float4*>(dst);
+    const float4 pt = P.pt[b];
+    d[0] = make_float4(m.x, m.y, m.z, __uint_as_float(gid));
+    d[1] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(cnt));
+    for (uint32_t i = 0; i < cnt; ++i) { d[2 + 2 * i] = P.sph_obj[s0 + i]; d[3 + 2 * i] = P.ws[s0 + i]; }
+}
+__device__ __forceinline__ void integrate_bin_compound_slab(const RbParams& P, const uint32_t b, const uint32_t f, const float4 p4, const float4 v4,
+                                                            const f3 p, const f3 v, const f3 m, const int do_bin) {
+    const uint32_t K = P.kstride, s0 = b * K, cnt = P.body_cnt[b];
+    const bool active = (f & RB_F_ACTIVE) != 0;
+    const float speed = mag3(v), dt = P.dt;
+    float ext = 0.f; bool any_in = false;
+    for (uint32_t i = 0; i < cnt; ++i) {
+        const float4 o = P.sph_obj[s0 + i];
+        const f3 c = mk3(o.x + m.x, o.y + m.y, o.z + m.z);
+        const float r = o.w;
+        const float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * dt + 0.01f * r, 1e-3f));
+        const bool in = active && sphere_in_world(c, r, P.half);        // Q3 / Q7, per sphere like OSP::updateOSP
+        P.ws[s0 + i] = make_float4(c.x, c.y, c.z, in ? r + margin : -1.0f);
+        any_in |= in;
+        ext = fmaxf(ext, fabsf(o.x) + r + margin);
+    }
+    bool binned = true;
+    if (P.dp && do_bin && active) {
+        const RbDistParams& D = *P.dp;
+        const uint32_t gid = D.gid[b];
+        // a body belongs to the slab its model translation lies in
+        int dir = -1;
+        if (m.x < D.slab_lo && D.has_left) dir = 0; else if (m.x >= D.slab_hi && D.has_right) dir = 1;
+        if (dir >= 0) {
+            const uint32_t kk = atomicAdd(&D.out_hdr[dir]->n_migr, 1u);
+            if (kk < D.migr_cap) {
+                float4* d = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(D.out_migr[dir]) + (size_t)kk * D.migr_stride);
+                d[0] = make_float4(p.x, p.y, p.z, p4.w); d[1] = make_float4(v.x, v.y, v.z, v4.w);
+                d[2] = make_float4(m.x, m.y, m.z, 0.f); d[3] = P.pt[b];
+                d[4] = make_float4(__uint_as_float(f), __uint_as_float(gid), __uint_as_float(cnt), 0.f);
+                for (uint32_t i = 0; i < cnt; ++i) d[5 + i] = P.sph_obj[s0 + i];
+                D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
+                if (any_in) {       // stays visible to its old owner for this tick
+                    const uint32_t g = atomicAdd(D.self_cnt, 1u);
+                    if (g < D.ghost_cap) write_ghost_body(reinterpret_cast<uint8_t*>(D.self_ghost) + (size_t)g * D.ghost_stride, P, b, s0, cnt, m, gid);
+                    else atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull);
+                }
+                binned = false;     // leaves this slab: not binned here
+            } else { atomicAdd(&D.out_hdr[dir]->migr_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }      // stays owned here one more tick
+        } else if (any_in) {
+            // a sphere of this body and a sphere of a neighbour's body can only meet if the bodies' reaches overlap across the face
+            const float reach = ext + D.ext_max;
+            for (int k = 0; k < 2; ++k) {
+                if (k == 0 ? !(D.has_left && m.x - reach < D.slab_lo) : !(D.has_right && m.x + reach >= D.slab_hi)) continue;
+                const uint32_t kk = atomicAdd(&D.out_hdr[k]->n_ghost, 1u);
+                if (kk < D.ghost_cap) write_ghost_body(reinterpret_cast<uint8_t*>(D.out_ghost[k]) + (size_t)kk * D.ghost_stride, P, b, s0, cnt, m, gid);
+                else { atomicAdd(&D.out_hdr[k]->ghost_overflow, 1u); atomicAdd(&P.counters[RB_C_HALO_OVF], 1ull); }
+            }
+        }
+    }
+    for (uint32_t i = 0; i < K; ++i) {
+        uint32_t k = RB_NONE;
+        if (i < cnt && binned) {
+            const float4 w = P.ws[s0 + i];
+            if (w.w >= 0.f) {
+                if (do_bin) { k = rb_sphere_col(P, w.x, w.z); P.rank[s0 + i] = atomicAdd(&P.col_count[k], 1u); }
+                else k = 0;
+            }
+        }
+        P.key[s0 + i] = k;
+    }
+}
+
 __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const int do_integrate, const int do_bin) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_owned = rb_n_owned(P);
@@ -110,6 +183,7 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             if (!lazy) P.mt[b] = make_float4(m.x, m.y, m.z, 0.f);
         }
     }
+    if (P.kstride) { if (b < n_owned) integrate_bin_compound_slab(P, b, f, p4, v4, p, v, m, do_bin); return; }
     if (!do_bin && !P.dn) return;
     float speed = mag3(v);
     uint32_t s0 = P.single ? b : P.body_start[b];
@@ -364,8 +438,10 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P, int vl
         for (uint32_t t = s; t < scan_tiles; t += gridDim.x * blockDim.x) scan_status[t] = 0ull;
         if (s == 0) *scan_ticket = 0u;
     }
-    if (P.dn) { if (s >= P.nb || (s >= P.dn[0] && (vl || s < P.nb - P.dn[1]))) return; }     // slab worlds: owned rows in front, ghosts at the end (not sorted on list ticks)
-    else if (s >= P.ns) return;
+    if (P.dn) {     // slab worlds: owned rows in front, ghosts at the end (not sorted on list ticks)
+        const uint32_t br = P.kstride ? s / P.kstride : s;
+        if (br >= P.nb || (br >= P.dn[0] && (vl || br < P.nb - P.dn[1]))) return;
+    } else if (s >= P.ns) return;
     uint32_t k = P.key[s];
     if (k == RB_NONE) return;
     k &= ~RB_HOT_BIT;
@@ -375,7 +451,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_scatter_kernel(RbParams P, int vl
     P.sorted[slot] = wsv;
     // bit 31: the body's contact flag, so that the collide kernel needs no per-body gather for bodies
     // that touch nothing this tick (Physics.cpp:201-207 only needs "was in contact")
-    uint32_t body = P.single ? s : P.sph_body[s];
+    uint32_t body = P.single ? s : rb_sph_owner(P, s);
     P.sorted_id[slot] = s | ((P.flags[body] & RB_F_CONTACT) ? RB_TRI_BIT : 0u);
 }
 
@@ -587,7 +663,7 @@ __device__ __forceinline__ void scan_partners(const RbParams& P, uint32_t A, f3 
             float dx = o.x - fc.x, dy = o.y - fc.y, dz = o.z - fc.z, rr = frm + o.w;
             if ((dx * dx + dy * dy) + dz * dz > rr * rr) continue;
             uint32_t sb = P.sorted_id[i] & ~RB_TRI_BIT;
-            uint32_t Bl = SINGLE ? sb : P.sph_body[sb];
+            uint32_t Bl = SINGLE ? sb : rb_sph_owner(P, sb);
             if (Bl == A) continue;
             T.cand_ss++;
             uint32_t B = rb_gid(P, Bl);
@@ -633,8 +709,8 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
         valid = tid < n_sorted;
         if (valid) { f0 = P.sorted[tid]; A = s0 = P.sorted_id[tid] & ~RB_TRI_BIT; nsph = 1; valid = A < rb_n_owned(P); }
     } else {
-        valid = tid < P.n_owned;
-        if (valid) { A = tid; s0 = P.body_start[A]; nsph = P.body_start[A + 1] - s0; valid = (P.flags[A] & RB_F_ACTIVE) != 0; }
+        valid = tid < rb_n_owned(P);
+        if (valid) { A = tid; s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A); valid = (P.flags[A] & RB_F_ACTIVE) != 0; }
     }
     if (valid) {
         BodyState S;
@@ -661,8 +737,8 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
             const bool lo_is_a = gA < best;
             if (RESOLVE || lo_is_a) {
                 // partner simulated from its frozen pose (it toggles exactly like us on every hit)
-                uint32_t t0 = SINGLE ? B : P.body_start[B];
-                uint32_t nb_sph = SINGLE ? 1 : P.body_start[B + 1] - t0;
+                uint32_t t0 = SINGLE ? B : rb_body_s0(P, B);
+                uint32_t nb_sph = SINGLE ? 1 : rb_body_ns(P, B);
                 f3 bmt = mk3(0.f, 0.f, 0.f), bpt = bmt, bwt = bmt;
                 bool b_toggled = false;
                 if (!SINGLE) { bmt = xyz(P.mt[B]); bpt = xyz(P.pt[B]); if (P.wt) bwt = xyz(P.wt[B]); }
@@ -684,7 +760,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
                         if (lo_is_a) T.tests_ss++;
                         if (!(radii - dist >= 0)) continue;
                         f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
-                        if (lo_is_a) { T.hits_ss++; record_hit(P, H, SINGLE ? gA : sa, SINGLE ? best : sb, radii - dist, n1, oa.w); }
+                        if (lo_is_a) { T.hits_ss++; record_hit(P, H, SINGLE ? gA : rb_sph_gid(P, A, s0, ia), SINGLE ? best : rb_sph_gid(P, B, t0, ib), radii - dist, n1, oa.w); }
                         if (RESOLVE) {
                             f3 n = n1;
                             if (!lo_is_a) { n = neg3(n); n = normalize3(n); }      // "Opposite reaction", normalised again
@@ -710,7 +786,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_collide_kernel(RbParams P) {
             if (SINGLE || P.key[sa] != RB_NONE) {
                 float4 fa = SINGLE ? f0 : P.ws[sa];
                 float4 oa = P.sph_obj[sa];
-                sphere_vs_triangles<RESOLVE>(P, S, H, T, SINGLE ? gA : sa, xyz(oa), oa.w, xyz(fa), fa.w, hit_any);
+                sphere_vs_triangles<RESOLVE>(P, S, H, T, SINGLE ? gA : rb_sph_gid(P, A, s0, i), xyz(oa), oa.w, xyz(fa), fa.w, hit_any);
             }
             if (i == nsph - 1) last_hit = hit_any;
         }
@@ -1618,26 +1694,52 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbP
         // at the current pose; per group, the lowest sphere with a hit takes its first one, every lane of the group resolves it
         // alike, the spheres in front of it are final and the ones behind it start over at the new pose.
         {
+            __shared__ uint32_t s_mask[RB_BLOCK];
+            const uint32_t wbase = threadIdx.x & ~31u;
             const bool live = chunk_live && !slow;
             uint32_t j0 = 0;
             bool done = !(live && sv && nc);
             while (true) {
-                uint32_t m = 0, my_t = 0;
-                if (!done) {
-                    const f3 cc = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
-                    for (uint32_t j = j0; j < nc; ++j) {
-                        const uint32_t t = s_cand[j][threadIdx.x];
+                // the tests the warp has left are pooled and dealt out 32 at a time (the owner's pose travels by shuffle), like P4
+                // of the single-sphere kernel: a body resting on four of its eight spheres keeps few lanes busy by itself
+                const uint32_t rem = done ? 0u : nc - j0;
+                if (!__any_sync(0xffffffffu, rem != 0u)) break;
+                const uint32_t incl = warp_incl_scan(rem, lane);
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const f3 cc = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);       // Sphere::getPosition at the current pose
+                s_mask[threadIdx.x] = 0;
+                __syncwarp();
+                for (uint32_t base = 0; base < total; base += 32) {
+                    const uint32_t item = base + lane;
+                    uint32_t lo = 0;                                   // owner = number of lanes whose inclusive count is <= item
+#pragma unroll
+                    for (int st = 16; st >= 1; st >>= 1) { uint32_t v = __shfl_sync(0xffffffffu, incl, (lo + st - 1) & 31); if (v <= item) lo += st; }
+                    const uint32_t owner = lo & 31;
+                    const uint32_t o_excl = __shfl_sync(0xffffffffu, incl - rem, owner), o_j0 = __shfl_sync(0xffffffffu, j0, owner);
+                    const float ox = __shfl_sync(0xffffffffu, cc.x, owner), oy = __shfl_sync(0xffffffffu, cc.y, owner), oz = __shfl_sync(0xffffffffu, cc.z, owner);
+                    const float orad = __shfl_sync(0xffffffffu, oa.w, owner);
+                    if (item < total) {
+                        const uint32_t k = item - o_excl;
+                        const uint32_t t = s_cand[o_j0 + k][wbase + owner];
                         const float4* tp = P.tri + 3ull * t;
                         const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
-                        if (sphere_triangle_detect(cc, oa.w, xyz(a4), xyz(b4), xyz(c4))) {
-                            m |= 1u << (j - j0);
-                            if (RESOLVE) { my_t = t; break; }
-                            const f3 q = closest_point(cc, xyz(a4), xyz(b4), xyz(c4));
-                            const f3 ov = sub3(cc, q);
-                            const float dist = mag3(ov);
-                            T.hits_st++; my_hit = true;
-                            record_hit(P, H, rb_sph_gid(P, A, s0, i), RB_TRI_BIT | t, oa.w - dist, mk3(ov.x / dist, ov.y / dist, ov.z / dist), oa.w);
-                        }
+                        if (sphere_triangle_detect(mk3(ox, oy, oz), orad, xyz(a4), xyz(b4), xyz(c4))) atomicOr(&s_mask[wbase + owner], 1u << k);
+                    }
+                    __syncwarp();
+                }
+                __syncwarp();
+                uint32_t m = s_mask[threadIdx.x], my_t = 0;
+                if (RESOLVE) { if (m) { m &= 0u - m; my_t = s_cand[j0 + (uint32_t)__ffs(m) - 1u][threadIdx.x]; } }      // (only the first hit counts: the pose changes with it)
+                else {
+                    for (uint32_t mm = m; mm; mm &= mm - 1u) {         // detection only: nothing moves, every hit is final
+                        const uint32_t t = s_cand[j0 + (uint32_t)__ffs(mm) - 1u][threadIdx.x];
+                        const float4* tp = P.tri + 3ull * t;
+                        const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                        const f3 q = closest_point(cc, xyz(a4), xyz(b4), xyz(c4));
+                        const f3 ov = sub3(cc, q);
+                        const float dist = mag3(ov);
+                        T.hits_st++; my_hit = true;
+                        record_hit(P, H, rb_sph_gid(P, A, s0, i), RB_TRI_BIT | t, oa.w - dist, mk3(ov.x / dist, ov.y / dist, ov.z / dist), oa.w);
                     }
                 }
                 const uint32_t hits_all = __ballot_sync(0xffffffffu, m != 0);
@@ -2390,7 +2492,10 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
         return 1;
     }
     uint32_t g = cdiv(P.nb, RB_BLOCK);
-    if (variant != 1) {         // a group of lanes per body (K4G)
+    // K4G (a group of lanes per body) is bit-identical to the per-body kernel and faster while bodies fall (C4: 0.94 against 1.20 ms)
+    // but not once they rest (1.56 against 1.51 ms: the speculative rounds re-test and four groups of a warp wait for each other):
+    // opt-in until the enumeration is split from the resolution (RB_COMPOUND_GROUP=1)
+    if (variant != 1 && P.grp_on) {
         const uint32_t gg = cdiv(P.nb << P.grp_lg, RB_BLOCK);
         if (resolve) {
             rb_collide_group_kernel<true><<<gg, RB_BLOCK, 0, st>>>(P);

@@ -24,6 +24,7 @@ void rb_config_default(rb_config* c) {
     c->world_half = 1000.0f; c->gravity = -9.8f; c->friction = 0.95f; c->pushout = 1.0001f; c->ss_damp = 0.1f;
     c->margin_cap = 0.0f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
     c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1; c->rm_max_hint = 0.0f; c->halo_ghost_cap = 0;
+    c->sphere_stride = 0; c->body_reach_hint = 0.0f;
 }
 
 const char* rb_last_error(const rb_world* w) { return w ? w->err.c_str() : g_create_error.c_str(); }
@@ -327,31 +328,54 @@ int rb_build(rb_world* w) {
     const uint32_t ns = (uint32_t)(w->h_obj.size() / 4);
     const bool slab = w->cfg.nranks > 1;
     P.single = (ns == nb) ? 1u : 0u;
-    if (slab && !P.single) return fail(w, RB_ERR_INVALID, "slab (multi-GPU) worlds support single-sphere bodies only in this version");
     if (slab && w->any_wt) return fail(w, RB_ERR_INVALID, "slab (multi-GPU) worlds need W.t = 0");
+    // compound bodies in slab worlds: rows come and go (migration), so a body keeps its spheres at a fixed stride K -- the largest
+    // sphere count anywhere, which every rank must agree on (rb_config.sphere_stride) -- instead of a CSR that would have to be compacted
+    uint32_t K = 0;
+    if (slab && (!P.single || w->cfg.sphere_stride > 1)) {
+        uint32_t kmax = 1; for (uint32_t b = 0; b < nb; b++) kmax = std::max(kmax, w->h_body_start[b + 1] - w->h_body_start[b]);
+        if (w->cfg.sphere_stride && kmax > w->cfg.sphere_stride) return fail(w, RB_ERR_INVALID, "a body has %u spheres, rb_config.sphere_stride is %u", kmax, w->cfg.sphere_stride);
+        K = std::max(kmax, w->cfg.sphere_stride);
+        P.single = 0u; P.kstride = K;
+        P.grp_lg = 2; while ((1u << P.grp_lg) < K && P.grp_lg < 5) P.grp_lg++;
+        { const char* v = getenv("RB_COMPOUND_GROUP"); P.grp_on = (v && *v == '1') ? 1u : 0u; }
+        // how far a body reaches from its model translation along x (the ghost criterion of K1): this rank's bodies and the hint
+        float ext = 0.f;
+        for (uint32_t b = 0; b < nb; b++) {
+            const float* W = &w->h_W[(size_t)b * 12];
+            for (uint32_t q = w->h_body_start[b]; q < w->h_body_start[b + 1]; q++) {
+                const float* o = &w->h_obj[(size_t)q * 4];
+                const float x = w->h_presummed[b] ? o[0] : W[0] * o[0] + W[1] * o[1] + W[2] * o[2], r = w->h_presummed[b] ? o[3] : W[0] * o[3];
+                ext = std::max(ext, std::fabs(x) + std::fabs(r));
+            }
+        }
+        w->ext_max = std::max(ext, w->cfg.body_reach_hint);
+    }
     // slab worlds keep room for immigrants and ghosts; counts live on the device (P.dn)
     // ghosts per face ~ n * reach / slab width; keep 16x headroom (overflow is detected and reported)
     uint32_t ghost_cap = 0;
     if (slab) {
         float rr = 0.f; for (size_t i = 3; i < w->h_obj.size(); i += 4) rr = std::max(rr, std::fabs(w->h_obj[i]));
         rr = std::max(rr, w->cfg.rm_max_hint);
+        if (K) rr = std::max(rr, w->ext_max);      // compound bodies are ghosts as far as they reach
         ghost_cap = w->cfg.halo_ghost_cap ? w->cfg.halo_ghost_cap : rb_halo_ghost_cap_auto(nb, rr, w->cfg.margin_cap, w->cfg.slab_hi - w->cfg.slab_lo);
     }
     w->ghost_cap = ghost_cap;
     const uint32_t cap = slab ? nb + std::max<uint32_t>(nb / 4, 4096u) + 3 * ghost_cap : nb;
     w->cap_local = cap;
-    P.nb = cap; P.ns = slab ? cap : ns; P.n_owned = nb;
+    P.nb = cap; P.ns = K ? cap * K : (slab ? cap : ns); P.n_owned = nb;
     w->n_owned_host = nb;
     P.half = w->cfg.world_half; P.gravity = w->cfg.gravity; P.friction = w->cfg.friction;
     P.pushout = w->cfg.pushout; P.ss_damp = w->cfg.ss_damp; P.margin_cap = w->cfg.margin_cap; P.dt = 0.f;
 
     // ---- spheres: pre-sum the W3x3 * object-centre part of GeometryMath::transform (GeometryMath.cpp:81-89) ----
-    std::vector<float> sph((size_t)std::max<uint32_t>(slab ? cap : ns, 1) * 4, 0.f);
+    std::vector<float> sph((size_t)std::max<uint32_t>(K ? cap * K : (slab ? cap : ns), 1) * 4, 0.f);
     float rmax = 0.f;
     for (uint32_t b = 0; b < nb; b++) {
         const float* W = &w->h_W[(size_t)b * 12];
-        for (uint32_t s = w->h_body_start[b]; s < w->h_body_start[b + 1]; s++) {
-            const float* o = &w->h_obj[(size_t)s * 4];
+        for (uint32_t q = w->h_body_start[b]; q < w->h_body_start[b + 1]; q++) {
+            const float* o = &w->h_obj[(size_t)q * 4];
+            const uint32_t s = K ? b * K + (q - w->h_body_start[b]) : q;      // (fixed stride in compound slab worlds)
             if (w->h_presummed[b]) {      // carried over from the world this one replaces (world_grow): already transformed, bit for bit
                 for (int k = 0; k < 4; k++) sph[(size_t)s * 4 + k] = o[k];
                 rmax = std::max(rmax, std::fabs(o[3]));
@@ -378,6 +402,7 @@ int rb_build(rb_world* w) {
     if (!(w->cfg.margin_cap > 0.f)) w->cfg.margin_cap = std::max(0.5f * rmax, 1e-3f);   // auto: half the largest radius
     P.margin_cap = w->cfg.margin_cap;
     P.rm_max = rmax + w->cfg.margin_cap;
+    if (K) w->ext_max += w->cfg.margin_cap;      // (reach of the farthest sphere grown by the largest margin)
     // persistent candidate lists: single worlds of single-sphere bodies stepped by rb_step with the default kernel
     w->vl_on = w->vl_on && P.single && ns > 0 && w->collide_variant == 2;
     if (w->vl_on) {
@@ -413,7 +438,7 @@ int rb_build(rb_world* w) {
     }
     // ---- device state ----
     float4 *d_pos, *d_vel, *d_mt, *d_pt, *d_sph, *d_ws, *d_sorted; uint32_t *d_flags, *d_key, *d_rank, *d_cc, *d_cs, *d_sid;
-    const size_t nba = slab ? cap : nb, nsa = slab ? cap : ns;
+    const size_t nba = slab ? cap : nb, nsa = K ? (size_t)cap * K : (slab ? cap : ns);
     ALLOC(d_pos, nba); ALLOC(d_vel, nba); ALLOC(d_mt, nba); ALLOC(d_pt, nba); ALLOC(d_flags, nba);
     ALLOC(d_sph, nsa); ALLOC(d_ws, nsa); ALLOC(d_key, nsa); ALLOC(d_rank, nsa); ALLOC(d_sorted, nsa); ALLOC(d_sid, nsa);
     if (slab) {
@@ -445,11 +470,24 @@ int rb_build(rb_world* w) {
     CU(cudaMemcpyAsync(d_pos, p4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_vel, v4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemcpyAsync(d_flags, w->h_flags.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, w->stream));
-    CU(cudaMemcpyAsync(d_sph, sph.data(), (size_t)ns * 16, cudaMemcpyHostToDevice, w->stream));
+    CU(cudaMemcpyAsync(d_sph, sph.data(), (K ? (size_t)nb * K : (size_t)ns) * 16, cudaMemcpyHostToDevice, w->stream));
     CU(cudaMemsetAsync(d_mt, 0, std::max<size_t>(nba, 1) * 16, w->stream));   // MVP() model = identity -> translation 0
     CU(cudaMemsetAsync(d_pt, 0, std::max<size_t>(nba, 1) * 16, w->stream));
     if (w->any_wt) { float4* d_wt; ALLOC(d_wt, nb); CU(cudaMemcpyAsync(d_wt, wt4.data(), (size_t)nb * 16, cudaMemcpyHostToDevice, w->stream)); P.wt = d_wt; }
-    if (!P.single) {
+    if (K) {
+        // fixed-stride compound bodies: spheres per row, every sphere row "not in the broadphase" until K1 says otherwise, commit records
+        std::vector<uint32_t> cnt(std::max<uint32_t>(nb, 1), 0u);
+        for (uint32_t b = 0; b < nb; b++) cnt[b] = w->h_body_start[b + 1] - w->h_body_start[b];
+        uint32_t* d_cnt_rows; ALLOC(d_cnt_rows, nba);
+        CU(cudaMemsetAsync(d_cnt_rows, 0, nba * 4, w->stream));
+        CU(cudaMemcpyAsync(d_cnt_rows, cnt.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, w->stream));
+        CU(cudaStreamSynchronize(w->stream));
+        P.body_cnt = d_cnt_rows;
+        CU(cudaMemsetAsync(d_key, 0xff, nsa * 4, w->stream));
+        uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
+        ALLOC(cb, nba); ALLOC(c1, nba); ALLOC(c2, nba); ALLOC(c3, nba); ALLOC(c4, nba); ALLOC(cf, nba);
+        P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
+    } else if (!P.single) {
         uint32_t *d_sb, *d_bs;
         ALLOC(d_sb, ns); ALLOC(d_bs, (size_t)nb + 1);
         CU(cudaMemcpyAsync(d_sb, w->h_sph_body.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, w->stream));
@@ -459,6 +497,7 @@ int rb_build(rb_world* w) {
         uint32_t kmax = 1; for (uint32_t b = 0; b < nb; b++) kmax = std::max(kmax, w->h_body_start[b + 1] - w->h_body_start[b]);
         P.grp_lg = 2; while ((1u << P.grp_lg) < kmax && P.grp_lg < 5) P.grp_lg++;
         { const char* v = getenv("RB_GROUP_LG"); if (v && *v) P.grp_lg = (uint32_t)std::min(5, std::max(1, atoi(v))); }      // (development switch)
+        { const char* v = getenv("RB_COMPOUND_GROUP"); P.grp_on = (v && *v == '1') ? 1u : 0u; }
         uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
         ALLOC(cb, nb); ALLOC(c1, nb); ALLOC(c2, nb); ALLOC(c3, nb); ALLOC(c4, nb); ALLOC(cf, nb);
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
@@ -541,7 +580,7 @@ int rb_build(rb_world* w) {
         }
     }
     // ---- contacts + counters ----
-    P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(slab ? cap : ns) * 4 + 1024;
+    P.contact_cap = w->cfg.max_contacts ? w->cfg.max_contacts : (unsigned long long)(K ? cap * K : (slab ? cap : ns)) * 4 + 1024;
     RbContactRec* d_c; ALLOC(d_c, (size_t)P.contact_cap); P.contacts = d_c;
     unsigned long long* d_cnt; ALLOC(d_cnt, RB_C_COUNT * (RB_STRIPES + 1)); P.counters = d_cnt; P.stripes = d_cnt + RB_C_COUNT;
     P.ncontact = d_cnt + RB_C_NCONTACT; w->ncontact_dev = P.ncontact; P.mt_in_valid = 1u;
@@ -865,6 +904,7 @@ int rb_query_contacts(rb_world* w, rb_contact* out, uint64_t cap, uint64_t* n, i
     const std::vector<uint32_t>& bs = w->h_body_start; const std::vector<uint32_t>& gs = w->h_geom_start;
     auto body_of = [&](uint32_t s, uint32_t& body, uint32_t& idx) {
         if (w->P.single) { body = s; idx = 0; return; }
+        if (w->P.kstride) { body = s / w->P.kstride; idx = s % w->P.kstride; return; }      // slab worlds: global body id * stride + sphere
         body = w->h_sph_body[s]; idx = s - bs[body];
     };
     for (uint64_t i = 0; i < have; i++) {
@@ -944,6 +984,7 @@ int rb_get_angular(rb_world* w, float* ap4, float* av4) {
 }
 int rb_get_world_spheres(rb_world* w, float* xyzr4) {
     if (!w || !w->built || !xyzr4) return RB_ERR_INVALID;
+    if (w->P.kstride) return fail(w, RB_ERR_INVALID, "rb_get_world_spheres is not available on slab worlds of compound bodies");
     w->vl_force = true;
     // recompute from the current model translations (no integration, no binning side effects on state)
     { int r = rb_plain_tick_params(w); if (r) return r; }

@@ -33,17 +33,40 @@ def owner_of(x: np.ndarray, nranks: int, half: float = 1000.0) -> np.ndarray:
 
 
 def partition_scene(scene, nranks: int, rank: int, half: float = 1000.0):
-    """(sub-scene with the bodies this rank owns at t=0, global body ids, slab, r_max over all ranks)."""
-    if scene.n_spheres != scene.n_bodies:
-        raise ValueError("slab worlds support single-sphere bodies only in this version")
-    own = owner_of(scene.body_pos[:, 0] + scene.obj_spheres[:, 0], nranks, half) == rank
+    """(sub-scene with the bodies this rank owns at t=0, global body ids, slab, r_max over all ranks).
+    A body belongs to the slab its model translation lies in (single-sphere bodies: the sphere centre, as before)."""
+    compound = scene.n_spheres != scene.n_bodies
+    start = np.asarray(scene.sphere_start, np.int64)
+    if compound:
+        own = owner_of(scene.body_pos[:, 0], nranks, half) == rank
+    else:
+        own = owner_of(scene.body_pos[:, 0] + scene.obj_spheres[:, 0], nranks, half) == rank
     ids = np.nonzero(own)[0].astype(np.uint32)
     s = copy.copy(scene)
     s.body_pos = np.ascontiguousarray(scene.body_pos[own]); s.body_vel = np.ascontiguousarray(scene.body_vel[own])
     s.body_active = scene.body_active[own]; s.body_gravity = scene.body_gravity[own]; s.body_scale = scene.body_scale[own]
-    s.obj_spheres = np.ascontiguousarray(scene.obj_spheres[own]); s.sphere_start = np.arange(len(ids) + 1, dtype=np.int32)
-    rmax = float((scene.obj_spheres[:, 3] * scene.body_scale).max()) if scene.n_bodies else 0.0
+    if compound:
+        cnt = (start[1:] - start[:-1])[own]
+        idx = np.concatenate([np.arange(start[b], start[b + 1]) for b in ids]) if len(ids) else np.zeros(0, np.int64)
+        s.obj_spheres = np.ascontiguousarray(scene.obj_spheres[idx]).reshape(-1, 4)
+        s.sphere_start = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    else:
+        s.obj_spheres = np.ascontiguousarray(scene.obj_spheres[own]); s.sphere_start = np.arange(len(ids) + 1, dtype=np.int32)
+    scale_per_sphere = np.repeat(scene.body_scale, start[1:] - start[:-1])
+    rmax = float((scene.obj_spheres[:, 3] * scale_per_sphere).max()) if scene.n_bodies else 0.0
     return s, ids, slab_bounds(rank, nranks, half), rmax
+
+
+def compound_layout(scene):
+    """(sphere_stride, body_reach_hint) every rank of a compound-body scene must pass: the largest sphere count of any body and
+    the farthest any body reaches from its model translation along x (|centre.x| + r, after the uniform scale)."""
+    start = np.asarray(scene.sphere_start, np.int64)
+    cnt = start[1:] - start[:-1]
+    if scene.n_spheres == scene.n_bodies:
+        return 0, 0.0
+    sc = np.repeat(scene.body_scale, cnt).astype(np.float32)
+    reach = np.abs(scene.obj_spheres[:, 0] * sc) + np.abs(scene.obj_spheres[:, 3] * sc)
+    return int(cnt.max()), float(reach.max()) * 1.0001
 
 
 def find_nccl() -> str:
@@ -134,9 +157,11 @@ class SlabGroup:
         self.worlds = []
         parts = [partition_scene(scene, nslabs, r) for r in range(nslabs)]
         # one halo buffer layout for everybody: the largest capacity any slab would pick by itself
-        cap = max(int(self.L.rb_halo_ghost_cap_auto(sub.n_bodies, float(rmax), 0.0, float(slab[1] - slab[0]))) for sub, _, slab, rmax in parts)
+        stride, reach = compound_layout(scene)
+        cap = max(int(self.L.rb_halo_ghost_cap_auto(sub.n_bodies, float(max(rmax, reach)), 0.0, float(slab[1] - slab[0]))) for sub, _, slab, rmax in parts)
         for r, (sub, ids, slab, rmax) in enumerate(parts):
-            w = World(sub, device=device, slab=slab, rank=r, nranks=nslabs, ids=ids, rm_max_hint=rmax, halo_ghost_cap=cap, **kw)
+            w = World(sub, device=device, slab=slab, rank=r, nranks=nslabs, ids=ids, rm_max_hint=rmax, halo_ghost_cap=cap,
+                      sphere_stride=stride, body_reach_hint=reach, **kw)
             self.worlds.append(w)
         for r, w in enumerate(self.worlds):
             left = self.worlds[r - 1].h if r > 0 else None

@@ -174,3 +174,52 @@ def test_slab_worlds_export_model_matrices(mods):
         seen[ids] += 1
     assert (seen == 1).all()
     single.close(); group.close()
+
+
+def _compound_crossing_scene(scenes, n=3000, seed=5, ragged=False):
+    """Compound bodies (8 spheres on a 2x2x2 lattice, or 1..8 when ragged) with lateral velocities, half of them started around
+    the slab faces so that ghosts of whole bodies and migrations carry the traffic."""
+    sc = scenes.config4(n, 400, seed)
+    rng = np.random.default_rng(seed)
+    sc.body_vel[:, 0] = rng.uniform(-12, 12, n).astype(np.float32)
+    sc.body_vel[:, 2] = rng.uniform(-3, 3, n).astype(np.float32)
+    k = n // 2
+    sc.body_pos[:k, 0] = (rng.choice([-200.0, 0.0, 200.0], k) + rng.uniform(-4, 4, k)).astype(np.float32)
+    sc.body_pos[:, 1] -= 1.0
+    if ragged:
+        cnt = rng.integers(1, 9, n)
+        keep = np.concatenate([np.arange(8 * b, 8 * b + cnt[b]) for b in range(n)])
+        sc.obj_spheres = np.ascontiguousarray(sc.obj_spheres[keep])
+        sc.sphere_start = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    return sc
+
+
+@pytest.mark.parametrize("nslabs,ragged", [(2, False), (4, True)])
+def test_compound_slab_group_bit_identical_to_single_world(mods, nslabs, ragged):
+    """BASELINE config 4 on several GPUs: compound bodies in x-slab worlds (fixed sphere stride per body row, ghost / migrant
+    records of whole bodies) against one world -- state, flags, model translations and contact sets bit-identical while
+    bodies collide with each other across the faces and migrate."""
+    World, dist, scenes = mods
+    sc = _compound_crossing_scene(scenes, ragged=ragged)
+    single = World(sc)
+    group = dist.SlabGroup(sc, nslabs)
+    migrated = 0
+    for k in range(160):
+        single.step(5)
+        group.step(5)
+        if k % 16 == 15 or k < 3:
+            a = single.state(); b = group.state(sc.n_bodies)
+            assert (b["owner"] >= 0).all(), "a body was lost in migration"
+            for key in ("pos", "vel", "model_t", "prev_t"):
+                assert np.array_equal(bits(a[key]), bits(b[key])), (k, key)
+            assert np.array_equal(a["flags"], b["flags"]), k
+            sa, sb = single.contact_sets(), group.contact_sets()
+            assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1]), k
+        migrated += sum(w.stats()["migrated_out_last"] for w in group.worlds)
+    assert migrated > 0, "the scene must exercise migration"
+    assert sum(w.stats()["halo_sent_last"] for w in group.worlds) > 0
+    st = single.stats()
+    assert st["hits_ss"] > 0 and st["hits_st"] > 0
+    b = group.state(sc.n_bodies)
+    assert np.array_equal(b["owner"], dist.owner_of(b["model_t"][:, 0], nslabs)), "ownership follows the model translation"
+    single.close(); group.close()
