@@ -19,6 +19,7 @@ Every line also carries `c5`: BASELINE config 5 at FIXED size -- 16,000,000 sphe
 8,000,000-triangle terrain plus static box "houses", split into N x-slabs (N = 1: one world) -- with its own
 steps/s, so that c5.steps_per_s at N=8 over N=1 is the strong-scaling figure of the north star, and a state
 checksum (xor over bodies of a hash of global id and position bits) that must be the same at every N.
+`c4` is the same for BASELINE config 4: 262,144 compound bodies x 8 collision spheres, split into N x-slabs.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref = its unmodified physics/ + math/
 sources; falls back to the C port): ONE real full-size C3 tick (octree build ~2.5 min + ~2 min per tick on one
@@ -305,14 +306,15 @@ def run_ours(args):
 
     stream = torch.cuda.Stream()
 
-    def make_world(sc, slab, ids, r_hint, max_contacts):
+    def make_world(sc, slab, ids, r_hint, max_contacts, stride=0, reach=0.0):
         cap = 0
         if N > 1:
             from reboot_b200 import dist as rbdist
-            cap = rbdist.common_ghost_cap(sc.n_bodies, r_hint, slab[1] - slab[0])      # one halo buffer layout on every rank
+            cap = rbdist.common_ghost_cap(sc.n_bodies, max(r_hint, reach), slab[1] - slab[0])      # one halo buffer layout on every rank
         t0 = time.perf_counter()
         w = World(sc, device=local_rank, stream=stream.cuda_stream, slab=slab, rank=rank, nranks=N,
-                  max_contacts=max_contacts, build=False, ids=ids, rm_max_hint=r_hint, halo_ghost_cap=cap)
+                  max_contacts=max_contacts, build=False, ids=ids, rm_max_hint=r_hint, halo_ghost_cap=cap,
+                  sphere_stride=stride if N > 1 else 0, body_reach_hint=reach if N > 1 else 0.0)
         w.build()
         build_s = time.perf_counter() - t0
         if N > 1:
@@ -455,6 +457,34 @@ def run_ours(args):
               "note": "strong scaling of the north star = c5.steps_per_s at N=8 over N=1; the checksum must be identical at every N (same scene, same ticks)"}
         w5.close()
 
+    # =============================== C4 at fixed size on N GPUs (compound bodies) ===============================
+    c4 = None
+    if not args.no_c4:
+        from reboot_b200 import scenes, dist as rbdist
+        sc4 = scenes.config4(args.c4_bodies)
+        stride4, reach4 = rbdist.compound_layout(sc4)
+        ids4, slab4 = None, (-1000.0, 1000.0)
+        if N > 1:
+            sc4, ids4, slab4, _ = rbdist.partition_scene(sc4, N, rank)
+        w4, c4_build_s = make_world(sc4, slab4, ids4, float(sc4.meta["r"]), 8 * sc4.n_spheres + 1024, stride4, reach4)
+        for _ in range(args.c4_settle + max(3, args.warmup)):
+            w4.step(DT_MS)
+        w4.sync()
+        a4 = w4.stats()
+        c4_steps = min(args.steps, 100)
+        c4_ms = timed(w4, c4_steps)
+        b4 = w4.stats()
+        c4_sum = xor_over_ranks(state_checksum(w4, ids4))
+        c4 = {"workload": f"C4 fixed size: {args.c4_bodies:,} compound bodies x 8 collision spheres on the C3 terrain (2,000,000 triangles), {N} x-slab(s)",
+              "steps_per_s": 1000.0 / c4_ms, "ms_per_step": c4_ms, "steps": c4_steps, "settle": args.c4_settle,
+              "ticks_before_checksum": args.c4_settle + max(3, args.warmup) + c4_steps, "checksum": f"{c4_sum:08x}",
+              "rank0": {"n_bodies": b4["n_bodies"], "contacts_last": b4["contacts_last"], "contacts_dropped": b4["contacts_dropped"], "margin_overflow": b4["margin_overflow"],
+                        "tests_per_step": (b4["tests_ss"] + b4["tests_st"] - a4["tests_ss"] - a4["tests_st"]) / c4_steps,
+                        "halo_recv_last": b4["halo_recv_last"], "migrated_out_last": b4["migrated_out_last"]},
+              "build_s": c4_build_s,
+              "note": "BASELINE config 4 (256k mobile models x 8 collision spheres, 1/2/4/8 GPUs): per-tick enumeration (compound bodies have no persistent lists yet); the checksum must be identical at every N"}
+        w4.close()
+
     if rank == 0:
         cpu = None
         if N == 1 and not args.no_cpu:
@@ -489,6 +519,8 @@ def run_ours(args):
         }
         if c5 is not None:
             line["c5"] = c5
+        if c4 is not None:
+            line["c4"] = c4
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
@@ -527,6 +559,9 @@ def main():
     ap.add_argument("--ref-full-ticks", type=int, default=1, help="real full-size C3 ticks the reference arm times (about 2 min each + 3 min of build)")
     ap.add_argument("--ref-tile-only", action="store_true", help="reference arm: only the bounded tile estimate")
     ap.add_argument("--no-c5", action="store_true", help="skip the fixed-size C5 sub-record")
+    ap.add_argument("--no-c4", action="store_true", help="skip the fixed-size C4 (compound bodies) sub-record")
+    ap.add_argument("--c4-bodies", type=int, default=262_144)
+    ap.add_argument("--c4-settle", type=int, default=600)
     ap.add_argument("--c5-spheres", type=int, default=16_000_000)
     ap.add_argument("--c5-settle", type=int, default=600)
     args = ap.parse_args()

@@ -30,6 +30,16 @@ def _scene(kind):
         k = n // 2
         sc.body_pos[:k, 0] = (rng.choice([-200.0, 0.0, 200.0], k) + rng.uniform(-3, 3, k)).astype(np.float32)
         return sc, [0, 2, 14, 59, 104, 149]
+    if kind == "compound":   # BASELINE config 4 across ranks: 8-sphere bodies crossing the face (ghosts and migrants are whole bodies)
+        n = 3000
+        sc = scenes.config4(n, 400, 5)
+        rng = np.random.default_rng(5)
+        sc.body_vel[:, 0] = rng.uniform(-12, 12, n).astype(np.float32)
+        sc.body_vel[:, 2] = rng.uniform(-3, 3, n).astype(np.float32)
+        k = n // 2
+        sc.body_pos[:k, 0] = (rng.choice([-200.0, 0.0, 200.0], k) + rng.uniform(-4, 4, k)).astype(np.float32)
+        sc.body_pos[:, 1] -= 1.0
+        return sc, [0, 2, 15, 63, 111, 159]
     n = 6000                 # comes to rest around the face: persistent lists reused, ghosts looked up every tick
     sc = scenes.falling_spheres(n, 400, 2.0, 0.5, (0.3, 1.5), True, 11, "rest")
     rng = np.random.default_rng(11)
@@ -57,8 +67,10 @@ def _worker(rank, nranks, port, halo, kind, q):
         from reboot_b200 import World, dist as rbdist
         sc, cps = _scene(kind)
         sub, ids, slab, rmax = rbdist.partition_scene(sc, nranks, rank)
-        cap = rbdist.common_ghost_cap(sub.n_bodies, rmax, slab[1] - slab[0])
-        w = World(sub, device=rank, slab=slab, rank=rank, nranks=nranks, ids=ids, rm_max_hint=rmax, halo_ghost_cap=cap)
+        stride, reach = rbdist.compound_layout(sc)
+        cap = rbdist.common_ghost_cap(sub.n_bodies, max(rmax, reach), slab[1] - slab[0])
+        w = World(sub, device=rank, slab=slab, rank=rank, nranks=nranks, ids=ids, rm_max_hint=rmax, halo_ghost_cap=cap,
+                  sphere_stride=stride, body_reach_hint=reach)
         if halo == "nccl":
             rbdist.init_world(w, rank, nranks)
         else:
@@ -78,7 +90,7 @@ def _worker(rank, nranks, port, halo, kind, q):
         q.put((rank, traceback.format_exc() + repr(e), None, None))
 
 
-@pytest.mark.parametrize("kind", ["cross", "rest"])
+@pytest.mark.parametrize("kind", ["cross", "rest", "compound"])
 @pytest.mark.parametrize("halo", ["p2p", "nccl"])
 def test_two_ranks_bit_identical_to_single_world(halo, kind):
     import torch
@@ -89,7 +101,7 @@ def test_two_ranks_bit_identical_to_single_world(halo, kind):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 1500) + (7 if halo == "nccl" else 0) + (13 if kind == "rest" else 0)
+    port = 29700 + (os.getpid() % 1500) + (7 if halo == "nccl" else 0) + (13 if kind == "rest" else 0) + (29 if kind == "compound" else 0)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, halo, kind, q)) for r in range(2)]
     for p in procs:
         p.start()
