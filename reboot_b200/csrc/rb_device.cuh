@@ -177,7 +177,10 @@ struct RbParams {
     uint32_t g_swap, g_nu, g_nv; float g_off_u, g_off_v;
     const RbDistParams* dp;       // device copy of the halo parameters (slab worlds with neighbours), else NULL
     // ---- compound bodies (multi-sphere entities, physics/src/Geometry.cpp:27-31) ----
-    uint32_t grp_on;              // compound bodies step through rb_collide_group_kernel (RB_COMPOUND_GROUP=1) instead of the per-body kernel
+    uint32_t grp_on;              // compound bodies: 0 per-body kernel, 1 rb_collide_group_kernel, 2 enumeration per sphere + resolution per body (RB_COMPOUND=legacy|group|split)
+    uint32_t* ce_hdr;             // split kernels, per sphere row: triangles (bits 0-7) | partners (8-15) | RB_CE_SLOW | RB_CE_OVER
+    uint32_t* ce_pg; uint32_t* ce_pl;   // [4][ns] partner body global id / row, ascending (slot-major)
+    uint32_t* ce_tri;             // [RB_CAND_MAX][ns] staged triangle ids, ascending (slot-major)
     uint32_t grp_lg;              // log2 of the lanes one body gets in rb_collide_group_kernel (2..5, from the largest sphere count)
     uint32_t kstride;             // slab worlds: the spheres of body row b sit at rows [b * kstride, b * kstride + body_cnt[b]) (0: CSR through body_start)
     uint32_t* body_cnt;           // kstride worlds: spheres per body row

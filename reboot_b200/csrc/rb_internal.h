@@ -28,6 +28,10 @@ extern "C" uint32_t rb_list_hot_rows(rb_world* w);
 extern "C" int rb_build_triangle_grid_device(rb_world* w, uint32_t n);      // rb_extras.cu: static triangle column grid (n columns per axis) from w->h_tri
 uint32_t rb_list_tile_bytes();
 uint32_t rb_list_partner_slots();   // partners a persistent list holds
+uint32_t rb_compound_tri_slots();   // triangle ids the split compound kernels stage per sphere
+#ifndef RB_COMPOUND_DEFAULT
+#define RB_COMPOUND_DEFAULT 2u       // compound bodies: 0 per-body kernel, 1 group kernel, 2 split enumeration / resolution
+#endif
 uint32_t rb_list_tile_rows();      // rows per triangle tile (= threads per block of the list step)
 void rb_launch_entity_set_position(float4* pos, float4* mt, float4* pt, const float4* wt, const uint32_t* inv, uint32_t body, const float* xyz, cudaStream_t st);
 void rb_launch_mt_refresh(const float4* pos, const float4* wt, float4* mt, uint32_t n, cudaStream_t st);

@@ -1803,6 +1803,187 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbP
     }
     collide_epilogue(P, H, T, lane);
 }
+
+// ------------------------------------------------------------------------------------------
+// K4E + K4R: compound bodies, the enumeration split from the resolution. What K4G's capture showed: the
+// enumeration -- pointer chasing through the sphere grid and the triangle columns -- is what gains from a lane per SPHERE;
+// the sequential test / resolve chain of a body does not. So:
+//   K4E  one thread per sphere row: the partner scan (the 4 smallest partner body ids, ascending, + "there were more") and the
+//        triangle walk (box-pruned ids, ascending, unique) of rb_collide_group_kernel, parked in slot-major global arrays;
+//   K4R  one thread per body, the first-generation kernel with every grid walk replaced by a read of those lists: partner
+//        bodies in ascending id merged over the body's spheres, then own spheres ascending x triangles ascending, each tested
+//        at the current pose and resolved at once. A sphere whose partner list overflowed re-scans above the last id it
+//        holds; a sphere wider than the fast triangle walk takes the generic walk.
+// Same candidates, same canonical order, same arithmetic as rb_collide_kernel<false, .>: bit-identical results.
+// ------------------------------------------------------------------------------------------
+#define RB_CE_SLOW (1u << 16)
+#define RB_CE_OVER (1u << 17)
+__global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbParams P, const uint32_t nrows) {
+    __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    const uint32_t n_own_rows = P.kstride ? rb_n_owned(P) * P.kstride : nrows;
+    const bool valid = s < n_own_rows && P.key[s] != RB_NONE;      // (inactive bodies, spheres outside the world cube and unused slots carry no key)
+    uint32_t A = 0, gA = 0;
+    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) { A = rb_sph_owner(P, s); gA = rb_gid(P, A); fa = P.ws[s]; }
+    uint32_t pg[RB_GRP_PART], pl[RB_GRP_PART];
+#pragma unroll
+    for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+    bool over = false;
+    group_scan_sphere<true>(P, valid, A, gA, xyz(fa), fa.w, 0u, pg, pl, over, T);
+    uint32_t nc; bool st_slow;
+    group_stage_triangles(P, valid, xyz(fa), fa.w, s_cand, nc, st_slow, T);
+    if (s < n_own_rows) {
+        uint32_t np = 0;
+#pragma unroll
+        for (int k = 0; k < RB_GRP_PART; ++k) if (pg[k] != RB_NONE) { P.ce_pg[(size_t)k * P.ns + s] = pg[k]; P.ce_pl[(size_t)k * P.ns + s] = pl[k]; np++; }
+        for (uint32_t j = 0; j < nc; ++j) P.ce_tri[(size_t)j * P.ns + s] = s_cand[j][threadIdx.x];
+        P.ce_hdr[s] = valid ? (nc | (np << 8) | (st_slow ? RB_CE_SLOW : 0u) | (over ? RB_CE_OVER : 0u)) : 0u;
+    }
+    collide_epilogue(P, H, T, lane);
+}
+
+// one staged triangle against sphere (so, r) of the body at its current pose: process_triangle without the prune
+template <bool RESOLVE>
+__device__ __forceinline__ void exact_triangle(const RbParams& P, BodyState& S, HitBuf& H, Tally& T, uint32_t sa_global, f3 so, float r, uint32_t t, bool& hit_any) {
+    const float4* tp = P.tri + 3ull * t;
+    const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+    const f3 TA = xyz(a4), TB = xyz(b4), TC = xyz(c4);
+    const f3 c = mk3(so.x + S.mt.x, so.y + S.mt.y, so.z + S.mt.z);
+    T.tests_st++;
+    if (!sphere_triangle_detect(c, r, TA, TB, TC)) return;
+    hit_any = true;
+    T.hits_st++;
+    const f3 q = closest_point(c, TA, TB, TC);
+    const f3 ov = sub3(c, q);
+    const float dist = mag3(ov);
+    const f3 o = mk3(ov.x / dist, ov.y / dist, ov.z / dist);
+    record_hit(P, H, sa_global, RB_TRI_BIT | t, r - dist, o, r);
+    if (RESOLVE) {
+        const f3 normal = mk3(a4.w, b4.w, c4.w);
+        const f3 delta = sub3(add3(mul3(o, r * P.pushout), q), c);
+        const float nc = dot3(S.v, normal);
+        const f3 rv = sub3(S.v, mul3(normal, nc));
+        body_set_position(S, add3(S.p, delta));
+        S.v = rv;
+        S.flags |= RB_F_CONTACT;
+    }
+}
+
+template <bool RESOLVE>
+__global__ void __launch_bounds__(RB_BLOCK) rb_compound_resolve_kernel(const RbParams P) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    bool valid = tid < rb_n_owned(P);
+    const uint32_t A = tid;
+    uint32_t s0 = 0, nsph = 0, flags_in = 0;
+    if (valid) { flags_in = P.flags[A]; valid = (flags_in & RB_F_ACTIVE) != 0; }
+    if (valid) {
+        s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A);
+        BodyState S;
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        S.wt = P.wt ? xyz(P.wt[A]) : mk3(0.f, 0.f, 0.f);
+        S.flags = flags_in; S.changed = false;
+        const f3 mt_frozen = S.mt;
+        const uint32_t gA = rb_gid(P, A);
+        // ---------------- sphere-sphere: partner bodies in ascending id, merged over the spheres' lists ----------------
+        uint32_t any_np = 0;
+        for (uint32_t i = 0; i < nsph; ++i) any_np |= P.ce_hdr[s0 + i] & 0xff00u;
+        uint32_t lo = 0;
+        while (any_np) {
+            uint32_t best = RB_NONE, best_local = RB_NONE;
+            for (uint32_t i = 0; i < nsph; ++i) {
+                const uint32_t sa = s0 + i, h = P.ce_hdr[sa], np = (h >> 8) & 0xffu;
+                bool found = false;
+                for (uint32_t k = 0; k < np; ++k) {
+                    const uint32_t g = P.ce_pg[(size_t)k * P.ns + sa];
+                    if (g >= lo) { if (g < best) { best = g; best_local = P.ce_pl[(size_t)k * P.ns + sa]; } found = true; break; }
+                }
+                if (!found && (h & RB_CE_OVER)) {       // its list is used up and there was more: the grid again, above lo
+                    const float4 fs = P.ws[sa];
+                    uint32_t eligible = 0;
+                    scan_partners<false>(P, A, xyz(fs), fs.w, lo, best, best_local, eligible, T);
+                }
+            }
+            if (best == RB_NONE) break;
+            const uint32_t B = best_local;
+            const bool lo_is_a = gA < best;
+            if (RESOLVE || lo_is_a) {
+                // partner simulated from its frozen pose (it toggles exactly like us on every hit)
+                const uint32_t t0 = rb_body_s0(P, B), nb_sph = rb_body_ns(P, B);
+                f3 bmt = xyz(P.mt[B]), bpt = xyz(P.pt[B]), bwt = mk3(0.f, 0.f, 0.f);
+                if (P.wt) bwt = xyz(P.wt[B]);
+                bool b_toggled = false;
+                const uint32_t n_out = lo_is_a ? nsph : nb_sph, n_in = lo_is_a ? nb_sph : nsph;
+                for (uint32_t io = 0; io < n_out; ++io)
+                    for (uint32_t ii = 0; ii < n_in; ++ii) {
+                        const uint32_t ia = lo_is_a ? io : ii, ib = lo_is_a ? ii : io;
+                        const uint32_t sa = s0 + ia, sb = t0 + ib;
+                        if (P.key[sa] == RB_NONE || P.key[sb] == RB_NONE) continue;
+                        const float4 oa = P.sph_obj[sa], ob = P.sph_obj[sb];
+                        const f3 ca = mk3(oa.x + S.mt.x, oa.y + S.mt.y, oa.z + S.mt.z);
+                        f3 cb;
+                        if (!b_toggled) cb = xyz(P.ws[sb]); else cb = mk3(ob.x + bmt.x, ob.y + bmt.y, ob.z + bmt.z);
+                        const f3 cn = lo_is_a ? sub3(ca, cb) : sub3(cb, ca);       // the lower body id plays "sphereA" / "modelA"
+                        const float dist = mag3(cn);
+                        const float radii = lo_is_a ? (oa.w + ob.w) : (ob.w + oa.w);
+                        if (lo_is_a) T.tests_ss++;
+                        if (!(radii - dist >= 0)) continue;
+                        const f3 n1 = mk3(cn.x / dist, cn.y / dist, cn.z / dist);
+                        if (lo_is_a) { T.hits_ss++; record_hit(P, H, rb_sph_gid(P, A, s0, ia), rb_sph_gid(P, B, t0, ib), radii - dist, n1, oa.w); }
+                        if (RESOLVE) {
+                            f3 n = n1;
+                            if (!lo_is_a) { n = neg3(n); n = normalize3(n); }
+                            const float sp = mag3(S.v);
+                            S.v = mul3(mul3(n, sp), P.ss_damp);
+                            body_set_position(S, S.pt);
+                            const f3 t = mk3(bwt.x + bpt.x, bwt.y + bpt.y, bwt.z + bpt.z);
+                            bpt = bmt; bmt = t; b_toggled = true;
+                        }
+                    }
+            }
+            lo = best + 1;
+        }
+        // ---------------- sphere-triangle: own spheres ascending, staged triangles in ascending id ----------------
+        bool last_hit = false;
+        for (uint32_t i = 0; i < nsph; ++i) {
+            const uint32_t sa = s0 + i;
+            bool hit_any = false;
+            if (P.key[sa] != RB_NONE) {
+                const uint32_t h = P.ce_hdr[sa];
+                const float4 oa = P.sph_obj[sa];
+                const uint32_t sid = rb_sph_gid(P, A, s0, i);
+                if (h & RB_CE_SLOW) { const float4 fs = P.ws[sa]; sphere_vs_triangles<RESOLVE>(P, S, H, T, sid, xyz(oa), oa.w, xyz(fs), fs.w, hit_any); }
+                else {
+                    const uint32_t nc = h & 0xffu;
+                    for (uint32_t j = 0; j < nc; ++j) exact_triangle<RESOLVE>(P, S, H, T, sid, xyz(oa), oa.w, P.ce_tri[(size_t)j * P.ns + sa], hit_any);
+                }
+            }
+            if (i == nsph - 1) last_hit = hit_any;
+        }
+        if (RESOLVE) {
+            if ((flags_in & RB_F_CONTACT) && !last_hit) S.flags &= ~RB_F_CONTACT;       // Physics.cpp:201-207
+            const float disp = mag3(sub3(S.mt, mt_frozen));
+            if (nsph && disp > P.ws[s0].w - P.sph_obj[s0].w) T.overflow++;
+            if (S.changed || S.flags != flags_in) {
+                // partners read our frozen pose concurrently: commit after the kernel (K5)
+                const uint32_t k = (uint32_t)atomicAdd(&P.counters[RB_C_NCHANGED], 1ull);
+                P.ch_body[k] = A;
+                P.ch_pos[k] = make_float4(S.p.x, S.p.y, S.p.z, 1.f);
+                P.ch_vel[k] = make_float4(S.v.x, S.v.y, S.v.z, 0.f);
+                P.ch_mt[k] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f);
+                P.ch_pt[k] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+                P.ch_flags[k] = S.flags;
+            }
+        }
+    }
+    collide_epilogue(P, H, T, lane);
+}
 #endif // !RB_CHAIN_TU
 
 // ------------------------------------------------------------------------------------------
@@ -2445,6 +2626,7 @@ void rb_launch_vl_scatter(const RbParams& P, uint32_t ncols, unsigned long long*
 uint32_t rb_list_tile_bytes() { return RB_LS_SMEM_BYTES; }
 uint32_t rb_list_tile_rows() { return RB_LS_BLOCK; }
 uint32_t rb_list_partner_slots() { return RB_SSLIST_MAX; }
+uint32_t rb_compound_tri_slots() { return RB_CAND_MAX; }
 int rb_launch_vl_collide(const RbParams& P, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join, bool with_enumerate, uint32_t hot_rows, int phase) {
     if (!P.nb) return 0;
     const uint32_t g = cdiv(P.ns, RB_LS_BLOCK);
@@ -2495,7 +2677,18 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
     // K4G (a group of lanes per body) is bit-identical to the per-body kernel and faster while bodies fall (C4: 0.94 against 1.20 ms)
     // but not once they rest (1.56 against 1.51 ms: the speculative rounds re-test and four groups of a warp wait for each other):
     // opt-in until the enumeration is split from the resolution (RB_COMPOUND_GROUP=1)
-    if (variant != 1 && P.grp_on) {
+    if (variant != 1 && P.grp_on == 2) {        // enumeration per sphere, resolution per body (K4E + K4R)
+        const uint32_t nrows = P.kstride ? P.nb * P.kstride : P.ns;
+        rb_compound_enum_kernel<<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
+        if (resolve) {
+            rb_compound_resolve_kernel<true><<<g, RB_BLOCK, 0, st>>>(P);
+            rb_commit_kernel<<<g, RB_BLOCK, 0, st>>>(P);
+            return 3;
+        }
+        rb_compound_resolve_kernel<false><<<g, RB_BLOCK, 0, st>>>(P);
+        return 2;
+    }
+    if (variant != 1 && P.grp_on == 1) {
         const uint32_t gg = cdiv(P.nb << P.grp_lg, RB_BLOCK);
         if (resolve) {
             rb_collide_group_kernel<true><<<gg, RB_BLOCK, 0, st>>>(P);

@@ -319,6 +319,16 @@ static int reorder_rows(rb_world* w, bool intick) {
     return RB_OK;
 }
 static int enqueue_broadphase(rb_world* w, int do_integrate);
+// which kernels step compound bodies (all bit-identical): RB_COMPOUND=legacy|group|split (RB_COMPOUND_GROUP=1 = group)
+static uint32_t compound_kernel_choice() {
+    const char* v = getenv("RB_COMPOUND");
+    if (v && !strcmp(v, "legacy")) return 0u;
+    if (v && !strcmp(v, "group")) return 1u;
+    if (v && !strcmp(v, "split")) return 2u;
+    const char* g = getenv("RB_COMPOUND_GROUP");
+    if (g && *g == '1') return 1u;
+    return RB_COMPOUND_DEFAULT;
+}
 int rb_build(rb_world* w) {
     if (!w) return RB_ERR_INVALID;
     if (w->built) return fail(w, RB_ERR_INVALID, "rb_build is call-once (Physics::addEntities, SURVEY Q9)");
@@ -338,7 +348,7 @@ int rb_build(rb_world* w) {
         K = std::max(kmax, w->cfg.sphere_stride);
         P.single = 0u; P.kstride = K;
         P.grp_lg = 2; while ((1u << P.grp_lg) < K && P.grp_lg < 5) P.grp_lg++;
-        { const char* v = getenv("RB_COMPOUND_GROUP"); P.grp_on = (v && *v == '1') ? 1u : 0u; }
+        P.grp_on = compound_kernel_choice();
         // how far a body reaches from its model translation along x (the ghost criterion of K1): this rank's bodies and the hint
         float ext = 0.f;
         for (uint32_t b = 0; b < nb; b++) {
@@ -497,10 +507,16 @@ int rb_build(rb_world* w) {
         uint32_t kmax = 1; for (uint32_t b = 0; b < nb; b++) kmax = std::max(kmax, w->h_body_start[b + 1] - w->h_body_start[b]);
         P.grp_lg = 2; while ((1u << P.grp_lg) < kmax && P.grp_lg < 5) P.grp_lg++;
         { const char* v = getenv("RB_GROUP_LG"); if (v && *v) P.grp_lg = (uint32_t)std::min(5, std::max(1, atoi(v))); }      // (development switch)
-        { const char* v = getenv("RB_COMPOUND_GROUP"); P.grp_on = (v && *v == '1') ? 1u : 0u; }
+        P.grp_on = compound_kernel_choice();
         uint32_t* cb; float4 *c1, *c2, *c3, *c4; uint32_t* cf;
         ALLOC(cb, nb); ALLOC(c1, nb); ALLOC(c2, nb); ALLOC(c3, nb); ALLOC(c4, nb); ALLOC(cf, nb);
         P.ch_body = cb; P.ch_pos = c1; P.ch_vel = c2; P.ch_mt = c3; P.ch_pt = c4; P.ch_flags = cf;
+    }
+    if (!P.single && P.grp_on == 2) {      // candidate lists of the split compound kernels (slot-major by sphere row)
+        uint32_t *ch, *cg, *cl, *ct;
+        ALLOC(ch, nsa); ALLOC(cg, (size_t)nsa * 4); ALLOC(cl, (size_t)nsa * 4); ALLOC(ct, (size_t)nsa * rb_compound_tri_slots());
+        CU(cudaMemsetAsync(ch, 0, (size_t)nsa * 4, w->stream));
+        P.ce_hdr = ch; P.ce_pg = cg; P.ce_pl = cl; P.ce_tri = ct;
     }
     if (w->vl_on) {
         float4* wb;

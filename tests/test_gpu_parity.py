@@ -477,42 +477,48 @@ def test_model_matrix_export_matches_oracle(World, port):
     w.close()
 
 
-def test_compound_group_kernel_bit_identical_to_per_body_kernel(World, monkeypatch):
-    """Compound bodies: the group kernel (RB_COMPOUND_GROUP=1: a group of lanes per body, per-sphere enumeration, speculative
-    canonical-order resolution) and the per-body kernel give identical state, contacts and test counts -- uniform 8-sphere bodies
-    piled closely enough to collide with each other, and ragged bodies (1..5 spheres) next to an inactive one."""
+def test_compound_kernels_bit_identical(World, monkeypatch):
+    """Compound bodies: the per-body kernel (RB_COMPOUND=legacy), the group kernel (group: a group of lanes per body, speculative
+    canonical-order resolution) and the split kernels (split, the default: enumeration per sphere into lists, resolution per body
+    from them) give identical state, contacts and test counts -- uniform 8-sphere bodies piled closely enough to collide with
+    each other, and ragged bodies (1..5 spheres) next to an inactive one."""
     from reboot_b200 import scenes
+    kinds = ("legacy", "group", "split")
     sc = scenes.config4(6000, 64)
-    w1 = World(sc)
-    monkeypatch.setenv("RB_COMPOUND_GROUP", "1")
-    w2 = World(sc)
-    monkeypatch.delenv("RB_COMPOUND_GROUP")
-    for k in range(250):
-        w1.step(5); w2.step(5)
-    a, b = w1.state(), w2.state()
-    for key in ("pos", "vel", "model_t", "prev_t"):
-        assert np.array_equal(bits(a[key]), bits(b[key])), key
-    assert np.array_equal(a["flags"], b["flags"])
-    assert np.array_equal(w1.contacts(), w2.contacts())
-    s1, s2 = w1.stats(), w2.stats()
-    for key in ("tests_st", "hits_st", "tests_ss", "hits_ss"):
-        assert s1[key] == s2[key], key
-    assert s1["hits_ss"] > 100 and s1["hits_st"] > 10000
-    w1.close(); w2.close()
-    tris, _ = scenes.terrain_triangles(8, 2.0, 1)
-    rng = np.random.default_rng(4)
     ws = []
-    for grp in ("0", "1"):
-        monkeypatch.setenv("RB_COMPOUND_GROUP", grp)
+    for kind in kinds:
+        monkeypatch.setenv("RB_COMPOUND", kind)
+        ws.append(World(sc))
+    monkeypatch.delenv("RB_COMPOUND")
+    for k in range(250):
+        for w in ws: w.step(5)
+    a = ws[0].state(); s1 = ws[0].stats(); c1 = ws[0].contacts()
+    for w, kind in zip(ws[1:], kinds[1:]):
+        b = w.state()
+        for key in ("pos", "vel", "model_t", "prev_t"):
+            assert np.array_equal(bits(a[key]), bits(b[key])), (kind, key)
+        assert np.array_equal(a["flags"], b["flags"]), kind
+        assert np.array_equal(c1, w.contacts()), kind
+        s2 = w.stats()
+        for key in ("tests_st", "hits_st", "tests_ss", "hits_ss"):
+            assert s1[key] == s2[key], (kind, key)
+    assert s1["hits_ss"] > 100 and s1["hits_st"] > 10000
+    for w in ws: w.close()
+    tris, _ = scenes.terrain_triangles(8, 2.0, 1)
+    ws = []
+    for kind in kinds:
+        monkeypatch.setenv("RB_COMPOUND", kind)
         w = World(); w.add_static_geometry(tris)
         rng = np.random.default_rng(4)
         for ns, p, fl in [(1, (0.0, 1.2, 0.0), 3), (3, (2.0, 1.3, 1.0), 3), (5, (-3.0, 1.4, 2.0), 3), (1, (1.0, 1.1, -3.0), 2), (2, (2.3, 1.6, 1.2), 3), (1, (1000.4, 0.0, 0.0), 3)]:
             obj = np.zeros((ns, 4), np.float32); obj[:, :3] = rng.uniform(-0.3, 0.3, (ns, 3)); obj[:, 3] = 0.5
             w.add_model(obj, p, (0, -1, 0), fl)
         w.build(); ws.append(w)
-    monkeypatch.delenv("RB_COMPOUND_GROUP")
+    monkeypatch.delenv("RB_COMPOUND")
     for k in range(120):
         for w in ws: w.step(5)
-        a, b = ws[0].state(), ws[1].state()
-        assert np.array_equal(bits(a["pos"]), bits(b["pos"])) and np.array_equal(bits(a["vel"]), bits(b["vel"])) and np.array_equal(a["flags"], b["flags"]), k
+        a = ws[0].state()
+        for w, kind in zip(ws[1:], kinds[1:]):
+            b = w.state()
+            assert np.array_equal(bits(a["pos"]), bits(b["pos"])) and np.array_equal(bits(a["vel"]), bits(b["vel"])) and np.array_equal(a["flags"], b["flags"]), (kind, k)
     for w in ws: w.close()

@@ -1,4 +1,4 @@
-"""A/B of the compound-body kernels: group kernel (default) vs first-generation kernel (RB_COLLIDE_V1=1), tick by tick."""
+"""A/B of the compound-body kernels: KIND=split|group (RB_COMPOUND) vs the per-body kernel (legacy), tick by tick."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -17,8 +17,8 @@ def make(edge):
     w.build(); return w
 
 edge = "--edge" in sys.argv
-os.environ.pop("RB_COLLIDE_V1", None); a = make(edge)
-os.environ["RB_COLLIDE_V1"] = "1"; b = make(edge); os.environ.pop("RB_COLLIDE_V1")
+os.environ["RB_COMPOUND"] = os.environ.get("KIND", "split"); a = make(edge)
+os.environ["RB_COMPOUND"] = "legacy"; b = make(edge); os.environ.pop("RB_COMPOUND")
 for k in range(int(os.environ.get("TICKS", "300"))):
     a.step(5); b.step(5)
     sa, sb = a.state(), b.state()
