@@ -45,7 +45,7 @@ struct __align__(16) RbContactRec {
 // counters[] layout (unsigned long long)
 enum { RB_C_TESTS_SS = 0, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_SS, RB_C_HITS_ST,
        RB_C_OVERFLOW, RB_C_DROPPED, RB_C_NCONTACT /* per step, reset */, RB_C_NCHANGED /* per step */,
-       RB_C_HALO_SENT, RB_C_MIGRATED,
+       RB_C_NSS /* per step: compound bodies with sphere-sphere partners (split kernels) */, RB_C_MIGRATED,
        RB_C_IMM_DROPPED /* sticky: immigrants a full slab could not take */, RB_C_HALO_OVF /* sticky: ghost / migrant records that did not fit a halo buffer */,
        RB_C_COUNT = 16 };
 
@@ -181,6 +181,9 @@ struct RbParams {
     uint32_t* ce_hdr;             // split kernels, per sphere row: triangles (bits 0-7) | partners (8-15) | RB_CE_SLOW | RB_CE_OVER
     uint32_t* ce_pg; uint32_t* ce_pl;   // [4][ns] partner body global id / row, ascending (slot-major)
     uint32_t* ce_tri;             // [RB_CAND_MAX][ns] staged triangle ids, ascending (slot-major)
+    // bodies with sphere-sphere partners run that phase in a launch of their own (dense warps), their state parked for the triangle phase
+    uint32_t* ss_npart; uint32_t* ss_list; uint32_t* ss_slot;   // per body: partners its spheres found (0 = none; reset by the triangle phase) | the list | body -> entry + 1
+    float4* ss_pos; float4* ss_vel; float4* ss_mt; float4* ss_pt;   // per entry: state after the sphere-sphere phase (flags in pos.w, "changed" in vel.w)
     uint32_t grp_lg;              // log2 of the lanes one body gets in rb_collide_group_kernel (2..5, from the largest sphere count)
     uint32_t kstride;             // slab worlds: the spheres of body row b sit at rows [b * kstride, b * kstride + body_cnt[b]) (0: CSR through body_start)
     uint32_t* body_cnt;           // kstride worlds: spheres per body row

@@ -408,7 +408,7 @@ static int dist_phase_a(rb_world* w, int do_integrate, int list_mode) {
     } else {
         int r = rb_plain_tick_params(w); if (r) return r;
         rb_launch_clear(nullptr, 0, w->d_dn + 1, 11, w->stream); w->launches++;            // n_ghost, self ghosts, emigrants, both out headers
-        rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
+        rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 6, w->stream); w->launches++;
     }
     if (w->profile) CU(cudaEventRecord(w->ev[0], w->stream));
     rb_launch_integrate_bin(P, do_integrate, list_mode ? list_mode : 1, w->stream); w->launches++;     // integrate + bin + halo pack

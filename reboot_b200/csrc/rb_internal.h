@@ -17,7 +17,7 @@ int rb_launch_scan(const uint32_t* in, uint32_t n, uint32_t* out, uint32_t* tile
 uint32_t rb_scan_tiles(uint32_t n);
 int rb_launch_scan_lookback(const uint32_t* in, uint32_t n, uint32_t* out, unsigned long long* status, uint32_t* ticket, cudaStream_t st);
 void rb_launch_scatter(const RbParams& P, cudaStream_t st);
-int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st);
+int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st, cudaStream_t side = nullptr, cudaEvent_t fork = nullptr, cudaEvent_t join = nullptr);
 void rb_launch_clear(void* a, size_t bytes_a, uint32_t* b, uint32_t words_b, cudaStream_t st);
 void rb_launch_vl_bin(const RbParams& P, cudaStream_t st);
 void rb_launch_vl_scan(const RbParams& P, uint32_t ncols, unsigned long long* status, uint32_t* ticket, cudaStream_t st);

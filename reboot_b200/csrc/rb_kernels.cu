@@ -1364,6 +1364,8 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
 // Same canonical order and arithmetic as rb_collide_kernel<false, .> (bit-identical results; RB_COLLIDE_V1=1 runs that one).
 // ------------------------------------------------------------------------------------------
 #define RB_GRP_PART 4
+#define RB_CE_SLOW (1u << 16)      // rb_compound_enum_kernel's header word: the sphere is wider than the fast triangle walk
+#define RB_CE_OVER (1u << 17)      // ... it found more partner bodies than a list holds
 
 // reductions over the aligned group of L lanes a body owns; every lane of the WARP takes part (xor partners below L stay inside the group)
 __device__ __forceinline__ uint32_t group_min(uint32_t v, const uint32_t L) {
@@ -1511,37 +1513,18 @@ __device__ __forceinline__ void group_bcast_state(BodyState& S, const uint32_t g
     S.changed = __shfl_sync(gmask, (int)S.changed, src) != 0;
 }
 
-template <bool RESOLVE>
-__global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbParams P) {
-    __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
-    const uint32_t lg = P.grp_lg, L = 1u << lg;
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31, sub = lane & (L - 1), gbase = lane & ~(L - 1);
+// The sphere-sphere phase of a body over the group of lanes it owns (warp-uniform: every lane of the warp takes part).
+// PRELOAD: the partner lists start from what rb_compound_enum_kernel parked instead of a scan of the sphere grid.
+template <bool RESOLVE, bool PRELOAD>
+__device__ __forceinline__ void group_sphere_sphere(const RbParams& P, const bool valid, const uint32_t A, const uint32_t gA, const uint32_t s0, const uint32_t nsph,
+                                                    BodyState& S, HitBuf& H, Tally& T, const uint32_t lg, const uint32_t nchunk_w) {
+    const uint32_t L = 1u << lg, lane = threadIdx.x & 31, sub = lane & (L - 1);
     const bool leader = sub == 0;
-    const uint32_t A = tid >> lg;
-    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
-    HitBuf H; H.n = 0;
-    bool valid = A < rb_n_owned(P);                 // (uniform over the group)
-    uint32_t s0 = 0, nsph = 0, flags_in = 0;
-    if (valid) { flags_in = P.flags[A]; valid = (flags_in & RB_F_ACTIVE) != 0; }
-    BodyState S; S.changed = false; S.flags = flags_in;
-    S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
-    uint32_t gA = 0;
-    if (valid) {
-        s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A);
-        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
-        if (P.wt) S.wt = xyz(P.wt[A]);
-        gA = rb_gid(P, A);
-    }
-    const f3 mt_frozen = S.mt;
-    const uint32_t nchunk_w = __reduce_max_sync(0xffffffffu, (nsph + L - 1) >> lg);      // chunks of L spheres, warp-wide maximum
-
-    // ---------------- sphere-sphere: partner bodies in ascending id ----------------
     {
         uint32_t pg[RB_GRP_PART], pl[RB_GRP_PART];
 #pragma unroll
         for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
-        bool over = false, need = valid;
+        bool over = false, need = valid, first_fill = true;
         uint32_t lo = 0;
         // spheres of A inside the broadphase (the lower body id counts the tests: one per pair of such spheres)
         uint32_t nA_in = 0;
@@ -1558,13 +1541,35 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbP
                     for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
                     over = false;
                 }
-                for (uint32_t c = 0; c < nchunk_w; ++c) {
-                    const uint32_t i = (c << lg) + sub;
-                    bool w = need && i < nsph && P.key[s0 + i] != RB_NONE;
-                    float4 fa = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (w) fa = P.ws[s0 + i];
-                    group_scan_sphere<RESOLVE>(P, w, A, gA, xyz(fa), fa.w, lo, pg, pl, over, T);
+                if (PRELOAD && first_fill) {
+                    // the lists the enumeration kernel parked (the 4 smallest partner ids of every sphere, ascending)
+                    for (uint32_t c = 0; c < nchunk_w; ++c) {
+                        const uint32_t i = (c << lg) + sub;
+                        if (!(need && i < nsph)) continue;
+                        const uint32_t sa = s0 + i, h = P.ce_hdr[sa], np = (h >> 8) & 0xffu;
+                        if (h & RB_CE_OVER) over = true;
+                        for (uint32_t k = 0; k < np; ++k) {
+                            uint32_t g = P.ce_pg[(size_t)k * P.ns + sa], Bl = P.ce_pl[(size_t)k * P.ns + sa];
+                            bool dup = false;
+#pragma unroll
+                            for (int q = 0; q < RB_GRP_PART; ++q) dup |= (pg[q] == g);
+                            if (dup) continue;
+#pragma unroll
+                            for (int q = 0; q < RB_GRP_PART; ++q)
+                                if (g < pg[q]) { uint32_t tg = pg[q], tl = pl[q]; pg[q] = g; pl[q] = Bl; g = tg; Bl = tl; }
+                            if (g != RB_NONE) over = true;
+                        }
+                    }
+                } else {
+                    for (uint32_t c = 0; c < nchunk_w; ++c) {
+                        const uint32_t i = (c << lg) + sub;
+                        bool w = need && i < nsph && P.key[s0 + i] != RB_NONE;
+                        float4 fa = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (w) fa = P.ws[s0 + i];
+                        group_scan_sphere<RESOLVE>(P, w, A, gA, xyz(fa), fa.w, lo, pg, pl, over, T);
+                    }
                 }
+                first_fill = false;
                 need = false;
             }
             uint32_t mine = RB_NONE, mine_l = RB_NONE;
@@ -1653,6 +1658,35 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbP
             __syncwarp();
         }
     }
+}
+
+template <bool RESOLVE>
+__global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbParams P) {
+    __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
+    const uint32_t lg = P.grp_lg, L = 1u << lg;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (L - 1), gbase = lane & ~(L - 1);
+    const bool leader = sub == 0;
+    const uint32_t A = tid >> lg;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    bool valid = A < rb_n_owned(P);                 // (uniform over the group)
+    uint32_t s0 = 0, nsph = 0, flags_in = 0;
+    if (valid) { flags_in = P.flags[A]; valid = (flags_in & RB_F_ACTIVE) != 0; }
+    BodyState S; S.changed = false; S.flags = flags_in;
+    S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
+    uint32_t gA = 0;
+    if (valid) {
+        s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A);
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        if (P.wt) S.wt = xyz(P.wt[A]);
+        gA = rb_gid(P, A);
+    }
+    const f3 mt_frozen = S.mt;
+    const uint32_t nchunk_w = __reduce_max_sync(0xffffffffu, (nsph + L - 1) >> lg);      // chunks of L spheres, warp-wide maximum
+
+    // ---------------- sphere-sphere: partner bodies in ascending id ----------------
+    group_sphere_sphere<RESOLVE, false>(P, valid, A, gA, s0, nsph, S, H, T, lg, nchunk_w);
 
     // ---------------- sphere-triangle: own spheres ascending, triangles in ascending id ----------------
     bool last_hit = false;
@@ -1816,8 +1850,6 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbP
 //        holds; a sphere wider than the fast triangle walk takes the generic walk.
 // Same candidates, same canonical order, same arithmetic as rb_collide_kernel<false, .>: bit-identical results.
 // ------------------------------------------------------------------------------------------
-#define RB_CE_SLOW (1u << 16)
-#define RB_CE_OVER (1u << 17)
 __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbParams P, const uint32_t nrows) {
     __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1842,6 +1874,8 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbP
         for (int k = 0; k < RB_GRP_PART; ++k) if (pg[k] != RB_NONE) { P.ce_pg[(size_t)k * P.ns + s] = pg[k]; P.ce_pl[(size_t)k * P.ns + s] = pl[k]; np++; }
         for (uint32_t j = 0; j < nc; ++j) P.ce_tri[(size_t)j * P.ns + s] = s_cand[j][threadIdx.x];
         P.ce_hdr[s] = valid ? (nc | (np << 8) | (st_slow ? RB_CE_SLOW : 0u) | (over ? RB_CE_OVER : 0u)) : 0u;
+        // the first sphere of a body that finds a partner enters the body in the sphere-sphere list
+        if (np && atomicAdd(&P.ss_npart[A], np) == 0u) P.ss_list[(uint32_t)atomicAdd(&P.counters[RB_C_NSS], 1ull)] = A;
     }
     collide_epilogue(P, H, T, lane);
 }
@@ -1873,27 +1907,42 @@ __device__ __forceinline__ void exact_triangle(const RbParams& P, BodyState& S, 
     }
 }
 
-template <bool RESOLVE>
+// PHASE 1: the bodies of the sphere-sphere list (one thread each: warps full of bodies that all have partners), state parked;
+// PHASE 2: the triangle phase, flags and deferred commit of the bodies WITHOUT partners -- independent of phase 1, so the two run
+//          side by side on two streams (phase 1 is a few long dependent chains, phase 2 fills the GPU);
+// PHASE 3: the same for the listed bodies, from the parked state.
+template <bool RESOLVE, int PHASE>
 __global__ void __launch_bounds__(RB_BLOCK) rb_compound_resolve_kernel(const RbParams P) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
     HitBuf H; H.n = 0;
-    bool valid = tid < rb_n_owned(P);
-    const uint32_t A = tid;
+    bool valid;
+    uint32_t A = tid;
+    if (PHASE == 1 || PHASE == 3) { if (blockIdx.x * blockDim.x >= (uint32_t)P.counters[RB_C_NSS]) return; valid = tid < (uint32_t)P.counters[RB_C_NSS]; if (valid) A = P.ss_list[tid]; }
+    else valid = tid < rb_n_owned(P) && P.ss_npart[tid] == 0u;
     uint32_t s0 = 0, nsph = 0, flags_in = 0;
     if (valid) { flags_in = P.flags[A]; valid = (flags_in & RB_F_ACTIVE) != 0; }
     if (valid) {
         s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A);
         BodyState S;
-        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        const f3 mt_frozen = xyz(P.mt[A]);
+        const uint32_t slot = (PHASE == 3 && RESOLVE) ? P.ss_slot[A] : 0u;
+        if (slot) {
+            const float4 a = P.ss_pos[slot - 1u], b = P.ss_vel[slot - 1u];
+            S.p = xyz(a); S.v = xyz(b); S.mt = xyz(P.ss_mt[slot - 1u]); S.pt = xyz(P.ss_pt[slot - 1u]);
+            S.flags = __float_as_uint(a.w); S.changed = __float_as_uint(b.w) != 0u;
+            P.ss_slot[A] = 0u;
+        } else {
+            S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = mt_frozen; S.pt = xyz(P.pt[A]);
+            S.flags = flags_in; S.changed = false;
+        }
+        if (PHASE == 3) P.ss_npart[A] = 0u;       // (ready for the next tick's enumeration)
         S.wt = P.wt ? xyz(P.wt[A]) : mk3(0.f, 0.f, 0.f);
-        S.flags = flags_in; S.changed = false;
-        const f3 mt_frozen = S.mt;
         const uint32_t gA = rb_gid(P, A);
         // ---------------- sphere-sphere: partner bodies in ascending id, merged over the spheres' lists ----------------
         uint32_t any_np = 0;
-        for (uint32_t i = 0; i < nsph; ++i) any_np |= P.ce_hdr[s0 + i] & 0xff00u;
+        if (PHASE == 1) for (uint32_t i = 0; i < nsph; ++i) any_np |= P.ce_hdr[s0 + i] & 0xff00u;
         uint32_t lo = 0;
         while (any_np) {
             uint32_t best = RB_NONE, best_local = RB_NONE;
@@ -1949,9 +1998,15 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_compound_resolve_kernel(const RbP
             }
             lo = best + 1;
         }
+        if (PHASE == 1 && RESOLVE) {      // parked for the triangle phase
+            P.ss_pos[tid] = make_float4(S.p.x, S.p.y, S.p.z, __uint_as_float(S.flags));
+            P.ss_vel[tid] = make_float4(S.v.x, S.v.y, S.v.z, __uint_as_float(S.changed ? 1u : 0u));
+            P.ss_mt[tid] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f); P.ss_pt[tid] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+            P.ss_slot[A] = tid + 1u;
+        }
         // ---------------- sphere-triangle: own spheres ascending, staged triangles in ascending id ----------------
         bool last_hit = false;
-        for (uint32_t i = 0; i < nsph; ++i) {
+        for (uint32_t i = 0; PHASE >= 2 && i < nsph; ++i) {
             const uint32_t sa = s0 + i;
             bool hit_any = false;
             if (P.key[sa] != RB_NONE) {
@@ -1966,7 +2021,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_compound_resolve_kernel(const RbP
             }
             if (i == nsph - 1) last_hit = hit_any;
         }
-        if (RESOLVE) {
+        if (RESOLVE && PHASE >= 2) {
             if ((flags_in & RB_F_CONTACT) && !last_hit) S.flags &= ~RB_F_CONTACT;       // Physics.cpp:201-207
             const float disp = mag3(sub3(S.mt, mt_frozen));
             if (nsph && disp > P.ws[s0].w - P.sph_obj[s0].w) T.overflow++;
@@ -1981,6 +2036,39 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_compound_resolve_kernel(const RbP
                 P.ch_flags[k] = S.flags;
             }
         }
+    }
+    collide_epilogue(P, H, T, lane);
+}
+
+// PHASE 1 with a group of lanes per listed body: the sphere pairs of a partner are dealt over the group and resolved in
+// canonical order by speculation (group_sphere_sphere), the state parked for the triangle phase by the group's first lane.
+template <bool RESOLVE>
+__global__ void __launch_bounds__(RB_BLOCK) rb_compound_ss_group_kernel(const RbParams P) {
+    const uint32_t lg = P.grp_lg, L = 1u << lg;
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, sub = lane & (L - 1);
+    const uint32_t e = tid >> lg;                   // entry of the sphere-sphere list (uniform over the group)
+    if (((blockIdx.x * blockDim.x) >> lg) >= (uint32_t)P.counters[RB_C_NSS]) return;      // (the launch is sized for every body: whole blocks beyond the list leave at once)
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    bool valid = e < (uint32_t)P.counters[RB_C_NSS];
+    uint32_t A = 0, s0 = 0, nsph = 0, flags_in = 0, gA = 0;
+    if (valid) { A = P.ss_list[e]; flags_in = P.flags[A]; valid = (flags_in & RB_F_ACTIVE) != 0; }
+    BodyState S; S.changed = false; S.flags = flags_in;
+    S.p = S.v = S.mt = S.pt = S.wt = mk3(0.f, 0.f, 0.f);
+    if (valid) {
+        s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A);
+        S.p = xyz(P.pos[A]); S.v = xyz(P.vel[A]); S.mt = xyz(P.mt[A]); S.pt = xyz(P.pt[A]);
+        if (P.wt) S.wt = xyz(P.wt[A]);
+        gA = rb_gid(P, A);
+    }
+    const uint32_t nchunk_w = __reduce_max_sync(0xffffffffu, (nsph + L - 1) >> lg);
+    group_sphere_sphere<RESOLVE, true>(P, valid, A, gA, s0, nsph, S, H, T, lg, nchunk_w);
+    if (RESOLVE && valid && sub == 0) {
+        P.ss_pos[e] = make_float4(S.p.x, S.p.y, S.p.z, __uint_as_float(S.flags));
+        P.ss_vel[e] = make_float4(S.v.x, S.v.y, S.v.z, __uint_as_float(S.changed ? 1u : 0u));
+        P.ss_mt[e] = make_float4(S.mt.x, S.mt.y, S.mt.z, 0.f); P.ss_pt[e] = make_float4(S.pt.x, S.pt.y, S.pt.z, 0.f);
+        P.ss_slot[A] = e + 1u;
     }
     collide_epilogue(P, H, T, lane);
 }
@@ -2660,7 +2748,7 @@ void rb_launch_list_step_early(const RbParams& P, cudaStream_t st, cudaStream_t 
     rb_list_step_kernel<<<cdiv(P.ns, RB_LS_BLOCK), RB_LS_BLOCK, rb_list_tile_bytes(), st>>>(P, 1);
     cudaStreamWaitEvent(st, join, 0);
 }
-int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st) {
+int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t st, cudaStream_t side, cudaEvent_t fork, cudaEvent_t join) {
     if (!P.nb) return 0;
     if (P.single) {
         uint32_t g = cdiv(P.ns, RB_BLOCK);
@@ -2680,13 +2768,30 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
     if (variant != 1 && P.grp_on == 2) {        // enumeration per sphere, resolution per body (K4E + K4R)
         const uint32_t nrows = P.kstride ? P.nb * P.kstride : P.ns;
         rb_compound_enum_kernel<<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
+        // (the sphere-sphere launch is sized for every body: the list's length only exists on the device; blocks beyond it return at once)
+        // RB_COMPOUND_SS_GROUP=1 (development switch): a group of lanes per listed body instead of one thread -- measured slower on C4
+        // (0.57 against 0.25 ms: bodies in sphere-sphere contact hit many times per tick, every hit costs the group another round)
+        static const int ss_group = [] { const char* v = getenv("RB_COMPOUND_SS_GROUP"); return v && *v == '1' ? 1 : 0; }();
+        const uint32_t gs = cdiv(P.nb << P.grp_lg, RB_BLOCK);
+        cudaStream_t s1 = side ? side : st;
+        if (side) { cudaEventRecord(fork, st); cudaStreamWaitEvent(side, fork, 0); }
         if (resolve) {
-            rb_compound_resolve_kernel<true><<<g, RB_BLOCK, 0, st>>>(P);
+            if (ss_group) rb_compound_ss_group_kernel<true><<<gs, RB_BLOCK, 0, s1>>>(P);
+            else rb_compound_resolve_kernel<true, 1><<<g, RB_BLOCK, 0, s1>>>(P);
+            if (side) cudaEventRecord(join, side);
+            rb_compound_resolve_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P);
+            if (side) cudaStreamWaitEvent(st, join, 0);
+            rb_compound_resolve_kernel<true, 3><<<g, RB_BLOCK, 0, st>>>(P);
             rb_commit_kernel<<<g, RB_BLOCK, 0, st>>>(P);
-            return 3;
+            return 5;
         }
-        rb_compound_resolve_kernel<false><<<g, RB_BLOCK, 0, st>>>(P);
-        return 2;
+        if (ss_group) rb_compound_ss_group_kernel<false><<<gs, RB_BLOCK, 0, s1>>>(P);
+        else rb_compound_resolve_kernel<false, 1><<<g, RB_BLOCK, 0, s1>>>(P);
+        if (side) cudaEventRecord(join, side);
+        rb_compound_resolve_kernel<false, 2><<<g, RB_BLOCK, 0, st>>>(P);
+        if (side) cudaStreamWaitEvent(st, join, 0);
+        rb_compound_resolve_kernel<false, 3><<<g, RB_BLOCK, 0, st>>>(P);
+        return 4;
     }
     if (variant != 1 && P.grp_on == 1) {
         const uint32_t gg = cdiv(P.nb << P.grp_lg, RB_BLOCK);

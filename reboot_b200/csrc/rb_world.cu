@@ -517,6 +517,17 @@ int rb_build(rb_world* w) {
         ALLOC(ch, nsa); ALLOC(cg, (size_t)nsa * 4); ALLOC(cl, (size_t)nsa * 4); ALLOC(ct, (size_t)nsa * rb_compound_tri_slots());
         CU(cudaMemsetAsync(ch, 0, (size_t)nsa * 4, w->stream));
         P.ce_hdr = ch; P.ce_pg = cg; P.ce_pl = cl; P.ce_tri = ct;
+        uint32_t *sn, *sl, *so; float4 *s1, *s2, *s3, *s4;
+        ALLOC(sn, nba); ALLOC(sl, nba); ALLOC(so, nba); ALLOC(s1, nba); ALLOC(s2, nba); ALLOC(s3, nba); ALLOC(s4, nba);
+        CU(cudaMemsetAsync(sn, 0, (size_t)nba * 4, w->stream)); CU(cudaMemsetAsync(so, 0, (size_t)nba * 4, w->stream));
+        P.ss_npart = sn; P.ss_list = sl; P.ss_slot = so; P.ss_pos = s1; P.ss_vel = s2; P.ss_mt = s3; P.ss_pt = s4;
+        // the sphere-sphere phase of the listed bodies runs next to the triangle phase of everybody else
+        { const char* v = getenv("RB_COMPOUND_SIDE");      // (development switch)
+          if (!(v && *v == '0')) {
+              int lo = 0, hi = 0; CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+              CU(cudaStreamCreateWithPriority(&w->vl_side, cudaStreamNonBlocking, hi));
+              CU(cudaEventCreateWithFlags(&w->vl_fork, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&w->vl_join, cudaEventDisableTiming));
+          } }
     }
     if (w->vl_on) {
         float4* wb;
@@ -649,8 +660,8 @@ static int enqueue_broadphase(rb_world* w, int do_integrate) {
 static int enqueue_collide(rb_world* w, bool resolve) {
     RbParams& P = w->P;
     // per-step counters: contact count + changed count
-    rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 4, w->stream); w->launches++;
-    w->launches += rb_launch_collide(P, resolve, w->collide_variant, w->stream);
+    rb_launch_clear(nullptr, 0, (uint32_t*)(P.counters + RB_C_NCONTACT), 6, w->stream); w->launches++;      // contacts, changed bodies, sphere-sphere list
+    w->launches += rb_launch_collide(P, resolve, w->collide_variant, w->stream, w->vl_side, w->vl_fork, w->vl_join);
     if (w->profile) {
         CU(cudaEventRecord(w->ev[4], w->stream));
         CU(cudaEventSynchronize(w->ev[4]));
