@@ -181,6 +181,11 @@ struct RbParams {
     uint32_t* ce_hdr;             // split kernels, per sphere row: triangles (bits 0-7) | partners (8-15) | RB_CE_SLOW | RB_CE_OVER
     uint32_t* ce_pg; uint32_t* ce_pl;   // [4][ns] partner body global id / row, ascending (slot-major)
     uint32_t* ce_tri;             // [RB_CAND_MAX][ns] staged triangle ids, ascending (slot-major)
+    // the triangle side of those lists is persistent: static geometry does not move, so a sphere's list -- staged for the sphere
+    // grown by ce_skin -- stays a superset of the per-tick candidates while displacement since then + this tick's margin <= ce_skin,
+    // and every sphere decides that for itself (no partner is involved: nothing like the hot-body table is needed)
+    float4* ce_build;             // per sphere row: centre the list was staged at (w < 0 or NaN: no reusable list)
+    float ce_skin;
     // bodies with sphere-sphere partners run that phase in a launch of their own (dense warps), their state parked for the triangle phase
     uint32_t* ss_npart; uint32_t* ss_list; uint32_t* ss_slot;   // per body: partners its spheres found (0 = none; reset by the triangle phase) | the list | body -> entry + 1
     float4* ss_pos; float4* ss_vel; float4* ss_mt; float4* ss_pt;   // per entry: state after the sphere-sphere phase (flags in pos.w, "changed" in vel.w)

@@ -144,6 +144,7 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
             for (uint32_t j = 0; j < P.kstride; ++j) {
                 const uint32_t a = h * P.kstride + j, b = last * P.kstride + j;
                 sph[a] = sph[b]; P.ws[a] = P.ws[b]; P.key[a] = P.key[b]; P.rank[a] = P.rank[b];
+                if (P.ce_build) P.ce_build[a].w = -1.0f;      // (another body's sphere now: its persistent triangle list is not this row's)
             }
         } else if (h != last) {
             P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
                     // the world sphere K1 computed on the old owner (same state, same formula)
                     const float4 o = r[5 + j];
                     D.sph_obj_w[s] = o;
+                    if (P.ce_build) P.ce_build[s].w = -1.0f;      // a new row: no persistent triangle list yet
                     const f3 c = mk3(o.x + mt.x, o.y + mt.y, o.z + mt.z);
                     const float margin = fminf(P.margin_cap, fmaxf(2.0f * speed * P.dt + 0.01f * o.w, 1e-3f));
                     const bool in = (flags & RB_F_ACTIVE) && sphere_in_world(c, o.w, P.half);

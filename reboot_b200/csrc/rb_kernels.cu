@@ -1867,14 +1867,31 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbP
     for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
     bool over = false;
     group_scan_sphere<true>(P, valid, A, gA, xyz(fa), fa.w, 0u, pg, pl, over, T);
+    // the triangle list: reused while the sphere stays inside the skin it was staged with, else staged again -- for the sphere
+    // grown by the skin if this tick's margin fits inside it (a fast mover's list would not even be valid now: per-tick radius)
+    bool reuse = false, persist = false;
+    uint32_t old_hdr = 0;
+    float stage_r = fa.w;
+    if (valid && P.ce_skin > 0.f) {
+        const float4 bb = P.ce_build[s];
+        const float r = P.sph_obj[s].w, margin = fa.w - r;
+        const float dx = fa.x - bb.x, dy = fa.y - bb.y, dz = fa.z - bb.z;
+        if (bb.w >= 0.f && sqrtf((dx * dx + dy * dy) + dz * dz) + margin <= P.ce_skin) { reuse = true; old_hdr = P.ce_hdr[s]; }
+        else if (margin <= P.ce_skin) { persist = true; stage_r = r + P.ce_skin; }
+    }
     uint32_t nc; bool st_slow;
-    group_stage_triangles(P, valid, xyz(fa), fa.w, s_cand, nc, st_slow, T);
+    group_stage_triangles(P, valid && !reuse, xyz(fa), stage_r, s_cand, nc, st_slow, T);
+    if (reuse) { nc = old_hdr & 0xffu; st_slow = (old_hdr & RB_CE_SLOW) != 0u; }
     if (s < n_own_rows) {
         uint32_t np = 0;
 #pragma unroll
         for (int k = 0; k < RB_GRP_PART; ++k) if (pg[k] != RB_NONE) { P.ce_pg[(size_t)k * P.ns + s] = pg[k]; P.ce_pl[(size_t)k * P.ns + s] = pl[k]; np++; }
-        for (uint32_t j = 0; j < nc; ++j) P.ce_tri[(size_t)j * P.ns + s] = s_cand[j][threadIdx.x];
+        if (!reuse) {
+            for (uint32_t j = 0; j < nc; ++j) P.ce_tri[(size_t)j * P.ns + s] = s_cand[j][threadIdx.x];
+            if (valid && P.ce_skin > 0.f) P.ce_build[s] = make_float4(fa.x, fa.y, fa.z, (persist && !st_slow) ? 0.f : -1.0f);
+        }
         P.ce_hdr[s] = valid ? (nc | (np << 8) | (st_slow ? RB_CE_SLOW : 0u) | (over ? RB_CE_OVER : 0u)) : 0u;
+        if (!valid && P.ce_skin > 0.f) P.ce_build[s].w = -1.0f;      // (not in the broadphase: the header word above no longer holds its list)
         // the first sphere of a body that finds a partner enters the body in the sphere-sphere list
         if (np && atomicAdd(&P.ss_npart[A], np) == 0u) P.ss_list[(uint32_t)atomicAdd(&P.counters[RB_C_NSS], 1ull)] = A;
     }

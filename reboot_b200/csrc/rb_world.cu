@@ -517,6 +517,14 @@ int rb_build(rb_world* w) {
         ALLOC(ch, nsa); ALLOC(cg, (size_t)nsa * 4); ALLOC(cl, (size_t)nsa * 4); ALLOC(ct, (size_t)nsa * rb_compound_tri_slots());
         CU(cudaMemsetAsync(ch, 0, (size_t)nsa * 4, w->stream));
         P.ce_hdr = ch; P.ce_pg = cg; P.ce_pl = cl; P.ce_tri = ct;
+        {   // persistent triangle lists: skin = 8 % of the smallest radius like the single-sphere lists (RB_COMPOUND_SKIN=<m>, 0 = off)
+            float rmin = rmax;
+            for (size_t i = 3; i < sph.size(); i += 4) if (sph[i] != 0.f) rmin = std::min(rmin, std::fabs(sph[i]));
+            P.ce_skin = std::max(0.08f * rmin, 4e-3f);
+            const char* v = getenv("RB_COMPOUND_SKIN"); if (v && *v) P.ce_skin = (float)atof(v);
+            float4* cb4; ALLOC(cb4, nsa); CU(cudaMemsetAsync(cb4, 0xff, (size_t)nsa * 16, w->stream));      // (NaN: no list yet)
+            P.ce_build = cb4;
+        }
         uint32_t *sn, *sl, *so; float4 *s1, *s2, *s3, *s4;
         ALLOC(sn, nba); ALLOC(sl, nba); ALLOC(so, nba); ALLOC(s1, nba); ALLOC(s2, nba); ALLOC(s3, nba); ALLOC(s4, nba);
         CU(cudaMemsetAsync(sn, 0, (size_t)nba * 4, w->stream)); CU(cudaMemsetAsync(so, 0, (size_t)nba * 4, w->stream));
