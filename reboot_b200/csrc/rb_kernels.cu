@@ -1882,6 +1882,20 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbP
     uint32_t nc; bool st_slow;
     group_stage_triangles(P, valid && !reuse, xyz(fa), stage_r, s_cand, nc, st_slow, T);
     if (reuse) { nc = old_hdr & 0xffu; st_slow = (old_hdr & RB_CE_SLOW) != 0u; }
+    if (persist && !st_slow && nc) {
+        // a list that is going to live is pruned with the exact predicate itself, run once at the build pose with the radius grown
+        // by the skin and a slack far above the predicate's rounding error (1e-5 of the world's half width): the distance to a
+        // triangle is 1-Lipschitz in the sphere centre, so what is dropped cannot test positive while the list is valid
+        const float prad = stage_r + fmaxf(1e-2f, 1e-5f * P.half);
+        uint32_t nu = 0;
+        for (uint32_t j = 0; j < nc; ++j) {
+            const uint32_t t = s_cand[j][threadIdx.x];
+            const float4* tp = P.tri + 3ull * t;
+            const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+            if (sphere_triangle_detect(xyz(fa), prad, xyz(a4), xyz(b4), xyz(c4))) s_cand[nu++][threadIdx.x] = t;
+        }
+        nc = nu;
+    }
     if (s < n_own_rows) {
         uint32_t np = 0;
 #pragma unroll
