@@ -178,7 +178,8 @@ struct RbParams {
     const RbDistParams* dp;       // device copy of the halo parameters (slab worlds with neighbours), else NULL
     // ---- compound bodies (multi-sphere entities, physics/src/Geometry.cpp:27-31) ----
     uint32_t grp_on;              // compound bodies: 0 per-body kernel, 1 rb_collide_group_kernel, 2 enumeration per sphere + resolution per body (RB_COMPOUND=legacy|group|split)
-    uint32_t* ce_hdr;             // split kernels, per sphere row: triangles (bits 0-7) | partners (8-15) | RB_CE_SLOW | RB_CE_OVER
+    uint32_t* ce_hdr;             // split kernels, per sphere row: triangles (bits 0-7) | RB_CE_SLOW
+    uint32_t* ce_ph;              // ... partners (bits 8-15) | RB_CE_OVER
     uint32_t* ce_pg; uint32_t* ce_pl;   // [4][ns] partner body global id / row, ascending (slot-major)
     uint32_t* ce_tri;             // [RB_CAND_MAX][ns] staged triangle ids, ascending (slot-major)
     // the triangle side of those lists is persistent: static geometry does not move, so a sphere's list -- staged for the sphere

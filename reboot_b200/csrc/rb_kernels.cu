@@ -521,14 +521,21 @@ __device__ __forceinline__ void store_contact(const RbParams& P, unsigned long l
     }
 }
 __device__ __forceinline__ void record_hit(const RbParams& P, HitBuf& H, uint32_t a, uint32_t b, float depth, f3 n, float r) {
-    if (H.n < RB_MAXLOCAL) {
-        uint32_t i = H.n;
-        H.a[i] = a; H.b[i] = b; H.depth[i] = depth; H.nx[i] = n.x; H.ny[i] = n.y; H.nz[i] = n.z; H.r[i] = r;
-    } else {   // rare: more contacts than the local buffer holds -> direct append
-        unsigned long long slot = atomicAdd(P.ncontact, 1ull);
-        store_contact(P, slot, a, b, depth, n.x, n.y, n.z, r);
-        if (slot >= P.contact_cap) atomicAdd(&P.counters[RB_C_DROPPED], 1ull);
+    if (H.n == RB_MAXLOCAL) {
+        // more contacts than the local buffer holds (two overlapping compound bodies hit dozens of times in a tick): the full
+        // buffer is appended with ONE atomic -- a dependent global atomic per hit was the longest stall of those bodies' chains
+        const unsigned long long base = atomicAdd(P.ncontact, (unsigned long long)RB_MAXLOCAL);
+        uint32_t dropped = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < RB_MAXLOCAL; ++i) {
+            store_contact(P, base + i, H.a[i], H.b[i], H.depth[i], H.nx[i], H.ny[i], H.nz[i], H.r[i]);
+            if (base + i >= P.contact_cap) dropped++;
+        }
+        if (dropped) atomicAdd(&P.counters[RB_C_DROPPED], (unsigned long long)dropped);
+        H.n = 0;
     }
+    const uint32_t i = H.n;
+    H.a[i] = a; H.b[i] = b; H.depth[i] = depth; H.nx[i] = n.x; H.ny[i] = n.y; H.nz[i] = n.z; H.r[i] = r;
     H.n++;
 }
 
@@ -1365,6 +1372,7 @@ __global__ void __launch_bounds__(RB_BLOCK, (MODE == 1) ? RB_COLLIDE_MINBLOCKS_E
 // Same canonical order and arithmetic as rb_collide_kernel<false, .> (bit-identical results; RB_COLLIDE_V1=1 runs that one).
 // ------------------------------------------------------------------------------------------
 #define RB_GRP_PART 4
+#define RB_SS_BLOCK 64              // threads per block of the sphere-sphere phase of the listed bodies (a few long chains: spread them over the SMs)
 #define RB_CE_SLOW (1u << 16)      // rb_compound_enum_kernel's header word: the sphere is wider than the fast triangle walk
 #define RB_CE_OVER (1u << 17)      // ... it found more partner bodies than a list holds
 
@@ -1547,7 +1555,7 @@ __device__ __forceinline__ void group_sphere_sphere(const RbParams& P, const boo
                     for (uint32_t c = 0; c < nchunk_w; ++c) {
                         const uint32_t i = (c << lg) + sub;
                         if (!(need && i < nsph)) continue;
-                        const uint32_t sa = s0 + i, h = P.ce_hdr[sa], np = (h >> 8) & 0xffu;
+                        const uint32_t sa = s0 + i, h = P.ce_ph[sa], np = (h >> 8) & 0xffu;
                         if (h & RB_CE_OVER) over = true;
                         for (uint32_t k = 0; k < np; ++k) {
                             uint32_t g = P.ce_pg[(size_t)k * P.ns + sa], Bl = P.ce_pl[(size_t)k * P.ns + sa];
@@ -1851,8 +1859,11 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_collide_group_kernel(const RbP
 //        holds; a sphere wider than the fast triangle walk takes the generic walk.
 // Same candidates, same canonical order, same arithmetic as rb_collide_kernel<false, .>: bit-identical results.
 // ------------------------------------------------------------------------------------------
+template <int PART>
 __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbParams P, const uint32_t nrows) {
-    __shared__ uint32_t s_cand[RB_CAND_MAX][RB_BLOCK];
+    // PART 1: the partner scan (what the sphere-sphere phase of the listed bodies waits for); PART 2: the triangle lists. Two
+    // launches, so that phase starts after the first and runs next to the second (and next to the others' triangle phase).
+    __shared__ uint32_t s_cand[PART == 2 ? RB_CAND_MAX : 1][RB_BLOCK];
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     Tally T = { 0, 0, 0, 0, 0, 0, 0 };
@@ -1862,52 +1873,58 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbP
     uint32_t A = 0, gA = 0;
     float4 fa = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) { A = rb_sph_owner(P, s); gA = rb_gid(P, A); fa = P.ws[s]; }
-    uint32_t pg[RB_GRP_PART], pl[RB_GRP_PART];
+    if (PART == 1) {
+        uint32_t pg[RB_GRP_PART], pl[RB_GRP_PART];
 #pragma unroll
-    for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
-    bool over = false;
-    group_scan_sphere<true>(P, valid, A, gA, xyz(fa), fa.w, 0u, pg, pl, over, T);
-    // the triangle list: reused while the sphere stays inside the skin it was staged with, else staged again -- for the sphere
-    // grown by the skin if this tick's margin fits inside it (a fast mover's list would not even be valid now: per-tick radius)
-    bool reuse = false, persist = false;
-    uint32_t old_hdr = 0;
-    float stage_r = fa.w;
-    if (valid && P.ce_skin > 0.f) {
-        const float4 bb = P.ce_build[s];
-        const float r = P.sph_obj[s].w, margin = fa.w - r;
-        const float dx = fa.x - bb.x, dy = fa.y - bb.y, dz = fa.z - bb.z;
-        if (bb.w >= 0.f && sqrtf((dx * dx + dy * dy) + dz * dz) + margin <= P.ce_skin) { reuse = true; old_hdr = P.ce_hdr[s]; }
-        else if (margin <= P.ce_skin) { persist = true; stage_r = r + P.ce_skin; }
-    }
-    uint32_t nc; bool st_slow;
-    group_stage_triangles(P, valid && !reuse, xyz(fa), stage_r, s_cand, nc, st_slow, T);
-    if (reuse) { nc = old_hdr & 0xffu; st_slow = (old_hdr & RB_CE_SLOW) != 0u; }
-    if (persist && !st_slow && nc) {
-        // a list that is going to live is pruned with the exact predicate itself, run once at the build pose with the radius grown
-        // by the skin and a slack far above the predicate's rounding error (1e-5 of the world's half width): the distance to a
-        // triangle is 1-Lipschitz in the sphere centre, so what is dropped cannot test positive while the list is valid
-        const float prad = stage_r + fmaxf(1e-2f, 1e-5f * P.half);
-        uint32_t nu = 0;
-        for (uint32_t j = 0; j < nc; ++j) {
-            const uint32_t t = s_cand[j][threadIdx.x];
-            const float4* tp = P.tri + 3ull * t;
-            const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
-            if (sphere_triangle_detect(xyz(fa), prad, xyz(a4), xyz(b4), xyz(c4))) s_cand[nu++][threadIdx.x] = t;
-        }
-        nc = nu;
-    }
-    if (s < n_own_rows) {
-        uint32_t np = 0;
+        for (int k = 0; k < RB_GRP_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+        bool over = false;
+        group_scan_sphere<true>(P, valid, A, gA, xyz(fa), fa.w, 0u, pg, pl, over, T);
+        if (s < n_own_rows) {
+            uint32_t np = 0;
 #pragma unroll
-        for (int k = 0; k < RB_GRP_PART; ++k) if (pg[k] != RB_NONE) { P.ce_pg[(size_t)k * P.ns + s] = pg[k]; P.ce_pl[(size_t)k * P.ns + s] = pl[k]; np++; }
-        if (!reuse) {
-            for (uint32_t j = 0; j < nc; ++j) P.ce_tri[(size_t)j * P.ns + s] = s_cand[j][threadIdx.x];
-            if (valid && P.ce_skin > 0.f) P.ce_build[s] = make_float4(fa.x, fa.y, fa.z, (persist && !st_slow) ? 0.f : -1.0f);
+            for (int k = 0; k < RB_GRP_PART; ++k) if (pg[k] != RB_NONE) { P.ce_pg[(size_t)k * P.ns + s] = pg[k]; P.ce_pl[(size_t)k * P.ns + s] = pl[k]; np++; }
+            P.ce_ph[s] = valid ? ((np << 8) | (over ? RB_CE_OVER : 0u)) : 0u;
+            // the first sphere of a body that finds a partner enters the body in the sphere-sphere list
+            if (np && atomicAdd(&P.ss_npart[A], np) == 0u) P.ss_list[(uint32_t)atomicAdd(&P.counters[RB_C_NSS], 1ull)] = A;
         }
-        P.ce_hdr[s] = valid ? (nc | (np << 8) | (st_slow ? RB_CE_SLOW : 0u) | (over ? RB_CE_OVER : 0u)) : 0u;
-        if (!valid && P.ce_skin > 0.f) P.ce_build[s].w = -1.0f;      // (not in the broadphase: the header word above no longer holds its list)
-        // the first sphere of a body that finds a partner enters the body in the sphere-sphere list
-        if (np && atomicAdd(&P.ss_npart[A], np) == 0u) P.ss_list[(uint32_t)atomicAdd(&P.counters[RB_C_NSS], 1ull)] = A;
+    } else {
+        // the triangle list: reused while the sphere stays inside the skin it was staged with, else staged again -- for the sphere
+        // grown by the skin if this tick's margin fits inside it (a fast mover's list would not even be valid now: per-tick radius)
+        bool reuse = false, persist = false;
+        uint32_t old_hdr = 0;
+        float stage_r = fa.w;
+        if (valid && P.ce_skin > 0.f) {
+            const float4 bb = P.ce_build[s];
+            const float r = P.sph_obj[s].w, margin = fa.w - r;
+            const float dx = fa.x - bb.x, dy = fa.y - bb.y, dz = fa.z - bb.z;
+            if (bb.w >= 0.f && sqrtf((dx * dx + dy * dy) + dz * dz) + margin <= P.ce_skin) { reuse = true; old_hdr = P.ce_hdr[s]; }
+            else if (margin <= P.ce_skin) { persist = true; stage_r = r + P.ce_skin; }
+        }
+        uint32_t nc; bool st_slow;
+        group_stage_triangles(P, valid && !reuse, xyz(fa), stage_r, s_cand, nc, st_slow, T);
+        if (reuse) { nc = old_hdr & 0xffu; st_slow = (old_hdr & RB_CE_SLOW) != 0u; }
+        if (persist && !st_slow && nc) {
+            // a list that is going to live is pruned with the exact predicate itself, run once at the build pose with the radius grown
+            // by the skin and a slack far above the predicate's rounding error (1e-5 of the world's half width): the distance to a
+            // triangle is 1-Lipschitz in the sphere centre, so what is dropped cannot test positive while the list is valid
+            const float prad = stage_r + fmaxf(1e-2f, 1e-5f * P.half);
+            uint32_t nu = 0;
+            for (uint32_t j = 0; j < nc; ++j) {
+                const uint32_t t = s_cand[j][threadIdx.x];
+                const float4* tp = P.tri + 3ull * t;
+                const float4 a4 = __ldg(tp), b4 = __ldg(tp + 1), c4 = __ldg(tp + 2);
+                if (sphere_triangle_detect(xyz(fa), prad, xyz(a4), xyz(b4), xyz(c4))) s_cand[nu++][threadIdx.x] = t;
+            }
+            nc = nu;
+        }
+        if (s < n_own_rows) {
+            if (!reuse) {
+                for (uint32_t j = 0; j < nc; ++j) P.ce_tri[(size_t)j * P.ns + s] = s_cand[j][threadIdx.x];
+                if (valid && P.ce_skin > 0.f) P.ce_build[s] = make_float4(fa.x, fa.y, fa.z, (persist && !st_slow) ? 0.f : -1.0f);
+            }
+            P.ce_hdr[s] = valid ? (nc | (st_slow ? RB_CE_SLOW : 0u)) : 0u;
+            if (!valid && P.ce_skin > 0.f) P.ce_build[s].w = -1.0f;      // (not in the broadphase: the header word above no longer holds its list)
+        }
     }
     collide_epilogue(P, H, T, lane);
 }
@@ -1974,12 +1991,12 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_compound_resolve_kernel(const RbP
         const uint32_t gA = rb_gid(P, A);
         // ---------------- sphere-sphere: partner bodies in ascending id, merged over the spheres' lists ----------------
         uint32_t any_np = 0;
-        if (PHASE == 1) for (uint32_t i = 0; i < nsph; ++i) any_np |= P.ce_hdr[s0 + i] & 0xff00u;
+        if (PHASE == 1) for (uint32_t i = 0; i < nsph; ++i) any_np |= P.ce_ph[s0 + i] & 0xff00u;
         uint32_t lo = 0;
         while (any_np) {
             uint32_t best = RB_NONE, best_local = RB_NONE;
             for (uint32_t i = 0; i < nsph; ++i) {
-                const uint32_t sa = s0 + i, h = P.ce_hdr[sa], np = (h >> 8) & 0xffu;
+                const uint32_t sa = s0 + i, h = P.ce_ph[sa], np = (h >> 8) & 0xffu;
                 bool found = false;
                 for (uint32_t k = 0; k < np; ++k) {
                     const uint32_t g = P.ce_pg[(size_t)k * P.ns + sa];
@@ -2823,7 +2840,7 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
     // opt-in until the enumeration is split from the resolution (RB_COMPOUND_GROUP=1)
     if (variant != 1 && P.grp_on == 2) {        // enumeration per sphere, resolution per body (K4E + K4R)
         const uint32_t nrows = P.kstride ? P.nb * P.kstride : P.ns;
-        rb_compound_enum_kernel<<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
+        rb_compound_enum_kernel<1><<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
         // (the sphere-sphere launch is sized for every body: the list's length only exists on the device; blocks beyond it return at once)
         // RB_COMPOUND_SS_GROUP=1 (development switch): a group of lanes per listed body instead of one thread -- measured slower on C4
         // (0.57 against 0.25 ms: bodies in sphere-sphere contact hit many times per tick, every hit costs the group another round)
@@ -2833,21 +2850,23 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
         if (side) { cudaEventRecord(fork, st); cudaStreamWaitEvent(side, fork, 0); }
         if (resolve) {
             if (ss_group) rb_compound_ss_group_kernel<true><<<gs, RB_BLOCK, 0, s1>>>(P);
-            else rb_compound_resolve_kernel<true, 1><<<g, RB_BLOCK, 0, s1>>>(P);
+            else rb_compound_resolve_kernel<true, 1><<<cdiv(P.nb, RB_SS_BLOCK), RB_SS_BLOCK, 0, s1>>>(P);
             if (side) cudaEventRecord(join, side);
+            rb_compound_enum_kernel<2><<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
             rb_compound_resolve_kernel<true, 2><<<g, RB_BLOCK, 0, st>>>(P);
             if (side) cudaStreamWaitEvent(st, join, 0);
             rb_compound_resolve_kernel<true, 3><<<g, RB_BLOCK, 0, st>>>(P);
             rb_commit_kernel<<<g, RB_BLOCK, 0, st>>>(P);
-            return 5;
+            return 6;
         }
         if (ss_group) rb_compound_ss_group_kernel<false><<<gs, RB_BLOCK, 0, s1>>>(P);
-        else rb_compound_resolve_kernel<false, 1><<<g, RB_BLOCK, 0, s1>>>(P);
+        else rb_compound_resolve_kernel<false, 1><<<cdiv(P.nb, RB_SS_BLOCK), RB_SS_BLOCK, 0, s1>>>(P);
         if (side) cudaEventRecord(join, side);
+        rb_compound_enum_kernel<2><<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
         rb_compound_resolve_kernel<false, 2><<<g, RB_BLOCK, 0, st>>>(P);
         if (side) cudaStreamWaitEvent(st, join, 0);
         rb_compound_resolve_kernel<false, 3><<<g, RB_BLOCK, 0, st>>>(P);
-        return 4;
+        return 5;
     }
     if (variant != 1 && P.grp_on == 1) {
         const uint32_t gg = cdiv(P.nb << P.grp_lg, RB_BLOCK);

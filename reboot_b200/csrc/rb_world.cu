@@ -517,6 +517,7 @@ int rb_build(rb_world* w) {
         ALLOC(ch, nsa); ALLOC(cg, (size_t)nsa * 4); ALLOC(cl, (size_t)nsa * 4); ALLOC(ct, (size_t)nsa * rb_compound_tri_slots());
         CU(cudaMemsetAsync(ch, 0, (size_t)nsa * 4, w->stream));
         P.ce_hdr = ch; P.ce_pg = cg; P.ce_pl = cl; P.ce_tri = ct;
+        { uint32_t* cp; ALLOC(cp, nsa); CU(cudaMemsetAsync(cp, 0, (size_t)nsa * 4, w->stream)); P.ce_ph = cp; }
         {   // persistent triangle lists: skin = 8 % of the smallest radius like the single-sphere lists (RB_COMPOUND_SKIN=<m>, 0 = off)
             float rmin = rmax;
             for (size_t i = 3; i < sph.size(); i += 4) if (sph[i] != 0.f) rmin = std::min(rmin, std::fabs(sph[i]));
