@@ -67,3 +67,49 @@ def test_owner_of_and_slab_bounds():
     x = np.array([-1500.0, -1000.0, -500.0001, -500.0, 0.0, 499.9, 500.0, 999.0, 1200.0])
     assert rbdist.owner_of(x, 4).tolist() == [0, 0, 0, 1, 2, 2, 3, 3, 3]
     assert (rbdist.owner_of(x, 1) == 0).all()
+
+
+def _compound_worker(rank, world_size, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from reboot_b200 import dist as rbdist, scenes
+    # ragged compound bodies (1..8 spheres): ownership by the body's model translation, spheres travel with their body
+    sc = scenes.config4(3000, 200, 7)
+    rng = np.random.default_rng(7)
+    cnt = rng.integers(1, 9, sc.n_bodies)
+    keep = np.concatenate([np.arange(8 * b, 8 * b + cnt[b]) for b in range(sc.n_bodies)])
+    sc.obj_spheres = np.ascontiguousarray(sc.obj_spheres[keep]); sc.sphere_start = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    sub, ids, slab, rmax = rbdist.partition_scene(sc, world_size, rank)
+    stride, reach = rbdist.compound_layout(sc)
+    owned = torch.zeros(sc.n_bodies, dtype=torch.int32)
+    owned[torch.from_numpy(ids.astype(np.int64))] = 1
+    dist.all_reduce(owned)
+    ok = bool((owned == 1).all())
+    ok &= bool((rbdist.owner_of(sub.body_pos[:, 0], world_size) == rank).all())
+    ok &= sub.n_spheres == int(cnt[ids].sum()) and sub.sphere_start[-1] == sub.n_spheres and len(sub.sphere_start) == len(ids) + 1
+    # every sub-scene sphere is the global scene's sphere of the same body and index
+    b0 = int(ids[0]); s0 = int(sc.sphere_start[b0])
+    ok &= np.array_equal(sub.obj_spheres[: cnt[b0]], sc.obj_spheres[s0: s0 + cnt[b0]])
+    # the layout every rank must agree on: the same on all of them, and it covers every body
+    lay = [None] * world_size
+    dist.all_gather_object(lay, (stride, round(reach, 6)))
+    ok &= all(l == lay[0] for l in lay) and stride == int(cnt.max()) and reach >= float((np.abs(sc.obj_spheres[:, 0]) + sc.obj_spheres[:, 3]).max())
+    ok &= abs(rmax - 0.4) < 1e-6
+    q.put((rank, ok, len(ids)))
+    dist.destroy_process_group()
+
+
+def test_compound_partition_world_size_2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_compound_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert sum(n for _, _, n in res) == 3000
