@@ -187,7 +187,8 @@ int         rb_get_model_matrices(rb_world* w, float* model16, float* prev16);
 int         rb_export_model_matrices(rb_world* w, const float** model16_dev, const float** prev16_dev);
 /* angular state, n_bodies * 4 floats each */
 int         rb_get_angular(rb_world* w, float* ang_pos4, float* ang_vel4);
-/* world-space spheres as Sphere::getPosition/getRadius see them: n_spheres * 4 floats */
+/* world-space spheres as Sphere::getPosition/getRadius see them: n_spheres * 4 floats
+ * (not available on multi-GPU worlds of compound bodies, whose sphere rows follow their bodies between ranks: RB_ERR_INVALID) */
 int         rb_get_world_spheres(rb_world* w, float* xyzr4);
 
 /* StateVector::setLinearPosition / setLinearVelocity (StateVector.cpp:122-135) for `count` bodies
