@@ -248,7 +248,10 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
             // lists switched off for now (the host sits out a phase of constant rebuilding on the per-tick kernel):
             // keep reporting how many bodies outrun the skin within one tick, so that it knows when to come back
             // (would a list last this body 8 ticks? displacement + margin after 8 ticks, a body in free fall accelerating on the way)
-            const float fall = ((f & RB_F_GRAVITY) && !(f & RB_F_CONTACT)) ? fabsf(P.gravity) * dt : 0.0f;
+            // (only a body that IS falling accelerates: one that rests on other spheres carries no contact flag either -- the flag is
+            // the triangles' -- but its speed never gets past the few g*dt it gains between two snap-backs. Without the speed test
+            // such bodies count as fast movers for good once the skin is small: r = 0.18 in the 8-GPU weak scene, lists never resumed)
+            const float fall = ((f & RB_F_GRAVITY) && !(f & RB_F_CONTACT) && speed > 4.0f * fabsf(P.gravity) * dt) ? fabsf(P.gravity) * dt : 0.0f;
             if (do_bin == 1 && P.vl && !(8.0f * (speed + 4.0f * fall) * dt + 2.0f * (speed + 8.0f * fall) * dt + 0.01f * r <= P.vl_skin)) {
                 volatile uint32_t* nf = P.vl + RB_VL_NFAST;
                 if (*nf < P.hot_flood) atomicAdd(&P.vl[RB_VL_NFAST], 1u);
