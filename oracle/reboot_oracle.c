@@ -532,6 +532,18 @@ static void physics_process_canonical(orc_world* w) {
     memcpy(snap, w->ent, sizeof(entity_t) * n);
     /* column grid over frozen spheres / triangles: pruning only */
     float slack = w->prune_slack;
+    /* the box around every entity's frozen spheres: a pair of entities whose boxes are further apart than the slack has no
+     * sphere pair within it either (the sphere-pair gap below is the Chebyshev gap of the spheres' own boxes): pruning only */
+    float* ebox = (float*)malloc(sizeof(float) * 6 * (size_t)n);
+    for (int e = w->n_geoms; e < n; e++) {
+        float* b = ebox + 6 * (size_t)e;
+        b[0] = b[1] = b[2] = 3.0e38f; b[3] = b[4] = b[5] = -3.0e38f;
+        for (int i = 0; i < snap[e].n_sph; i++) {
+            sphere_t q = entity_sphere(&snap[e], i);
+            if (q.c.x - q.r < b[0]) b[0] = q.c.x - q.r; if (q.c.y - q.r < b[1]) b[1] = q.c.y - q.r; if (q.c.z - q.r < b[2]) b[2] = q.c.z - q.r;
+            if (q.c.x + q.r > b[3]) b[3] = q.c.x + q.r; if (q.c.y + q.r > b[4]) b[4] = q.c.y + q.r; if (q.c.z + q.r > b[5]) b[5] = q.c.z + q.r;
+        }
+    }
     for (int ea = w->n_geoms; ea < n; ea++) {
         entity_t* A = &w->ent[ea];
         if (!(A->st.flags & F_ACTIVE)) continue;
@@ -545,6 +557,11 @@ static void physics_process_canonical(orc_world* w) {
             if (eb == ea) continue;
             const entity_t* Bf = &snap[eb];
             if (!(Bf->st.flags & F_ACTIVE)) continue;
+            {   /* (boxes further apart than the slack, grown by a margin for the rounding of the box corners) */
+                const float* ba = ebox + 6 * (size_t)ea; const float* bb = ebox + 6 * (size_t)eb;
+                const float m = slack + 1e-3f;
+                if (ba[0] - bb[3] > m || bb[0] - ba[3] > m || ba[1] - bb[4] > m || bb[1] - ba[4] > m || ba[2] - bb[5] > m || bb[2] - ba[5] > m) continue;
+            }
             /* prune: some sphere pair within slack at the frozen poses */
             int near = 0;
             for (int i = 0; i < A->n_sph && !near; i++)
@@ -605,6 +622,7 @@ static void physics_process_canonical(orc_world* w) {
         if (!w->frozen && prev_contact && !last_hit) A->st.flags &= ~F_CONTACT;
         free(in_world);
     }
+    free(ebox);
     free(snap);
 }
 

@@ -525,3 +525,29 @@ def test_compound_kernels_bit_identical(World, monkeypatch):
             b = w.state()
             assert np.array_equal(bits(a["pos"]), bits(b["pos"])) and np.array_equal(bits(a["vel"]), bits(b["vel"])) and np.array_equal(a["flags"], b["flags"]), (kind, k)
     for w in ws: w.close()
+
+
+def test_c4_subscene_10k_compound_bodies_vs_canonical_oracle(World, port):
+    """BASELINE config 4 at 1/25 of its size: 10,240 bodies x 8 collision spheres, dense enough that bodies overlap each other
+    and the terrain from the first tick (about 0.7M sphere-sphere and 0.1M sphere-triangle tests per tick) -- state, flags,
+    model translations bit-identical to the canonical-order oracle after every tick, contact sets of a frozen detection too."""
+    from reboot_b200 import scenes
+    sc = scenes.config4(10240, 96, 31)
+    sc.body_pos[:, 1] -= 1.6          # start close to the ground: contacts within the first ticks
+    w = World(sc)
+    o = port.OrcWorld(sc, octree=False)
+    for k in range(8):
+        w.step(5); o.step(5, port.ORDER_CANONICAL)
+        a, b = w.state(), o.state()
+        for key in ("pos", "vel", "model_t", "prev_t"):
+            assert np.array_equal(bits(a[key]), bits(b[key])), (k, key)
+        assert np.array_equal(a["flags"], b["flags"]), k
+    st = w.stats()
+    assert st["hits_ss"] > 10000 and st["hits_st"] > 1000
+    w.integrate(5); o.integrate(5)
+    w.detect()
+    ss_g, st_g = w.contact_sets()
+    ss_o, st_o = o.contact_sets(o.detect(port.ORDER_CANONICAL))
+    assert np.array_equal(ss_g, ss_o) and np.array_equal(st_g, st_o)
+    assert len(ss_g) > 1000 and len(st_g) > 100
+    w.close()
