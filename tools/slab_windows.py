@@ -9,7 +9,8 @@ rank = int(os.environ["RANK"]); lr = int(os.environ["LOCAL_RANK"]); N = int(os.e
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 stream = torch.cuda.Stream()
-sc, slab = bench.c3_weak_scene(N, rank)
+SN = int(os.environ.get("SCENE_N", str(N)))      # SCENE_N=8 on 2 GPUs: the first two slabs of the 8-way scene (small spheres, short skin)
+sc, slab = bench.c3_weak_scene(SN, rank)
 ids = np.arange(sc.n_bodies, dtype=np.uint32) + np.uint32(rank * bench.C3_SPHERES)
 w = World(sc, device=lr, stream=stream.cuda_stream, slab=slab, rank=rank, nranks=N, max_contacts=8 * sc.n_spheres, build=False, ids=ids, rm_max_hint=float(sc.meta["r"]))
 w.build()
