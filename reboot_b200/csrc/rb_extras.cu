@@ -222,13 +222,12 @@ int rb_get_static_cells(rb_world* w, float* boxes6, uint32_t* ntri) {
     CU(cudaSetDevice(w->cfg.device));
     const uint32_t n = w->P.tcx * w->P.tcz;
     if (!n) return RB_OK;
-    float* d_b = nullptr; uint32_t* d_n = nullptr;
-    CU(cudaMalloc(&d_b, (size_t)n * 6 * sizeof(float))); CU(cudaMalloc(&d_n, (size_t)n * sizeof(uint32_t)));
+    if (!w->d_cells_box) { ALLOC(w->d_cells_box, (size_t)n * 6); ALLOC(w->d_cells_n, n); }      // (the static structure never changes: kept with the world)
+    float* d_b = w->d_cells_box; uint32_t* d_n = w->d_cells_n;
     rb_static_cells_kernel<<<(n + RB_BLOCK - 1) / RB_BLOCK, RB_BLOCK, 0, w->stream>>>(w->P, d_b, d_n); w->launches++;
     cudaError_t e = cudaMemcpyAsync(boxes6, d_b, (size_t)n * 6 * sizeof(float), cudaMemcpyDeviceToHost, w->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ntri, d_n, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
-    cudaFree(d_b); cudaFree(d_n);
     if (e != cudaSuccess) return fail(w, RB_ERR_CUDA, "rb_get_static_cells: %s", cudaGetErrorString(e));
     return RB_OK;
 }

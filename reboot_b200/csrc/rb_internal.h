@@ -137,6 +137,7 @@ struct rb_world {
     bool vl_never_off = false;               // RB_VL_NEVER_OFF=1 (tests): never sit a rebuild-heavy phase out on the per-tick kernel
     unsigned long long* h_sticky = nullptr;  // pinned: sticky overflow counters of slab worlds, fetched at the pace points of rb_step
     void* d_cull_out = nullptr; void* d_cull_cubes = nullptr; uint32_t* d_cull_cnt = nullptr; uint32_t cull_cap = 0;   // frustum-culling scratch (rb_extras.cu)
+    float* d_cells_box = nullptr; uint32_t* d_cells_n = nullptr;      // rb_get_static_cells scratch, kept with the world
     cudaEvent_t vl_pace[2] = { nullptr, nullptr }; bool vl_pace_armed[2] = { false, false };   // bounded host run-ahead (see rb_step)
     cudaStream_t vl_side = nullptr; cudaEvent_t vl_fork = nullptr, vl_join = nullptr;   // the hot bodies' launch runs next to the list kernel
     int collide_variant = 2;                 // 1 first generation, 2 fused phased kernel (default), 3 enumerate + resolve launches (measured slower: 0.342 vs 0.331 ms)

@@ -43,7 +43,9 @@ namespace RB_KNS {
 // with the translation matrix of :326-338), so a world sphere centre is
 // ((W00*ox + W01*oy) + W02*oz) + (W03 + px): the bracket is pre-summed on the host (sph_obj.xyz).
 // ------------------------------------------------------------------------------------------
-// raise the rebuild flag (many threads may want to in the same tick: only the first few actually store)
+// raise the rebuild flag (many threads may want to in the same tick: only the first few actually store). The plain volatile
+// read / write pair races benignly: every writer stores the same value 1, nobody clears the word during K1, and a thread that
+// reads a stale 0 merely stores 1 once more; the reason bits go through atomicOr because they accumulate.
 __device__ __forceinline__ void vl_request_rebuild(const RbParams& P, uint32_t why) {
     volatile uint32_t* v = P.vl;
     if (!v[RB_VL_REBUILD]) v[RB_VL_REBUILD] = 1u;
