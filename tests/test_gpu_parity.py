@@ -551,3 +551,53 @@ def test_c4_subscene_10k_compound_bodies_vs_canonical_oracle(World, port):
     assert np.array_equal(ss_g, ss_o) and np.array_equal(st_g, st_o)
     assert len(ss_g) > 1000 and len(st_g) > 100
     w.close()
+
+
+def test_full_size_c4_properties(World, port):
+    """BASELINE.json config 4 at full size (262,144 bodies x 8 collision spheres on the 2M-triangle terrain): nothing dropped,
+    detection idempotent and state-neutral, sampled sphere-triangle and every sphere-sphere contact re-verified with the oracle
+    predicates at the reported sphere centres, and the whole run bit-identical between the default (split, persistent triangle
+    lists) and the per-body kernels (state checksum after 300 ticks)."""
+    import os
+    from reboot_b200 import scenes
+    sc = scenes.config4()
+    assert sc.n_bodies == 262_144 and sc.n_spheres == 8 * 262_144 and sc.n_tris == 2_000_000
+    w = World(sc, max_contacts=8 * sc.n_spheres)
+    for k in range(300):
+        w.step(5)
+    st = w.stats()
+    assert st["contacts_dropped"] == 0 and st["hits_st"] > 1000 and st["hits_ss"] > 1000
+    w.integrate(5)
+    s0 = w.state()
+    w.detect(); c1 = w.contacts()
+    w.detect(); c2 = w.contacts()
+    assert len(c1) > 1000 and np.array_equal(c1, c2)
+    s1 = w.state()
+    assert np.array_equal(bits(s0["pos"]), bits(s1["pos"])) and np.array_equal(s0["flags"], s1["flags"])
+    # world sphere centre = object centre + model translation (identity W), radius 0.4
+    obj = sc.obj_spheres.reshape(sc.n_bodies, 8, 4)
+    centre = lambda body, sph: (obj[body, sph, :3] + s0["model_t"][body]).astype(np.float32)
+    tris = sc.tris[0]
+    rng = np.random.default_rng(0)
+    stc = c1[c1["kind"] == 1]
+    pick = stc[rng.choice(len(stc), min(3000, len(stc)), replace=False)]
+    assert port.pred_sphere_triangle(centre(pick["body"], pick["sphere"]), 0.4, tris[pick["other_prim"]]).all()
+    ssc = c1[c1["kind"] == 0]
+    assert len(ssc) > 100 and (ssc["body"] < ssc["other"]).all()
+    d = np.linalg.norm(centre(ssc["body"], ssc["sphere"]).astype(np.float64) - centre(ssc["other"], ssc["other_prim"]), axis=1)
+    assert (d <= 0.8 + 1e-5).all()
+    w.close()
+    # the same 300 ticks with the per-body kernel: identical state
+    os.environ["RB_COMPOUND"] = "legacy"
+    try:
+        w2 = World(sc, max_contacts=8 * sc.n_spheres)
+    finally:
+        del os.environ["RB_COMPOUND"]
+    for k in range(300):
+        w2.step(5)
+    w2.integrate(5)
+    s2 = w2.state()
+    for key in ("pos", "vel", "model_t", "prev_t"):
+        assert np.array_equal(bits(s0[key]), bits(s2[key])), key
+    assert np.array_equal(s0["flags"], s2["flags"])
+    w2.close()
