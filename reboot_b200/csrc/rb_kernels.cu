@@ -1934,6 +1934,90 @@ __global__ void __launch_bounds__(RB_BLOCK, 3) rb_compound_enum_kernel(const RbP
     collide_epilogue(P, H, T, lane);
 }
 
+// K4P: the partner scan of a compound body, one thread per BODY. The spheres of a body sit within a radius or two of each other,
+// so their eight scans of the sphere grid (rb_compound_enum_kernel<1>) read nearly the same columns -- and find the seven
+// siblings every time; here the body walks the union of those column ranges once and tests every foreign sphere against its own
+// spheres with the same grown-radius reject, i.e. it keeps exactly the partner bodies the per-sphere scans keep. The list
+// (ascending, unique) is parked in the per-sphere slots the resolution reads: entries 0-3 with sphere 0, 4-7 with sphere 1.
+#define RB_BODY_PART 8
+__global__ void __launch_bounds__(RB_BLOCK) rb_compound_partner_kernel(const RbParams P) {
+    const uint32_t A = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    Tally T = { 0, 0, 0, 0, 0, 0, 0 };
+    HitBuf H; H.n = 0;
+    const bool owned = A < rb_n_owned(P);
+    bool valid = owned && (P.flags[A] & RB_F_ACTIVE) != 0;
+    uint32_t s0 = 0, nsph = 0;
+    if (owned) { s0 = rb_body_s0(P, A); nsph = rb_body_ns(P, A); }
+    float ulo = 3.0e38f, uhi = -3.0e38f, vlo = 3.0e38f, vhi = -3.0e38f;
+    uint32_t nin = 0;
+    if (valid) {
+        for (uint32_t i = 0; i < nsph; ++i) {
+            if (P.key[s0 + i] == RB_NONE) continue;
+            const float4 fa = P.ws[s0 + i];
+            const float reach = fa.w + P.rm_max, fu = rb_gu(P, fa.x, fa.z), fv = rb_gv(P, fa.x, fa.z);
+            ulo = fminf(ulo, fu - reach); uhi = fmaxf(uhi, fu + reach); vlo = fminf(vlo, fv - reach); vhi = fmaxf(vhi, fv + reach);
+            nin++;
+        }
+    }
+    valid = valid && nin != 0u;
+    uint32_t pg[RB_BODY_PART], pl[RB_BODY_PART];
+#pragma unroll
+    for (int k = 0; k < RB_BODY_PART; ++k) { pg[k] = RB_NONE; pl[k] = RB_NONE; }
+    bool over = false;
+    if (valid) {
+        const uint32_t cx0 = rb_col(ulo, P.g_off_u, P.s_inv_w, P.g_nu), cx1 = rb_col(uhi, P.g_off_u, P.s_inv_w, P.g_nu);
+        const uint32_t cz0 = rb_col(vlo, P.g_off_v, P.s_inv_w, P.g_nv), cz1 = rb_col(vhi, P.g_off_v, P.s_inv_w, P.g_nv);
+        for (uint32_t cz = cz0; cz <= cz1; ++cz) {
+            uint32_t i = P.col_start[cz * P.g_nu + cx0];
+            const uint32_t e = P.col_start[cz * P.g_nu + cx1 + 1];      // u-adjacent columns are contiguous in the sort
+            for (; i < e; ++i) {
+                const uint32_t sid = P.sorted_id[i] & ~RB_TRI_BIT;
+                if (sid - s0 < nsph && !P.kstride) continue;             // a sibling (CSR: the body's spheres are one id range)
+                const uint32_t Bl = rb_sph_owner(P, sid);
+                if (Bl == A) continue;
+                const float4 o = P.sorted[i];
+                uint32_t pass = 0;
+                for (uint32_t k = 0; k < nsph; ++k) {
+                    if (P.key[s0 + k] == RB_NONE) continue;
+                    const float4 fa = P.ws[s0 + k];
+                    const float dx = o.x - fa.x, dy = o.y - fa.y, dz = o.z - fa.z, rr = fa.w + o.w;
+                    if (!((dx * dx + dy * dy) + dz * dz > rr * rr)) pass++;
+                }
+                if (!pass) continue;
+                T.cand_ss += pass;
+                uint32_t g = rb_gid(P, Bl), bl = Bl;
+                bool dup = false;
+#pragma unroll
+                for (int k = 0; k < RB_BODY_PART; ++k) dup |= (pg[k] == g);
+                if (dup) continue;
+#pragma unroll
+                for (int k = 0; k < RB_BODY_PART; ++k)
+                    if (g < pg[k]) { const uint32_t tg = pg[k], tl = pl[k]; pg[k] = g; pl[k] = bl; g = tg; bl = tl; }
+                if (g != RB_NONE) over = true;          // pushed off the end (or never fitted)
+            }
+        }
+    }
+    if (owned) {
+        uint32_t count = 0;
+#pragma unroll
+        for (int k = 0; k < RB_BODY_PART; ++k) count += pg[k] != RB_NONE;
+        const uint32_t cap = min((uint32_t)RB_BODY_PART, RB_GRP_PART * nsph);
+        if (count > cap) { over = true; count = cap; }
+        for (uint32_t i = 0; i < nsph; ++i) {
+            const uint32_t np = count > RB_GRP_PART * i ? min(count - RB_GRP_PART * i, (uint32_t)RB_GRP_PART) : 0u;
+            P.ce_ph[s0 + i] = (np << 8) | (over ? RB_CE_OVER : 0u);
+            if (i < RB_BODY_PART / RB_GRP_PART) {
+#pragma unroll
+                for (uint32_t k = 0; k < RB_GRP_PART; ++k)
+                    if (k < np) { P.ce_pg[(size_t)k * P.ns + s0 + i] = pg[RB_GRP_PART * i + k]; P.ce_pl[(size_t)k * P.ns + s0 + i] = pl[RB_GRP_PART * i + k]; }
+            }
+        }
+        if (count) { P.ss_npart[A] = count; P.ss_list[(uint32_t)atomicAdd(&P.counters[RB_C_NSS], 1ull)] = A; }
+    }
+    collide_epilogue(P, H, T, lane);
+}
+
 // one staged triangle against sphere (so, r) of the body at its current pose: process_triangle without the prune
 template <bool RESOLVE>
 __device__ __forceinline__ void exact_triangle(const RbParams& P, BodyState& S, HitBuf& H, Tally& T, uint32_t sa_global, f3 so, float r, uint32_t t, bool& hit_any) {
@@ -2845,7 +2929,11 @@ int rb_launch_collide(const RbParams& P, bool resolve, int variant, cudaStream_t
     // opt-in until the enumeration is split from the resolution (RB_COMPOUND_GROUP=1)
     if (variant != 1 && P.grp_on == 2) {        // enumeration per sphere, resolution per body (K4E + K4R)
         const uint32_t nrows = P.kstride ? P.nb * P.kstride : P.ns;
-        rb_compound_enum_kernel<1><<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
+        // RB_COMPOUND_PARTNERS=body (development switch): the partner scan per body (K4P) instead of per sphere row -- fewer column
+        // reads, but 8x fewer threads with longer serial walks: measured slower on C4 (collide stage 0.62 against 0.58 ms)
+        static const int per_body = [] { const char* v = getenv("RB_COMPOUND_PARTNERS"); return v && !strcmp(v, "body") ? 1 : 0; }();
+        if (per_body) rb_compound_partner_kernel<<<g, RB_BLOCK, 0, st>>>(P);
+        else rb_compound_enum_kernel<1><<<cdiv(nrows, RB_BLOCK), RB_BLOCK, 0, st>>>(P, nrows);
         // (the sphere-sphere launch is sized for every body: the list's length only exists on the device; blocks beyond it return at once)
         // RB_COMPOUND_SS_GROUP=1 (development switch): a group of lanes per listed body instead of one thread -- measured slower on C4
         // (0.57 against 0.25 ms: bodies in sphere-sphere contact hit many times per tick, every hit costs the group another round)
