@@ -519,6 +519,13 @@ def test_compound_kernels_bit_identical(World, monkeypatch):
         w.build(); ws.append(w)
     monkeypatch.delenv("RB_COMPOUND")
     for k in range(120):
+        # host edits behind the persistent triangle lists' back: a teleport, a kick, a body switched off and on again, Entity::setPosition
+        for w in ws:
+            if k == 30: w.set_state(1, pos=np.array([[2.6, 1.25, 0.4]], np.float32))
+            if k == 45: w.set_state(2, vel=np.array([[1.5, 0.5, -2.0]], np.float32))
+            if k == 55: w.set_flags(0, np.array([0], np.uint32), 1)
+            if k == 75: w.set_flags(0, np.array([1], np.uint32), 1)
+            if k == 90: w.entity_set_position(4, (2.2, 1.4, 1.1))
         for w in ws: w.step(5)
         a = ws[0].state()
         for w, kind in zip(ws[1:], kinds[1:]):
