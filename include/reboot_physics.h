@@ -70,6 +70,9 @@ typedef struct rb_config {
      * migrate between ranks, so every body keeps its spheres at a fixed stride -- the SAME on every rank */
     uint32_t sphere_stride;  /* largest sphere count of any body over ALL ranks (0 = this rank's own; 1 = single-sphere worlds) */
     float    body_reach_hint;/* largest max_i(|centre_i.x| + r_i) of any body over ALL ranks, world units after W (0 = this rank's own) */
+    uint32_t slab_forces;    /* multi-GPU: 1 = bodies take forces / torques / angular state (StateVector::setForce / setTorque,
+                              * math/src/StateVector.cpp:147-167): the arrays exist from the build on and travel with migrating
+                              * bodies. The SAME on every rank. 0 = rb_set_force / rb_set_torque / rb_set_angular are refused */
 } rb_config;
 
 /* initial state of a body: StateVector setters, math/include/StateVector.h:48-60 */

@@ -22,7 +22,7 @@ class RbConfig(C.Structure):
                 ("ss_damp", C.c_float), ("margin_cap", C.c_float), ("device", C.c_int32), ("stream", C.c_void_p),
                 ("max_contacts", C.c_uint64), ("slab_lo", C.c_float), ("slab_hi", C.c_float),
                 ("rank", C.c_int32), ("nranks", C.c_int32), ("rm_max_hint", C.c_float), ("halo_ghost_cap", C.c_uint32),
-                ("sphere_stride", C.c_uint32), ("body_reach_hint", C.c_float)]
+                ("sphere_stride", C.c_uint32), ("body_reach_hint", C.c_float), ("slab_forces", C.c_uint32)]
 
 
 class RbBodyInit(C.Structure):

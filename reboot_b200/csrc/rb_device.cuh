@@ -52,7 +52,8 @@ enum { RB_C_TESTS_SS = 0, RB_C_TESTS_ST, RB_C_CAND_SS, RB_C_CAND_ST, RB_C_HITS_S
 // ---- multi-GPU halo exchange records (rb_dist.cu) ------------------------------------------------
 struct __align__(16) RbHaloHeader { uint32_t n_ghost, n_migr, ghost_overflow, migr_overflow; };
 struct __align__(16) RbGhostRec { float4 ws; float r; uint32_t gid; uint32_t pad0, pad1; };                 // 32 B
-struct __align__(16) RbMigrRec { float4 pos, vel, mt, pt, obj; uint32_t flags, gid, pad0, pad1; };          // 96 B
+struct __align__(16) RbMigrRec { float4 pos, vel, mt, pt, obj; uint32_t flags, gid, pad0, pad1;            // 160 B
+                                 float4 force, torque, apos, avel; };      // StateVector's force | mass, torque, angular position / velocity (defaults when the world has none)
 
 struct RbDistParams {
     RbHaloHeader* out_hdr[2]; RbGhostRec* out_ghost[2]; RbMigrRec* out_migr[2];      // 0 = left, 1 = right
@@ -63,7 +64,7 @@ struct RbDistParams {
     float slab_lo, slab_hi; int has_left, has_right;
     float mig_band;               // list ticks: a body up to this far beyond a face stays with its owner until the next scheduled rebuild
     // compound bodies (P.kstride): records are byte strings of a per-world size -- a ghost body is {mt | gid, pt | spheres,
-    // spheres x {obj, ws}}, a migrant {pos, vel, mt, pt, {flags, gid, spheres, -}, spheres x obj} -- and a body reaches as far
+    // spheres x {obj, ws}}, a migrant {pos, vel, mt, pt, {flags, gid, spheres, -}, force, torque, apos, avel, spheres x obj} -- and a body reaches as far
     // from its model translation as its farthest sphere: ext_max is the largest such reach (grown by the margin cap) anywhere
     uint32_t ghost_stride, migr_stride;
     float ext_max;

@@ -141,6 +141,8 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
             // compound bodies: the K sphere rows travel with the body row
             P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
             D.gid[h] = D.gid[last]; P.body_cnt[h] = P.body_cnt[last];
+            if (P.force) P.force[h] = P.force[last];
+            if (P.avel) { P.torque[h] = P.torque[last]; P.apos[h] = P.apos[last]; P.avel[h] = P.avel[last]; }
             for (uint32_t j = 0; j < P.kstride; ++j) {
                 const uint32_t a = h * P.kstride + j, b = last * P.kstride + j;
                 sph[a] = sph[b]; P.ws[a] = P.ws[b]; P.key[a] = P.key[b]; P.rank[a] = P.rank[b];
@@ -149,6 +151,8 @@ __global__ void rb_halo_remove_kernel(RbParams P, RbDistParams D, const uint32_t
         } else if (h != last) {
             P.pos[h] = P.pos[last]; P.vel[h] = P.vel[last]; P.mt[h] = P.mt[last]; P.pt[h] = P.pt[last]; P.flags[h] = P.flags[last];
             sph[h] = sph[last]; D.gid[h] = D.gid[last]; P.ws[h] = P.ws[last]; P.key[h] = P.key[last]; P.rank[h] = P.rank[last];
+            if (P.force) P.force[h] = P.force[last];
+            if (P.avel) { P.torque[h] = P.torque[last]; P.apos[h] = P.apos[last]; P.avel[h] = P.avel[last]; }
         }
         n = last;
     }
@@ -177,13 +181,15 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
             const float4 pos = r[0], vel = r[1], mt = r[2], pt = r[3], h = r[4];
             const uint32_t flags = __float_as_uint(h.x), gid = __float_as_uint(h.y), cnt = __float_as_uint(h.z);
             P.pos[i] = pos; P.vel[i] = vel; P.mt[i] = mt; P.pt[i] = pt; P.flags[i] = flags; D.gid[i] = gid; P.body_cnt[i] = cnt;
+            if (P.force) P.force[i] = r[5];
+            if (P.avel) { P.torque[i] = r[6]; P.apos[i] = r[7]; P.avel[i] = r[8]; }
             const float speed = mag3(xyz(vel));
             for (uint32_t j = 0; j < K; ++j) {
                 const uint32_t s = i * K + j;
                 uint32_t k = RB_NONE;
                 if (j < cnt) {
                     // the world sphere K1 computed on the old owner (same state, same formula)
-                    const float4 o = r[5 + j];
+                    const float4 o = r[9 + j];
                     D.sph_obj_w[s] = o;
                     if (P.ce_build) P.ce_build[s].w = -1.0f;      // a new row: no persistent triangle list yet
                     const f3 c = mk3(o.x + mt.x, o.y + mt.y, o.z + mt.z);
@@ -231,6 +237,8 @@ __global__ void __launch_bounds__(RB_BLOCK) rb_halo_unpack_kernel(RbParams P, Rb
         // per-tick clears never touch; the next rb_step / rb_step_group / rb_get_state / rb_get_stats fails with RB_ERR_CAPACITY.
         if (i >= ghost_floor) { atomicSub(&D.dn[0], 1u); atomicAdd(&D.counters[RB_C_IMM_DROPPED], 1ull); return; }
         P.pos[i] = m.pos; P.vel[i] = m.vel; P.mt[i] = m.mt; P.pt[i] = m.pt; P.flags[i] = m.flags;
+        if (P.force) P.force[i] = m.force;
+        if (P.avel) { P.torque[i] = m.torque; P.apos[i] = m.apos; P.avel[i] = m.avel; }
         D.sph_obj_w[i] = m.obj; D.gid[i] = m.gid;
         // same world sphere K1 computed on the old owner (same state, same formula)
         f3 c = mk3(m.obj.x + m.mt.x, m.obj.y + m.mt.y, m.obj.z + m.mt.z);
@@ -280,7 +288,7 @@ static int dist_alloc(rb_world* w) {
     RbDist* d = new RbDist();
     d->ghost_cap = w->ghost_cap;
     d->migr_cap = std::max<uint32_t>(1024u, w->ghost_cap / 8);
-    if (w->P.kstride) { d->ghost_stride = 32u + 32u * w->P.kstride; d->migr_stride = 80u + 16u * w->P.kstride; }
+    if (w->P.kstride) { d->ghost_stride = 32u + 32u * w->P.kstride; d->migr_stride = 144u + 16u * w->P.kstride; }
     size_t bytes = sizeof(RbHaloHeader) + (size_t)d->ghost_cap * d->ghost_stride + (size_t)d->migr_cap * d->migr_stride;
     bytes = (bytes + 255) / 256 * 256;
     d->buf_bytes = bytes;

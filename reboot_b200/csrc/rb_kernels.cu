@@ -92,7 +92,9 @@ __device__ __forceinline__ void integrate_bin_compound_slab(const RbParams& P, c
                 d[0] = make_float4(p.x, p.y, p.z, p4.w); d[1] = make_float4(v.x, v.y, v.z, v4.w);
                 d[2] = make_float4(m.x, m.y, m.z, 0.f); d[3] = P.pt[b];
                 d[4] = make_float4(__uint_as_float(f), __uint_as_float(gid), __uint_as_float(cnt), 0.f);
-                for (uint32_t i = 0; i < cnt; ++i) d[5 + i] = P.sph_obj[s0 + i];
+                d[5] = P.force ? P.force[b] : make_float4(0.f, 0.f, 0.f, 1.0f); d[6] = P.torque ? P.torque[b] : make_float4(0.f, 0.f, 0.f, 0.f);
+                d[7] = P.apos ? P.apos[b] : make_float4(0.f, 0.f, 0.f, 0.f); d[8] = P.avel ? P.avel[b] : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (uint32_t i = 0; i < cnt; ++i) d[9 + i] = P.sph_obj[s0 + i];
                 D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
                 if (any_in) {       // stays visible to its old owner for this tick
                     const uint32_t g = atomicAdd(D.self_cnt, 1u);
@@ -221,6 +223,8 @@ __device__ __forceinline__ void rb_integrate_bin_body(const RbParams& P, const i
                 if (kk < D.migr_cap) {
                     RbMigrRec mr; mr.pos = make_float4(p.x, p.y, p.z, p4.w); mr.vel = make_float4(v.x, v.y, v.z, v4.w);
                     mr.mt = make_float4(m.x, m.y, m.z, 0.f); mr.pt = P.pt[b]; mr.obj = o; mr.flags = f; mr.gid = D.gid[b]; mr.pad0 = mr.pad1 = 0;
+                    mr.force = P.force ? P.force[b] : make_float4(0.f, 0.f, 0.f, 1.0f); mr.torque = P.torque ? P.torque[b] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    mr.apos = P.apos ? P.apos[b] : make_float4(0.f, 0.f, 0.f, 0.f); mr.avel = P.avel ? P.avel[b] : make_float4(0.f, 0.f, 0.f, 0.f);
                     D.out_migr[dir][kk] = mr;
                     D.emig[atomicAdd(D.emig_cnt, 1u)] = b;
                     if (do_bin >= 2) vl_request_rebuild(P, 1u);      // rows move (swap-remove): every list is stale, in the grid or not

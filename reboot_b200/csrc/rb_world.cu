@@ -24,7 +24,7 @@ void rb_config_default(rb_config* c) {
     c->world_half = 1000.0f; c->gravity = -9.8f; c->friction = 0.95f; c->pushout = 1.0001f; c->ss_damp = 0.1f;
     c->margin_cap = 0.0f; c->device = 0; c->stream = nullptr; c->max_contacts = 0;
     c->slab_lo = -1000.0f; c->slab_hi = 1000.0f; c->rank = 0; c->nranks = 1; c->rm_max_hint = 0.0f; c->halo_ghost_cap = 0;
-    c->sphere_stride = 0; c->body_reach_hint = 0.0f;
+    c->sphere_stride = 0; c->body_reach_hint = 0.0f; c->slab_forces = 0;
 }
 
 const char* rb_last_error(const rb_world* w) { return w ? w->err.c_str() : g_create_error.c_str(); }
@@ -319,6 +319,7 @@ static int reorder_rows(rb_world* w, bool intick) {
     return RB_OK;
 }
 static int enqueue_broadphase(rb_world* w, int do_integrate);
+static int ensure_angular(rb_world* w);
 // which kernels step compound bodies (all bit-identical): RB_COMPOUND=legacy|group|split (RB_COMPOUND_GROUP=1 = group)
 static uint32_t compound_kernel_choice() {
     const char* v = getenv("RB_COMPOUND");
@@ -627,6 +628,9 @@ int rb_build(rb_world* w) {
     CU(cudaStreamSynchronize(w->stream));
     int r = build_triangle_grid(w);
     if (r) return r;
+    // slab worlds whose bodies take forces / torques / angular state: the arrays exist from the start (a migrant arriving later
+    // must find them), sized for every row this rank can ever hold
+    if (slab && w->cfg.slab_forces) { r = ensure_angular(w); if (r) return r; }
     // ---- prime the model transforms: Entity::_updateKinematics(0) on every entity (SURVEY Appendix A;
     // note StateVector::update(0) still applies the friction factor to bodies in contact / without gravity) ----
     P.dt = 0.0f;
@@ -1011,7 +1015,8 @@ int rb_get_model_matrices(rb_world* w, float* model16, float* prev16) {
 }
 int rb_get_angular(rb_world* w, float* ap4, float* av4) {
     if (!w || !w->built) return RB_ERR_INVALID;
-    size_t nb = w->P.n_owned;
+    if (w->d_dn) { int r = rb_dist_refresh_counts(w); if (r) return r; }      // slab worlds: the rows this rank owns now
+    size_t nb = w->n_owned_host;
     if (!w->P.avel) { if (ap4) memset(ap4, 0, nb * 16); if (av4) memset(av4, 0, nb * 16); return RB_OK; }
     if (ap4) { int r = read_rows_f4(w, w->P.apos, ap4, nb); if (r) return r; }
     if (av4) { int r = read_rows_f4(w, w->P.avel, av4, nb); if (r) return r; }
@@ -1060,7 +1065,13 @@ int rb_set_state(rb_world* w, uint32_t first, uint32_t count, const float* pos4,
 // Slab (multi-GPU) worlds move rows between ranks; force / torque / angular arrays do not travel with them,
 // so the setters refuse instead of leaving a force on a row that now holds another body.
 static int no_slab(rb_world* w, const char* what) {
-    if (w && w->d_dn) return fail(w, RB_ERR_INVALID, "%s is not available on slab (multi-GPU) worlds: migrating bodies do not carry force / torque / angular state", what);
+    if (w && w->d_dn) return fail(w, RB_ERR_INVALID, "%s is not available on slab (multi-GPU) worlds", what);
+    return RB_OK;
+}
+// force / torque / angular state on slab worlds: only when the world was created for it (rb_config.slab_forces on every rank:
+// the arrays exist from the build on, the migrant records carry them)
+static int slab_dynamics_ok(rb_world* w, const char* what) {
+    if (w && w->d_dn && !w->cfg.slab_forces) return fail(w, RB_ERR_INVALID, "%s on a slab (multi-GPU) world needs rb_config.slab_forces = 1 on every rank (migrating bodies then carry force / torque / angular state)", what);
     return RB_OK;
 }
 // Entity::setPosition (model/src/Entity.cpp:373-391) from the host, e.g. a teleport by game logic: unlike rb_set_state it
@@ -1105,7 +1116,7 @@ static int ensure_angular(rb_world* w) {
 }
 int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
     int r = range_ok(w, first, count); if (r) return r;
-    r = no_slab(w, "rb_set_force"); if (r) return r;
+    r = slab_dynamics_ok(w, "rb_set_force"); if (r) return r;
     if (!xyz4) return fail(w, RB_ERR_INVALID, "xyz4 is NULL");
     r = ensure_force(w); if (r) return r;
     r = ensure_stage(w, count); if (r) return r;
@@ -1115,7 +1126,7 @@ int rb_set_force(rb_world* w, uint32_t first, uint32_t count, const float* xyz4)
 }
 int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4) {
     int r = range_ok(w, first, count); if (r) return r;
-    r = no_slab(w, "rb_set_torque"); if (r) return r;
+    r = slab_dynamics_ok(w, "rb_set_torque"); if (r) return r;
     if (!xyz4) return fail(w, RB_ERR_INVALID, "xyz4 is NULL");
     r = ensure_angular(w); if (r) return r;
     r = ensure_stage(w, count); if (r) return r;
@@ -1126,7 +1137,7 @@ int rb_set_torque(rb_world* w, uint32_t first, uint32_t count, const float* xyz4
 }
 int rb_set_angular(rb_world* w, uint32_t first, uint32_t count, const float* ap4, const float* av4) {
     int r = range_ok(w, first, count); if (r) return r;
-    r = no_slab(w, "rb_set_angular"); if (r) return r;
+    r = slab_dynamics_ok(w, "rb_set_angular"); if (r) return r;
     r = ensure_angular(w); if (r) return r;
     if (ap4) { r = write_rows_f4(w, w->P.apos, first, count, ap4); if (r) return r; CU(cudaStreamSynchronize(w->stream)); }
     if (av4) { r = write_rows_f4(w, w->P.avel, first, count, av4); if (r) return r; }

@@ -24,7 +24,7 @@ class RebootError(RuntimeError):
 class World:
     def __init__(self, scene=None, device: int = 0, stream=None, max_contacts: int = 0, margin_cap: float | None = None,
                  slab=None, rank: int = 0, nranks: int = 1, build: bool = True, ids=None, rm_max_hint: float = 0.0,
-                 halo_ghost_cap: int = 0, sphere_stride: int = 0, body_reach_hint: float = 0.0):
+                 halo_ghost_cap: int = 0, sphere_stride: int = 0, body_reach_hint: float = 0.0, slab_forces: bool = False):
         self.L = _lib.load()
         cfg = RbConfig()
         self.L.rb_config_default(C.byref(cfg))
@@ -38,7 +38,7 @@ class World:
         cfg.rank, cfg.nranks = rank, nranks
         cfg.rm_max_hint = rm_max_hint
         cfg.halo_ghost_cap = int(halo_ghost_cap)
-        cfg.sphere_stride = int(sphere_stride); cfg.body_reach_hint = float(body_reach_hint)
+        cfg.sphere_stride = int(sphere_stride); cfg.body_reach_hint = float(body_reach_hint); cfg.slab_forces = 1 if slab_forces else 0
         self.cfg = cfg
         self._ids = ids
         h = C.c_void_p()

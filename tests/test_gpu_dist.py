@@ -223,3 +223,49 @@ def test_compound_slab_group_bit_identical_to_single_world(mods, nslabs, ragged)
     b = group.state(sc.n_bodies)
     assert np.array_equal(b["owner"], dist.owner_of(b["model_t"][:, 0], nslabs)), "ownership follows the model translation"
     single.close(); group.close()
+
+
+def test_slab_group_forces_torques_angular_travel_with_migrants(mods):
+    """rb_config.slab_forces: bodies of slab worlds take StateVector::setForce / setTorque input and carry angular state; the
+    arrays travel with migrating bodies (migrant records) and with rows moved by the swap-remove. Forces are re-applied every tick
+    by GLOBAL body id (gated by the contact / gravity flags like the reference), torques once -- state, angular state, flags and
+    contact sets bit-identical to a single world."""
+    World, dist, scenes = mods
+    sc = _crossing_scene(scenes, n=3000, seed=8)
+    rng = np.random.default_rng(8)
+    F = np.zeros((sc.n_bodies, 3), np.float32); F[:, 0] = rng.uniform(-30, 30, sc.n_bodies); F[:, 2] = rng.uniform(-10, 10, sc.n_bodies)
+    Tq = rng.uniform(-2, 2, (sc.n_bodies, 3)).astype(np.float32)
+    Av = rng.uniform(-1, 1, (sc.n_bodies, 3)).astype(np.float32)
+    single = World(sc)
+    single.set_torque(0, Tq); single.set_angular(0, avel=Av)
+    group = dist.SlabGroup(sc, 2, slab_forces=True)
+    for w in group.worlds:
+        ids = w.body_ids()
+        w.set_torque(0, Tq[ids]); w.set_angular(0, avel=Av[ids])
+    migrated = 0
+    for k in range(120):
+        single.set_force(0, F)
+        for w in group.worlds:
+            w.set_force(0, F[w.body_ids()])
+        single.step(5); group.step(5)
+        migrated += sum(w.stats()["migrated_out_last"] for w in group.worlds)
+        if k % 20 == 19 or k < 2:
+            a = single.state(); b = group.state(sc.n_bodies)
+            for key in ("pos", "vel", "model_t", "prev_t"):
+                assert np.array_equal(bits(a[key]), bits(b[key])), (k, key)
+            assert np.array_equal(a["flags"], b["flags"]), k
+            ap, av = single.angular()
+            gp, gv = np.zeros_like(ap), np.zeros_like(av)
+            for w in group.worlds:
+                ids = w.body_ids(); p_, v_ = w.angular()
+                gp[ids] = p_[: len(ids)]; gv[ids] = v_[: len(ids)]
+            assert np.array_equal(bits(ap), bits(gp)) and np.array_equal(bits(av), bits(gv)), k
+            sa, sb = single.contact_sets(), group.contact_sets()
+            assert np.array_equal(sa[0], sb[0]) and np.array_equal(sa[1], sb[1]), k
+    assert migrated > 0, "the scene must exercise migration"
+    # without the flag the setters are refused (migrants would lose the state)
+    plain = dist.SlabGroup(sc, 2)
+    from reboot_b200 import RebootError
+    with pytest.raises(RebootError):
+        plain.worlds[0].set_force(0, F[plain.worlds[0].body_ids()])
+    plain.close(); single.close(); group.close()
